@@ -1,0 +1,282 @@
+"""ctypes binding of include/bgt_b200.h.  No computation happens in this file."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SCAN_COUNTS, SCAN_HAP_BITS, SCAN_HAP_BYTES, SCAN_DEVICE_OUT = 0x01, 0x02, 0x04, 0x10
+MAX_GROUPS = 32
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(HERE, "lib", "libbgt_b200.so")
+
+
+class ScanOut(C.Structure):
+    _fields_ = [("counts", C.c_void_p), ("passed", C.c_void_p), ("hap_bits", C.c_void_p * 2), ("hap_bytes", C.c_void_p * 2),
+                ("totals", C.c_int64 * 4)]
+
+
+class SynthCfg(C.Structure):
+    _fields_ = [("n_samples", C.c_int32), ("n_rows", C.c_int64), ("shift", C.c_int32), ("seed", C.c_uint64),
+                ("r_max", C.c_int32), ("p1_one_in", C.c_int32)]
+
+
+# every symbol include/bgt_b200.h declares: name -> (restype, argtypes)
+_vp, _i64, _int = C.c_void_p, C.c_int64, C.c_int
+SIGNATURES = {
+    "b200_abi_version": (_int, []),
+    "b200_device_count": (_int, []),
+    "b200_strerror": (C.c_char_p, []),
+    "b200_ctx_create": (_vp, [_int]),
+    "b200_ctx_destroy": (None, [_vp]),
+    "b200_ctx_sync": (_int, [_vp]),
+    "b200_host_alloc": (_vp, [C.c_size_t]),
+    "b200_host_free": (None, [_vp]),
+    "b200_pbf_load": (_vp, [_vp, _vp, C.c_size_t, _i64, _i64]),
+    "b200_pbf_open": (_vp, [_vp, C.c_char_p, _i64, _i64]),
+    "b200_pbf_close": (None, [_vp]),
+    "b200_pbf_m": (_int, [_vp]),
+    "b200_pbf_g": (_int, [_vp]),
+    "b200_pbf_shift": (_int, [_vp]),
+    "b200_pbf_n": (_i64, [_vp]),
+    "b200_pbf_row_beg": (_i64, [_vp]),
+    "b200_pbf_row_end": (_i64, [_vp]),
+    "b200_pbf_row_bytes": (_i64, [_vp, _i64, _i64, _int]),
+    "b200_pbf_bad_rows": (_i64, [_vp]),
+    "b200_query_create": (_vp, [_vp, _vp, _int, _vp, _vp, _int, C.c_char_p, C.POINTER(_int)]),
+    "b200_query_destroy": (None, [_vp]),
+    "b200_query_n_track": (_int, [_vp]),
+    "b200_query_hap_words": (_int, [_vp]),
+    "b200_query_counts_stride": (_int, [_vp]),
+    "b200_scan": (_i64, [_vp, _vp, _vp, _i64, _i64, C.c_uint, C.POINTER(ScanOut)]),
+    "b200_scan_collect": (_int, [_vp, C.POINTER(_i64)]),
+    "b200_last_ms": (C.c_double, [_vp, _int]),
+    "b200_kernel_launches": (_i64, [_vp]),
+    "b200_mark": (_int, [_vp, _int]),
+    "b200_mark_elapsed_ms": (C.c_double, [_vp, _int, _int]),
+    "b200_synth_generate": (_vp, [_vp, C.POINTER(SynthCfg)]),
+    "b200_pbf_image_size": (C.c_size_t, [_vp]),
+    "b200_pbf_image_download": (_int, [_vp, _vp, C.c_size_t]),
+}
+
+
+def load_library(path=None):
+    """dlopen libbgt_b200.so and type every entry point.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or lib_path()
+    if not os.path.exists(path):
+        raise B200Error("libbgt_b200.so is not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                        "there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+def lib():
+    return load_library()
+
+
+def _err():
+    return lib().b200_strerror().decode()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One GPU (b200_ctx_t)."""
+
+    def __init__(self, device=0):
+        self.h = lib().b200_ctx_create(device)
+        if not self.h:
+            raise B200Error(_err())
+        self.device = device
+
+    def sync(self):
+        if lib().b200_ctx_sync(self.h) != 0:
+            raise B200Error(_err())
+
+    def last_ms(self, which):
+        return lib().b200_last_ms(self.h, which)
+
+    def mark(self, slot):
+        if lib().b200_mark(self.h, slot) != 0:
+            raise B200Error(_err())
+
+    def mark_elapsed_ms(self, a, b):
+        return lib().b200_mark_elapsed_ms(self.h, a, b)
+
+    @property
+    def launches(self):
+        return lib().b200_kernel_launches(self.h)
+
+    def close(self):
+        if self.h:
+            lib().b200_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class Pbf:
+    """A .pbf (or a row shard) resident in HBM (b200_pbf_t); the stand-in for pbf_open_r (pbwt.c:221-262)."""
+
+    def __init__(self, ctx, handle):
+        if not handle:
+            raise B200Error(_err())
+        self.ctx, self.h = ctx, handle
+        L = lib()
+        self.m, self.g, self.shift, self.n = L.b200_pbf_m(handle), L.b200_pbf_g(handle), L.b200_pbf_shift(handle), L.b200_pbf_n(handle)
+        self.row_beg, self.row_end = L.b200_pbf_row_beg(handle), L.b200_pbf_row_end(handle)
+        self.bad_rows = L.b200_pbf_bad_rows(handle)
+
+    @classmethod
+    def from_bytes(cls, ctx, data, row_beg=0, row_end=-1):
+        buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        return cls(ctx, lib().b200_pbf_load(ctx.h, _ptr(buf), buf.size, row_beg, row_end))
+
+    @classmethod
+    def open(cls, ctx, fn, row_beg=0, row_end=-1):
+        return cls(ctx, lib().b200_pbf_open(ctx.h, os.fsencode(fn), row_beg, row_end))
+
+    def row_bytes(self, beg, end, with_snapshots=True):
+        v = lib().b200_pbf_row_bytes(self.h, beg, end, int(with_snapshots))
+        if v < 0:
+            raise B200Error(_err())
+        return v
+
+    def image(self, out=None):
+        """Download the complete file image (only when fully resident, e.g. generated cohorts)."""
+        n = lib().b200_pbf_image_size(self.h)
+        if n == 0:
+            raise B200Error("no complete file image resident")
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        if lib().b200_pbf_image_download(self.h, _ptr(out), out.size) != 0:
+            raise B200Error(_err())
+        return out
+
+    def close(self):
+        if self.h:
+            lib().b200_pbf_close(self.h)
+            self.h = None
+
+
+def synth_cohort(ctx, n_samples, n_rows, seed=1, shift=13, r_max=64, p1_one_in=16):
+    """Generate a truthful synthetic cohort on the device and return it resident."""
+    cfg = SynthCfg(n_samples, n_rows, shift, seed, r_max, p1_one_in)
+    return Pbf(ctx, lib().b200_synth_generate(ctx.h, C.byref(cfg)))
+
+
+class Query:
+    """Sample selection, groups and site filter of one `bgt view` (bgt_prepare + bgtm_add_group + bgtm_set_flt_site)."""
+
+    def __init__(self, ctx, pbf, out_samples=None, group=None, n_groups=1, flt=None):
+        self.out_samples = None if out_samples is None else np.ascontiguousarray(out_samples, dtype=np.int32)
+        self.group = None if group is None else np.ascontiguousarray(group, dtype=np.uint32)
+        n_out = pbf.m // 2 if self.out_samples is None else self.out_samples.size
+        if self.group is not None and self.group.size != n_out:
+            raise ValueError("group must have one entry per selected sample")
+        err = C.c_int(0)
+        self.h = lib().b200_query_create(ctx.h, pbf.h, n_out, _ptr(self.out_samples), _ptr(self.group), n_groups,
+                                         flt.encode() if flt is not None else None, C.byref(err))
+        self.flt_err = err.value
+        if not self.h:
+            raise B200Error(_err())
+        self.n_track = lib().b200_query_n_track(self.h)
+        self.words = lib().b200_query_hap_words(self.h)
+        self.stride = lib().b200_query_counts_stride(self.h)
+        self.n_groups = n_groups
+
+    def close(self):
+        if self.h:
+            lib().b200_query_destroy(self.h)
+            self.h = None
+
+
+def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, hap_bytes=False, out=None):
+    """b200_scan with host outputs.  Returns dict(n, counts, passed, hap_bits, hap_bytes, totals)."""
+    if n_rows is None:
+        n_rows = pbf.row_end - row_beg
+    n_alloc = max(int(n_rows), 0)
+    res = out or {}
+    if counts and "counts" not in res:
+        res["counts"] = np.empty((n_alloc, query.stride), dtype=np.int32)
+    if "passed" not in res:
+        res["passed"] = np.empty(n_alloc, dtype=np.uint8)
+    if hap_bits and "hap_bits" not in res:
+        res["hap_bits"] = [np.empty((n_alloc, query.words), dtype=np.uint32) for _ in range(2)]
+    if hap_bytes and "hap_bytes" not in res:
+        res["hap_bytes"] = [np.empty((n_alloc, query.n_track), dtype=np.uint8) for _ in range(2)]
+    so = ScanOut()
+    so.counts = _ptr(res["counts"]) if counts else None
+    so.passed = _ptr(res["passed"])
+    flags = SCAN_COUNTS if counts else 0
+    if hap_bits:
+        flags |= SCAN_HAP_BITS
+        so.hap_bits[0], so.hap_bits[1] = _ptr(res["hap_bits"][0]), _ptr(res["hap_bits"][1])
+    if hap_bytes:
+        flags |= SCAN_HAP_BYTES
+        so.hap_bytes[0], so.hap_bytes[1] = _ptr(res["hap_bytes"][0]), _ptr(res["hap_bytes"][1])
+    done = lib().b200_scan(ctx.h, pbf.h, query.h, row_beg, n_rows, flags, C.byref(so))
+    if done < 0:
+        raise B200Error(_err())
+    res["n"] = done
+    res["totals"] = [so.totals[i] for i in range(4)]
+    for k in ("counts", "passed"):
+        if k in res and res[k] is not None:
+            res[k] = res[k][:done]
+    return res
+
+
+def scan_device(ctx, pbf, query, row_beg, n_rows, d_counts=0, d_pass=0, d_hap_bits=(0, 0)):
+    """b200_scan with B200_SCAN_DEVICE_OUT: outputs are device pointers (ints), the call returns without syncing.
+    Follow with collect(ctx) to wait, check device error flags and fetch totals / kernel timings."""
+    so = ScanOut()
+    so.counts = d_counts or None
+    so.passed = d_pass or None
+    flags = SCAN_DEVICE_OUT | (SCAN_COUNTS if d_counts else 0)
+    if d_hap_bits[0]:
+        flags |= SCAN_HAP_BITS
+        so.hap_bits[0], so.hap_bits[1] = d_hap_bits
+    done = lib().b200_scan(ctx.h, pbf.h, query.h, row_beg, n_rows, flags, C.byref(so))
+    if done < 0:
+        raise B200Error(_err())
+    return done
+
+
+def collect(ctx):
+    tot = (C.c_int64 * 4)()
+    if lib().b200_scan_collect(ctx.h, tot) != 0:
+        raise B200Error(_err())
+    return [tot[i] for i in range(4)]
+
+
+def host_alloc(n_bytes):
+    """Pinned host memory as a uint8 numpy array (b200_host_alloc); keep the returned array alive, free with host_free."""
+    p = lib().b200_host_alloc(n_bytes)
+    if not p:
+        raise B200Error(_err())
+    return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n_bytes,))
+
+
+def host_free(arr):
+    lib().b200_host_free(arr.ctypes.data_as(C.c_void_p))

@@ -1,0 +1,707 @@
+// api.cu -- the C ABI of libbgt_b200.so (include/bgt_b200.h): handles, HBM residency, launch orchestration.
+// Host logic only; every per-site computation is in pbwt_kernels.cu / synth.cu.  No CPU fallback exists:
+// without a CUDA device b200_ctx_create() fails and nothing else can be called.
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../include/bgt_b200.h"
+#include "pbwt_kernels.cuh"
+#include "flt.h"
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------------ errors
+
+static thread_local char g_err[512] = "";
+
+static void set_err(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+#define CU_OK(call) cu_ok((call), #call, __LINE__)
+static bool cu_ok(cudaError_t e, const char *what, int line)
+{
+	if (e == cudaSuccess) return true;
+	set_err("CUDA error at api.cu:%d: %s: %s", line, what, cudaGetErrorString(e));
+	return false;
+}
+
+// ------------------------------------------------------------------------------------------------ handles
+
+struct DevBuf { // grow-only device scratch
+	void *p = nullptr; size_t cap = 0;
+	bool reserve(size_t n) {
+		if (n <= cap) return true;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		if (!CU_OK(cudaMalloc(&p, n))) return false;
+		cap = n;
+		return true;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct b200_ctx_s {
+	int dev = 0;
+	cudaStream_t st = nullptr;
+	cudaEvent_t ev[8] = {};   // 0/1 walk, 2/3 scan, 4/5 h2d, 6/7 d2h
+	cudaEvent_t mark[4] = {};
+	double last_ms[4] = {0, 0, 0, 0};
+	int64_t launches = 0;
+	int *d_err = nullptr;
+	unsigned long long *d_acc = nullptr; // [0..3] totals, [4] bad rows
+	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2];
+	int sm_count = 148;
+};
+
+struct b200_pbf_s {
+	b200_ctx_t *ctx = nullptr;
+	int m = 0, g = 0, shift = 0, BS = 0;
+	int64_t n = 0;               // rows in the file
+	int blk0 = 0, n_blk = 0;     // resident checkpoint blocks [blk0, blk0+n_blk)
+	int64_t n_blk_file = 0;
+	std::vector<int> rows_in_blk;
+	std::vector<uint64_t> h_rowoff;   // [n_blk][BS+1], relative to d_img
+	std::vector<uint64_t> h_blkoff;   // [n_blk] offset of the 'S' record, relative to d_img
+	uint8_t *d_img = nullptr; size_t img_bytes = 0; uint64_t file_off0 = 0;
+	size_t file_size = 0;             // size of the complete file image (0 unless fully resident)
+	uint64_t *d_rowoff = nullptr, *d_blkoff = nullptr;
+	int *d_rows_in_blk = nullptr, *d_blk_tile_beg = nullptr;
+	int2 *d_tiles = nullptr;
+	uint32_t *d_n1 = nullptr;
+	int32_t *d_rank0 = nullptr;
+	int64_t bad_rows = 0;
+};
+
+struct b200_query_s {
+	b200_ctx_t *ctx = nullptr;
+	int m = 0, n_out = 0, n_track = 0, G = 1, words = 0;
+	bool full = true;
+	int32_t *d_track = nullptr;
+	uint8_t *d_tgrp = nullptr;
+	int32_t *d_gsize = nullptr;
+	flt_prog_t prog;
+	flt_prog_t *d_prog = nullptr;
+	bool has_flt = false;
+};
+
+// ------------------------------------------------------------------------------------------------ context
+
+extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+extern "C" int b200_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+extern "C" const char *b200_strerror(void) { return g_err; }
+
+extern "C" b200_ctx_t *b200_ctx_create(int device)
+{
+	int n = b200_device_count();
+	if (n <= 0) { set_err("no CUDA device: libbgt_b200 has no CPU fallback"); return nullptr; }
+	if (device < 0 || device >= n) { set_err("device %d out of range (0..%d)", device, n - 1); return nullptr; }
+	if (!CU_OK(cudaSetDevice(device))) return nullptr;
+	cudaDeviceProp prop;
+	if (!CU_OK(cudaGetDeviceProperties(&prop, device))) return nullptr;
+	if (prop.major < 10) { set_err("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return nullptr; }
+	b200_ctx_t *c = new b200_ctx_t();
+	c->dev = device; c->sm_count = prop.multiProcessorCount;
+	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+	for (int i = 0; ok && i < 8; ++i) ok = CU_OK(cudaEventCreate(&c->ev[i]));
+	for (int i = 0; ok && i < 4; ++i) ok = CU_OK(cudaEventCreate(&c->mark[i]));
+	ok = ok && CU_OK(cudaMalloc(&c->d_err, sizeof(int))) && CU_OK(cudaMalloc(&c->d_acc, 8 * sizeof(unsigned long long)));
+	ok = ok && CU_OK(cudaMemset(c->d_err, 0, sizeof(int))) && CU_OK(cudaMemset(c->d_acc, 0, 8 * sizeof(unsigned long long)));
+	if (!ok) { b200_ctx_destroy(c); return nullptr; }
+	return c;
+}
+
+extern "C" void b200_ctx_destroy(b200_ctx_t *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->dev);
+	if (c->st) cudaStreamSynchronize(c->st);
+	c->cnt_raw.release(); c->counts.release(); c->pass.release();
+	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
+	for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
+	if (c->d_err) cudaFree(c->d_err);
+	if (c->d_acc) cudaFree(c->d_acc);
+	if (c->st) cudaStreamDestroy(c->st);
+	delete c;
+}
+
+extern "C" int b200_ctx_sync(b200_ctx_t *c)
+{
+	if (!c) return -1;
+	cudaSetDevice(c->dev);
+	return CU_OK(cudaStreamSynchronize(c->st)) ? 0 : -1;
+}
+
+extern "C" void *b200_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (!CU_OK(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault))) return nullptr;
+	return p;
+}
+
+extern "C" void b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" double b200_last_ms(b200_ctx_t *c, int which) { return (c && which >= 0 && which < 4) ? c->last_ms[which] : -1.0; }
+extern "C" int64_t b200_kernel_launches(b200_ctx_t *c) { return c ? c->launches : 0; }
+
+extern "C" int b200_mark(b200_ctx_t *c, int slot)
+{
+	if (!c || slot < 0 || slot >= 4) return -1;
+	cudaSetDevice(c->dev);
+	return CU_OK(cudaEventRecord(c->mark[slot], c->st)) ? 0 : -1;
+}
+
+extern "C" double b200_mark_elapsed_ms(b200_ctx_t *c, int a, int b)
+{
+	if (!c || a < 0 || a >= 4 || b < 0 || b >= 4) return -1.0;
+	cudaSetDevice(c->dev);
+	float ms = 0;
+	if (!CU_OK(cudaEventSynchronize(c->mark[b])) || !CU_OK(cudaEventElapsedTime(&ms, c->mark[a], c->mark[b]))) return -1.0;
+	return ms;
+}
+
+// ------------------------------------------------------------------------------------------------ PBF residency
+
+static void pbf_free_device(b200_pbf_t *pb)
+{
+	if (pb->d_img) cudaFree(pb->d_img);
+	if (pb->d_rowoff) cudaFree(pb->d_rowoff);
+	if (pb->d_blkoff) cudaFree(pb->d_blkoff);
+	if (pb->d_rows_in_blk) cudaFree(pb->d_rows_in_blk);
+	if (pb->d_blk_tile_beg) cudaFree(pb->d_blk_tile_beg);
+	if (pb->d_tiles) cudaFree(pb->d_tiles);
+	if (pb->d_n1) cudaFree(pb->d_n1);
+	if (pb->d_rank0) cudaFree(pb->d_rank0);
+}
+
+extern "C" void b200_pbf_close(b200_pbf_t *pb)
+{
+	if (!pb) return;
+	cudaSetDevice(pb->ctx->dev);
+	cudaStreamSynchronize(pb->ctx->st);
+	pbf_free_device(pb);
+	delete pb;
+}
+
+// Tiles: maximal groups of consecutive rows of one block with <= T_MAX rows and <= RAW_CAP bytes; a row that is
+// larger than RAW_CAP on its own becomes a single-row "big" tile (streamed in pieces by the kernel).
+static void plan_tiles(const b200_pbf_t *pb, std::vector<int2> &tiles, std::vector<int> &blk_tile_beg)
+{
+	const int BS = pb->BS;
+	blk_tile_beg.assign(pb->n_blk + 1, 0);
+	tiles.clear();
+	for (int b = 0; b < pb->n_blk; ++b) {
+		blk_tile_beg[b] = (int)tiles.size();
+		const uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
+		const int rows = pb->rows_in_blk[b];
+		int r = 0;
+		while (r < rows) {
+			if (ro[r + 1] - ro[r] > (uint64_t)RAW_CAP) { tiles.push_back(make_int2(r, (int)(1u | 0x80000000u))); ++r; continue; }
+			int e = r + 1;
+			while (e < rows && e - r < T_MAX && ro[e + 1] - ro[r] <= (uint64_t)RAW_CAP) ++e;
+			tiles.push_back(make_int2(r, e - r));
+			r = e;
+		}
+	}
+	blk_tile_beg[pb->n_blk] = (int)tiles.size();
+}
+
+// Upload the row index, plan tiles, compute per-row n1, [generator: run the chain], invert the snapshots.
+static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain)
+{
+	b200_ctx_t *c = pb->ctx;
+	const int BS = pb->BS, nb = pb->n_blk;
+	std::vector<int2> tiles;
+	std::vector<int> btb;
+	plan_tiles(pb, tiles, btb);
+	const size_t n_tiles = tiles.size();
+	bool ok = CU_OK(cudaMalloc(&pb->d_rowoff, sizeof(uint64_t) * (size_t)nb * (BS + 1) + 8)) &&
+	          CU_OK(cudaMalloc(&pb->d_blkoff, sizeof(uint64_t) * (nb + 1))) &&
+	          CU_OK(cudaMalloc(&pb->d_rows_in_blk, sizeof(int) * (nb + 1))) &&
+	          CU_OK(cudaMalloc(&pb->d_blk_tile_beg, sizeof(int) * (nb + 1))) &&
+	          CU_OK(cudaMalloc(&pb->d_tiles, sizeof(int2) * (n_tiles + 1))) &&
+	          CU_OK(cudaMalloc(&pb->d_n1, sizeof(uint32_t) * (size_t)nb * BS * 2 + 8)) &&
+	          CU_OK(cudaMalloc(&pb->d_rank0, sizeof(int32_t) * (size_t)nb * 2 * (size_t)pb->m + 8));
+	if (!ok) return false;
+	ok = CU_OK(cudaMemcpyAsync(pb->d_rowoff, pb->h_rowoff.data(), sizeof(uint64_t) * (size_t)nb * (BS + 1), cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_blkoff, pb->h_blkoff.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_rows_in_blk, pb->rows_in_blk.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_blk_tile_beg, btb.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_tiles, tiles.data(), sizeof(int2) * n_tiles, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemsetAsync(pb->d_n1, 0, sizeof(uint32_t) * (size_t)nb * BS * 2, c->st)) &&
+	     CU_OK(cudaMemsetAsync(pb->d_rank0, 0, sizeof(int32_t) * (size_t)nb * 2 * (size_t)pb->m, c->st)) &&
+	     CU_OK(cudaMemsetAsync(c->d_acc + 4, 0, sizeof(unsigned long long), c->st)) &&
+	     CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
+	if (!ok) return false;
+	if (!CU_OK(launch_rowmeta(pb->d_img, pb->d_rowoff, nb, pb->shift, 0, pb->d_rows_in_blk, (uint32_t)pb->m, pb->d_n1, c->d_acc + 4, c->st))) return false;
+	++c->launches;
+	if (synth_chain) {
+		WalkParams P;
+		memset(&P, 0, sizeof(P));
+		P.img = pb->d_img; P.rowoff = pb->d_rowoff; P.n1 = pb->d_n1; P.tiles = pb->d_tiles; P.blk_tile_beg = pb->d_blk_tile_beg;
+		P.snap_img = pb->d_img; P.blkoff = pb->d_blkoff;
+		P.m = pb->m; P.n_track = pb->m; P.G = 1; P.words = (pb->m + 31) / 32; P.shift = pb->shift;
+		P.n_blk_chain = nb; P.blk_row0 = 0; P.row_lo = 0; P.row_hi = pb->n; P.err = c->d_err;
+		// tgrp is read for valid entries: borrow the (zeroed) n1 buffer?  No: allocate a zero group map.
+		uint8_t *d_zero = nullptr;
+		if (!CU_OK(cudaMalloc(&d_zero, (size_t)pb->m + 16)) || !CU_OK(cudaMemsetAsync(d_zero, 0, (size_t)pb->m + 16, c->st))) return false;
+		P.tgrp = d_zero;
+		const int C = pb->m > 148 * 2 * WALK_NT * 4 ? 4 : pb->m > 148 * 2 * WALK_NT * 2 ? 2 : 1;
+		const int slices = (pb->m + WALK_NT * C - 1) / (WALK_NT * C);
+		ok = CU_OK(launch_walk(P, C, false, true, slices, nb, c->st));
+		++c->launches;
+		ok = ok && CU_OK(cudaStreamSynchronize(c->st));
+		cudaFree(d_zero);
+		if (!ok) return false;
+	}
+	if (!CU_OK(launch_invert_snapshots(pb->d_img, pb->d_blkoff, nb, pb->m, pb->d_rank0, c->d_err, c->st))) return false;
+	++c->launches;
+	unsigned long long bad = 0;
+	int err = 0;
+	ok = CU_OK(cudaMemcpyAsync(&bad, c->d_acc + 4, sizeof(bad), cudaMemcpyDeviceToHost, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(err), cudaMemcpyDeviceToHost, c->st)) &&
+	     CU_OK(cudaStreamSynchronize(c->st));
+	if (!ok) return false;
+	pb->bad_rows = (int64_t)bad;
+	if (err & 1) { set_err("corrupt PBF: an 'S' snapshot holds a column index >= m"); return false; }
+	if (err & 8) { set_err("internal: TMA copy never completed"); return false; }
+	return true;
+}
+
+// the file indexes checkpoint blocks only (pbwt.c:297); walk the length prefixes of the rows inside
+static bool walk_block(const uint8_t *f, size_t flen, uint64_t off, int m, int g, int rows, uint64_t *roff)
+{
+	if (off >= flen || f[off] != 'S') return false;
+	uint64_t pos = off + 1 + (uint64_t)g * 4 * (uint64_t)m;
+	for (int r = 0; r < rows; ++r) {
+		if (pos >= flen || f[pos] != 'B') return false;
+		roff[r] = pos++;
+		for (int p = 0; p < g; ++p) {
+			int32_t l;
+			if (pos + 4 > flen) return false;
+			memcpy(&l, f + pos, 4);
+			if (l < 0 || pos + 4 + (uint64_t)l > flen) return false;
+			pos += 4 + (uint64_t)l;
+		}
+	}
+	roff[rows] = pos;
+	return true;
+}
+
+extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
+{
+	if (!c || !f) { set_err("b200_pbf_load: null argument"); return nullptr; }
+	cudaSetDevice(c->dev);
+	if (flen < 16 + 13 + 8 || memcmp(f, "PBF\1", 4) != 0) { set_err("not a PBF file (bad magic)"); return nullptr; } // pbwt.c:231-235
+	int32_t hdr[3];
+	memcpy(hdr, f + 4, 12);
+	uint64_t ioff;
+	memcpy(&ioff, f + flen - 8, 8);
+	if (ioff + 13 > flen || f[ioff] != 'I') { set_err("PBF has no index record; it cannot be made resident"); return nullptr; } // pbwt.c:247-258
+	int64_t n; int32_t n_idx;
+	memcpy(&n, f + ioff + 1, 8);
+	memcpy(&n_idx, f + ioff + 9, 4);
+	const int m = hdr[0], g = hdr[1], shift = hdr[2];
+	if (g != 2) { set_err("PBF has %d bit planes; the BGT genotype path uses exactly 2 (import.c:68)", g); return nullptr; }
+	if (m <= 0 || m >= (1 << 30) || shift < 0 || shift > 24 || n < 0 || n_idx < 0 || ioff + 13 + 8ull * n_idx > flen) { set_err("PBF header out of range (m=%d shift=%d n=%lld)", m, shift, (long long)n); return nullptr; }
+	const int BS = 1 << shift;
+	if ((int64_t)n_idx != (n + BS - 1) / BS) { set_err("PBF index has %d entries for %lld rows", n_idx, (long long)n); return nullptr; }
+	if (row_end < 0 || row_end > n) row_end = n;
+	if (row_beg < 0) row_beg = 0;
+	if (row_beg > row_end) row_beg = row_end;
+	std::vector<uint64_t> idx(n_idx);
+	memcpy(idx.data(), f + ioff + 13, 8ull * n_idx);
+
+	b200_pbf_t *pb = new b200_pbf_t();
+	pb->ctx = c; pb->m = m; pb->g = g; pb->shift = shift; pb->BS = BS; pb->n = n; pb->n_blk_file = n_idx;
+	pb->blk0 = (int)(row_beg >> shift);
+	const int blk1 = row_end > row_beg ? (int)((row_end + BS - 1) >> shift) : pb->blk0;
+	pb->n_blk = blk1 - pb->blk0;
+	const int nb = pb->n_blk;
+	const uint64_t byte_beg = nb ? idx[pb->blk0] : ioff, byte_end = (nb && blk1 < n_idx) ? idx[blk1] : ioff;
+	pb->file_off0 = byte_beg & ~(uint64_t)15;
+	if (pb->blk0 == 0 && blk1 == n_idx) { pb->file_off0 = 0; pb->file_size = flen; }
+	const uint64_t copy_end = pb->file_size ? flen : byte_end;
+	pb->img_bytes = (size_t)(copy_end - pb->file_off0);
+
+	bool ok = CU_OK(cudaMalloc(&pb->d_img, pb->img_bytes + 64));
+	ok = ok && CU_OK(cudaEventRecord(c->ev[4], c->st));
+	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img, f + pb->file_off0, pb->img_bytes, cudaMemcpyHostToDevice, c->st));
+	ok = ok && CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st));
+	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st));
+	if (!ok) { pbf_free_device(pb); delete pb; return nullptr; }
+
+	// row offsets: independent per block -> a few host threads, overlapping the H2D copy above
+	pb->rows_in_blk.resize(nb);
+	pb->h_rowoff.assign((size_t)nb * (BS + 1), 0);
+	pb->h_blkoff.resize(nb);
+	for (int b = 0; b < nb; ++b) {
+		const int64_t r0 = (int64_t)(pb->blk0 + b) << shift;
+		pb->rows_in_blk[b] = (int)(n - r0 < BS ? n - r0 : BS);
+		pb->h_blkoff[b] = idx[pb->blk0 + b] - pb->file_off0;
+	}
+	{
+		const int nt = nb < 2 ? 1 : (nb < 8 ? nb : 8);
+		std::vector<int> bad(nt, 0);
+		std::vector<std::thread> th;
+		for (int t = 0; t < nt; ++t)
+			th.emplace_back([&, t]() {
+				for (int b = t; b < nb; b += nt) {
+					uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
+					if (!walk_block(f, (size_t)ioff + 1, idx[pb->blk0 + b], m, g, pb->rows_in_blk[b], ro)) { bad[t] = 1; return; }
+					for (int r = 0; r <= pb->rows_in_blk[b]; ++r) ro[r] -= pb->file_off0;
+				}
+			});
+		for (auto &x : th) x.join();
+		for (int t = 0; t < nt; ++t) if (bad[t]) ok = false;
+	}
+	if (!ok) { set_err("corrupt PBF: record tags/lengths inside a checkpoint block do not parse"); cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	if (!pbf_finish_resident(pb, false)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	float ms = 0;
+	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
+	return pb;
+}
+
+extern "C" b200_pbf_t *b200_pbf_open(b200_ctx_t *c, const char *fn, int64_t row_beg, int64_t row_end)
+{
+	if (!fn) { set_err("b200_pbf_open: null file name"); return nullptr; }
+	const int fd = open(fn, O_RDONLY);
+	if (fd < 0) { set_err("cannot open '%s'", fn); return nullptr; }
+	struct stat sb;
+	if (fstat(fd, &sb) != 0 || sb.st_size < 16) { close(fd); set_err("'%s' is not a PBF file", fn); return nullptr; }
+	void *mp = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+	close(fd);
+	if (mp == MAP_FAILED) { set_err("mmap of '%s' failed", fn); return nullptr; }
+	b200_pbf_t *pb = b200_pbf_load(c, (const uint8_t*)mp, (size_t)sb.st_size, row_beg, row_end);
+	munmap(mp, (size_t)sb.st_size);
+	return pb;
+}
+
+extern "C" int b200_pbf_m(const b200_pbf_t *pb) { return pb ? pb->m : -1; }
+extern "C" int b200_pbf_g(const b200_pbf_t *pb) { return pb ? pb->g : -1; }
+extern "C" int b200_pbf_shift(const b200_pbf_t *pb) { return pb ? pb->shift : -1; }
+extern "C" int64_t b200_pbf_n(const b200_pbf_t *pb) { return pb ? pb->n : -1; }
+extern "C" int64_t b200_pbf_row_beg(const b200_pbf_t *pb) { return pb ? (int64_t)pb->blk0 << pb->shift : -1; }
+extern "C" int64_t b200_pbf_row_end(const b200_pbf_t *pb)
+{
+	if (!pb) return -1;
+	const int64_t e = (int64_t)(pb->blk0 + pb->n_blk) << pb->shift;
+	return e < pb->n ? e : pb->n;
+}
+extern "C" int64_t b200_pbf_bad_rows(const b200_pbf_t *pb) { return pb ? pb->bad_rows : -1; }
+extern "C" size_t b200_pbf_image_size(const b200_pbf_t *pb) { return pb ? pb->file_size : 0; }
+
+extern "C" int64_t b200_pbf_row_bytes(const b200_pbf_t *pb, int64_t row_beg, int64_t row_end, int with_snapshots)
+{
+	if (!pb) return -1;
+	if (row_beg < b200_pbf_row_beg(pb) || row_end > b200_pbf_row_end(pb) || row_beg > row_end) { set_err("row range not resident"); return -1; }
+	int64_t bytes = 0;
+	const int BS = pb->BS;
+	for (int64_t k = row_beg; k < row_end;) {
+		const int b = (int)(k >> pb->shift) - pb->blk0, r = (int)(k & (BS - 1));
+		const int64_t in_blk = pb->rows_in_blk[b] - r;
+		const int64_t take = row_end - k < in_blk ? row_end - k : in_blk;
+		const uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
+		bytes += (int64_t)(ro[r + take] - ro[r]);
+		if (with_snapshots && r == 0) bytes += 1 + (int64_t)pb->g * 4 * pb->m;
+		k += take;
+	}
+	return bytes;
+}
+
+extern "C" int b200_pbf_image_download(const b200_pbf_t *pb, uint8_t *dst, size_t n_bytes)
+{
+	if (!pb || !dst) return -1;
+	if (!pb->file_size || n_bytes < pb->file_size) { set_err("no complete file image resident, or buffer too small"); return -1; }
+	cudaSetDevice(pb->ctx->dev);
+	if (!CU_OK(cudaMemcpyAsync(dst, pb->d_img, pb->file_size, cudaMemcpyDeviceToHost, pb->ctx->st))) return -1;
+	return CU_OK(cudaStreamSynchronize(pb->ctx->st)) ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------ query
+
+extern "C" void b200_query_destroy(b200_query_t *q)
+{
+	if (!q) return;
+	cudaSetDevice(q->ctx->dev);
+	cudaStreamSynchronize(q->ctx->st);
+	if (q->d_track) cudaFree(q->d_track);
+	if (q->d_tgrp) cudaFree(q->d_tgrp);
+	if (q->d_gsize) cudaFree(q->d_gsize);
+	if (q->d_prog) cudaFree(q->d_prog);
+	delete q;
+}
+
+extern "C" b200_query_t *b200_query_create(b200_ctx_t *c, const b200_pbf_t *pb, int n_out, const int32_t *out_samples,
+                                           const uint32_t *group, int n_groups, const char *flt, int *flt_err)
+{
+	if (flt_err) *flt_err = 0;
+	if (!c || !pb) { set_err("b200_query_create: null argument"); return nullptr; }
+	cudaSetDevice(c->dev);
+	const int n_samples = pb->m / 2;
+	if (n_groups < 1 || n_groups > B200_MAX_GROUPS) { set_err("n_groups=%d out of range 1..%d", n_groups, B200_MAX_GROUPS); return nullptr; }
+	if (out_samples == nullptr) n_out = n_samples;
+	if (n_out < 0 || n_out > n_samples) { set_err("n_out=%d out of range", n_out); return nullptr; }
+	b200_query_t *q = new b200_query_t();
+	q->ctx = c; q->m = pb->m; q->n_out = n_out; q->n_track = 2 * n_out; q->G = n_groups;
+	q->words = (q->n_track + 31) / 32;
+	// pbwt.c:377: asking for >= m columns means "decode everything"; out[] is ascending, so that is the identity
+	q->full = (q->n_track >= pb->m);
+	std::vector<int32_t> track(q->n_track ? q->n_track : 1);
+	std::vector<uint8_t> tgrp(q->n_track ? q->n_track : 1);
+	std::vector<int32_t> gsize(B200_MAX_GROUPS, 0);
+	for (int i = 0; i < n_out; ++i) {
+		const int s = out_samples ? out_samples[i] : i;
+		if (s < 0 || s >= n_samples || (i && out_samples && s <= out_samples[i - 1])) { set_err("out_samples must be ascending sample indices in 0..%d", n_samples - 1); delete q; return nullptr; }
+		const uint32_t gr = group ? group[i] : 1u;
+		if (gr < 1 || gr > (uint32_t)n_groups) { set_err("group[%d]=%u out of range 1..%d", i, gr, n_groups); delete q; return nullptr; }
+		track[2 * i] = 2 * s; track[2 * i + 1] = 2 * s + 1;      // bgt.c:240-242
+		tgrp[2 * i] = tgrp[2 * i + 1] = (uint8_t)(gr - 1);       // bgt.c:743-744
+		gsize[gr - 1] += 2;
+	}
+	const int perr = flt_compile(flt, n_groups, &q->prog);
+	if (perr) { if (flt_err) *flt_err = perr; set_err("filter expression does not parse (kexpr error mask 0x%x)", perr); delete q; return nullptr; }
+	q->has_flt = q->prog.n > 0;
+	bool ok = CU_OK(cudaMalloc(&q->d_tgrp, tgrp.size() + 16)) && CU_OK(cudaMalloc(&q->d_gsize, sizeof(int32_t) * B200_MAX_GROUPS)) &&
+	          CU_OK(cudaMalloc(&q->d_prog, sizeof(flt_prog_t)));
+	if (ok && !q->full) ok = CU_OK(cudaMalloc(&q->d_track, sizeof(int32_t) * track.size()));
+	ok = ok && CU_OK(cudaMemcpyAsync(q->d_tgrp, tgrp.data(), tgrp.size(), cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(q->d_gsize, gsize.data(), sizeof(int32_t) * B200_MAX_GROUPS, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(q->d_prog, &q->prog, sizeof(flt_prog_t), cudaMemcpyHostToDevice, c->st));
+	if (ok && !q->full) ok = CU_OK(cudaMemcpyAsync(q->d_track, track.data(), sizeof(int32_t) * track.size(), cudaMemcpyHostToDevice, c->st));
+	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
+	if (!ok) { b200_query_destroy(q); return nullptr; }
+	return q;
+}
+
+extern "C" int b200_query_n_track(const b200_query_t *q) { return q ? q->n_track : -1; }
+extern "C" int b200_query_hap_words(const b200_query_t *q) { return q ? q->words : -1; }
+extern "C" int b200_query_counts_stride(const b200_query_t *q) { return q ? 3 + 3 * q->G : -1; }
+
+// ------------------------------------------------------------------------------------------------ scan
+
+static int pick_cols_per_thread(const b200_ctx_t *c, int n_track, int n_blk)
+{
+	// enough CTAs to fill the chip twice over (2 resident CTAs per SM), else fewer columns per thread
+	for (int C = 8; C > 1; C >>= 1) {
+		const long long ctas = (long long)((n_track + WALK_NT * C - 1) / (WALK_NT * C)) * n_blk;
+		if (ctas >= 4LL * c->sm_count && n_track >= WALK_NT * C) return C;
+	}
+	return 1;
+}
+
+extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_query_t *q, int64_t row_beg, int64_t n_rows,
+                             unsigned flags, b200_scan_out_t *out)
+{
+	if (!c || !pb || !q || !out) { set_err("b200_scan: null argument"); return -1; }
+	if (pb->ctx != c || q->ctx != c) { set_err("b200_scan: handles belong to another context"); return -1; }
+	if (q->m != pb->m) { set_err("b200_scan: query was built for m=%d, PBF has m=%d", q->m, pb->m); return -1; }
+	cudaSetDevice(c->dev);
+	if (row_beg < 0 || n_rows < 0) { set_err("b200_scan: negative row range"); return -1; }
+	if (row_beg + n_rows > pb->n) n_rows = pb->n - row_beg > 0 ? pb->n - row_beg : 0;
+	out->totals[0] = out->totals[1] = out->totals[2] = out->totals[3] = 0;
+	if (n_rows == 0) return 0;
+	if (row_beg < b200_pbf_row_beg(pb) || row_beg + n_rows > b200_pbf_row_end(pb)) { set_err("b200_scan: rows [%lld,%lld) are not resident", (long long)row_beg, (long long)(row_beg + n_rows)); return -1; }
+	const bool dev_out = flags & B200_SCAN_DEVICE_OUT;
+	const bool want_bits = (flags & B200_SCAN_HAP_BITS) && out->hap_bits[0] && out->hap_bits[1];
+	const bool want_bytes = (flags & B200_SCAN_HAP_BYTES) && out->hap_bytes[0] && out->hap_bytes[1];
+	const bool emit = want_bits || want_bytes;
+	const bool want_counts = (flags & B200_SCAN_COUNTS) && out->counts;
+	const bool host_flt = q->has_flt && q->prog.needs_host;
+	if (host_flt && dev_out) { set_err("filters using ** are evaluated with the host libm; not available with B200_SCAN_DEVICE_OUT"); return -1; }
+	const int G = q->G, stride = 3 + 3 * G, words = q->words, n_track = q->n_track;
+	const size_t nr = (size_t)n_rows;
+
+	// ---- device outputs: the caller's buffers (DEVICE_OUT) or context scratch
+	int32_t *d_counts = nullptr; uint8_t *d_pass = nullptr; uint32_t *d_bits[2] = {nullptr, nullptr}; uint8_t *d_bytes[2] = {nullptr, nullptr};
+	if (!c->cnt_raw.reserve(nr * G * 3 * sizeof(int32_t))) return -1;
+	if (dev_out) {
+		d_counts = out->counts; d_pass = out->pass;
+		if (want_bits) { d_bits[0] = out->hap_bits[0]; d_bits[1] = out->hap_bits[1]; }
+		if (want_bytes) { d_bytes[0] = out->hap_bytes[0]; d_bytes[1] = out->hap_bytes[1]; }
+	} else {
+		if (want_counts || host_flt) { if (!c->counts.reserve(nr * stride * sizeof(int32_t))) return -1; d_counts = (int32_t*)c->counts.p; }
+		if (out->pass) { if (!c->pass.reserve(nr)) return -1; d_pass = (uint8_t*)c->pass.p; }
+	}
+	if (emit && !d_bits[0]) {
+		for (int p = 0; p < 2; ++p) { if (!c->hapbits[p].reserve(nr * words * sizeof(uint32_t))) return -1; d_bits[p] = (uint32_t*)c->hapbits[p].p; }
+	}
+	if (want_bytes && !d_bytes[0]) {
+		for (int p = 0; p < 2; ++p) { if (!c->hapbytes[p].reserve(nr * (size_t)n_track)) return -1; d_bytes[p] = (uint8_t*)c->hapbytes[p].p; }
+	}
+
+	// ---- launch
+	const int b_first = (int)(row_beg >> pb->shift) - pb->blk0;
+	const int b_last = (int)((row_beg + n_rows - 1) >> pb->shift) - pb->blk0;
+	const int n_blk = b_last - b_first + 1;
+	WalkParams P;
+	memset(&P, 0, sizeof(P));
+	P.img = pb->d_img; P.rowoff = pb->d_rowoff; P.n1 = pb->d_n1; P.tiles = pb->d_tiles; P.blk_tile_beg = pb->d_blk_tile_beg;
+	P.rank0 = pb->d_rank0; P.track = q->full ? nullptr : q->d_track; P.tgrp = q->d_tgrp;
+	P.cnt_raw = (int32_t*)c->cnt_raw.p; P.hap[0] = d_bits[0]; P.hap[1] = d_bits[1];
+	P.m = pb->m; P.n_track = n_track; P.G = G; P.words = words; P.shift = pb->shift;
+	P.blk_first = b_first; P.blk_row0 = (long long)pb->blk0 << pb->shift; P.row_lo = row_beg; P.row_hi = row_beg + n_rows; P.err = c->d_err;
+	const int C = pick_cols_per_thread(c, n_track, n_blk);
+	const int slices = (n_track + WALK_NT * C - 1) / (WALK_NT * C);
+
+	bool ok = CU_OK(cudaEventRecord(c->ev[2], c->st)) &&
+	          CU_OK(cudaMemsetAsync(c->cnt_raw.p, 0, nr * G * 3 * sizeof(int32_t), c->st)) &&
+	          CU_OK(cudaMemsetAsync(c->d_acc, 0, 4 * sizeof(unsigned long long), c->st)) &&
+	          CU_OK(cudaEventRecord(c->ev[0], c->st));
+	if (ok && n_track > 0) { ok = CU_OK(launch_walk(P, C, emit, false, slices, n_blk, c->st)); c->launches += (n_blk + 32767) / 32768; }
+	ok = ok && CU_OK(cudaEventRecord(c->ev[1], c->st));
+	ok = ok && CU_OK(launch_finalize(P.cnt_raw, n_rows, G, q->d_gsize, q->d_prog, q->has_flt && !host_flt, d_counts, d_pass, c->d_acc, c->st));
+	++c->launches;
+	if (ok && want_bytes) {
+		for (int p = 0; p < 2 && ok; ++p) { ok = CU_OK(launch_unpack_bits(d_bits[p], n_rows, words, n_track, d_bytes[p], c->st)); ++c->launches; }
+	}
+	ok = ok && CU_OK(cudaEventRecord(c->ev[3], c->st));
+	if (!ok) return -1;
+	if (dev_out) return n_rows; // asynchronous: totals are not available in this mode
+
+	// ---- results to the host
+	unsigned long long tot[4] = {0, 0, 0, 0};
+	int err = 0;
+	ok = CU_OK(cudaEventRecord(c->ev[6], c->st));
+	if (ok && (want_counts || host_flt)) {
+		int32_t *dst = want_counts ? out->counts : nullptr;
+		std::vector<int32_t> tmp;
+		if (!dst) { tmp.resize(nr * stride); dst = tmp.data(); }
+		ok = CU_OK(cudaMemcpyAsync(dst, d_counts, nr * stride * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+		if (ok && host_flt) { // `**` goes through the host libm (kexpr.c:150), on the device-computed counts
+			ok = CU_OK(cudaStreamSynchronize(c->st));
+			unsigned long long np = 0;
+			for (size_t k = 0; ok && k < nr; ++k) { const int pass = flt_eval(&q->prog, dst + k * stride); if (out->pass) out->pass[k] = (uint8_t)pass; np += pass; }
+			tot[3] = np;
+		}
+	}
+	if (ok && out->pass && !host_flt) ok = CU_OK(cudaMemcpyAsync(out->pass, d_pass, nr, cudaMemcpyDeviceToHost, c->st));
+	for (int p = 0; p < 2 && ok; ++p) {
+		if (want_bits) ok = CU_OK(cudaMemcpyAsync(out->hap_bits[p], d_bits[p], nr * words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
+		if (ok && want_bytes) ok = CU_OK(cudaMemcpyAsync(out->hap_bytes[p], d_bytes[p], nr * (size_t)n_track, cudaMemcpyDeviceToHost, c->st));
+	}
+	unsigned long long dtot[4];
+	ok = ok && CU_OK(cudaMemcpyAsync(dtot, c->d_acc, sizeof(dtot), cudaMemcpyDeviceToHost, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(err), cudaMemcpyDeviceToHost, c->st)) &&
+	     CU_OK(cudaEventRecord(c->ev[7], c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+	if (!ok) return -1;
+	if (err) { set_err("device error flags 0x%x during scan", err); return -1; }
+	out->totals[0] = (int64_t)dtot[0]; out->totals[1] = (int64_t)dtot[1]; out->totals[2] = (int64_t)dtot[2];
+	out->totals[3] = host_flt ? (int64_t)tot[3] : (int64_t)dtot[3];
+	float ms;
+	if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->last_ms[0] = ms;
+	if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->last_ms[1] = ms;
+	if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->last_ms[3] = ms;
+	return n_rows;
+}
+
+// after a DEVICE_OUT scan + b200_ctx_sync: fetch kernel timings and totals
+extern "C" int b200_scan_collect(b200_ctx_t *c, int64_t totals[4])
+{
+	if (!c) return -1;
+	cudaSetDevice(c->dev);
+	unsigned long long dtot[4];
+	int err = 0;
+	bool ok = CU_OK(cudaMemcpyAsync(dtot, c->d_acc, sizeof(dtot), cudaMemcpyDeviceToHost, c->st)) &&
+	          CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(err), cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+	if (!ok) return -1;
+	if (err) { set_err("device error flags 0x%x during scan", err); return -1; }
+	if (totals) for (int i = 0; i < 4; ++i) totals[i] = (int64_t)dtot[i];
+	float ms;
+	if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->last_ms[0] = ms;
+	if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->last_ms[1] = ms;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ synthetic cohort
+
+extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cfg)
+{
+	if (!c || !cfg) { set_err("b200_synth_generate: null argument"); return nullptr; }
+	cudaSetDevice(c->dev);
+	if (cfg->n_samples <= 0 || cfg->n_samples >= (1 << 29) || cfg->n_rows <= 0 || cfg->shift < 0 || cfg->shift > 24) { set_err("b200_synth_generate: bad shape"); return nullptr; }
+	SynthCfg sc;
+	sc.m = 2u * (uint32_t)cfg->n_samples; sc.n_rows = cfg->n_rows; sc.shift = cfg->shift; sc.seed = cfg->seed;
+	sc.r_max = cfg->r_max > 0 ? cfg->r_max : 64; sc.p1_one_in = cfg->p1_one_in > 0 ? cfg->p1_one_in : 16;
+	const int BS = 1 << sc.shift;
+	const int64_t n = sc.n_rows;
+	const int nb = (int)((n + BS - 1) / BS);
+	const size_t snap = 1 + 8 * (size_t)sc.m;
+
+	b200_pbf_t *pb = new b200_pbf_t();
+	pb->ctx = c; pb->m = (int)sc.m; pb->g = 2; pb->shift = sc.shift; pb->BS = BS; pb->n = n; pb->n_blk_file = nb; pb->blk0 = 0; pb->n_blk = nb;
+	uint32_t *d_len2 = nullptr; uint64_t *d_flat = nullptr;
+	std::vector<uint32_t> len2((size_t)n * 2);
+	std::vector<uint64_t> flat((size_t)n);
+	std::vector<uint8_t> tail;
+	bool ok = CU_OK(cudaMalloc(&d_len2, sizeof(uint32_t) * 2 * (size_t)n));
+	ok = ok && CU_OK(launch_synth_lengths(sc, d_len2, c->st));
+	++c->launches;
+	ok = ok && CU_OK(cudaMemcpyAsync(len2.data(), d_len2, sizeof(uint32_t) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+	if (d_len2) cudaFree(d_len2);
+	if (!ok) { delete pb; return nullptr; }
+	// file layout: header, per block 'S' + 2 planes of int32[m], rows, 'I' record, trailing offset
+	pb->rows_in_blk.resize(nb);
+	pb->h_rowoff.assign((size_t)nb * (BS + 1), 0);
+	pb->h_blkoff.resize(nb);
+	uint64_t pos = 16;
+	for (int b = 0; b < nb; ++b) {
+		const int64_t r0 = (int64_t)b << sc.shift;
+		const int rows = (int)(n - r0 < BS ? n - r0 : BS);
+		pb->rows_in_blk[b] = rows;
+		pb->h_blkoff[b] = pos;
+		pos += snap;
+		uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
+		for (int r = 0; r < rows; ++r) {
+			ro[r] = flat[r0 + r] = pos;
+			pos += 9 + (uint64_t)len2[(r0 + r) * 2] + len2[(r0 + r) * 2 + 1];
+		}
+		ro[rows] = pos;
+	}
+	const uint64_t ioff = pos;
+	tail.resize(1 + 8 + 4 + 8 * (size_t)nb + 8);
+	{ // pbwt.c:268-276
+		uint8_t *t = tail.data();
+		const int32_t n_idx = nb;
+		*t++ = 'I'; memcpy(t, &n, 8); t += 8; memcpy(t, &n_idx, 4); t += 4;
+		memcpy(t, pb->h_blkoff.data(), 8 * (size_t)nb); t += 8 * (size_t)nb;
+		memcpy(t, &ioff, 8);
+	}
+	pb->file_size = pb->img_bytes = (size_t)(ioff + tail.size());
+	pb->file_off0 = 0;
+	uint8_t hdr[16];
+	{ const int32_t v[3] = {(int32_t)sc.m, 2, sc.shift}; memcpy(hdr, "PBF\1", 4); memcpy(hdr + 4, v, 12); } // pbwt.c:214-216
+	ok = CU_OK(cudaMalloc(&pb->d_img, pb->img_bytes + 64)) && CU_OK(cudaMalloc(&d_flat, sizeof(uint64_t) * (size_t)n));
+	ok = ok && CU_OK(cudaMemsetAsync(pb->d_img, 0, pb->img_bytes + 64, c->st));
+	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img, hdr, 16, cudaMemcpyHostToDevice, c->st));
+	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img + ioff, tail.data(), tail.size(), cudaMemcpyHostToDevice, c->st));
+	for (int b = 0; ok && b < nb; ++b) ok = CU_OK(cudaMemsetAsync(pb->d_img + pb->h_blkoff[b], 'S', 1, c->st));
+	ok = ok && CU_OK(cudaMemcpyAsync(d_flat, flat.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->st));
+	ok = ok && CU_OK(launch_synth_write(sc, d_flat, pb->d_img, c->st));
+	++c->launches;
+	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
+	if (d_flat) cudaFree(d_flat);
+	if (!ok || !pbf_finish_resident(pb, true)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	return pb;
+}

@@ -1,0 +1,64 @@
+// pbwt_kernels.cuh -- device-side data structures and launch wrappers of the PBWT hot path (sm_100a).
+//
+// Data layout in HBM (all owned by b200_pbf_t, see api.cu):
+//   img      : the .pbf byte image (or the byte range of the resident checkpoint blocks), 16-byte aligned
+//              base, >= 64 bytes of zero padding behind it (TMA bulk copies are 16-byte granular).
+//   rowoff   : uint64 [n_blk][BS+1], offset (relative to img) of the 'B' record of every row of every
+//              resident block, entry BS (or rows_in_block) = end of the block's last row.  BS = 1<<shift.
+//   n1       : uint32 [n_blk][BS][2], number of 1 bits of every (row, plane) = sum of its 1-run lengths.
+//   tiles    : int2   [n_tiles], {first row in block, n_rows | big<<31}; blk_tile_beg int [n_blk+1].
+//   rank0    : int32  [n_blk][2][m], rank of every column under the block's 'S' snapshot (inverse permutation).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "flt.h"
+
+namespace b200 {
+
+constexpr int WALK_NT   = 512;          // threads per CTA of the rank-walk kernel
+constexpr int WALK_NW   = WALK_NT / 32;
+constexpr int RAW_CAP   = 8192;         // RLE bytes staged per tile
+constexpr int RAW_BYTES = RAW_CAP + 32; // + 16-byte alignment slack at both ends
+constexpr int T_MAX     = 64;           // rows per tile
+constexpr int B200_MAX_GROUPS_K = 32;   // BGT_MAX_GROUPS, bgt.h:13
+
+struct RowMeta { uint32_t off[2], len[2], n1[2]; };
+
+struct WalkParams {
+	const uint8_t  *img;
+	const uint64_t *rowoff;
+	const uint32_t *n1;
+	const int2     *tiles;
+	const int      *blk_tile_beg;
+	const int32_t  *rank0;
+	const int32_t  *track;     // tracked column ids [n_track] or nullptr (identity: every column)
+	const uint8_t  *tgrp;      // 0-based group of every tracked column
+	int32_t        *cnt_raw;   // [rows out][G][3] = #ALT, #missing, #other-ALT per group (zero-initialised, accumulated)
+	uint32_t       *hap[2];    // [rows out][words] bit planes (EMIT only)
+	uint8_t        *snap_img;  // CHAIN only: image to write 'S' snapshots into
+	const uint64_t *blkoff;    // CHAIN only: offset of the 'S' record of every block
+	int m, n_track, G, words, shift;
+	int blk_first;             // resident-block index handled by blockIdx.y == 0
+	int n_blk_chain;           // CHAIN only: blocks to run through
+	long long blk_row0;        // absolute row of resident block 0
+	long long row_lo, row_hi;  // absolute rows to produce output for
+	int *err;
+};
+
+size_t walk_smem_bytes(int C, int G);
+// C = tracked columns per thread (1,2,4,8); emit = write genotype bit planes; chain = generator mode
+cudaError_t launch_walk(const WalkParams &P, int C, bool emit, bool chain, int slices, int n_blk, cudaStream_t st);
+
+cudaError_t launch_rowmeta(const uint8_t *img, const uint64_t *rowoff, int n_blk, int shift, long long n_rows_total_in_blocks,
+                           const int *rows_in_blk, uint32_t m, uint32_t *n1, unsigned long long *bad, cudaStream_t st);
+cudaError_t launch_invert_snapshots(const uint8_t *img, const uint64_t *blkoff, int n_blk, int m, int32_t *rank0, int *err, cudaStream_t st);
+cudaError_t launch_finalize(const int32_t *cnt_raw, long long n_rows, int G, const int32_t *gsize, const flt_prog_t *prog, int use_flt,
+                            int32_t *counts, uint8_t *pass, unsigned long long *totals, cudaStream_t st);
+cudaError_t launch_unpack_bits(const uint32_t *bits, long long n_rows, int words, int n_track, uint8_t *bytes, cudaStream_t st);
+
+// synthetic cohort generator (synth.cu)
+struct SynthCfg { uint32_t m; long long n_rows; int shift; uint64_t seed; int r_max; int p1_one_in; };
+cudaError_t launch_synth_lengths(const SynthCfg &c, uint32_t *len2 /*[n_rows][2]*/, cudaStream_t st);
+cudaError_t launch_synth_write(const SynthCfg &c, const uint64_t *rowoff_flat /*[n_rows] absolute*/, uint8_t *img, cudaStream_t st);
+
+} // namespace b200

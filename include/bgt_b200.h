@@ -1,0 +1,118 @@
+/*
+ * bgt_b200.h -- C ABI of libbgt_b200.so: the B200 (sm_100a) implementation of BGT's genotype hot path.
+ *
+ * Plain pointers and sizes only.  Every entry point names the reference interface it stands in for
+ * (file:line in lh3/bgt).  The reference-side bindings (how bgt.c / pbwt.c call these) are in
+ * INTEGRATION.md; the pbwt.h-compatible seam built on top of this ABI is include/pbwt_b200.h.
+ *
+ * Threading: one b200_ctx_t per host thread / GPU; a b200_pbf_t is immutable after load and may be
+ * shared by queries of the same context.  All functions return <0 (or NULL) on error and leave a
+ * message retrievable with b200_strerror().  There is no CPU fallback: without a CUDA device
+ * b200_ctx_create() fails.
+ */
+#ifndef BGT_B200_H
+#define BGT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_MAX_GROUPS 32      /* BGT_MAX_GROUPS, bgt.h:13 */
+#define B200_ABI_VERSION 1
+
+typedef struct b200_ctx_s   b200_ctx_t;    /* one GPU: device, stream, scratch */
+typedef struct b200_pbf_s   b200_pbf_t;    /* a .pbf (or a row shard of it) resident in HBM; stands in for pbf_t, pbwt.c:176-197 */
+typedef struct b200_query_s b200_query_t;  /* tracked haplotypes + sample groups + site filter of one `bgt view` */
+
+/* ---------------------------------------------------------------- context */
+int         b200_abi_version(void);
+int         b200_device_count(void);                 /* <=0: no usable CUDA device */
+const char *b200_strerror(void);                     /* last error of the calling thread */
+b200_ctx_t *b200_ctx_create(int device);
+void        b200_ctx_destroy(b200_ctx_t *ctx);
+int         b200_ctx_sync(b200_ctx_t *ctx);
+void       *b200_host_alloc(size_t bytes);           /* pinned host memory for images/results */
+void        b200_host_free(void *p);
+
+/* ---------------------------------------------------------------- PBF image (pbwt.c:221-262 pbf_open_r, :264-286 pbf_close) */
+/* bytes = the complete .pbf file image in host memory.  Rows [row_beg,row_end) (row_end<0: to the end)
+ * are made resident: the checkpoint blocks covering them are uploaded, the row offsets inside the
+ * blocks are walked (the file only indexes block starts, pbwt.c:297) and the snapshots are inverted
+ * into per-column start ranks.  Region sharding across GPUs = one call per rank with its own row range. */
+b200_pbf_t *b200_pbf_load(b200_ctx_t *ctx, const uint8_t *bytes, size_t n_bytes, int64_t row_beg, int64_t row_end);
+b200_pbf_t *b200_pbf_open(b200_ctx_t *ctx, const char *fn, int64_t row_beg, int64_t row_end);
+void        b200_pbf_close(b200_pbf_t *pb);
+int         b200_pbf_m(const b200_pbf_t *pb);        /* pbf_get_m, pbwt.c:391 */
+int         b200_pbf_g(const b200_pbf_t *pb);        /* pbf_get_g, pbwt.c:390 */
+int         b200_pbf_shift(const b200_pbf_t *pb);    /* pbf_get_shift, pbwt.c:393 */
+int64_t     b200_pbf_n(const b200_pbf_t *pb);        /* pbf_get_n, pbwt.c:392 (64-bit here) */
+int64_t     b200_pbf_row_beg(const b200_pbf_t *pb);  /* first resident row (multiple of 1<<shift) */
+int64_t     b200_pbf_row_end(const b200_pbf_t *pb);
+/* algorithmic input bytes of rows [beg,end): their 'B' records (+ the 'S' records of the checkpoints in range) */
+int64_t     b200_pbf_row_bytes(const b200_pbf_t *pb, int64_t row_beg, int64_t row_end, int with_snapshots);
+/* number of rows whose RLE did not sum to m (corrupt stream); the reference has undefined behaviour there */
+int64_t     b200_pbf_bad_rows(const b200_pbf_t *pb);
+
+/* ---------------------------------------------------------------- query (bgt.c:207-246 bgt_prepare, :408-416 bgtm_add_group, :444-455 bgtm_set_flt_site) */
+/* out_samples: ascending sample indices (bgt_t.out, bgt.c:214-220); tracked haplotype columns are 2s and
+ * 2s+1 (bgt.c:239-242).  NULL = all samples.  group: 1-based group of every selected sample (bgtm_t.group,
+ * bgt.c:616); NULL = all in group 1.  flt: `-f` expression or NULL; *flt_err receives the kexpr-style parse
+ * error mask (kexpr.h:10-16) and NULL is returned when it is non-zero. */
+b200_query_t *b200_query_create(b200_ctx_t *ctx, const b200_pbf_t *pb, int n_out, const int32_t *out_samples,
+                                const uint32_t *group, int n_groups, const char *flt, int *flt_err);
+void          b200_query_destroy(b200_query_t *q);
+int           b200_query_n_track(const b200_query_t *q);     /* 2*n_out */
+int           b200_query_hap_words(const b200_query_t *q);   /* 32-bit words per plane per row of hap_bits */
+int           b200_query_counts_stride(const b200_query_t *q); /* 3 + 3*n_groups */
+
+/* ---------------------------------------------------------------- the scan (pbwt.c:313-337 pbf_read per row + bgt.c:735-757 bgtm_cal_info + bgt.c:712-719 bgtm_pass_site_flt) */
+#define B200_SCAN_COUNTS     0x01  /* per-site AN/AC[/AN#/AC#] */
+#define B200_SCAN_HAP_BITS   0x02  /* genotype rows as two bit planes, bit i of word w = tracked haplotype 32w+i */
+#define B200_SCAN_HAP_BYTES  0x04  /* genotype rows as pbf_read returns them: one byte per tracked haplotype per plane */
+#define B200_SCAN_DEVICE_OUT 0x10  /* output pointers are device pointers; no D2H, call returns without syncing */
+
+typedef struct {
+	int32_t  *counts;        /* [n_rows][3+3G]: AN, AC(first ALT), AC(<M>), then (AN#, AC#, AC#<M>) per group (bgt_info_t, bgt.h:44-47) */
+	uint8_t  *pass;          /* [n_rows]: 1 if the site passes the filter (always 1 without a filter) */
+	uint32_t *hap_bits[2];   /* [n_rows][hap_words] per plane */
+	uint8_t  *hap_bytes[2];  /* [n_rows][n_track] per plane */
+	int64_t   totals[4];     /* out: sum AN, sum AC, sum AC<M>, rows passed -- the per-shard figures the multi-GPU all-reduce sums */
+} b200_scan_out_t;
+
+/* Scan rows [row_beg,row_beg+n_rows) (must be resident).  Unwanted outputs: NULL pointers / flags off.
+ * Returns rows scanned or <0. */
+int64_t b200_scan(b200_ctx_t *ctx, const b200_pbf_t *pb, const b200_query_t *q, int64_t row_beg, int64_t n_rows,
+                  unsigned flags, b200_scan_out_t *out);
+
+/* After a B200_SCAN_DEVICE_OUT scan: wait for it, fetch its totals and kernel timings. */
+int     b200_scan_collect(b200_ctx_t *ctx, int64_t totals[4]);
+
+/* device time (ms) of the kernels of the last b200_scan on this context, measured with CUDA events on the
+ * context's stream: which = 0 rank-walk kernel, 1 whole scan (all kernels), 2 H2D of the last load, 3 D2H */
+double  b200_last_ms(b200_ctx_t *ctx, int which);
+int64_t b200_kernel_launches(b200_ctx_t *ctx);      /* kernels launched by this context so far */
+/* user timing marks on the context's stream (slot 0..3): record now / device ms between two recorded marks (syncs) */
+int     b200_mark(b200_ctx_t *ctx, int slot);
+double  b200_mark_elapsed_ms(b200_ctx_t *ctx, int slot_a, int slot_b);
+
+/* ---------------------------------------------------------------- synthetic cohort (SURVEY 8d generator; rows drawn in PBWT-rank space, truthful snapshots) */
+typedef struct {
+	int32_t  n_samples;      /* m = 2*n_samples */
+	int64_t  n_rows;
+	int32_t  shift;          /* 13 */
+	uint64_t seed;
+	int32_t  r_max;          /* plane 0: 1+U[0,r_max) intervals of 1s per row, log-uniform length in [1,m/2] */
+	int32_t  p1_one_in;      /* plane 1 non-empty in one of p1_one_in rows (16), 1-3 short intervals */
+} b200_synth_t;
+/* Generates the .pbf image on the device and returns it resident for rows [0,n_rows). */
+b200_pbf_t *b200_synth_generate(b200_ctx_t *ctx, const b200_synth_t *cfg);
+size_t      b200_pbf_image_size(const b200_pbf_t *pb);             /* bytes of the complete file image, 0 if only a shard is held */
+int         b200_pbf_image_download(const b200_pbf_t *pb, uint8_t *dst, size_t n_bytes); /* device image -> host */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

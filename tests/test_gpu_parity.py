@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libbgt_b200.so) against the oracle on the same inputs.
+
+Bar: bit-exact (integer / byte work).  Sizes are what the oracle finishes in seconds; the full BASELINE shapes
+are covered through size-independent properties in test_gpu_fullsize.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from cohorts import edge_rows, haplo_matrix, random_matrix
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+EX1 = np.array([[0, 1, 2, 0], [2, 0, 1, 1], [1, 0, 1, 1], [0, 1, 0, 1], [1, 2, 0, 0], [1, 0, 1, 2], [0, 1, 1, 1]], np.uint8)
+
+FILTERS = ["AC>0", "AN>0&&AC/AN>.05", "AC1/AN1>0.1&&AC2==0", "AC1/AN1>=0.1&&AC2==0", "AC/AN", "AC3>0", "AC*2+1-AN%7",
+           "AC//3==AN>>2", "-AC+AN", "!AC", "~AC&255", "AC**2>AN", "abs(AC-AN)>3", "log(AC)>0", "AC==AN||AC<2",
+           "AC1+AC2==AC", "AN1/AN2", "0x10+010+AC>30", "'a'=='a'&&AC", "AC/0", "AC-(-AC)", "AC1/AN1-AC2/AN2>0.05", ".5*AN>AC",
+           "AC%4==3", "AN2-AC2<3||AC1>AN1/2"]
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import bgt_b200
+    return bgt_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(b200):
+    c = b200.Context(0)
+    yield c
+    c.close()
+
+
+def codes(res, which="hap_bytes"):
+    return res[which][0] | (res[which][1] << 1)
+
+
+def unpack_bits(bits, n_track):
+    b = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")
+    return b[:, :n_track]
+
+
+def check_scan(b200, ctx, orc, pbf_bytes, out_samples=None, group=None, n_groups=1, flt=None, row_beg=0, n_rows=None, hap=True):
+    """Run the same query through the GPU library and the oracle and require identical results."""
+    want_p = orc.Pbf(pbf_bytes)
+    if n_rows is None:
+        n_rows = want_p.n - row_beg
+    want = want_p.scan(row_beg, n_rows, out_samples=out_samples, group=group, n_groups=n_groups, flt=flt, want_hap=hap)
+    want_p.close()
+    pb = b200.Pbf.from_bytes(ctx, pbf_bytes)
+    q = b200.Query(ctx, pb, out_samples=out_samples, group=group, n_groups=n_groups, flt=flt)
+    got = b200.scan(ctx, pb, q, row_beg, n_rows, counts=True, hap_bits=hap, hap_bytes=hap)
+    q.close()
+    pb.close()
+    assert got["n"] == want["n"]
+    assert (got["counts"] == want["counts"]).all(), "AC/AN differ"
+    assert (got["passed"] == want["passed"]).all(), "filter verdicts differ for %r" % flt
+    if hap:
+        assert (got["hap_bytes"][0][:got["n"]] == want["hap0"]).all() and (got["hap_bytes"][1][:got["n"]] == want["hap1"]).all()
+        nt = want["hap0"].shape[1]
+        assert (unpack_bits(got["hap_bits"][0][:got["n"]], nt) == want["hap0"]).all()
+        assert (unpack_bits(got["hap_bits"][1][:got["n"]], nt) == want["hap1"]).all()
+    assert got["totals"][0] == int(want["counts"][:, 0].astype(np.int64).sum())
+    assert got["totals"][1] == int(want["counts"][:, 1].astype(np.int64).sum())
+    assert got["totals"][2] == int(want["counts"][:, 2].astype(np.int64).sum())
+    assert got["totals"][3] == int(want["passed"].sum())
+    return got
+
+
+def test_ex1_fixture(b200, ctx, oracle):
+    pbf = oracle.encode_pbf(EX1)
+    got = check_scan(b200, ctx, oracle, pbf)
+    assert (codes(got) == EX1).all()
+    with open(os.path.join(GOLD, "ex1.pbf"), "rb") as f:
+        got = check_scan(b200, ctx, oracle, f.read(), flt="AC>0")
+    assert (codes(got) == EX1).all()
+    # reference fixture semantics: one sample = columns 2s, 2s+1
+    got = check_scan(b200, ctx, oracle, pbf, out_samples=[1])
+    assert (codes(got) == EX1[:, 2:4]).all()
+
+
+@pytest.mark.parametrize("name", ["hap_200x96", "rnd_300x37"])
+def test_golden_reference_files(b200, ctx, oracle, name):
+    mat = np.load(os.path.join(GOLD, name + ".npy"))
+    if mat.shape[1] % 2:
+        pytest.skip("odd column count: not a diploid cohort")
+    with open(os.path.join(GOLD, name + ".s5.pbf"), "rb") as f:
+        pbf = f.read()
+    got = check_scan(b200, ctx, oracle, pbf, flt="AC>0")
+    assert (codes(got) == mat).all()
+
+
+@pytest.mark.parametrize("shape", [(700, 96, 6), (300, 38, 5), (2100, 334, 9), (64, 2, 3), (130, 4098, 4), (40, 70002, 3)])
+def test_full_decode_and_counts(b200, ctx, oracle, shape):
+    n, m, shift = shape
+    mat = haplo_matrix(n, m, 7 + n)
+    pbf = oracle.encode_pbf(mat, shift=shift)
+    got = check_scan(b200, ctx, oracle, pbf, flt="AC>0")
+    assert (codes(got) == mat).all()
+
+
+def test_random_dense_planes(b200, ctx, oracle):
+    mat = random_matrix(400, 1000, 11)
+    pbf = oracle.encode_pbf(mat, shift=6)
+    got = check_scan(b200, ctx, oracle, pbf, flt="AN>0&&AC/AN>.05")
+    assert (codes(got) == mat).all()
+
+
+@pytest.mark.parametrize("m", [5000, 70002])
+def test_rle_alphabet_edges(b200, ctx, oracle, m):
+    mat = edge_rows(m)
+    pbf = oracle.encode_pbf(mat, shift=3)
+    got = check_scan(b200, ctx, oracle, pbf)
+    assert (codes(got) == mat).all()
+
+
+def test_rows_larger_than_staging_buffer(b200, ctx, oracle):
+    # alternating 0101... rows are m bytes of RLE each: > 8 KB, so the kernel streams them in pieces
+    m = 30000
+    rng = np.random.default_rng(5)
+    rows = [(np.arange(m) & 1).astype(np.uint8), haplo_matrix(1, m, 1)[0], ((np.arange(m) // 2) & 1).astype(np.uint8) * 3,
+            (rng.random(m) < 0.5).astype(np.uint8), (rng.random(m) < 0.3).astype(np.uint8) * 2, haplo_matrix(1, m, 2)[0],
+            (np.arange(m) & 1).astype(np.uint8) ^ 1]
+    mat = np.array(rows * 3, dtype=np.uint8)
+    pbf = oracle.encode_pbf(mat, shift=2)
+    grp = (np.arange(m // 2) % 2 + 1).astype(np.uint32)
+    got = check_scan(b200, ctx, oracle, pbf, group=grp, n_groups=2, flt="AC1/AN1>0.1&&AC2==0")
+    assert (codes(got) == mat).all()
+
+
+@pytest.mark.parametrize("n_rows", [8191, 8192, 8193, 16385])
+def test_checkpoint_boundaries_shift13(b200, ctx, oracle, n_rows):
+    mat = haplo_matrix(n_rows, 64, 13, switch=0.05)
+    pbf = oracle.encode_pbf(mat, shift=13)
+    got = check_scan(b200, ctx, oracle, pbf, flt="AC>0", hap=True)
+    assert (codes(got) == mat).all()
+
+
+def test_groups_and_filters(b200, ctx, oracle):
+    n, m = 900, 600
+    mat = haplo_matrix(n, m, 21)
+    pbf = oracle.encode_pbf(mat, shift=7)
+    ns = m // 2
+    two = (np.arange(ns) % 2 + 1).astype(np.uint32)             # 50/50 groups A/B as in BASELINE config 3
+    for flt in FILTERS:
+        check_scan(b200, ctx, oracle, pbf, group=two, n_groups=2, flt=flt, hap=False)
+    for flt in ("AC>0", "AC1>0", "AN1==AN", "AC2>0"):
+        check_scan(b200, ctx, oracle, pbf, flt=flt, hap=False)     # single implicit group
+    rng = np.random.default_rng(9)
+    for G in (3, 5, 32):
+        grp = rng.integers(1, G + 1, size=ns).astype(np.uint32)
+        check_scan(b200, ctx, oracle, pbf, group=grp, n_groups=G, flt="AC%d>0&&AN1>0" % G, hap=False)
+    # groups over a subset of samples: the rest is not tracked at all (bgt.c:214-220)
+    sel = np.sort(rng.choice(ns, size=120, replace=False)).astype(np.int32)
+    grp = rng.integers(1, 3, size=sel.size).astype(np.uint32)
+    got = check_scan(b200, ctx, oracle, pbf, out_samples=sel, group=grp, n_groups=2, flt="AC1/AN1>0.1&&AC2==0")
+    cols = np.stack([2 * sel, 2 * sel + 1], axis=1).ravel()
+    assert (codes(got) == mat[:, cols]).all()
+
+
+def test_subset_extraction(b200, ctx, oracle):
+    # BASELINE config 4 shape, scaled: a 200-sample subset out of many, crossing checkpoints
+    n, m = 1500, 6000
+    mat = haplo_matrix(n, m, 33)
+    pbf = oracle.encode_pbf(mat, shift=8)
+    rng = np.random.default_rng(1)
+    sel = np.sort(rng.choice(m // 2, size=200, replace=False)).astype(np.int32)
+    got = check_scan(b200, ctx, oracle, pbf, out_samples=sel)
+    cols = np.stack([2 * sel, 2 * sel + 1], axis=1).ravel()
+    assert (codes(got) == mat[:, cols]).all()
+    got = check_scan(b200, ctx, oracle, pbf, out_samples=np.array([17], np.int32), flt="AC>0")
+    assert (codes(got) == mat[:, 34:36]).all()
+
+
+@pytest.mark.parametrize("rng_seed", [0, 1])
+def test_row_ranges_seek(b200, ctx, oracle, rng_seed):
+    # pbf_seek semantics (pbwt.c:349-372): start mid-block, cross blocks, end anywhere
+    n, m, shift = 1000, 128, 6
+    mat = haplo_matrix(n, m, 40 + rng_seed)
+    pbf = oracle.encode_pbf(mat, shift=shift)
+    rng = np.random.default_rng(rng_seed)
+    for beg, cnt in [(0, 1), (63, 2), (64, 64), (65, 300), (999, 1), (500, 500)] + [(int(rng.integers(0, n - 1)), int(rng.integers(1, 200))) for _ in range(4)]:
+        cnt = min(cnt, n - beg)
+        got = check_scan(b200, ctx, oracle, pbf, row_beg=beg, n_rows=cnt, flt="AC>0")
+        assert (codes(got) == mat[beg:beg + cnt]).all()
+
+
+def test_row_shards_resident(b200, ctx, oracle):
+    # region sharding: make only some checkpoint blocks resident (b200_pbf_load row range) and scan inside them
+    n, m, shift = 700, 90, 5
+    mat = haplo_matrix(n, m, 51)
+    pbf = oracle.encode_pbf(mat, shift=shift)
+    want = oracle.Pbf(pbf).scan(0, n, flt="AC>0", want_hap=True)
+    for beg, end in [(0, 700), (0, 32), (96, 200), (333, 700), (640, 700)]:
+        pb = b200.Pbf.from_bytes(ctx, pbf, beg, end)
+        assert pb.row_beg <= beg and pb.row_end >= end and pb.row_beg % 32 == 0
+        q = b200.Query(ctx, pb, flt="AC>0")
+        got = b200.scan(ctx, pb, q, beg, end - beg, hap_bytes=True)
+        assert (got["counts"] == want["counts"][beg:end]).all()
+        assert (got["passed"] == want["passed"][beg:end]).all()
+        assert (got["hap_bytes"][0] == want["hap0"][beg:end]).all()
+        with pytest.raises(b200.B200Error):
+            if pb.row_beg > 0:
+                b200.scan(ctx, pb, q, 0, 1)
+            else:
+                raise b200.B200Error("n/a")
+        q.close()
+        pb.close()
+
+
+def test_noncanonical_rle_streams(b200, ctx, oracle):
+    m = 40
+    rows = [(bytes([5 << 1, 1, 3 << 1, 12 << 1 | 1, 32, (16 + 1) << 1, 4 << 1]), bytes([(16 + 2) << 1, 8 << 1 | 1])),
+            (bytes([10 << 1 | 1, 10 << 1 | 1, 33, 10 << 1, 10 << 1]), bytes([(16 + 2) << 1 | 1, 33, 8 << 1])),
+            (bytes([1, 7 << 1, 1, 33, 13 << 1 | 1, (16 + 1) << 1, 4 << 1 | 1]), bytes([(16 + 2) << 1, 8 << 1]))] * 5
+    pbf = oracle.encode_pbf_rle(m, rows, shift=2)
+    check_scan(b200, ctx, oracle, pbf, flt="AC>0")
+
+
+def test_error_behaviour(b200, ctx, oracle):
+    with pytest.raises(b200.B200Error):
+        b200.Pbf.from_bytes(ctx, b"not a pbf file at all, but long enough to carry a header.....")
+    pbf = oracle.encode_pbf(EX1)
+    pb = b200.Pbf.from_bytes(ctx, pbf)
+    for bad in ["AC>", "(AC>0", "AC>0)", "AC=0", "'abc"]:
+        with pytest.raises(b200.B200Error):
+            b200.Query(ctx, pb, flt=bad)
+    with pytest.raises(b200.B200Error):
+        b200.Query(ctx, pb, out_samples=[1, 0])           # not ascending
+    with pytest.raises(b200.B200Error):
+        b200.Query(ctx, pb, group=[1, 3], n_groups=2)     # group id out of range
+    q = b200.Query(ctx, pb)
+    assert b200.scan(ctx, pb, q, 7, 5)["n"] == 0          # past the end: nothing, like pbf_read returning NULL
+    assert b200.scan(ctx, pb, q, 5, 50)["n"] == 2
+    q.close()
+    pb.close()
+    # truncated file: index record missing
+    with pytest.raises(b200.B200Error):
+        b200.Pbf.from_bytes(ctx, pbf[:-9])
+
+
+def test_synth_generator_is_truthful_and_canonical(b200, ctx, oracle):
+    # the device generator must produce exactly the file the reference encoder writes for the decoded matrix
+    for n_samples, n_rows, shift, seed in [(40, 300, 5, 1), (333, 200, 6, 2), (1500, 70, 4, 3)]:
+        pb = b200.synth_cohort(ctx, n_samples, n_rows, seed=seed, shift=shift, r_max=16, p1_one_in=4)
+        img = pb.image().tobytes()
+        mat = oracle.decode_all(img)
+        assert mat.shape == (n_rows, 2 * n_samples)
+        assert oracle.encode_pbf(mat, shift=shift) == img, "generated file is not what the encoder writes for its own matrix"
+        q = b200.Query(ctx, pb, flt="AC>0")
+        got = b200.scan(ctx, pb, q, 0, n_rows, hap_bytes=True)
+        assert (codes(got) == mat).all()
+        want = oracle.Pbf(img).scan(0, n_rows, flt="AC>0")
+        assert (got["counts"] == want["counts"]).all() and (got["passed"] == want["passed"]).all()
+        # and the image loads back through the host path
+        pb2 = b200.Pbf.from_bytes(ctx, img)
+        got2 = b200.scan(ctx, pb2, q, 0, n_rows)
+        assert (got2["counts"] == want["counts"]).all()
+        assert pb2.row_bytes(0, n_rows) == oracle.Pbf(img).row_bytes(0, n_rows)
+        q.close(); pb.close(); pb2.close()
