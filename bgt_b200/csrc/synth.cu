@@ -36,10 +36,16 @@ __device__ int draw_intervals(const SynthCfg &c, long long row, int plane, uint3
 		int rmax = c.r_max < 1 ? 1 : (c.r_max > SYNTH_MAX_IV ? SYNTH_MAX_IV : c.r_max);
 		n = 1 + (int)(g.next() % (uint64_t)rmax);
 		const uint32_t cap = m / 2 ? m / 2 : 1;
-		int kmax = 31 - __clz(cap);
+		const int kmax = 31 - __clz(cap);
+		// allele count of the row: uniform over octaves of [1, m/2] = log-uniform, i.e. a 1/x-like spectrum in
+		// which rare variants dominate; it is spread over n intervals of 1s (fewer when the count is smaller)
+		const int k = (int)(g.next() % (uint64_t)(kmax + 1));
+		uint32_t ac = (1u << k) + (uint32_t)(g.next() % (1ull << k));
+		if (ac > cap) ac = cap;
+		if ((uint32_t)n > ac) n = (int)ac;
+		const uint32_t span = 2 * (ac / (uint32_t)n) - 1;     // interval length uniform in [1, 2*ac/n - 1], mean ac/n
 		for (int i = 0; i < n; ++i) {
-			const int k = (int)(g.next() % (uint64_t)(kmax + 1));
-			uint32_t len = (1u << k) + (uint32_t)(g.next() % (1ull << k)); // uniform over octaves = log-uniform
+			uint32_t len = 1 + (uint32_t)(g.next() % (uint64_t)span);
 			if (len > cap) len = cap;
 			ln[i] = len;
 			st[i] = (uint32_t)(g.next() % (uint64_t)(m - len + 1));

@@ -104,7 +104,7 @@ typedef struct {
 	int64_t  n_rows;
 	int32_t  shift;          /* 13 */
 	uint64_t seed;
-	int32_t  r_max;          /* plane 0: 1+U[0,r_max) intervals of 1s per row, log-uniform length in [1,m/2] */
+	int32_t  r_max;          /* plane 0: the row's allele count is log-uniform in [1,m/2], spread over 1+U[0,r_max) intervals of 1s in rank order */
 	int32_t  p1_one_in;      /* plane 1 non-empty in one of p1_one_in rows (16), 1-3 short intervals */
 } b200_synth_t;
 /* Generates the .pbf image on the device and returns it resident for rows [0,n_rows). */

@@ -84,12 +84,11 @@ def test_ex1_fixture(b200, ctx, oracle):
 @pytest.mark.parametrize("name", ["hap_200x96", "rnd_300x37"])
 def test_golden_reference_files(b200, ctx, oracle, name):
     mat = np.load(os.path.join(GOLD, name + ".npy"))
-    if mat.shape[1] % 2:
-        pytest.skip("odd column count: not a diploid cohort")
     with open(os.path.join(GOLD, name + ".s5.pbf"), "rb") as f:
         pbf = f.read()
     got = check_scan(b200, ctx, oracle, pbf, flt="AC>0")
-    assert (codes(got) == mat).all()
+    nt = 2 * (mat.shape[1] // 2)     # an odd column count leaves the last column untracked (subset mode, pbwt.c:377)
+    assert (codes(got) == mat[:, :nt]).all()
 
 
 @pytest.mark.parametrize("shape", [(700, 96, 6), (300, 38, 5), (2100, 334, 9), (64, 2, 3), (130, 4098, 4), (40, 70002, 3)])
