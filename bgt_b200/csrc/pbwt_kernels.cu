@@ -185,24 +185,37 @@ __device__ __forceinline__ void parse_runs(const uint8_t *raw, uint32_t off, uin
 	tot0 = tot; ones0 = ones;
 }
 
-// C independent branch-free binary searches over the n run starts at ts[0..n): last run whose start <= rank.
-template<int C>
-__device__ __forceinline__ void lookup_runs(uint32_t (&r)[C], const uint32_t *ts, const int32_t *td, uint32_t n,
-                                            uint32_t zeros_total, uint32_t &bits)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
 {
-	uint32_t lo[C];
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+	return v;
+}
+
+// byte distance between a run's start (ts[]) and its delta (td[]) in shared memory: the two tables are adjacent
+constexpr uint32_t TD_MINUS_TS = sizeof(uint32_t) * RAW_BYTES;
+
+// C independent branch-free binary searches over the n run starts at shared address ts_saddr: last run whose
+// start <= rank.  The cursor is kept as a shared-memory ADDRESS so one level costs add / LDS / compare / select.
+template<int C>
+__device__ __forceinline__ void lookup_runs(uint32_t (&r)[C], uint32_t ts_saddr, uint32_t n, uint32_t zeros_total, uint32_t &bits)
+{
+	uint32_t a[C];
 	#pragma unroll
-	for (int c = 0; c < C; ++c) lo[c] = 0;
+	for (int c = 0; c < C; ++c) a[c] = ts_saddr;
 	for (uint32_t len = n; len > 1;) {
-		const uint32_t half = len >> 1;
+		const uint32_t half = len >> 1, h4 = half << 2;
 		#pragma unroll
-		for (int c = 0; c < C; ++c) lo[c] += ts[lo[c] + half] <= r[c] ? half : 0u;
+		for (int c = 0; c < C; ++c) {
+			const uint32_t t = a[c] + h4;
+			a[c] = lds_u32(t) <= r[c] ? t : a[c];
+		}
 		len -= half;
 	}
 	uint32_t b = 0;
 	#pragma unroll
 	for (int c = 0; c < C; ++c) {
-		r[c] += (uint32_t)td[lo[c]];
+		r[c] += lds_u32(a[c] + TD_MINUS_TS);
 		b |= (r[c] >= zeros_total ? 1u : 0u) << c;
 	}
 	bits = b;
@@ -210,20 +223,20 @@ __device__ __forceinline__ void lookup_runs(uint32_t (&r)[C], const uint32_t *ts
 
 // same, restricted to the columns whose rank lies in [cs, ce) and that were not resolved by an earlier piece
 template<int C>
-__device__ __forceinline__ void lookup_runs_piece(uint32_t (&r)[C], const uint32_t *ts, const int32_t *td, uint32_t n,
-                                                  uint32_t zeros_total, uint32_t cs, uint32_t ce, uint32_t &done, uint32_t &bits)
+__device__ __forceinline__ void lookup_runs_piece(uint32_t (&r)[C], uint32_t ts_saddr, uint32_t n, uint32_t zeros_total,
+                                                  uint32_t cs, uint32_t ce, uint32_t &done, uint32_t &bits)
 {
 	#pragma unroll
 	for (int c = 0; c < C; ++c) {
 		const bool act = !((done >> c) & 1u) && r[c] >= cs && r[c] < ce;
 		if (!act) continue;
-		uint32_t lo = 0;
+		uint32_t a = ts_saddr;
 		for (uint32_t len = n; len > 1;) {
-			const uint32_t half = len >> 1;
-			lo += ts[lo + half] <= r[c] ? half : 0u;
+			const uint32_t half = len >> 1, t = a + (half << 2);
+			a = lds_u32(t) <= r[c] ? t : a;
 			len -= half;
 		}
-		r[c] += (uint32_t)td[lo];
+		r[c] += lds_u32(a + TD_MINUS_TS);
 		bits |= (r[c] >= zeros_total ? 1u : 0u) << c;
 		done |= 1u << c;
 	}
@@ -236,7 +249,7 @@ struct WalkSmem {
 	int32_t  *td;
 	RowMeta  *meta;
 	int32_t  *rowcnt;   // [T_MAX][G][3]
-	uint32_t *gmask;    // [NW][C][G]
+	uint8_t  *gmask;    // [G][NT]: bit c = slot c of this thread belongs to group g (generic-G path only)
 	uint32_t *scratch;  // [8]
 };
 
@@ -246,42 +259,69 @@ __host__ __device__ inline size_t walk_smem_layout(int C, int G, size_t off[8])
 	off[0] = o; o += 16;                                  // mbarrier
 	off[1] = o; o += RAW_BYTES;                           // raw
 	off[2] = o; o += sizeof(uint32_t) * RAW_BYTES;        // ts
-	off[3] = o; o += sizeof(int32_t) * RAW_BYTES;         // td
+	off[3] = o; o += sizeof(int32_t) * RAW_BYTES;         // td (must directly follow ts: TD_MINUS_TS)
 	off[4] = o; o += sizeof(RowMeta) * T_MAX;             // meta
 	off[5] = o; o += sizeof(int32_t) * T_MAX * G * 3;     // rowcnt
-	off[6] = o; o += sizeof(uint32_t) * WALK_NW * C * G;  // gmask
+	off[6] = o; o += (G > 2 ? (size_t)G * WALK_NT : 16);  // gmask
+	o = (o + 15) & ~(size_t)15;
 	off[7] = o; o += sizeof(uint32_t) * 8;                // scratch
+	(void)C;
 	return (o + 15) & ~(size_t)15;
 }
 
 size_t walk_smem_bytes(int C, int G) { size_t off[8]; return walk_smem_layout(C, G, off); }
 
-// per-row reduction of the C x 32 codes of this warp into the tile's shared counters / the bit-plane output
-template<int C, bool EMIT>
-__device__ __forceinline__ void reduce_row(uint32_t bits0, uint32_t bits1, bool zero0, bool zero1, const WalkSmem &S,
-                                           const WalkParams &P, int r_in_tile, long long out_row, int warp, int lane, int slice_base)
+// Per-row reduction (bgt.c:743-756).  bits0/bits1: bit c = plane-0/1 bit of this thread's column slot c (already
+// masked to valid slots).  Every thread popcounts its own C codes per group, one REDUX.SUM per counter folds the
+// warp, lane 0 adds to the tile's shared counters.  gm0/gm1: per-thread slot masks of groups 1 and 2 (G <= 2).
+template<int C>
+__device__ __forceinline__ void count_row(uint32_t bits0, uint32_t bits1, bool zero1, uint32_t gm0, uint32_t gm1,
+                                          const WalkSmem &S, int G, int r_in_tile, int tid, int lane)
 {
-	int c1 = 0, c2 = 0, c3 = 0;
+	const uint32_t x1 = bits0 & ~bits1, x2 = ~bits0 & bits1, x3 = bits0 & bits1;  // ALT, missing, other-ALT
+	int32_t *rc = S.rowcnt + r_in_tile * G * 3;
+	if (G <= 2) {
+		#pragma unroll
+		for (int g = 0; g < 2; ++g) {
+			if (g >= G) break;
+			const uint32_t gm = g ? gm1 : gm0;
+			const int s1 = __reduce_add_sync(FULL_MASK, __popc(x1 & gm));
+			if (lane == 0 && s1) atomicAdd(rc + g * 3, s1);
+			if (!zero1) {
+				const int s2 = __reduce_add_sync(FULL_MASK, __popc(x2 & gm));
+				const int s3 = __reduce_add_sync(FULL_MASK, __popc(x3 & gm));
+				if (lane == 0 && s2) atomicAdd(rc + g * 3 + 1, s2);
+				if (lane == 0 && s3) atomicAdd(rc + g * 3 + 2, s3);
+			}
+		}
+	} else {
+		for (int g = 0; g < G; ++g) {
+			const uint32_t gm = S.gmask[g * WALK_NT + tid];
+			const int s1 = __reduce_add_sync(FULL_MASK, __popc(x1 & gm));
+			if (lane == 0 && s1) atomicAdd(rc + g * 3, s1);
+			if (!zero1) {
+				const int s2 = __reduce_add_sync(FULL_MASK, __popc(x2 & gm));
+				const int s3 = __reduce_add_sync(FULL_MASK, __popc(x3 & gm));
+				if (lane == 0 && s2) atomicAdd(rc + g * 3 + 1, s2);
+				if (lane == 0 && s3) atomicAdd(rc + g * 3 + 2, s3);
+			}
+		}
+	}
+}
+
+// genotype rows as two bit planes: one ballot per 32 consecutive tracked columns per plane
+template<int C>
+__device__ __forceinline__ void emit_row(uint32_t bits0, uint32_t bits1, const WalkParams &P, long long out_row,
+                                         int warp, int lane, int slice_base)
+{
 	uint32_t w0 = 0, w1 = 0;
 	#pragma unroll
 	for (int c = 0; c < C; ++c) {
-		const uint32_t b0 = zero0 ? 0u : __ballot_sync(FULL_MASK, (bits0 >> c) & 1u);
-		const uint32_t b1 = zero1 ? 0u : __ballot_sync(FULL_MASK, (bits1 >> c) & 1u);
-		if (lane < P.G) {
-			const uint32_t mg = S.gmask[(warp * C + c) * P.G + lane];
-			c1 += __popc(b0 & ~b1 & mg);   // code 1: ALT           (bgt.c:746-756)
-			c2 += __popc(~b0 & b1 & mg);   // code 2: missing
-			c3 += __popc(b0 & b1 & mg);    // code 3: other ALT <M>
-		}
-		if (EMIT && lane == c) { w0 = b0; w1 = b1; }
+		const uint32_t b0 = __ballot_sync(FULL_MASK, (bits0 >> c) & 1u);
+		const uint32_t b1 = __ballot_sync(FULL_MASK, (bits1 >> c) & 1u);
+		if (lane == c) { w0 = b0; w1 = b1; }
 	}
-	if (lane < P.G) {
-		int32_t *rc = S.rowcnt + (r_in_tile * P.G + lane) * 3;
-		if (c1) atomicAdd(rc, c1);
-		if (c2) atomicAdd(rc + 1, c2);
-		if (c3) atomicAdd(rc + 2, c3);
-	}
-	if (EMIT && lane < C) {
+	if (lane < C) {
 		const int wi = (slice_base + lane * WALK_NT) / 32 + warp;
 		if (wi < P.words) {
 			P.hap[0][(size_t)out_row * P.words + wi] = w0;
@@ -299,7 +339,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 		size_t off[8];
 		walk_smem_layout(C, P.G, off);
 		S.mbar = (uint64_t*)(smem + off[0]); S.raw = smem + off[1]; S.ts = (uint32_t*)(smem + off[2]); S.td = (int32_t*)(smem + off[3]);
-		S.meta = (RowMeta*)(smem + off[4]); S.rowcnt = (int32_t*)(smem + off[5]); S.gmask = (uint32_t*)(smem + off[6]);
+		S.meta = (RowMeta*)(smem + off[4]); S.rowcnt = (int32_t*)(smem + off[5]); S.gmask = smem + off[6];
 		S.scratch = (uint32_t*)(smem + off[7]);
 	}
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -310,17 +350,19 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 	// ---- which columns this thread owns, their groups, their start ranks
 	uint32_t r0[C], r1[C];
 	int32_t col[C];
-	uint32_t validbits = 0;
+	uint32_t validbits = 0, gm0 = 0, gm1 = 0;
+	if (P.G > 2) for (int g = 0; g < P.G; ++g) S.gmask[g * WALK_NT + tid] = 0;
 	#pragma unroll
 	for (int c = 0; c < C; ++c) {
 		const int e = slice_base + c * WALK_NT + tid;
 		const bool v = e < P.n_track;
 		col[c] = v ? (P.track ? P.track[e] : e) : 0;
 		validbits |= (v ? 1u : 0u) << c;
-		const int grp = v ? (int)P.tgrp[e] : -1;
-		for (int g = 0; g < P.G; ++g) {
-			const uint32_t mk = __ballot_sync(FULL_MASK, grp == g);
-			if (lane == 0) S.gmask[(warp * C + c) * P.G + g] = mk;
+		if (v && !CHAIN) {
+			const int grp = (int)P.tgrp[e];
+			if (grp == 0) gm0 |= 1u << c;
+			else if (grp == 1) gm1 |= 1u << c;
+			if (P.G > 2) S.gmask[grp * WALK_NT + tid] |= (uint8_t)(1u << c);
 		}
 		r0[c] = r1[c] = CHAIN ? (uint32_t)col[c] : 0u; // generator: identity before row 0 (pbwt.c:103)
 	}
@@ -329,6 +371,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 	__syncthreads();
 
 	uint32_t parity = 0;
+	const uint32_t ts_saddr = smem_u32(S.ts);
 	const int blk_lo = CHAIN ? 0 : P.blk_first + (int)blockIdx.y;
 	const int blk_hi = CHAIN ? P.n_blk_chain : blk_lo + 1;
 
@@ -411,14 +454,14 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 					const RowMeta mt = S.meta[r];
 					uint32_t bits0 = 0, bits1 = 0;
 					const bool triv0 = mt.n1[0] == 0 || mt.n1[0] == m, triv1 = mt.n1[1] == 0 || mt.n1[1] == m;
-					if (!triv0) lookup_runs<C>(r0, S.ts + mt.off[0], S.td + mt.off[0], mt.len[0], m - mt.n1[0], bits0);
+					if (!triv0) lookup_runs<C>(r0, ts_saddr + 4u * mt.off[0], mt.len[0], m - mt.n1[0], bits0);
 					else if (mt.n1[0]) bits0 = 0xffffffffu;
-					if (!triv1) lookup_runs<C>(r1, S.ts + mt.off[1], S.td + mt.off[1], mt.len[1], m - mt.n1[1], bits1);
+					if (!triv1) lookup_runs<C>(r1, ts_saddr + 4u * mt.off[1], mt.len[1], m - mt.n1[1], bits1);
 					else if (mt.n1[1]) bits1 = 0xffffffffu;
 					if (!CHAIN && arow >= P.row_lo) {
 						const bool zero0 = mt.n1[0] == 0, zero1 = mt.n1[1] == 0;
-						if (EMIT || !(zero0 && zero1))
-							reduce_row<C, EMIT>(bits0 & validbits, bits1 & validbits, zero0, zero1, S, P, r, arow - P.row_lo, warp, lane, slice_base);
+						if (!(zero0 && zero1)) count_row<C>(bits0 & validbits, bits1 & validbits, zero1, gm0, gm1, S, P.G, r, tid, lane);
+						if (EMIT) emit_row<C>(bits0 & validbits, bits1 & validbits, P, arow - P.row_lo, warp, lane, slice_base);
 					}
 				}
 			} else {
@@ -447,15 +490,17 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 						}
 						__syncthreads();
 						const uint32_t ce = S.scratch[2];
-						if (p == 0) lookup_runs_piece<C>(r0, S.ts, S.td, n, m - n1, cs, ce, done, bits[0]);
-						else        lookup_runs_piece<C>(r1, S.ts, S.td, n, m - n1, cs, ce, done, bits[1]);
+						if (p == 0) lookup_runs_piece<C>(r0, ts_saddr, n, m - n1, cs, ce, done, bits[0]);
+						else        lookup_runs_piece<C>(r1, ts_saddr, n, m - n1, cs, ce, done, bits[1]);
 						__syncthreads();
 						if (tid == 0) { S.scratch[0] = S.scratch[2]; S.scratch[1] = S.scratch[3]; }
 					}
 					__syncthreads();
 				}
-				if (!CHAIN && arow >= P.row_lo && arow < P.row_hi)
-					reduce_row<C, EMIT>(bits[0] & validbits, bits[1] & validbits, n1p[0] == 0, n1p[1] == 0, S, P, 0, arow - P.row_lo, warp, lane, slice_base);
+				if (!CHAIN && arow >= P.row_lo && arow < P.row_hi) {
+					if (n1p[0] || n1p[1]) count_row<C>(bits[0] & validbits, bits[1] & validbits, n1p[1] == 0, gm0, gm1, S, P.G, 0, tid, lane);
+					if (EMIT) emit_row<C>(bits[0] & validbits, bits[1] & validbits, P, arow - P.row_lo, warp, lane, slice_base);
+				}
 				if (tid == 0) prefetch(t + 1);
 			}
 
