@@ -52,6 +52,7 @@ SIGNATURES = {
     "b200_pbf_row_bytes": (_i64, [_vp, _i64, _i64, _int]),
     "b200_pbf_bad_rows": (_i64, [_vp]),
     "b200_query_create": (_vp, [_vp, _vp, _int, _vp, _vp, _int, C.c_char_p, C.POINTER(_int)]),
+    "b200_query_create_cols": (_vp, [_vp, _vp, _int, _vp]),
     "b200_query_destroy": (None, [_vp]),
     "b200_query_n_track": (_int, [_vp]),
     "b200_query_hap_words": (_int, [_vp]),
@@ -205,6 +206,20 @@ class Query:
         self.words = lib().b200_query_hap_words(self.h)
         self.stride = lib().b200_query_counts_stride(self.h)
         self.n_groups = n_groups
+
+    @classmethod
+    def columns(cls, ctx, pbf, cols=None):
+        """Column-level selection in list order (pbf_subset, pbwt.c:374-388)."""
+        self = cls.__new__(cls)
+        self.cols = None if cols is None else np.ascontiguousarray(cols, dtype=np.int32)
+        self.h = lib().b200_query_create_cols(ctx.h, pbf.h, 0 if self.cols is None else self.cols.size, _ptr(self.cols))
+        if not self.h:
+            raise B200Error(_err())
+        self.n_track = lib().b200_query_n_track(self.h)
+        self.words = lib().b200_query_hap_words(self.h)
+        self.stride = lib().b200_query_counts_stride(self.h)
+        self.n_groups, self.flt_err = 1, 0
+        return self
 
     def close(self):
         if self.h:

@@ -495,6 +495,31 @@ extern "C" b200_query_t *b200_query_create(b200_ctx_t *c, const b200_pbf_t *pb, 
 	return q;
 }
 
+extern "C" b200_query_t *b200_query_create_cols(b200_ctx_t *c, const b200_pbf_t *pb, int n_cols, const int32_t *cols)
+{
+	if (!c || !pb) { set_err("b200_query_create_cols: null argument"); return nullptr; }
+	cudaSetDevice(c->dev);
+	if (n_cols <= 0 || n_cols >= pb->m || cols == nullptr) { n_cols = pb->m; cols = nullptr; } // pbwt.c:377
+	b200_query_t *q = new b200_query_t();
+	q->ctx = c; q->m = pb->m; q->n_out = n_cols / 2; q->n_track = n_cols; q->G = 1; q->words = (n_cols + 31) / 32;
+	q->full = (cols == nullptr);
+	memset(&q->prog, 0, sizeof(q->prog));
+	std::vector<int32_t> gsize(B200_MAX_GROUPS, 0);
+	gsize[0] = n_cols;
+	for (int i = 0; cols && i < n_cols; ++i)
+		if (cols[i] < 0 || cols[i] >= pb->m) { set_err("column %d out of range 0..%d", cols[i], pb->m - 1); delete q; return nullptr; }
+	bool ok = CU_OK(cudaMalloc(&q->d_tgrp, (size_t)n_cols + 16)) && CU_OK(cudaMalloc(&q->d_gsize, sizeof(int32_t) * B200_MAX_GROUPS)) &&
+	          CU_OK(cudaMalloc(&q->d_prog, sizeof(flt_prog_t)));
+	if (ok && cols) ok = CU_OK(cudaMalloc(&q->d_track, sizeof(int32_t) * (size_t)n_cols));
+	ok = ok && CU_OK(cudaMemsetAsync(q->d_tgrp, 0, (size_t)n_cols + 16, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(q->d_gsize, gsize.data(), sizeof(int32_t) * B200_MAX_GROUPS, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(q->d_prog, &q->prog, sizeof(flt_prog_t), cudaMemcpyHostToDevice, c->st));
+	if (ok && cols) ok = CU_OK(cudaMemcpyAsync(q->d_track, cols, sizeof(int32_t) * (size_t)n_cols, cudaMemcpyHostToDevice, c->st));
+	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
+	if (!ok) { b200_query_destroy(q); return nullptr; }
+	return q;
+}
+
 extern "C" int b200_query_n_track(const b200_query_t *q) { return q ? q->n_track : -1; }
 extern "C" int b200_query_hap_words(const b200_query_t *q) { return q ? q->words : -1; }
 extern "C" int b200_query_counts_stride(const b200_query_t *q) { return q ? 3 + 3 * q->G : -1; }

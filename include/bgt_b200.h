@@ -63,8 +63,12 @@ int64_t     b200_pbf_bad_rows(const b200_pbf_t *pb);
  * error mask (kexpr.h:10-16) and NULL is returned when it is non-zero. */
 b200_query_t *b200_query_create(b200_ctx_t *ctx, const b200_pbf_t *pb, int n_out, const int32_t *out_samples,
                                 const uint32_t *group, int n_groups, const char *flt, int *flt_err);
+/* Column-level selection, the stand-in for pbf_subset (pbwt.c:374-388): cols = any list of column indices in any
+ * order (duplicates allowed); outputs come in list order.  n_cols <= 0 or >= m or cols == NULL selects every column
+ * (pbwt.c:377).  One group, no filter. */
+b200_query_t *b200_query_create_cols(b200_ctx_t *ctx, const b200_pbf_t *pb, int n_cols, const int32_t *cols);
 void          b200_query_destroy(b200_query_t *q);
-int           b200_query_n_track(const b200_query_t *q);     /* 2*n_out */
+int           b200_query_n_track(const b200_query_t *q);     /* 2*n_out (or the number of columns) */
 int           b200_query_hap_words(const b200_query_t *q);   /* 32-bit words per plane per row of hap_bits */
 int           b200_query_counts_stride(const b200_query_t *q); /* 3 + 3*n_groups */
 
