@@ -63,6 +63,8 @@ SIGNATURES = {
     "b200_kernel_launches": (_i64, [_vp]),
     "b200_mark": (_int, [_vp, _int]),
     "b200_mark_elapsed_ms": (C.c_double, [_vp, _int, _int]),
+    "b200_flt_eval_host": (_int, [C.c_char_p, _int, _vp, _i64, _vp]),
+    "b200_pbf_plan": (_int, [_vp, C.c_size_t, _i64, _i64, C.POINTER(_i64)]),
     "b200_synth_generate": (_vp, [_vp, C.POINTER(SynthCfg)]),
     "b200_pbf_image_size": (C.c_size_t, [_vp]),
     "b200_pbf_image_download": (_int, [_vp, _vp, C.c_size_t]),
@@ -295,3 +297,23 @@ def host_alloc(n_bytes):
 
 def host_free(arr):
     lib().b200_host_free(arr.ctypes.data_as(C.c_void_p))
+
+
+def flt_eval_host(flt, n_groups, counts):
+    """Host evaluation of a site filter with the library's own compiler + byte-code (b200_flt_eval_host)."""
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    out = np.zeros(counts.shape[0], dtype=np.uint8)
+    err = lib().b200_flt_eval_host(flt.encode(), n_groups, _ptr(counts), counts.shape[0], _ptr(out))
+    if err:
+        raise B200Error("filter parse error 0x%x" % err if err > 0 else _err())
+    return out
+
+
+def pbf_plan(data, row_beg=0, row_end=-1):
+    """Host-side index walk + tile plan of a .pbf image (no device needed)."""
+    buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    info = (C.c_int64 * 8)()
+    if lib().b200_pbf_plan(_ptr(buf), buf.size, row_beg, row_end, info) != 0:
+        raise B200Error(_err())
+    keys = ("m", "shift", "n", "blocks", "tiles", "big_tiles", "max_tile_bytes", "max_row_bytes")
+    return dict(zip(keys, [info[i] for i in range(8)]))

@@ -309,10 +309,11 @@ static bool walk_block(const uint8_t *f, size_t flen, uint64_t off, int m, int g
 	return true;
 }
 
-extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
+// Host half of making rows [row_beg,row_end) resident: header / index parse (pbwt.c:231-258), block range,
+// per-block row offsets (a few host threads).  Offsets are relative to pb->file_off0.
+static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
 {
-	if (!c || !f) { set_err("b200_pbf_load: null argument"); return nullptr; }
-	cudaSetDevice(c->dev);
+	if (!f) { set_err("null PBF image"); return nullptr; }
 	if (flen < 16 + 13 + 8 || memcmp(f, "PBF\1", 4) != 0) { set_err("not a PBF file (bad magic)"); return nullptr; } // pbwt.c:231-235
 	int32_t hdr[3];
 	memcpy(hdr, f + 4, 12);
@@ -334,7 +335,7 @@ extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t fle
 	memcpy(idx.data(), f + ioff + 13, 8ull * n_idx);
 
 	b200_pbf_t *pb = new b200_pbf_t();
-	pb->ctx = c; pb->m = m; pb->g = g; pb->shift = shift; pb->BS = BS; pb->n = n; pb->n_blk_file = n_idx;
+	pb->m = m; pb->g = g; pb->shift = shift; pb->BS = BS; pb->n = n; pb->n_blk_file = n_idx;
 	pb->blk0 = (int)(row_beg >> shift);
 	const int blk1 = row_end > row_beg ? (int)((row_end + BS - 1) >> shift) : pb->blk0;
 	pb->n_blk = blk1 - pb->blk0;
@@ -344,15 +345,6 @@ extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t fle
 	if (pb->blk0 == 0 && blk1 == n_idx) { pb->file_off0 = 0; pb->file_size = flen; }
 	const uint64_t copy_end = pb->file_size ? flen : byte_end;
 	pb->img_bytes = (size_t)(copy_end - pb->file_off0);
-
-	bool ok = CU_OK(cudaMalloc(&pb->d_img, pb->img_bytes + 64));
-	ok = ok && CU_OK(cudaEventRecord(c->ev[4], c->st));
-	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img, f + pb->file_off0, pb->img_bytes, cudaMemcpyHostToDevice, c->st));
-	ok = ok && CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st));
-	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st));
-	if (!ok) { pbf_free_device(pb); delete pb; return nullptr; }
-
-	// row offsets: independent per block -> a few host threads, overlapping the H2D copy above
 	pb->rows_in_blk.resize(nb);
 	pb->h_rowoff.assign((size_t)nb * (BS + 1), 0);
 	pb->h_blkoff.resize(nb);
@@ -361,6 +353,7 @@ extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t fle
 		pb->rows_in_blk[b] = (int)(n - r0 < BS ? n - r0 : BS);
 		pb->h_blkoff[b] = idx[pb->blk0 + b] - pb->file_off0;
 	}
+	bool ok = true;
 	{
 		const int nt = nb < 2 ? 1 : (nb < 8 ? nb : 8);
 		std::vector<int> bad(nt, 0);
@@ -376,11 +369,64 @@ extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t fle
 		for (auto &x : th) x.join();
 		for (int t = 0; t < nt; ++t) if (bad[t]) ok = false;
 	}
-	if (!ok) { set_err("corrupt PBF: record tags/lengths inside a checkpoint block do not parse"); cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
-	if (!pbf_finish_resident(pb, false)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	if (!ok) { set_err("corrupt PBF: record tags/lengths inside a checkpoint block do not parse"); delete pb; return nullptr; }
+	return pb;
+}
+
+extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
+{
+	if (!c || !f) { set_err("b200_pbf_load: null argument"); return nullptr; }
+	cudaSetDevice(c->dev);
+	// the H2D copy of the block range is queued first (its extent only needs the header and the index record); the
+	// row walk below then overlaps it
+	b200_pbf_t *pb = pbf_index_host(f, flen, row_beg, row_end);
+	if (!pb) return nullptr;
+	pb->ctx = c;
+	bool ok = CU_OK(cudaMalloc(&pb->d_img, pb->img_bytes + 64));
+	ok = ok && CU_OK(cudaEventRecord(c->ev[4], c->st));
+	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img, f + pb->file_off0, pb->img_bytes, cudaMemcpyHostToDevice, c->st));
+	ok = ok && CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st));
+	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st));
+	if (!ok || !pbf_finish_resident(pb, false)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
 	return pb;
+}
+
+extern "C" int b200_pbf_plan(const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end, int64_t info[8])
+{
+	b200_pbf_t *pb = pbf_index_host(f, flen, row_beg, row_end);
+	if (!pb) return -1;
+	std::vector<int2> tiles;
+	std::vector<int> btb;
+	plan_tiles(pb, tiles, btb);
+	int64_t n_big = 0, max_tile = 0, max_row = 0;
+	for (int b = 0; b < pb->n_blk; ++b) {
+		const uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (pb->BS + 1);
+		for (int t = btb[b]; t < btb[b + 1]; ++t) {
+			const int r = tiles[t].x, nr = tiles[t].y & 0x7fffffff;
+			const int64_t bytes = (int64_t)(ro[r + nr] - ro[r]);
+			if (tiles[t].y < 0) ++n_big; else if (bytes > max_tile) max_tile = bytes;
+		}
+		for (int r = 0; r < pb->rows_in_blk[b]; ++r) if ((int64_t)(ro[r + 1] - ro[r]) > max_row) max_row = (int64_t)(ro[r + 1] - ro[r]);
+	}
+	if (info) {
+		info[0] = pb->m; info[1] = pb->shift; info[2] = pb->n; info[3] = pb->n_blk; info[4] = (int64_t)tiles.size();
+		info[5] = n_big; info[6] = max_tile; info[7] = max_row;
+	}
+	delete pb;
+	return 0;
+}
+
+extern "C" int b200_flt_eval_host(const char *flt, int n_groups, const int32_t *counts, int64_t n_rows, uint8_t *pass)
+{
+	if (n_groups < 1 || n_groups > B200_MAX_GROUPS) { set_err("n_groups out of range"); return -1; }
+	flt_prog_t prog;
+	const int err = flt_compile(flt, n_groups, &prog);
+	if (err) { set_err("filter expression does not parse (kexpr error mask 0x%x)", err); return err; }
+	const int stride = 3 + 3 * n_groups;
+	for (int64_t k = 0; k < n_rows; ++k) pass[k] = (uint8_t)flt_eval(&prog, counts + k * stride);
+	return 0;
 }
 
 extern "C" b200_pbf_t *b200_pbf_open(b200_ctx_t *c, const char *fn, int64_t row_beg, int64_t row_end)

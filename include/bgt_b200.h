@@ -102,6 +102,16 @@ int64_t b200_kernel_launches(b200_ctx_t *ctx);      /* kernels launched by this 
 int     b200_mark(b200_ctx_t *ctx, int slot);
 double  b200_mark_elapsed_ms(b200_ctx_t *ctx, int slot_a, int slot_b);
 
+/* ---------------------------------------------------------------- host logic, callable without a device */
+/* Compile `flt` exactly as b200_query_create does and evaluate it on the host for n_rows count vectors
+ * ([n_rows][3+3*n_groups], the layout b200_scan writes).  Returns the kexpr-style parse error mask (0 = ok).
+ * This is the evaluator the scan itself uses for filters containing `**` (host libm). */
+int     b200_flt_eval_host(const char *flt, int n_groups, const int32_t *counts, int64_t n_rows, uint8_t *pass);
+/* Parse a .pbf image, walk the row index of rows [row_beg,row_end) and plan the kernel's row tiles.
+ * info[0..7] = m, shift, rows in file, resident blocks, tiles, oversized single-row tiles, largest ordinary tile in
+ * bytes, largest row in bytes.  Returns 0 or <0 (message in b200_strerror()). */
+int     b200_pbf_plan(const uint8_t *bytes, size_t n_bytes, int64_t row_beg, int64_t row_end, int64_t info[8]);
+
 /* ---------------------------------------------------------------- synthetic cohort (SURVEY 8d generator; rows drawn in PBWT-rank space, truthful snapshots) */
 typedef struct {
 	int32_t  n_samples;      /* m = 2*n_samples */
