@@ -13,7 +13,7 @@ def shard_rows(n_rows, shift, rank, world):
     per = (n_blk + world - 1) // world
     b0 = min(rank * per, n_blk)
     b1 = min(b0 + per, n_blk)
-    return b0 * bs, min(b1 * bs, n_rows)
+    return min(b0 * bs, n_rows), min(b1 * bs, n_rows)
 
 
 def allreduce_totals(totals, device=None):

@@ -148,3 +148,59 @@ def test_kexpr_vs_ref(ref):
         err = C.c_int(0)
         assert not ref.lib().orc_expr_parse(s.encode(), C.byref(err))
         assert err.value == want[1], s
+
+
+# ---------------------------------------------------------------- restated scan vs the reference's own `bgt view`
+
+def _parse_view(vcf):
+    recs = {}
+    for ln in vcf.split(b"\n"):
+        if not ln or ln[:1] == b"#":
+            continue
+        f = ln.split(b"\t")
+        info = {}
+        for kv in f[7].split(b";"):
+            if b"=" in kv:
+                k, v = kv.split(b"=")
+                info[k.decode()] = [int(x) for x in v.split(b",")]
+        recs[(int(f[1]) - 1000) // 10] = (info, f[9:] if len(f) > 9 else None)
+    return recs
+
+
+@pytest.mark.parametrize("case", [("AC>0", False), ("AN>0&&AC/AN>.05", False), ("AC1/AN1>0.1&&AC2==0", True), ("AC3>0", True), (None, True)])
+def test_scan_vs_ref_view(ref, case, tmp_path):
+    """orc_scan (cal_info + filter + decode) against `bgt view` of the unmodified reference on the same database."""
+    import subprocess
+    flt, two_groups = case
+    n, m = 400, 120
+    mat = haplo_matrix(n, m, 31, p_missing_row=0.2, p_multi_row=0.2)
+    pbf = ref.encode_pbf(mat, shift=6)
+    prefix = str(tmp_path / "x.bgt")
+    with open(prefix + ".pbf", "wb") as f:
+        f.write(pbf)
+    subprocess.run([ref.MKSITES, prefix], check=True, stderr=subprocess.DEVNULL)
+    args = ["view"]
+    grp, G = None, 1
+    if two_groups:
+        args += ["-s", 'grp=="A"', "-s", 'grp=="B"']
+        grp, G = (np.arange(m // 2) % 2 + 1).astype(np.uint32), 2
+    if flt:
+        args += ["-f", flt]
+    else:
+        args += ["-C"]
+    recs = _parse_view(ref.ref_run(["bgt"] + args + [prefix]))
+    got = ref.Pbf(pbf).scan(0, n, group=grp, n_groups=G, flt=flt, want_hap=True)
+    assert sorted(recs) == [k for k in range(n) if got["passed"][k]]
+    gt = {0: b"0", 1: b"1", 2: b".", 3: b"2"}
+    for k, (info, gts) in recs.items():
+        c = got["counts"][k]
+        multi = bool((mat[k] == 3).any())
+        assert info["AN"] == [c[0]] and info["AC"] == ([c[1], c[2]] if multi else [c[1]])
+        if G == 2:
+            for g in range(2):
+                assert info["AN%d" % (g + 1)] == [c[3 + 3 * g]]
+                assert info["AC%d" % (g + 1)] == ([c[4 + 3 * g], c[5 + 3 * g]] if multi else [c[4 + 3 * g]])
+        code = got["hap0"][k] | (got["hap1"][k] << 1)
+        assert (code == mat[k]).all()
+        want_gt = [gt[int(code[2 * s])] + b"/" + gt[int(code[2 * s + 1])] for s in range(m // 2)]
+        assert gts == want_gt
