@@ -194,7 +194,7 @@ def test_scan_vs_ref_view(ref, case, tmp_path):
     gt = {0: b"0", 1: b"1", 2: b".", 3: b"2"}
     for k, (info, gts) in recs.items():
         c = got["counts"][k]
-        multi = bool((mat[k] == 3).any())
+        multi = bool((mat[k] & 2).any())   # mksites writes "<M>" whenever plane 1 of the row is not empty
         assert info["AN"] == [c[0]] and info["AC"] == ([c[1], c[2]] if multi else [c[1]])
         if G == 2:
             for g in range(2):
