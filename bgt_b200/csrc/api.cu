@@ -633,7 +633,8 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	P.cnt_raw = (int32_t*)c->cnt_raw.p; P.hap[0] = d_bits[0]; P.hap[1] = d_bits[1];
 	P.m = pb->m; P.n_track = n_track; P.G = G; P.words = words; P.shift = pb->shift;
 	P.blk_first = b_first; P.blk_row0 = (long long)pb->blk0 << pb->shift; P.row_lo = row_beg; P.row_hi = row_beg + n_rows; P.err = c->d_err;
-	const int C = pick_cols_per_thread(c, n_track, n_blk);
+	const int forced = (int)((flags >> 8) & 15u);
+	const int C = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : pick_cols_per_thread(c, n_track, n_blk);
 	const int slices = (n_track + WALK_NT * C - 1) / (WALK_NT * C);
 
 	bool ok = CU_OK(cudaEventRecord(c->ev[2], c->st)) &&
