@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SCAN_COUNTS, SCAN_HAP_BITS, SCAN_HAP_BYTES, SCAN_DEVICE_OUT = 0x01, 0x02, 0x04, 0x10
+SCAN_COUNTS, SCAN_HAP_BITS, SCAN_HAP_BYTES, SCAN_DEVICE_OUT, SCAN_NO_SPLIT = 0x01, 0x02, 0x04, 0x10, 0x20
 MAX_GROUPS = 32
 
 _lib = None
@@ -229,7 +229,7 @@ class Query:
             self.h = None
 
 
-def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, hap_bytes=False, out=None, cols_per_thread=0):
+def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, hap_bytes=False, out=None, cols_per_thread=0, no_split=False):
     """b200_scan with host outputs.  Returns dict(n, counts, passed, hap_bits, hap_bytes, totals)."""
     if n_rows is None:
         n_rows = pbf.row_end - row_beg
@@ -246,7 +246,7 @@ def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, h
     so = ScanOut()
     so.counts = _ptr(res["counts"]) if counts else None
     so.passed = _ptr(res["passed"])
-    flags = (SCAN_COUNTS if counts else 0) | (int(cols_per_thread) << 8)
+    flags = (SCAN_COUNTS if counts else 0) | (int(cols_per_thread) << 8) | (SCAN_NO_SPLIT if no_split else 0)
     if hap_bits:
         flags |= SCAN_HAP_BITS
         so.hap_bits[0], so.hap_bits[1] = _ptr(res["hap_bits"][0]), _ptr(res["hap_bits"][1])
@@ -264,13 +264,13 @@ def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, h
     return res
 
 
-def scan_device(ctx, pbf, query, row_beg, n_rows, d_counts=0, d_pass=0, d_hap_bits=(0, 0)):
+def scan_device(ctx, pbf, query, row_beg, n_rows, d_counts=0, d_pass=0, d_hap_bits=(0, 0), no_split=False):
     """b200_scan with B200_SCAN_DEVICE_OUT: outputs are device pointers (ints), the call returns without syncing.
     Follow with collect(ctx) to wait, check device error flags and fetch totals / kernel timings."""
     so = ScanOut()
     so.counts = d_counts or None
     so.passed = d_pass or None
-    flags = SCAN_DEVICE_OUT | (SCAN_COUNTS if d_counts else 0)
+    flags = SCAN_DEVICE_OUT | (SCAN_COUNTS if d_counts else 0) | (SCAN_NO_SPLIT if no_split else 0)
     if d_hap_bits[0]:
         flags |= SCAN_HAP_BITS
         so.hap_bits[0], so.hap_bits[1] = d_hap_bits

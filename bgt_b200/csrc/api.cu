@@ -63,7 +63,7 @@ struct b200_ctx_s {
 	int64_t launches = 0;
 	int *d_err = nullptr;
 	unsigned long long *d_acc = nullptr; // [0..3] totals, [4] bad rows
-	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2];
+	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], wmask, wlist, wcount, blk_lists, blk_split;
 	int sm_count = 148;
 };
 
@@ -84,6 +84,18 @@ struct b200_pbf_s {
 	uint32_t *d_n1 = nullptr;
 	int32_t *d_rank0 = nullptr;
 	int64_t bad_rows = 0;
+	// "plane-1 view" of the resident blocks: only the rows whose second bit plane (missing / other-ALT codes) is not
+	// empty, as a miniature PBF image the walk kernel can run on (first phase of the split scan)
+	bool p1_ready = false;
+	int p1_cap = 0;                      // capacity of the per-block column set W
+	std::vector<uint8_t> blk_sparse;     // [n_blk] 1 = the block's plane-1 ones fit p1_cap (split scan applies)
+	std::vector<int> p1_rows_in_blk;
+	uint8_t *d_p1img = nullptr;
+	uint64_t *d_p1_rowoff = nullptr;
+	uint32_t *d_p1_n1 = nullptr;
+	int2 *d_p1_tiles = nullptr;
+	int *d_p1_blk_tile_beg = nullptr;
+	int64_t p1_rows = 0;
 };
 
 struct b200_query_s {
@@ -138,6 +150,7 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	if (c->st) cudaStreamSynchronize(c->st);
 	c->cnt_raw.release(); c->counts.release(); c->pass.release();
 	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
+	c->wmask.release(); c->wlist.release(); c->wcount.release(); c->blk_lists.release(); c->blk_split.release();
 	for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
 	if (c->d_err) cudaFree(c->d_err);
@@ -193,6 +206,11 @@ static void pbf_free_device(b200_pbf_t *pb)
 	if (pb->d_tiles) cudaFree(pb->d_tiles);
 	if (pb->d_n1) cudaFree(pb->d_n1);
 	if (pb->d_rank0) cudaFree(pb->d_rank0);
+	if (pb->d_p1img) cudaFree(pb->d_p1img);
+	if (pb->d_p1_rowoff) cudaFree(pb->d_p1_rowoff);
+	if (pb->d_p1_n1) cudaFree(pb->d_p1_n1);
+	if (pb->d_p1_tiles) cudaFree(pb->d_p1_tiles);
+	if (pb->d_p1_blk_tile_beg) cudaFree(pb->d_p1_blk_tile_beg);
 }
 
 extern "C" void b200_pbf_close(b200_pbf_t *pb)
@@ -206,15 +224,15 @@ extern "C" void b200_pbf_close(b200_pbf_t *pb)
 
 // Tiles: maximal groups of consecutive rows of one block with <= T_MAX rows and <= RAW_CAP bytes; a row that is
 // larger than RAW_CAP on its own becomes a single-row "big" tile (streamed in pieces by the kernel).
-static void plan_tiles(const b200_pbf_t *pb, std::vector<int2> &tiles, std::vector<int> &blk_tile_beg)
+static void plan_tiles_of(int n_blk, int BS, const std::vector<uint64_t> &rowoff, const std::vector<int> &rows_in_blk,
+                          std::vector<int2> &tiles, std::vector<int> &blk_tile_beg)
 {
-	const int BS = pb->BS;
-	blk_tile_beg.assign(pb->n_blk + 1, 0);
+	blk_tile_beg.assign(n_blk + 1, 0);
 	tiles.clear();
-	for (int b = 0; b < pb->n_blk; ++b) {
+	for (int b = 0; b < n_blk; ++b) {
 		blk_tile_beg[b] = (int)tiles.size();
-		const uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
-		const int rows = pb->rows_in_blk[b];
+		const uint64_t *ro = rowoff.data() + (size_t)b * (BS + 1);
+		const int rows = rows_in_blk[b];
 		int r = 0;
 		while (r < rows) {
 			if (ro[r + 1] - ro[r] > (uint64_t)RAW_CAP) { tiles.push_back(make_int2(r, (int)(1u | 0x80000000u))); ++r; continue; }
@@ -224,7 +242,99 @@ static void plan_tiles(const b200_pbf_t *pb, std::vector<int2> &tiles, std::vect
 			r = e;
 		}
 	}
-	blk_tile_beg[pb->n_blk] = (int)tiles.size();
+	blk_tile_beg[n_blk] = (int)tiles.size();
+}
+
+static void plan_tiles(const b200_pbf_t *pb, std::vector<int2> &tiles, std::vector<int> &blk_tile_beg)
+{
+	plan_tiles_of(pb->n_blk, pb->BS, pb->h_rowoff, pb->rows_in_blk, tiles, blk_tile_beg);
+}
+
+// Build the plane-1 view from a host copy of the image (img0 = the byte that pb->h_rowoff offsets are relative to).
+// Per resident block: the rows whose plane 1 has at least one 1 bit, re-framed as records 'B', l0 = 0, l1, bytes so
+// that the walk kernel sees an empty plane 0; n1 is known here, so no row-meta pass is needed.
+static bool build_plane1_view(b200_pbf_t *pb, const uint8_t *img0)
+{
+	b200_ctx_t *c = pb->ctx;
+	const int nb = pb->n_blk, BS = pb->BS;
+	const uint32_t m = (uint32_t)pb->m;
+	pb->p1_cap = (((pb->m / 4 > 4096 ? pb->m / 4 : 4096) + 2047) / 2048) * 2048;
+	pb->blk_sparse.assign(nb, 1);
+	pb->p1_rows_in_blk.assign(nb, 0);
+	std::vector<std::vector<uint8_t>> rec(nb);
+	std::vector<std::vector<uint32_t>> n1s(nb), lens(nb);
+	{
+		const int nt = nb < 2 ? 1 : (nb < 8 ? nb : 8);
+		std::vector<std::thread> th;
+		for (int t = 0; t < nt; ++t)
+			th.emplace_back([&, t]() {
+				for (int b = t; b < nb; b += nt) {
+					const uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
+					uint64_t ones_sum = 0;
+					for (int r = 0; r < pb->rows_in_blk[b]; ++r) {
+						const uint8_t *p = img0 + ro[r] + 1;
+						int32_t l0, l1;
+						memcpy(&l0, p, 4);
+						p += 4 + l0;
+						memcpy(&l1, p, 4);
+						p += 4;
+						uint64_t ones = 0, tot = 0;
+						for (int32_t i = 0; i < l1; ++i) {
+							const uint32_t v = p[i] >> 1, len = (v & 15u) << ((v >> 4) << 2);
+							tot += len;
+							if (p[i] & 1) ones += len;
+						}
+						if (ones == 0 || tot != m) continue;          // empty (or corrupt: decodes as empty, see rowmeta_kernel)
+						if (ones == m) pb->blk_sparse[b] = 0;          // every column carries the code: W would be everything
+						ones_sum += ones;
+						const int32_t zero = 0;
+						rec[b].push_back('B');
+						rec[b].insert(rec[b].end(), (const uint8_t*)&zero, (const uint8_t*)&zero + 4);
+						rec[b].insert(rec[b].end(), (const uint8_t*)&l1, (const uint8_t*)&l1 + 4);
+						rec[b].insert(rec[b].end(), p, p + l1);
+						n1s[b].push_back((uint32_t)ones);
+						lens[b].push_back(9u + (uint32_t)l1);
+					}
+					if (ones_sum > (uint64_t)pb->p1_cap) pb->blk_sparse[b] = 0;
+					pb->p1_rows_in_blk[b] = (int)n1s[b].size();
+				}
+			});
+		for (auto &x : th) x.join();
+	}
+	std::vector<uint64_t> rowoff((size_t)nb * (BS + 1), 0);
+	std::vector<uint32_t> n1((size_t)nb * BS * 2, 0);
+	std::vector<uint8_t> img;
+	size_t total = 0;
+	for (int b = 0; b < nb; ++b) total += ((rec[b].size() + 15) & ~(size_t)15);
+	img.reserve(total + 64);
+	pb->p1_rows = 0;
+	for (int b = 0; b < nb; ++b) {
+		uint64_t pos = img.size();
+		uint64_t *ro = rowoff.data() + (size_t)b * (BS + 1);
+		for (size_t r = 0; r < n1s[b].size(); ++r) {
+			ro[r] = pos; pos += lens[b][r];
+			n1[((size_t)b * BS + r) * 2 + 1] = n1s[b][r];
+		}
+		ro[n1s[b].size()] = pos;
+		img.insert(img.end(), rec[b].begin(), rec[b].end());
+		img.resize((img.size() + 15) & ~(size_t)15, 0);
+		pb->p1_rows += (int64_t)n1s[b].size();
+	}
+	img.resize(img.size() + 64, 0);
+	std::vector<int2> tiles;
+	std::vector<int> btb;
+	plan_tiles_of(nb, BS, rowoff, pb->p1_rows_in_blk, tiles, btb);
+	bool ok = CU_OK(cudaMalloc(&pb->d_p1img, img.size())) && CU_OK(cudaMalloc(&pb->d_p1_rowoff, rowoff.size() * 8 + 8)) &&
+	          CU_OK(cudaMalloc(&pb->d_p1_n1, n1.size() * 4 + 8)) && CU_OK(cudaMalloc(&pb->d_p1_tiles, (tiles.size() + 1) * sizeof(int2))) &&
+	          CU_OK(cudaMalloc(&pb->d_p1_blk_tile_beg, (nb + 1) * sizeof(int)));
+	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_p1img, img.data(), img.size(), cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_p1_rowoff, rowoff.data(), rowoff.size() * 8, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_p1_n1, n1.data(), n1.size() * 4, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_p1_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_p1_blk_tile_beg, btb.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaStreamSynchronize(c->st));
+	pb->p1_ready = ok;
+	return ok;
 }
 
 // Upload the row index, plan tiles, compute per-row n1, [generator: run the chain], invert the snapshots.
@@ -269,7 +379,7 @@ static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain)
 		P.tgrp = d_zero;
 		const int C = pb->m > 148 * 2 * WALK_NT * 4 ? 4 : pb->m > 148 * 2 * WALK_NT * 2 ? 2 : 1;
 		const int slices = (pb->m + WALK_NT * C - 1) / (WALK_NT * C);
-		ok = CU_OK(launch_walk(P, C, false, true, slices, nb, c->st));
+		ok = CU_OK(launch_walk(P, C, WALK_MODE_CHAIN, slices, nb, c->st));
 		++c->launches;
 		ok = ok && CU_OK(cudaStreamSynchronize(c->st));
 		cudaFree(d_zero);
@@ -387,7 +497,7 @@ extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t fle
 	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img, f + pb->file_off0, pb->img_bytes, cudaMemcpyHostToDevice, c->st));
 	ok = ok && CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st));
 	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st));
-	if (!ok || !pbf_finish_resident(pb, false)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	if (!ok || !pbf_finish_resident(pb, false) || !build_plane1_view(pb, f + pb->file_off0)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
 	return pb;
@@ -634,16 +744,58 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	P.m = pb->m; P.n_track = n_track; P.G = G; P.words = words; P.shift = pb->shift;
 	P.blk_first = b_first; P.blk_row0 = (long long)pb->blk0 << pb->shift; P.row_lo = row_beg; P.row_hi = row_beg + n_rows; P.err = c->d_err;
 	const int forced = (int)((flags >> 8) & 15u);
-	const int C = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : pick_cols_per_thread(c, n_track, n_blk);
-	const int slices = (n_track + WALK_NT * C - 1) / (WALK_NT * C);
+
+	// Split scan (all columns, one group, counts only): #ALT of a site is the number of ones of its plane-0 row, known
+	// from the RLE alone; only the columns that carry a missing / other-ALT code somewhere in the block (the set W,
+	// from the block's plane-1 rows) have to be walked to resolve the joint codes.  Blocks whose W would be large
+	// (pb->blk_sparse == 0) and every other kind of query take the general walk over all tracked columns.
+	const bool split = q->full && G == 1 && !emit && pb->p1_ready && !(flags & B200_SCAN_NO_SPLIT) && n_track > 0;
+	std::vector<int> lists;          // [general blocks..., split blocks...]
+	std::vector<uint8_t> split_flag(pb->n_blk, 0);
+	int n_gen = 0, n_split = 0;
+	for (int b = b_first; b <= b_last; ++b) if (!(split && pb->blk_sparse[b])) { lists.push_back(b); ++n_gen; }
+	for (int b = b_first; b <= b_last; ++b) if (split && pb->blk_sparse[b]) { lists.push_back(b); split_flag[b] = 1; ++n_split; }
+	if (!c->blk_lists.reserve(lists.size() * sizeof(int) + 16) || !c->blk_split.reserve((size_t)pb->n_blk + 16)) return -1;
+	const int *d_gen_list = (const int*)c->blk_lists.p, *d_split_list = d_gen_list + n_gen;
+	FinalizeSplit sp;
+	memset(&sp, 0, sizeof(sp));
 
 	bool ok = CU_OK(cudaEventRecord(c->ev[2], c->st)) &&
 	          CU_OK(cudaMemsetAsync(c->cnt_raw.p, 0, nr * G * 3 * sizeof(int32_t), c->st)) &&
 	          CU_OK(cudaMemsetAsync(c->d_acc, 0, 4 * sizeof(unsigned long long), c->st)) &&
+	          CU_OK(cudaMemcpyAsync(c->blk_lists.p, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
+	          CU_OK(cudaMemcpyAsync(c->blk_split.p, split_flag.data(), (size_t)pb->n_blk, cudaMemcpyHostToDevice, c->st)) &&
 	          CU_OK(cudaEventRecord(c->ev[0], c->st));
-	if (ok && n_track > 0) { ok = CU_OK(launch_walk(P, C, emit, false, slices, n_blk, c->st)); c->launches += (n_blk + 32767) / 32768; }
+	if (ok && n_track > 0 && n_gen > 0) {
+		P.blk_list = d_gen_list;
+		const int Cg = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : pick_cols_per_thread(c, n_track, n_gen);
+		ok = CU_OK(launch_walk(P, Cg, emit ? WALK_MODE_EMIT : WALK_MODE_COUNT, (n_track + WALK_NT * Cg - 1) / (WALK_NT * Cg), n_gen, c->st));
+		c->launches += (n_gen + 32767) / 32768;
+	}
+	if (ok && n_split > 0) {
+		const int cap = pb->p1_cap;
+		if (!c->wmask.reserve((size_t)pb->n_blk * words * sizeof(uint32_t)) || !c->wlist.reserve((size_t)pb->n_blk * cap * sizeof(int32_t)) ||
+		    !c->wcount.reserve((size_t)pb->n_blk * sizeof(int))) return -1;
+		// phase 1: W mask per block = OR of the block's plane-1 rows (all columns, but only the few non-empty rows)
+		WalkParams A = P;
+		A.img = pb->d_p1img; A.rowoff = pb->d_p1_rowoff; A.n1 = pb->d_p1_n1; A.tiles = pb->d_p1_tiles; A.blk_tile_beg = pb->d_p1_blk_tile_beg;
+		A.cnt_raw = nullptr; A.hap[0] = A.hap[1] = nullptr; A.wmask = (uint32_t*)c->wmask.p; A.blk_list = d_split_list;
+		A.row_lo = 0; A.row_hi = (long long)1 << 60; A.blk_row0 = 0;
+		const int Ca = pick_cols_per_thread(c, n_track, n_split);
+		ok = CU_OK(launch_walk(A, Ca, WALK_MODE_ORMASK, (n_track + WALK_NT * Ca - 1) / (WALK_NT * Ca), n_split, c->st));
+		// W list per block
+		ok = ok && CU_OK(launch_wmask_compact((const uint32_t*)c->wmask.p, words, cap, d_split_list, n_split, (int32_t*)c->wlist.p, (int*)c->wcount.p, c->st));
+		// phase 2: walk only W through the real rows, count the plane-1 codes (missing, other-ALT) where they occur
+		WalkParams B = P;
+		B.track = (const int32_t*)c->wlist.p; B.track_stride = cap; B.n_track_blk = (const int*)c->wcount.p; B.n_track = cap;
+		B.blk_list = d_split_list; B.joint_only = 1;
+		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : 4;
+		ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_COUNT, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
+		c->launches += 3;
+		sp.blk_split = (const uint8_t*)c->blk_split.p; sp.n1 = pb->d_n1; sp.row_lo = row_beg; sp.blk_row0 = P.blk_row0; sp.shift = pb->shift;
+	}
 	ok = ok && CU_OK(cudaEventRecord(c->ev[1], c->st));
-	ok = ok && CU_OK(launch_finalize(P.cnt_raw, n_rows, G, q->d_gsize, q->d_prog, q->has_flt && !host_flt, d_counts, d_pass, c->d_acc, c->st));
+	ok = ok && CU_OK(launch_finalize(P.cnt_raw, n_rows, G, q->d_gsize, q->d_prog, q->has_flt && !host_flt, d_counts, d_pass, c->d_acc, sp, c->st));
 	++c->launches;
 	if (ok && want_bytes) {
 		for (int p = 0; p < 2 && ok; ++p) { ok = CU_OK(launch_unpack_bits(d_bits[p], n_rows, words, n_track, d_bytes[p], c->st)); ++c->launches; }
@@ -775,5 +927,12 @@ extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cf
 	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
 	if (d_flat) cudaFree(d_flat);
 	if (!ok || !pbf_finish_resident(pb, true)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	{ // the plane-1 view is built from a host copy of the generated image
+		uint8_t *h = (uint8_t*)b200_host_alloc(pb->img_bytes);
+		ok = h && CU_OK(cudaMemcpyAsync(h, pb->d_img, pb->img_bytes, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st)) &&
+		     build_plane1_view(pb, h);
+		b200_host_free(h);
+		if (!ok) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	}
 	return pb;
 }

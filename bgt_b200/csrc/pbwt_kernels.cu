@@ -330,9 +330,20 @@ __device__ __forceinline__ void emit_row(uint32_t bits0, uint32_t bits1, const W
 	}
 }
 
-template<int C, bool EMIT, bool CHAIN>
+// MODE: what the walk produces besides advancing the ranks
+//   WALK_COUNT  per-site per-group counters                      (the `view -G` scan)
+//   WALK_EMIT   counters + genotype rows as bit planes           (seam A, `view` with genotypes, subsets)
+//   WALK_CHAIN  nothing per site; one chain through ALL blocks that dumps the running permutation in front of
+//               every block (synthetic cohort generator)
+//   WALK_ORMASK nothing per site; per block the OR of the plane-1 rows = the set W of columns that carry a
+//               missing / other-ALT code anywhere in the block (first phase of the split scan, see api.cu)
+enum { WALK_COUNT = 0, WALK_EMIT = 1, WALK_CHAIN = 2, WALK_ORMASK = 3 };
+
+template<int C, int MODE>
 __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams P)
 {
+	constexpr bool EMIT = MODE == WALK_EMIT, CHAIN = MODE == WALK_CHAIN, ORMASK = MODE == WALK_ORMASK;
+	constexpr bool COUNT = MODE == WALK_COUNT || MODE == WALK_EMIT;
 	extern __shared__ __align__(128) uint8_t smem[];
 	WalkSmem S;
 	{
@@ -346,6 +357,12 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 	const int BS = 1 << P.shift;
 	const int slice_base = blockIdx.x * (WALK_NT * C);
 	const uint32_t m = (uint32_t)P.m;
+	// the checkpoint block of this CTA (a list when only some blocks take this path) and its tracked columns
+	// (one list for the whole scan, or one list per block when the set was derived per block)
+	const int blk_own = CHAIN ? 0 : (P.blk_list ? P.blk_list[blockIdx.y] : P.blk_first + (int)blockIdx.y);
+	const int n_track = P.n_track_blk ? P.n_track_blk[blk_own] : P.n_track;
+	const int32_t *track = P.track ? P.track + (size_t)blk_own * P.track_stride : nullptr;
+	if (slice_base >= n_track) return;
 
 	// ---- which columns this thread owns, their groups, their start ranks
 	uint32_t r0[C], r1[C];
@@ -355,11 +372,11 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 	#pragma unroll
 	for (int c = 0; c < C; ++c) {
 		const int e = slice_base + c * WALK_NT + tid;
-		const bool v = e < P.n_track;
-		col[c] = v ? (P.track ? P.track[e] : e) : 0;
+		const bool v = e < n_track;
+		col[c] = v ? (track ? track[e] : e) : 0;
 		validbits |= (v ? 1u : 0u) << c;
-		if (v && !CHAIN) {
-			const int grp = (int)P.tgrp[e];
+		if (v && COUNT) {
+			const int grp = (int)P.tgrp[P.track_stride ? col[c] : e];   // per-block lists: groups are per column
 			if (grp == 0) gm0 |= 1u << c;
 			else if (grp == 1) gm1 |= 1u << c;
 			if (P.G > 2) S.gmask[grp * WALK_NT + tid] |= (uint8_t)(1u << c);
@@ -372,8 +389,9 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 
 	uint32_t parity = 0;
 	const uint32_t ts_saddr = smem_u32(S.ts);
-	const int blk_lo = CHAIN ? 0 : P.blk_first + (int)blockIdx.y;
+	const int blk_lo = blk_own;
 	const int blk_hi = CHAIN ? P.n_blk_chain : blk_lo + 1;
+	uint32_t wacc = 0;   // ORMASK: lane c accumulates the plane-1 ballots of column slot c
 
 	for (int blk = blk_lo; blk < blk_hi; ++blk) {
 		const long long blk_row = P.blk_row0 + ((long long)blk << P.shift);
@@ -458,10 +476,18 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 					else if (mt.n1[0]) bits0 = 0xffffffffu;
 					if (!triv1) lookup_runs<C>(r1, ts_saddr + 4u * mt.off[1], mt.len[1], m - mt.n1[1], bits1);
 					else if (mt.n1[1]) bits1 = 0xffffffffu;
-					if (!CHAIN && arow >= P.row_lo) {
+					if (COUNT && arow >= P.row_lo) {
 						const bool zero0 = mt.n1[0] == 0, zero1 = mt.n1[1] == 0;
-						if (!(zero0 && zero1)) count_row<C>(bits0 & validbits, bits1 & validbits, zero1, gm0, gm1, S, P.G, r, tid, lane);
+						if (!(zero0 && zero1) && !(P.joint_only && zero1))
+							count_row<C>(bits0 & validbits, bits1 & validbits, zero1, gm0, gm1, S, P.G, r, tid, lane);
 						if (EMIT) emit_row<C>(bits0 & validbits, bits1 & validbits, P, arow - P.row_lo, warp, lane, slice_base);
+					}
+					if (ORMASK && mt.n1[1]) {
+						#pragma unroll
+						for (int c = 0; c < C; ++c) {
+							const uint32_t b1 = __ballot_sync(FULL_MASK, ((bits1 & validbits) >> c) & 1u);
+							if (lane == c) wacc |= b1;
+						}
 					}
 				}
 			} else {
@@ -497,16 +523,24 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 					}
 					__syncthreads();
 				}
-				if (!CHAIN && arow >= P.row_lo && arow < P.row_hi) {
-					if (n1p[0] || n1p[1]) count_row<C>(bits[0] & validbits, bits[1] & validbits, n1p[1] == 0, gm0, gm1, S, P.G, 0, tid, lane);
+				if (COUNT && arow >= P.row_lo && arow < P.row_hi) {
+					if ((n1p[0] || n1p[1]) && !(P.joint_only && n1p[1] == 0))
+						count_row<C>(bits[0] & validbits, bits[1] & validbits, n1p[1] == 0, gm0, gm1, S, P.G, 0, tid, lane);
 					if (EMIT) emit_row<C>(bits[0] & validbits, bits[1] & validbits, P, arow - P.row_lo, warp, lane, slice_base);
+				}
+				if (ORMASK && n1p[1]) {
+					#pragma unroll
+					for (int c = 0; c < C; ++c) {
+						const uint32_t b1 = __ballot_sync(FULL_MASK, ((bits[1] & validbits) >> c) & 1u);
+						if (lane == c) wacc |= b1;
+					}
 				}
 				if (tid == 0) prefetch(t + 1);
 			}
 
 			// ---- flush the tile's counters
 			__syncthreads();
-			if (!CHAIN) {
+			if (COUNT) {
 				const int per_row = P.G * 3;
 				for (int i = tid; i < nr * per_row; i += WALK_NT) {
 					const int v = S.rowcnt[i];
@@ -521,50 +555,90 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 		}
 		if (CHAIN) __syncthreads();
 	}
+	if (ORMASK && lane < C) {
+		const int wi = (slice_base + lane * WALK_NT) / 32 + warp;
+		if (wi < P.words) P.wmask[(size_t)blk_own * P.words + wi] = wacc;
+	}
 }
 
-template<int C, bool EMIT, bool CHAIN>
+template<int C, int MODE>
 static cudaError_t launch_walk_t(const WalkParams &P, int slices, int n_blk, cudaStream_t st)
 {
 	const size_t smem = walk_smem_bytes(C, P.G);
-	cudaError_t e = cudaFuncSetAttribute(pbwt_walk_kernel<C, EMIT, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(pbwt_walk_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	for (int b0 = 0; b0 < n_blk; b0 += 32768) {
 		WalkParams Q = P;
-		Q.blk_first = P.blk_first + b0;
+		if (P.blk_list) Q.blk_list = P.blk_list + b0; else Q.blk_first = P.blk_first + b0;
 		const int nb = n_blk - b0 < 32768 ? n_blk - b0 : 32768;
-		dim3 grid(slices, CHAIN ? 1 : nb, 1);
-		pbwt_walk_kernel<C, EMIT, CHAIN><<<grid, WALK_NT, smem, st>>>(Q);
-		if (CHAIN) break;
+		dim3 grid(slices, MODE == WALK_CHAIN ? 1 : nb, 1);
+		pbwt_walk_kernel<C, MODE><<<grid, WALK_NT, smem, st>>>(Q);
+		if (MODE == WALK_CHAIN) break;
 	}
 	return cudaGetLastError();
 }
 
-cudaError_t launch_walk(const WalkParams &P, int C, bool emit, bool chain, int slices, int n_blk, cudaStream_t st)
+template<int MODE>
+static cudaError_t launch_walk_c(const WalkParams &P, int C, int slices, int n_blk, cudaStream_t st)
+{
+	switch (C) {
+	case 1: return launch_walk_t<1, MODE>(P, slices, n_blk, st);
+	case 2: return launch_walk_t<2, MODE>(P, slices, n_blk, st);
+	case 4: return launch_walk_t<4, MODE>(P, slices, n_blk, st);
+	default: return launch_walk_t<8, MODE>(P, slices, n_blk, st);
+	}
+}
+
+cudaError_t launch_walk(const WalkParams &P, int C, int mode, int slices, int n_blk, cudaStream_t st)
 {
 	if (slices <= 0 || n_blk <= 0) return cudaSuccess;
-	if (chain) {
-		switch (C) {
-		case 1: return launch_walk_t<1, false, true>(P, slices, n_blk, st);
-		case 2: return launch_walk_t<2, false, true>(P, slices, n_blk, st);
-		case 4: return launch_walk_t<4, false, true>(P, slices, n_blk, st);
-		default: return launch_walk_t<8, false, true>(P, slices, n_blk, st);
-		}
+	switch (mode) {
+	case WALK_EMIT: return launch_walk_c<WALK_EMIT>(P, C, slices, n_blk, st);
+	case WALK_CHAIN: return launch_walk_c<WALK_CHAIN>(P, C, slices, n_blk, st);
+	case WALK_ORMASK: return launch_walk_c<WALK_ORMASK>(P, C, slices, n_blk, st);
+	default: return launch_walk_c<WALK_COUNT>(P, C, slices, n_blk, st);
 	}
-	if (emit) {
-		switch (C) {
-		case 1: return launch_walk_t<1, true, false>(P, slices, n_blk, st);
-		case 2: return launch_walk_t<2, true, false>(P, slices, n_blk, st);
-		case 4: return launch_walk_t<4, true, false>(P, slices, n_blk, st);
-		default: return launch_walk_t<8, true, false>(P, slices, n_blk, st);
-		}
+}
+
+// ------------------------------------------------------------------------------------------------ W mask -> W list
+
+// One CTA per block: the set bits of wmask[blk][words] become the ascending column list wlist[blk][0..count).
+__global__ void __launch_bounds__(1024) wmask_compact_kernel(const uint32_t *__restrict__ wmask, int words, int cap,
+                                                             const int *__restrict__ blk_list, int32_t *__restrict__ wlist, int *__restrict__ wcount)
+{
+	__shared__ int warp_tot[32];
+	__shared__ int carry;
+	const int blk = blk_list[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t *wm = wmask + (size_t)blk * words;
+	int32_t *out = wlist + (size_t)blk * cap;
+	if (tid == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < words; base += 1024) {
+		const int w = base + tid;
+		const uint32_t bits = w < words ? wm[w] : 0u;
+		const int cnt = __popc(bits);
+		int x = cnt;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL_MASK, x, d); if (lane >= d) x += t; }
+		if (lane == 31) warp_tot[warp] = x;
+		__syncthreads();
+		int before = carry;
+		for (int i = 0; i < warp; ++i) before += warp_tot[i];
+		int pos = before + x - cnt;
+		uint32_t b = bits;
+		while (b) { const int k = __ffs(b) - 1; b &= b - 1; if (pos < cap) out[pos] = w * 32 + k; ++pos; }
+		__syncthreads();
+		if (tid == 1023) carry = before + x;
+		__syncthreads();
 	}
-	switch (C) {
-	case 1: return launch_walk_t<1, false, false>(P, slices, n_blk, st);
-	case 2: return launch_walk_t<2, false, false>(P, slices, n_blk, st);
-	case 4: return launch_walk_t<4, false, false>(P, slices, n_blk, st);
-	default: return launch_walk_t<8, false, false>(P, slices, n_blk, st);
-	}
+	if (tid == 0) wcount[blk] = carry < cap ? carry : cap;
+}
+
+cudaError_t launch_wmask_compact(const uint32_t *wmask, int words, int cap, const int *blk_list, int n_blk, int32_t *wlist, int *wcount, cudaStream_t st)
+{
+	if (n_blk <= 0) return cudaSuccess;
+	wmask_compact_kernel<<<n_blk, 1024, 0, st>>>(wmask, words, cap, blk_list, wlist, wcount);
+	return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
@@ -573,7 +647,7 @@ cudaError_t launch_walk(const WalkParams &P, int C, bool emit, bool chain, int s
 __global__ void __launch_bounds__(256) finalize_kernel(const int32_t *__restrict__ cnt_raw, long long n_rows, int G,
                                                        const int32_t *__restrict__ gsize, const flt_prog_t *__restrict__ prog, int use_flt,
                                                        int32_t *__restrict__ counts, uint8_t *__restrict__ pass,
-                                                       unsigned long long *__restrict__ totals)
+                                                       unsigned long long *__restrict__ totals, const FinalizeSplit sp)
 {
 	const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	long long t_an = 0, t_ac0 = 0, t_ac1 = 0, t_pass = 0;
@@ -582,7 +656,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(const int32_t *__restrict
 		const int32_t *c = cnt_raw + (size_t)row * G * 3;
 		int32_t an = 0, ac0 = 0, ac1 = 0;
 		for (int g = 0; g < G; ++g) {
-			const int32_t c1 = c[g * 3], c2 = c[g * 3 + 1], c3 = c[g * 3 + 2];
+			int32_t c1 = c[g * 3];
+			const int32_t c2 = c[g * 3 + 1], c3 = c[g * 3 + 2];
+			if (sp.blk_split) { // split scan: the walk only counted the plane-1 codes; #ALT = (ones of plane 0) - #other-ALT
+				const long long arow = sp.row_lo + row;
+				const int blk = (int)((arow - sp.blk_row0) >> sp.shift);
+				if (sp.blk_split[blk]) c1 = (int32_t)sp.n1[((size_t)blk << sp.shift << 1) + (size_t)(arow - sp.blk_row0 - ((long long)blk << sp.shift)) * 2] - c3;
+			}
 			const int32_t gan = gsize[g] - c2;            // c0 + c1 + c3
 			v[3 + 3 * g] = gan; v[4 + 3 * g] = c1; v[5 + 3 * g] = c3;
 			an += gan; ac0 += c1; ac1 += c3;
@@ -608,10 +688,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const int32_t *__restrict
 }
 
 cudaError_t launch_finalize(const int32_t *cnt_raw, long long n_rows, int G, const int32_t *gsize, const flt_prog_t *prog, int use_flt,
-                            int32_t *counts, uint8_t *pass, unsigned long long *totals, cudaStream_t st)
+                            int32_t *counts, uint8_t *pass, unsigned long long *totals, const FinalizeSplit &sp, cudaStream_t st)
 {
 	if (n_rows <= 0) return cudaSuccess;
-	finalize_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(cnt_raw, n_rows, G, gsize, prog, use_flt, counts, pass, totals);
+	finalize_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(cnt_raw, n_rows, G, gsize, prog, use_flt, counts, pass, totals, sp);
 	return cudaGetLastError();
 }
 

@@ -35,6 +35,11 @@ struct WalkParams {
 	const uint8_t  *tgrp;      // 0-based group of every tracked column
 	int32_t        *cnt_raw;   // [rows out][G][3] = #ALT, #missing, #other-ALT per group (zero-initialised, accumulated)
 	uint32_t       *hap[2];    // [rows out][words] bit planes (EMIT only)
+	uint32_t       *wmask;     // ORMASK only: [blocks][words] OR of the plane-1 rows of every block
+	const int      *blk_list;  // resident-block indices handled by this launch (nullptr: blk_first + blockIdx.y)
+	const int      *n_track_blk; // per-block number of tracked columns (nullptr: n_track)
+	long long       track_stride; // > 0: track holds one list per resident block, this many entries apart
+	int             joint_only;   // count only on rows whose plane 1 is not empty (second phase of the split scan)
 	uint8_t        *snap_img;  // CHAIN only: image to write 'S' snapshots into
 	const uint64_t *blkoff;    // CHAIN only: offset of the 'S' record of every block
 	int m, n_track, G, words, shift;
@@ -46,14 +51,19 @@ struct WalkParams {
 };
 
 size_t walk_smem_bytes(int C, int G);
-// C = tracked columns per thread (1,2,4,8); emit = write genotype bit planes; chain = generator mode
-cudaError_t launch_walk(const WalkParams &P, int C, bool emit, bool chain, int slices, int n_blk, cudaStream_t st);
+// C = tracked columns per thread (1,2,4,8); mode = WALK_COUNT / WALK_EMIT / WALK_CHAIN / WALK_ORMASK (pbwt_kernels.cu)
+enum { WALK_MODE_COUNT = 0, WALK_MODE_EMIT = 1, WALK_MODE_CHAIN = 2, WALK_MODE_ORMASK = 3 };
+cudaError_t launch_walk(const WalkParams &P, int C, int mode, int slices, int n_blk, cudaStream_t st);
+cudaError_t launch_wmask_compact(const uint32_t *wmask, int words, int cap, const int *blk_list, int n_blk, int32_t *wlist, int *wcount, cudaStream_t st);
+
+// split scan: rows of blocks flagged in blk_split take #ALT from the plane-0 marginal n1[row][0] (all columns, one group)
+struct FinalizeSplit { const uint8_t *blk_split; const uint32_t *n1; long long row_lo, blk_row0; int shift; };
 
 cudaError_t launch_rowmeta(const uint8_t *img, const uint64_t *rowoff, int n_blk, int shift, long long n_rows_total_in_blocks,
                            const int *rows_in_blk, uint32_t m, uint32_t *n1, unsigned long long *bad, cudaStream_t st);
 cudaError_t launch_invert_snapshots(const uint8_t *img, const uint64_t *blkoff, int n_blk, int m, int32_t *rank0, int *err, cudaStream_t st);
 cudaError_t launch_finalize(const int32_t *cnt_raw, long long n_rows, int G, const int32_t *gsize, const flt_prog_t *prog, int use_flt,
-                            int32_t *counts, uint8_t *pass, unsigned long long *totals, cudaStream_t st);
+                            int32_t *counts, uint8_t *pass, unsigned long long *totals, const FinalizeSplit &sp, cudaStream_t st);
 cudaError_t launch_unpack_bits(const uint32_t *bits, long long n_rows, int words, int n_track, uint8_t *bytes, cudaStream_t st);
 
 // synthetic cohort generator (synth.cu)

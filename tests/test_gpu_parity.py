@@ -259,3 +259,38 @@ def test_synth_generator_is_truthful_and_canonical(b200, ctx, oracle):
         assert (got2["counts"] == want["counts"]).all()
         assert pb2.row_bytes(0, n_rows) == oracle.Pbf(img).row_bytes(0, n_rows)
         q.close(); pb.close(); pb2.close()
+
+
+@pytest.mark.parametrize("case", ["sparse", "dense", "mixed", "allones", "wide"])
+def test_split_scan_equals_general_and_oracle(b200, ctx, oracle, case):
+    """Count-only full-cohort scans take the split path (plane-0 marginal + walk of the columns that carry plane-1 codes);
+    it must agree with the general walk and with the oracle whatever the density of plane 1."""
+    rng = np.random.default_rng(12)
+    if case == "sparse":
+        mat = haplo_matrix(900, 8200, 5, p_missing_row=0.1, p_multi_row=0.1)
+    elif case == "dense":
+        mat = random_matrix(300, 4400, 6)
+    elif case == "mixed":
+        mat = haplo_matrix(600, 4400, 7)
+        mat[300:420] = random_matrix(120, 4400, 8)
+    elif case == "allones":
+        mat = haplo_matrix(200, 4400, 9)
+        mat[50] = 2; mat[51] = 3; mat[120] = 1; mat[121] = 0
+    else:
+        mat = haplo_matrix(70, 70002, 10, p_missing_row=0.3, p_multi_row=0.3)
+    shift = 6 if case != "wide" else 4
+    pbf = oracle.encode_pbf(mat, shift=shift)
+    n = mat.shape[0]
+    want = oracle.Pbf(pbf).scan(0, n, flt="AC>0")
+    pb = b200.Pbf.from_bytes(ctx, pbf)
+    q = b200.Query(ctx, pb, flt="AC>0")
+    for kw in (dict(), dict(no_split=True), dict(cols_per_thread=1), dict(cols_per_thread=8)):
+        got = b200.scan(ctx, pb, q, 0, n, **kw)
+        assert (got["counts"] == want["counts"]).all(), (case, kw)
+        assert (got["passed"] == want["passed"]).all()
+    for beg, cnt in ((37, 200), (63, 2), (n - 5, 5)):
+        cnt = min(cnt, n - beg)
+        got = b200.scan(ctx, pb, q, beg, cnt)
+        assert (got["counts"] == want["counts"][beg:beg + cnt]).all(), (case, beg)
+    q.close()
+    pb.close()
