@@ -63,7 +63,7 @@ struct b200_ctx_s {
 	int64_t launches = 0;
 	int *d_err = nullptr;
 	unsigned long long *d_acc = nullptr; // [0..3] totals, [4] bad rows
-	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], wmask, wlist, wcount, blk_lists, blk_split;
+	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], qcol, qrow, qcount, blk_lists, blk_split;
 	int sm_count = 148;
 };
 
@@ -95,6 +95,8 @@ struct b200_pbf_s {
 	uint32_t *d_p1_n1 = nullptr;
 	int2 *d_p1_tiles = nullptr;
 	int *d_p1_blk_tile_beg = nullptr;
+	uint16_t *d_p1_realrow = nullptr;
+	int *d_p1_rows_in_blk = nullptr;
 	int64_t p1_rows = 0;
 };
 
@@ -150,7 +152,7 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	if (c->st) cudaStreamSynchronize(c->st);
 	c->cnt_raw.release(); c->counts.release(); c->pass.release();
 	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
-	c->wmask.release(); c->wlist.release(); c->wcount.release(); c->blk_lists.release(); c->blk_split.release();
+	c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
 	for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
 	if (c->d_err) cudaFree(c->d_err);
@@ -211,6 +213,8 @@ static void pbf_free_device(b200_pbf_t *pb)
 	if (pb->d_p1_n1) cudaFree(pb->d_p1_n1);
 	if (pb->d_p1_tiles) cudaFree(pb->d_p1_tiles);
 	if (pb->d_p1_blk_tile_beg) cudaFree(pb->d_p1_blk_tile_beg);
+	if (pb->d_p1_realrow) cudaFree(pb->d_p1_realrow);
+	if (pb->d_p1_rows_in_blk) cudaFree(pb->d_p1_rows_in_blk);
 }
 
 extern "C" void b200_pbf_close(b200_pbf_t *pb)
@@ -262,7 +266,7 @@ static bool build_plane1_view(b200_pbf_t *pb, const uint8_t *img0)
 	pb->blk_sparse.assign(nb, 1);
 	pb->p1_rows_in_blk.assign(nb, 0);
 	std::vector<std::vector<uint8_t>> rec(nb);
-	std::vector<std::vector<uint32_t>> n1s(nb), lens(nb);
+	std::vector<std::vector<uint32_t>> n1s(nb), lens(nb), rrow(nb);
 	{
 		const int nt = nb < 2 ? 1 : (nb < 8 ? nb : 8);
 		std::vector<std::thread> th;
@@ -293,9 +297,10 @@ static bool build_plane1_view(b200_pbf_t *pb, const uint8_t *img0)
 						rec[b].insert(rec[b].end(), (const uint8_t*)&l1, (const uint8_t*)&l1 + 4);
 						rec[b].insert(rec[b].end(), p, p + l1);
 						n1s[b].push_back((uint32_t)ones);
+						rrow[b].push_back((uint32_t)r);
 						lens[b].push_back(9u + (uint32_t)l1);
 					}
-					if (ones_sum > (uint64_t)pb->p1_cap) pb->blk_sparse[b] = 0;
+					if (ones_sum > (uint64_t)pb->p1_cap || n1s[b].size() >= (size_t)SELECT_MAX_ROWS || rec[b].size() > (size_t)SELECT_MAX_BYTES || BS > 65536) pb->blk_sparse[b] = 0;
 					pb->p1_rows_in_blk[b] = (int)n1s[b].size();
 				}
 			});
@@ -303,6 +308,7 @@ static bool build_plane1_view(b200_pbf_t *pb, const uint8_t *img0)
 	}
 	std::vector<uint64_t> rowoff((size_t)nb * (BS + 1), 0);
 	std::vector<uint32_t> n1((size_t)nb * BS * 2, 0);
+	std::vector<uint16_t> realrow((size_t)nb * BS, 0);
 	std::vector<uint8_t> img;
 	size_t total = 0;
 	for (int b = 0; b < nb; ++b) total += ((rec[b].size() + 15) & ~(size_t)15);
@@ -314,6 +320,7 @@ static bool build_plane1_view(b200_pbf_t *pb, const uint8_t *img0)
 		for (size_t r = 0; r < n1s[b].size(); ++r) {
 			ro[r] = pos; pos += lens[b][r];
 			n1[((size_t)b * BS + r) * 2 + 1] = n1s[b][r];
+			realrow[(size_t)b * BS + r] = (uint16_t)rrow[b][r];
 		}
 		ro[n1s[b].size()] = pos;
 		img.insert(img.end(), rec[b].begin(), rec[b].end());
@@ -326,12 +333,15 @@ static bool build_plane1_view(b200_pbf_t *pb, const uint8_t *img0)
 	plan_tiles_of(nb, BS, rowoff, pb->p1_rows_in_blk, tiles, btb);
 	bool ok = CU_OK(cudaMalloc(&pb->d_p1img, img.size())) && CU_OK(cudaMalloc(&pb->d_p1_rowoff, rowoff.size() * 8 + 8)) &&
 	          CU_OK(cudaMalloc(&pb->d_p1_n1, n1.size() * 4 + 8)) && CU_OK(cudaMalloc(&pb->d_p1_tiles, (tiles.size() + 1) * sizeof(int2))) &&
-	          CU_OK(cudaMalloc(&pb->d_p1_blk_tile_beg, (nb + 1) * sizeof(int)));
+	          CU_OK(cudaMalloc(&pb->d_p1_blk_tile_beg, (nb + 1) * sizeof(int))) && CU_OK(cudaMalloc(&pb->d_p1_realrow, realrow.size() * 2 + 8)) &&
+	          CU_OK(cudaMalloc(&pb->d_p1_rows_in_blk, (nb + 1) * sizeof(int)));
 	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_p1img, img.data(), img.size(), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_rowoff, rowoff.data(), rowoff.size() * 8, cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_n1, n1.data(), n1.size() * 4, cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_blk_tile_beg, btb.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_p1_realrow, realrow.data(), realrow.size() * 2, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(pb->d_p1_rows_in_blk, pb->p1_rows_in_blk.data(), nb * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaStreamSynchronize(c->st));
 	pb->p1_ready = ok;
 	return ok;
@@ -774,24 +784,22 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	}
 	if (ok && n_split > 0) {
 		const int cap = pb->p1_cap;
-		if (!c->wmask.reserve((size_t)pb->n_blk * words * sizeof(uint32_t)) || !c->wlist.reserve((size_t)pb->n_blk * cap * sizeof(int32_t)) ||
-		    !c->wcount.reserve((size_t)pb->n_blk * sizeof(int))) return -1;
-		// phase 1: W mask per block = OR of the block's plane-1 rows (all columns, but only the few non-empty rows)
-		WalkParams A = P;
-		A.img = pb->d_p1img; A.rowoff = pb->d_p1_rowoff; A.n1 = pb->d_p1_n1; A.tiles = pb->d_p1_tiles; A.blk_tile_beg = pb->d_p1_blk_tile_beg;
-		A.cnt_raw = nullptr; A.hap[0] = A.hap[1] = nullptr; A.wmask = (uint32_t*)c->wmask.p; A.blk_list = d_split_list;
-		A.row_lo = 0; A.row_hi = (long long)1 << 60; A.blk_row0 = 0;
-		const int Ca = pick_cols_per_thread(c, n_track, n_split);
-		ok = CU_OK(launch_walk(A, Ca, WALK_MODE_ORMASK, (n_track + WALK_NT * Ca - 1) / (WALK_NT * Ca), n_split, c->st));
-		// W list per block
-		ok = ok && CU_OK(launch_wmask_compact((const uint32_t*)c->wmask.p, words, cap, d_split_list, n_split, (int32_t*)c->wlist.p, (int*)c->wcount.p, c->st));
-		// phase 2: walk only W through the real rows, count the plane-1 codes (missing, other-ALT) where they occur
+		if (!c->qcol.reserve((size_t)pb->n_blk * cap * sizeof(int32_t)) || !c->qrow.reserve((size_t)pb->n_blk * cap * sizeof(uint16_t)) ||
+		    !c->qcount.reserve((size_t)pb->n_blk * sizeof(int))) return -1;
+		// phase 1 (plane1.cu): the (column, row) pairs that carry a plane-1 bit, per block, in row order
+		SelectParams A;
+		A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow;
+		A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
+		A.m = pb->m; A.shift = pb->shift; A.cap = cap;
+		A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err;
+		ok = CU_OK(launch_plane1_select(A, n_split, c->st));
+		// phase 2: walk those haplotypes through plane 0 up to their row and add code 3 (other-ALT) or 2 (missing) there
 		WalkParams B = P;
-		B.track = (const int32_t*)c->wlist.p; B.track_stride = cap; B.n_track_blk = (const int*)c->wcount.p; B.n_track = cap;
-		B.blk_list = d_split_list; B.joint_only = 1;
-		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : 4;
-		ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_COUNT, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
-		c->launches += 3;
+		B.track = (const int32_t*)c->qcol.p; B.qrow = (const uint16_t*)c->qrow.p; B.track_stride = cap;
+		B.n_track_blk = (const int*)c->qcount.p; B.n_track = cap; B.blk_list = d_split_list;
+		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : 8;
+		ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_QUERY, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
+		c->launches += 2;
 		sp.blk_split = (const uint8_t*)c->blk_split.p; sp.n1 = pb->d_n1; sp.row_lo = row_beg; sp.blk_row0 = P.blk_row0; sp.shift = pb->shift;
 	}
 	ok = ok && CU_OK(cudaEventRecord(c->ev[1], c->st));

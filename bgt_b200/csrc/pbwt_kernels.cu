@@ -335,14 +335,15 @@ __device__ __forceinline__ void emit_row(uint32_t bits0, uint32_t bits1, const W
 //   WALK_EMIT   counters + genotype rows as bit planes           (seam A, `view` with genotypes, subsets)
 //   WALK_CHAIN  nothing per site; one chain through ALL blocks that dumps the running permutation in front of
 //               every block (synthetic cohort generator)
-//   WALK_ORMASK nothing per site; per block the OR of the plane-1 rows = the set W of columns that carry a
-//               missing / other-ALT code anywhere in the block (first phase of the split scan, see api.cu)
-enum { WALK_COUNT = 0, WALK_EMIT = 1, WALK_CHAIN = 2, WALK_ORMASK = 3 };
+//   WALK_QUERY  second phase of the split scan (api.cu): the tracked entries are (column, target row) pairs -- the
+//               haplotypes that carry a missing / other-ALT code at that row (plane1_select_kernel).  Only plane 0 is
+//               walked, an entry contributes its code at its target row and the CTA stops after its last target.
+enum { WALK_COUNT = 0, WALK_EMIT = 1, WALK_CHAIN = 2, WALK_QUERY = 3 };
 
 template<int C, int MODE>
 __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams P)
 {
-	constexpr bool EMIT = MODE == WALK_EMIT, CHAIN = MODE == WALK_CHAIN, ORMASK = MODE == WALK_ORMASK;
+	constexpr bool EMIT = MODE == WALK_EMIT, CHAIN = MODE == WALK_CHAIN, QUERY = MODE == WALK_QUERY;
 	constexpr bool COUNT = MODE == WALK_COUNT || MODE == WALK_EMIT;
 	extern __shared__ __align__(128) uint8_t smem[];
 	WalkSmem S;
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 	// ---- which columns this thread owns, their groups, their start ranks
 	uint32_t r0[C], r1[C];
 	int32_t col[C];
+	uint32_t tgt[C];     // QUERY: target row (within the block) of every entry
 	uint32_t validbits = 0, gm0 = 0, gm1 = 0;
 	if (P.G > 2) for (int g = 0; g < P.G; ++g) S.gmask[g * WALK_NT + tid] = 0;
 	#pragma unroll
@@ -375,7 +377,8 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 		const bool v = e < n_track;
 		col[c] = v ? (track ? track[e] : e) : 0;
 		validbits |= (v ? 1u : 0u) << c;
-		if (v && COUNT) {
+		tgt[c] = (QUERY && v) ? (uint32_t)P.qrow[(size_t)blk_own * P.track_stride + e] : 0xffffffffu;
+		if (v && (COUNT || QUERY)) {
 			const int grp = (int)P.tgrp[P.track_stride ? col[c] : e];   // per-block lists: groups are per column
 			if (grp == 0) gm0 |= 1u << c;
 			else if (grp == 1) gm1 |= 1u << c;
@@ -391,10 +394,16 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 	const uint32_t ts_saddr = smem_u32(S.ts);
 	const int blk_lo = blk_own;
 	const int blk_hi = CHAIN ? P.n_blk_chain : blk_lo + 1;
-	uint32_t wacc = 0;   // ORMASK: lane c accumulates the plane-1 ballots of column slot c
+	// QUERY: entries are sorted by target row, so the last valid entry of this slice bounds the rows this CTA needs
+	int q_stop = 0x7fffffff;
+	if (QUERY) {
+		const int last = (slice_base + WALK_NT * C < n_track ? slice_base + WALK_NT * C : n_track) - 1;
+		q_stop = (int)P.qrow[(size_t)blk_own * P.track_stride + last] + 1;
+	}
 
 	for (int blk = blk_lo; blk < blk_hi; ++blk) {
 		const long long blk_row = P.blk_row0 + ((long long)blk << P.shift);
+		const long long row_hi = (QUERY && blk_row + q_stop < P.row_hi) ? blk_row + q_stop : P.row_hi;
 		const uint64_t *roff = P.rowoff + (size_t)blk * (BS + 1);
 		if (CHAIN) { // pbwt.c:292-301: dump the running permutation of both planes in front of the block
 			uint8_t *Sp = P.snap_img + P.blkoff[blk] + 1;
@@ -419,7 +428,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 		auto prefetch = [&](int t) {
 			if (t >= t_end) return;
 			const int2 tl = P.tiles[t];
-			if (tl.y < 0 || blk_row + tl.x >= P.row_hi) return;
+			if (tl.y < 0 || blk_row + tl.x >= row_hi) return;
 			const uint64_t beg = roff[tl.x] & ~(uint64_t)15, end = (roff[tl.x + tl.y] + 15) & ~(uint64_t)15;
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic-proxy accesses to raw[] before the async-proxy write
 			mbar_expect_tx(S.mbar, (uint32_t)(end - beg));
@@ -431,7 +440,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 			const int2 tl = P.tiles[t];
 			const int r_first = tl.x, nr = tl.y & 0x7fffffff;
 			const bool big = tl.y < 0;
-			if (blk_row + r_first >= P.row_hi) break;
+			if (blk_row + r_first >= row_hi) break;
 
 			if (!big) {
 				// ---- wait for the tile's bytes
@@ -457,6 +466,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 				// ---- parse: one warp per (row, plane); constant planes need no table
 				for (int task = warp; task < nr * 2; task += WALK_NW) {
 					const int r = task >> 1, p = task & 1;
+					if (QUERY && p == 1) continue;
 					const RowMeta &mt = S.meta[r];
 					const uint32_t n1 = mt.n1[p];
 					if (n1 == 0 || n1 == m) continue;
@@ -468,26 +478,27 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 				// ---- walk
 				for (int r = 0; r < nr; ++r) {
 					const long long arow = blk_row + r_first + r;
-					if (arow >= P.row_hi) break;
+					if (arow >= row_hi) break;
 					const RowMeta mt = S.meta[r];
 					uint32_t bits0 = 0, bits1 = 0;
 					const bool triv0 = mt.n1[0] == 0 || mt.n1[0] == m, triv1 = mt.n1[1] == 0 || mt.n1[1] == m;
 					if (!triv0) lookup_runs<C>(r0, ts_saddr + 4u * mt.off[0], mt.len[0], m - mt.n1[0], bits0);
 					else if (mt.n1[0]) bits0 = 0xffffffffu;
-					if (!triv1) lookup_runs<C>(r1, ts_saddr + 4u * mt.off[1], mt.len[1], m - mt.n1[1], bits1);
-					else if (mt.n1[1]) bits1 = 0xffffffffu;
+					if (!QUERY) {
+						if (!triv1) lookup_runs<C>(r1, ts_saddr + 4u * mt.off[1], mt.len[1], m - mt.n1[1], bits1);
+						else if (mt.n1[1]) bits1 = 0xffffffffu;
+					}
 					if (COUNT && arow >= P.row_lo) {
 						const bool zero0 = mt.n1[0] == 0, zero1 = mt.n1[1] == 0;
-						if (!(zero0 && zero1) && !(P.joint_only && zero1))
+						if (!(zero0 && zero1))
 							count_row<C>(bits0 & validbits, bits1 & validbits, zero1, gm0, gm1, S, P.G, r, tid, lane);
 						if (EMIT) emit_row<C>(bits0 & validbits, bits1 & validbits, P, arow - P.row_lo, warp, lane, slice_base);
 					}
-					if (ORMASK && mt.n1[1]) {
+					if (QUERY && arow >= P.row_lo) { // entries whose target is this row: code 3 if their plane-0 bit is set, else 2
+						uint32_t hit = 0;
 						#pragma unroll
-						for (int c = 0; c < C; ++c) {
-							const uint32_t b1 = __ballot_sync(FULL_MASK, ((bits1 & validbits) >> c) & 1u);
-							if (lane == c) wacc |= b1;
-						}
+						for (int c = 0; c < C; ++c) hit |= (tgt[c] == (uint32_t)(r_first + r) ? 1u : 0u) << c;
+						if (__any_sync(FULL_MASK, hit != 0)) count_row<C>(bits0 & hit, hit, false, gm0, gm1, S, P.G, r, tid, lane);
 					}
 				}
 			} else {
@@ -501,6 +512,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 					const uint32_t l = ld_u32_unaligned(pp), n1 = n1p[p];
 					const uint8_t *rle = pp + 4;
 					pp = rle + l;
+					if (QUERY && p == 1) continue;
 					if (n1 == 0 || n1 == m) { bits[p] = n1 ? 0xffffffffu : 0u; continue; }
 					uint32_t done = 0;
 					if (tid == 0) { S.scratch[0] = 0; S.scratch[1] = 0; }
@@ -523,30 +535,29 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 					}
 					__syncthreads();
 				}
-				if (COUNT && arow >= P.row_lo && arow < P.row_hi) {
-					if ((n1p[0] || n1p[1]) && !(P.joint_only && n1p[1] == 0))
+				if (COUNT && arow >= P.row_lo && arow < row_hi) {
+					if (n1p[0] || n1p[1])
 						count_row<C>(bits[0] & validbits, bits[1] & validbits, n1p[1] == 0, gm0, gm1, S, P.G, 0, tid, lane);
 					if (EMIT) emit_row<C>(bits[0] & validbits, bits[1] & validbits, P, arow - P.row_lo, warp, lane, slice_base);
 				}
-				if (ORMASK && n1p[1]) {
+				if (QUERY && arow >= P.row_lo && arow < row_hi) {
+					uint32_t hit = 0;
 					#pragma unroll
-					for (int c = 0; c < C; ++c) {
-						const uint32_t b1 = __ballot_sync(FULL_MASK, ((bits[1] & validbits) >> c) & 1u);
-						if (lane == c) wacc |= b1;
-					}
+					for (int c = 0; c < C; ++c) hit |= (tgt[c] == (uint32_t)r_first ? 1u : 0u) << c;
+					if (__any_sync(FULL_MASK, hit != 0)) count_row<C>(bits[0] & hit, hit, false, gm0, gm1, S, P.G, 0, tid, lane);
 				}
 				if (tid == 0) prefetch(t + 1);
 			}
 
 			// ---- flush the tile's counters
 			__syncthreads();
-			if (COUNT) {
+			if (COUNT || QUERY) {
 				const int per_row = P.G * 3;
 				for (int i = tid; i < nr * per_row; i += WALK_NT) {
 					const int v = S.rowcnt[i];
 					if (v) {
 						const long long arow = blk_row + r_first + i / per_row;
-						if (arow >= P.row_lo && arow < P.row_hi)
+						if (arow >= P.row_lo && arow < row_hi)
 							atomicAdd(P.cnt_raw + (size_t)(arow - P.row_lo) * per_row + i % per_row, v);
 						S.rowcnt[i] = 0;
 					}
@@ -554,10 +565,6 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 			}
 		}
 		if (CHAIN) __syncthreads();
-	}
-	if (ORMASK && lane < C) {
-		const int wi = (slice_base + lane * WALK_NT) / 32 + warp;
-		if (wi < P.words) P.wmask[(size_t)blk_own * P.words + wi] = wacc;
 	}
 }
 
@@ -595,50 +602,9 @@ cudaError_t launch_walk(const WalkParams &P, int C, int mode, int slices, int n_
 	switch (mode) {
 	case WALK_EMIT: return launch_walk_c<WALK_EMIT>(P, C, slices, n_blk, st);
 	case WALK_CHAIN: return launch_walk_c<WALK_CHAIN>(P, C, slices, n_blk, st);
-	case WALK_ORMASK: return launch_walk_c<WALK_ORMASK>(P, C, slices, n_blk, st);
+	case WALK_QUERY: return launch_walk_c<WALK_QUERY>(P, C, slices, n_blk, st);
 	default: return launch_walk_c<WALK_COUNT>(P, C, slices, n_blk, st);
 	}
-}
-
-// ------------------------------------------------------------------------------------------------ W mask -> W list
-
-// One CTA per block: the set bits of wmask[blk][words] become the ascending column list wlist[blk][0..count).
-__global__ void __launch_bounds__(1024) wmask_compact_kernel(const uint32_t *__restrict__ wmask, int words, int cap,
-                                                             const int *__restrict__ blk_list, int32_t *__restrict__ wlist, int *__restrict__ wcount)
-{
-	__shared__ int warp_tot[32];
-	__shared__ int carry;
-	const int blk = blk_list[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t *wm = wmask + (size_t)blk * words;
-	int32_t *out = wlist + (size_t)blk * cap;
-	if (tid == 0) carry = 0;
-	__syncthreads();
-	for (int base = 0; base < words; base += 1024) {
-		const int w = base + tid;
-		const uint32_t bits = w < words ? wm[w] : 0u;
-		const int cnt = __popc(bits);
-		int x = cnt;
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL_MASK, x, d); if (lane >= d) x += t; }
-		if (lane == 31) warp_tot[warp] = x;
-		__syncthreads();
-		int before = carry;
-		for (int i = 0; i < warp; ++i) before += warp_tot[i];
-		int pos = before + x - cnt;
-		uint32_t b = bits;
-		while (b) { const int k = __ffs(b) - 1; b &= b - 1; if (pos < cap) out[pos] = w * 32 + k; ++pos; }
-		__syncthreads();
-		if (tid == 1023) carry = before + x;
-		__syncthreads();
-	}
-	if (tid == 0) wcount[blk] = carry < cap ? carry : cap;
-}
-
-cudaError_t launch_wmask_compact(const uint32_t *wmask, int words, int cap, const int *blk_list, int n_blk, int32_t *wlist, int *wcount, cudaStream_t st)
-{
-	if (n_blk <= 0) return cudaSuccess;
-	wmask_compact_kernel<<<n_blk, 1024, 0, st>>>(wmask, words, cap, blk_list, wlist, wcount);
-	return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ finalize

@@ -35,11 +35,10 @@ struct WalkParams {
 	const uint8_t  *tgrp;      // 0-based group of every tracked column
 	int32_t        *cnt_raw;   // [rows out][G][3] = #ALT, #missing, #other-ALT per group (zero-initialised, accumulated)
 	uint32_t       *hap[2];    // [rows out][words] bit planes (EMIT only)
-	uint32_t       *wmask;     // ORMASK only: [blocks][words] OR of the plane-1 rows of every block
+	const uint16_t *qrow;      // QUERY only: target row (within the block) of every tracked entry, ascending per block
 	const int      *blk_list;  // resident-block indices handled by this launch (nullptr: blk_first + blockIdx.y)
 	const int      *n_track_blk; // per-block number of tracked columns (nullptr: n_track)
 	long long       track_stride; // > 0: track holds one list per resident block, this many entries apart
-	int             joint_only;   // count only on rows whose plane 1 is not empty (second phase of the split scan)
 	uint8_t        *snap_img;  // CHAIN only: image to write 'S' snapshots into
 	const uint64_t *blkoff;    // CHAIN only: offset of the 'S' record of every block
 	int m, n_track, G, words, shift;
@@ -51,10 +50,28 @@ struct WalkParams {
 };
 
 size_t walk_smem_bytes(int C, int G);
-// C = tracked columns per thread (1,2,4,8); mode = WALK_COUNT / WALK_EMIT / WALK_CHAIN / WALK_ORMASK (pbwt_kernels.cu)
-enum { WALK_MODE_COUNT = 0, WALK_MODE_EMIT = 1, WALK_MODE_CHAIN = 2, WALK_MODE_ORMASK = 3 };
+// C = tracked columns per thread (1,2,4,8); mode = WALK_COUNT / WALK_EMIT / WALK_CHAIN / WALK_QUERY (pbwt_kernels.cu)
+enum { WALK_MODE_COUNT = 0, WALK_MODE_EMIT = 1, WALK_MODE_CHAIN = 2, WALK_MODE_QUERY = 3 };
 cudaError_t launch_walk(const WalkParams &P, int C, int mode, int slices, int n_blk, cudaStream_t st);
-cudaError_t launch_wmask_compact(const uint32_t *wmask, int words, int cap, const int *blk_list, int n_blk, int32_t *wlist, int *wcount, cudaStream_t st);
+
+// plane-1 select (plane1.cu): per block, the (column, row) pairs that carry a plane-1 bit, in row order
+struct SelectParams {
+	const uint8_t  *p1img;        // plane-1 view: records 'B', l0 = 0, l1, bytes of the rows whose plane 1 is not empty
+	const uint64_t *p1_rowoff;    // [blocks][BS+1]
+	const uint32_t *p1_n1;        // [blocks][BS][2]
+	const uint16_t *p1_realrow;   // [blocks][BS] row (within the block) of every view row
+	const int      *p1_rows_in_blk;
+	const uint8_t  *img;          // the real image (for the block's plane-1 snapshot)
+	const uint64_t *blkoff;
+	const int      *blk_list;
+	int m, shift, cap;
+	int32_t  *qcol;               // out [blocks][cap]
+	uint16_t *qrow;               // out [blocks][cap]
+	int      *qcount;             // out [blocks]
+	int      *err;
+};
+constexpr int SELECT_MAX_ROWS = 4096, SELECT_MAX_BYTES = 48 * 1024;
+cudaError_t launch_plane1_select(const SelectParams &P, int n_blk, cudaStream_t st);
 
 // split scan: rows of blocks flagged in blk_split take #ALT from the plane-0 marginal n1[row][0] (all columns, one group)
 struct FinalizeSplit { const uint8_t *blk_split; const uint32_t *n1; long long row_lo, blk_row0; int shift; };
