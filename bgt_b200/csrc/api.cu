@@ -54,7 +54,13 @@ struct DevBuf { // grow-only device scratch
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct PoolBlock { void *p; size_t size; };
+
 struct b200_ctx_s {
+	// device-memory pool: PBF windows are loaded and dropped repeatedly (seam A/B, end-to-end scans); cudaMalloc /
+	// cudaFree of hundreds of MB cost milliseconds to hundreds of milliseconds, so freed blocks are kept for reuse
+	std::vector<PoolBlock> pool_free_list, pool_live;
+	size_t pool_cached = 0;
 	int dev = 0;
 	cudaStream_t st = nullptr;
 	cudaEvent_t ev[8] = {};   // 0/1 walk, 2/3 scan, 4/5 h2d, 6/7 d2h
@@ -67,8 +73,16 @@ struct b200_ctx_s {
 	int sm_count = 148;
 };
 
+struct P1Block { // rows of one checkpoint block whose plane 1 is not empty, re-framed (see build_plane1_view)
+	std::vector<uint8_t> rec;
+	std::vector<uint32_t> n1s, lens, rrow;
+	uint64_t ones_sum = 0;
+	bool all_ones = false;
+};
+
 struct b200_pbf_s {
 	b200_ctx_t *ctx = nullptr;
+	std::vector<P1Block> p1blocks;
 	int m = 0, g = 0, shift = 0, BS = 0;
 	int64_t n = 0;               // rows in the file
 	int blk0 = 0, n_blk = 0;     // resident checkpoint blocks [blk0, blk0+n_blk)
@@ -93,8 +107,6 @@ struct b200_pbf_s {
 	uint8_t *d_p1img = nullptr;
 	uint64_t *d_p1_rowoff = nullptr;
 	uint32_t *d_p1_n1 = nullptr;
-	int2 *d_p1_tiles = nullptr;
-	int *d_p1_blk_tile_beg = nullptr;
 	uint16_t *d_p1_realrow = nullptr;
 	int *d_p1_rows_in_blk = nullptr;
 	int64_t p1_rows = 0;
@@ -111,6 +123,51 @@ struct b200_query_s {
 	flt_prog_t *d_prog = nullptr;
 	bool has_flt = false;
 };
+
+// ------------------------------------------------------------------------------------------------ device-memory pool
+
+static bool pool_malloc(b200_ctx_t *c, void **out, size_t bytes)
+{
+	if (bytes == 0) bytes = 16;
+	int best = -1;
+	for (size_t i = 0; i < c->pool_free_list.size(); ++i) {
+		const size_t sz = c->pool_free_list[i].size;
+		if (sz >= bytes && sz <= bytes * 2 + (1u << 20) && (best < 0 || sz < c->pool_free_list[best].size)) best = (int)i;
+	}
+	if (best >= 0) {
+		PoolBlock b = c->pool_free_list[best];
+		c->pool_free_list.erase(c->pool_free_list.begin() + best);
+		c->pool_cached -= b.size;
+		c->pool_live.push_back(b);
+		*out = b.p;
+		return true;
+	}
+	void *p = nullptr;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) { // out of memory: drop the cache and retry once
+		cudaGetLastError();
+		for (auto &b : c->pool_free_list) cudaFree(b.p);
+		c->pool_free_list.clear(); c->pool_cached = 0;
+		if (!CU_OK(cudaMalloc(&p, bytes))) return false;
+	}
+	c->pool_live.push_back({p, bytes});
+	*out = p;
+	return true;
+}
+
+static void pool_free(b200_ctx_t *c, void *p)
+{
+	if (!p) return;
+	for (size_t i = 0; i < c->pool_live.size(); ++i)
+		if (c->pool_live[i].p == p) {
+			PoolBlock b = c->pool_live[i];
+			c->pool_live.erase(c->pool_live.begin() + i);
+			if (c->pool_cached + b.size > ((size_t)16 << 30)) { cudaFree(b.p); return; }
+			c->pool_free_list.push_back(b);
+			c->pool_cached += b.size;
+			return;
+		}
+	cudaFree(p);
+}
 
 // ------------------------------------------------------------------------------------------------ context
 
@@ -155,6 +212,8 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
 	for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
+	for (auto &b : c->pool_free_list) cudaFree(b.p);
+	for (auto &b : c->pool_live) cudaFree(b.p);
 	if (c->d_err) cudaFree(c->d_err);
 	if (c->d_acc) cudaFree(c->d_acc);
 	if (c->st) cudaStreamDestroy(c->st);
@@ -200,21 +259,19 @@ extern "C" double b200_mark_elapsed_ms(b200_ctx_t *c, int a, int b)
 
 static void pbf_free_device(b200_pbf_t *pb)
 {
-	if (pb->d_img) cudaFree(pb->d_img);
-	if (pb->d_rowoff) cudaFree(pb->d_rowoff);
-	if (pb->d_blkoff) cudaFree(pb->d_blkoff);
-	if (pb->d_rows_in_blk) cudaFree(pb->d_rows_in_blk);
-	if (pb->d_blk_tile_beg) cudaFree(pb->d_blk_tile_beg);
-	if (pb->d_tiles) cudaFree(pb->d_tiles);
-	if (pb->d_n1) cudaFree(pb->d_n1);
-	if (pb->d_rank0) cudaFree(pb->d_rank0);
-	if (pb->d_p1img) cudaFree(pb->d_p1img);
-	if (pb->d_p1_rowoff) cudaFree(pb->d_p1_rowoff);
-	if (pb->d_p1_n1) cudaFree(pb->d_p1_n1);
-	if (pb->d_p1_tiles) cudaFree(pb->d_p1_tiles);
-	if (pb->d_p1_blk_tile_beg) cudaFree(pb->d_p1_blk_tile_beg);
-	if (pb->d_p1_realrow) cudaFree(pb->d_p1_realrow);
-	if (pb->d_p1_rows_in_blk) cudaFree(pb->d_p1_rows_in_blk);
+	pool_free(pb->ctx, pb->d_img);
+	pool_free(pb->ctx, pb->d_rowoff);
+	pool_free(pb->ctx, pb->d_blkoff);
+	pool_free(pb->ctx, pb->d_rows_in_blk);
+	pool_free(pb->ctx, pb->d_blk_tile_beg);
+	pool_free(pb->ctx, pb->d_tiles);
+	pool_free(pb->ctx, pb->d_n1);
+	pool_free(pb->ctx, pb->d_rank0);
+	pool_free(pb->ctx, pb->d_p1img);
+	pool_free(pb->ctx, pb->d_p1_rowoff);
+	pool_free(pb->ctx, pb->d_p1_n1);
+	pool_free(pb->ctx, pb->d_p1_realrow);
+	pool_free(pb->ctx, pb->d_p1_rows_in_blk);
 }
 
 extern "C" void b200_pbf_close(b200_pbf_t *pb)
@@ -254,96 +311,87 @@ static void plan_tiles(const b200_pbf_t *pb, std::vector<int2> &tiles, std::vect
 	plan_tiles_of(pb->n_blk, pb->BS, pb->h_rowoff, pb->rows_in_blk, tiles, blk_tile_beg);
 }
 
-// Build the plane-1 view from a host copy of the image (img0 = the byte that pb->h_rowoff offsets are relative to).
-// Per resident block: the rows whose plane 1 has at least one 1 bit, re-framed as records 'B', l0 = 0, l1, bytes so
-// that the walk kernel sees an empty plane 0; n1 is known here, so no row-meta pass is needed.
-static bool build_plane1_view(b200_pbf_t *pb, const uint8_t *img0)
+// Collect, for one resident block, the rows whose plane 1 has at least one 1 bit (img0 = the byte that the row
+// offsets are relative to).  Called right after the block's length-prefix walk, while its records are cache-warm.
+static void collect_plane1_block(const uint8_t *img0, const uint64_t *ro, int rows, uint32_t m, P1Block &o)
+{
+	for (int r = 0; r < rows; ++r) {
+		const uint8_t *p = img0 + ro[r] + 1;
+		int32_t l0, l1;
+		memcpy(&l0, p, 4);
+		p += 4 + l0;
+		memcpy(&l1, p, 4);
+		p += 4;
+		uint64_t ones = 0, tot = 0;
+		for (int32_t i = 0; i < l1; ++i) {
+			const uint32_t v = p[i] >> 1, len = (v & 15u) << ((v >> 4) << 2);
+			tot += len;
+			if (p[i] & 1) ones += len;
+		}
+		if (ones == 0 || tot != m) continue;          // empty (or corrupt: decodes as empty, see rowmeta_kernel)
+		if (ones == m) o.all_ones = true;             // every column carries the code: the set would be everything
+		o.ones_sum += ones;
+		const int32_t zero = 0;
+		o.rec.push_back('B');
+		o.rec.insert(o.rec.end(), (const uint8_t*)&zero, (const uint8_t*)&zero + 4);
+		o.rec.insert(o.rec.end(), (const uint8_t*)&l1, (const uint8_t*)&l1 + 4);
+		o.rec.insert(o.rec.end(), p, p + l1);
+		o.n1s.push_back((uint32_t)ones);
+		o.lens.push_back(9u + (uint32_t)l1);
+		o.rrow.push_back((uint32_t)r);
+	}
+}
+
+// Assemble the plane-1 view of the resident blocks from pb->p1blocks: per block the rows whose plane 1 is not
+// empty, as records 'B', l0 = 0, l1, bytes (an empty plane 0), with their n1 and their row number in the block.
+static bool build_plane1_view(b200_pbf_t *pb)
 {
 	b200_ctx_t *c = pb->ctx;
 	const int nb = pb->n_blk, BS = pb->BS;
-	const uint32_t m = (uint32_t)pb->m;
 	pb->p1_cap = (((pb->m / 4 > 4096 ? pb->m / 4 : 4096) + 2047) / 2048) * 2048;
 	pb->blk_sparse.assign(nb, 1);
 	pb->p1_rows_in_blk.assign(nb, 0);
-	std::vector<std::vector<uint8_t>> rec(nb);
-	std::vector<std::vector<uint32_t>> n1s(nb), lens(nb), rrow(nb);
-	{
-		const int nt = nb < 2 ? 1 : (nb < 8 ? nb : 8);
-		std::vector<std::thread> th;
-		for (int t = 0; t < nt; ++t)
-			th.emplace_back([&, t]() {
-				for (int b = t; b < nb; b += nt) {
-					const uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
-					uint64_t ones_sum = 0;
-					for (int r = 0; r < pb->rows_in_blk[b]; ++r) {
-						const uint8_t *p = img0 + ro[r] + 1;
-						int32_t l0, l1;
-						memcpy(&l0, p, 4);
-						p += 4 + l0;
-						memcpy(&l1, p, 4);
-						p += 4;
-						uint64_t ones = 0, tot = 0;
-						for (int32_t i = 0; i < l1; ++i) {
-							const uint32_t v = p[i] >> 1, len = (v & 15u) << ((v >> 4) << 2);
-							tot += len;
-							if (p[i] & 1) ones += len;
-						}
-						if (ones == 0 || tot != m) continue;          // empty (or corrupt: decodes as empty, see rowmeta_kernel)
-						if (ones == m) pb->blk_sparse[b] = 0;          // every column carries the code: W would be everything
-						ones_sum += ones;
-						const int32_t zero = 0;
-						rec[b].push_back('B');
-						rec[b].insert(rec[b].end(), (const uint8_t*)&zero, (const uint8_t*)&zero + 4);
-						rec[b].insert(rec[b].end(), (const uint8_t*)&l1, (const uint8_t*)&l1 + 4);
-						rec[b].insert(rec[b].end(), p, p + l1);
-						n1s[b].push_back((uint32_t)ones);
-						rrow[b].push_back((uint32_t)r);
-						lens[b].push_back(9u + (uint32_t)l1);
-					}
-					if (ones_sum > (uint64_t)pb->p1_cap || n1s[b].size() >= (size_t)SELECT_MAX_ROWS || rec[b].size() > (size_t)SELECT_MAX_BYTES || BS > 65536) pb->blk_sparse[b] = 0;
-					pb->p1_rows_in_blk[b] = (int)n1s[b].size();
-				}
-			});
-		for (auto &x : th) x.join();
+	for (int b = 0; b < nb; ++b) {
+		const P1Block &o = pb->p1blocks[b];
+		if (o.all_ones || o.ones_sum > (uint64_t)pb->p1_cap || o.n1s.size() >= (size_t)SELECT_MAX_ROWS || o.rec.size() > (size_t)SELECT_MAX_BYTES || BS > 65536)
+			pb->blk_sparse[b] = 0;
+		pb->p1_rows_in_blk[b] = (int)o.n1s.size();
 	}
+	std::vector<P1Block> &rec_blocks = pb->p1blocks;
 	std::vector<uint64_t> rowoff((size_t)nb * (BS + 1), 0);
 	std::vector<uint32_t> n1((size_t)nb * BS * 2, 0);
 	std::vector<uint16_t> realrow((size_t)nb * BS, 0);
 	std::vector<uint8_t> img;
 	size_t total = 0;
-	for (int b = 0; b < nb; ++b) total += ((rec[b].size() + 15) & ~(size_t)15);
+	for (int b = 0; b < nb; ++b) total += ((rec_blocks[b].rec.size() + 15) & ~(size_t)15);
 	img.reserve(total + 64);
 	pb->p1_rows = 0;
 	for (int b = 0; b < nb; ++b) {
 		uint64_t pos = img.size();
 		uint64_t *ro = rowoff.data() + (size_t)b * (BS + 1);
-		for (size_t r = 0; r < n1s[b].size(); ++r) {
-			ro[r] = pos; pos += lens[b][r];
-			n1[((size_t)b * BS + r) * 2 + 1] = n1s[b][r];
-			realrow[(size_t)b * BS + r] = (uint16_t)rrow[b][r];
+		for (size_t r = 0; r < rec_blocks[b].n1s.size(); ++r) {
+			ro[r] = pos; pos += rec_blocks[b].lens[r];
+			n1[((size_t)b * BS + r) * 2 + 1] = rec_blocks[b].n1s[r];
+			realrow[(size_t)b * BS + r] = (uint16_t)rec_blocks[b].rrow[r];
 		}
-		ro[n1s[b].size()] = pos;
-		img.insert(img.end(), rec[b].begin(), rec[b].end());
+		ro[rec_blocks[b].n1s.size()] = pos;
+		img.insert(img.end(), rec_blocks[b].rec.begin(), rec_blocks[b].rec.end());
 		img.resize((img.size() + 15) & ~(size_t)15, 0);
-		pb->p1_rows += (int64_t)n1s[b].size();
+		pb->p1_rows += (int64_t)rec_blocks[b].n1s.size();
 	}
 	img.resize(img.size() + 64, 0);
-	std::vector<int2> tiles;
-	std::vector<int> btb;
-	plan_tiles_of(nb, BS, rowoff, pb->p1_rows_in_blk, tiles, btb);
-	bool ok = CU_OK(cudaMalloc(&pb->d_p1img, img.size())) && CU_OK(cudaMalloc(&pb->d_p1_rowoff, rowoff.size() * 8 + 8)) &&
-	          CU_OK(cudaMalloc(&pb->d_p1_n1, n1.size() * 4 + 8)) && CU_OK(cudaMalloc(&pb->d_p1_tiles, (tiles.size() + 1) * sizeof(int2))) &&
-	          CU_OK(cudaMalloc(&pb->d_p1_blk_tile_beg, (nb + 1) * sizeof(int))) && CU_OK(cudaMalloc(&pb->d_p1_realrow, realrow.size() * 2 + 8)) &&
-	          CU_OK(cudaMalloc(&pb->d_p1_rows_in_blk, (nb + 1) * sizeof(int)));
+	bool ok = pool_malloc(c, (void**)&pb->d_p1img, img.size()) && pool_malloc(c, (void**)&pb->d_p1_rowoff, rowoff.size() * 8 + 8) &&
+	          pool_malloc(c, (void**)&pb->d_p1_n1, n1.size() * 4 + 8) &&
+	          pool_malloc(c, (void**)&pb->d_p1_realrow, realrow.size() * 2 + 8) &&
+	          pool_malloc(c, (void**)&pb->d_p1_rows_in_blk, (nb + 1) * sizeof(int));
 	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_p1img, img.data(), img.size(), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_rowoff, rowoff.data(), rowoff.size() * 8, cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_n1, n1.data(), n1.size() * 4, cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_p1_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_p1_blk_tile_beg, btb.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_realrow, realrow.data(), realrow.size() * 2, cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_rows_in_blk, pb->p1_rows_in_blk.data(), nb * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaStreamSynchronize(c->st));
 	pb->p1_ready = ok;
+	std::vector<P1Block>().swap(pb->p1blocks);
 	return ok;
 }
 
@@ -356,13 +404,13 @@ static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain)
 	std::vector<int> btb;
 	plan_tiles(pb, tiles, btb);
 	const size_t n_tiles = tiles.size();
-	bool ok = CU_OK(cudaMalloc(&pb->d_rowoff, sizeof(uint64_t) * (size_t)nb * (BS + 1) + 8)) &&
-	          CU_OK(cudaMalloc(&pb->d_blkoff, sizeof(uint64_t) * (nb + 1))) &&
-	          CU_OK(cudaMalloc(&pb->d_rows_in_blk, sizeof(int) * (nb + 1))) &&
-	          CU_OK(cudaMalloc(&pb->d_blk_tile_beg, sizeof(int) * (nb + 1))) &&
-	          CU_OK(cudaMalloc(&pb->d_tiles, sizeof(int2) * (n_tiles + 1))) &&
-	          CU_OK(cudaMalloc(&pb->d_n1, sizeof(uint32_t) * (size_t)nb * BS * 2 + 8)) &&
-	          CU_OK(cudaMalloc(&pb->d_rank0, sizeof(int32_t) * (size_t)nb * 2 * (size_t)pb->m + 8));
+	bool ok = pool_malloc(c, (void**)&pb->d_rowoff, sizeof(uint64_t) * (size_t)nb * (BS + 1) + 8) &&
+	          pool_malloc(c, (void**)&pb->d_blkoff, sizeof(uint64_t) * (nb + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_rows_in_blk, sizeof(int) * (nb + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_blk_tile_beg, sizeof(int) * (nb + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_tiles, sizeof(int2) * (n_tiles + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_n1, sizeof(uint32_t) * (size_t)nb * BS * 2 + 8) &&
+	          pool_malloc(c, (void**)&pb->d_rank0, sizeof(int32_t) * (size_t)nb * 2 * (size_t)pb->m + 8);
 	if (!ok) return false;
 	ok = CU_OK(cudaMemcpyAsync(pb->d_rowoff, pb->h_rowoff.data(), sizeof(uint64_t) * (size_t)nb * (BS + 1), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_blkoff, pb->h_blkoff.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, c->st)) &&
@@ -466,6 +514,7 @@ static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg
 	const uint64_t copy_end = pb->file_size ? flen : byte_end;
 	pb->img_bytes = (size_t)(copy_end - pb->file_off0);
 	pb->rows_in_blk.resize(nb);
+	pb->p1blocks.assign(nb, P1Block());
 	pb->h_rowoff.assign((size_t)nb * (BS + 1), 0);
 	pb->h_blkoff.resize(nb);
 	for (int b = 0; b < nb; ++b) {
@@ -475,7 +524,9 @@ static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg
 	}
 	bool ok = true;
 	{
-		const int nt = nb < 2 ? 1 : (nb < 8 ? nb : 8);
+		int hw = (int)std::thread::hardware_concurrency();
+		hw = hw < 8 ? 8 : (hw > 32 ? 32 : hw);
+		const int nt = nb < 2 ? 1 : (nb < hw ? nb : hw);
 		std::vector<int> bad(nt, 0);
 		std::vector<std::thread> th;
 		for (int t = 0; t < nt; ++t)
@@ -483,6 +534,7 @@ static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg
 				for (int b = t; b < nb; b += nt) {
 					uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
 					if (!walk_block(f, (size_t)ioff + 1, idx[pb->blk0 + b], m, g, pb->rows_in_blk[b], ro)) { bad[t] = 1; return; }
+					collect_plane1_block(f, ro, pb->rows_in_blk[b], (uint32_t)m, pb->p1blocks[b]);
 					for (int r = 0; r <= pb->rows_in_blk[b]; ++r) ro[r] -= pb->file_off0;
 				}
 			});
@@ -502,12 +554,12 @@ extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t fle
 	b200_pbf_t *pb = pbf_index_host(f, flen, row_beg, row_end);
 	if (!pb) return nullptr;
 	pb->ctx = c;
-	bool ok = CU_OK(cudaMalloc(&pb->d_img, pb->img_bytes + 64));
+	bool ok = pool_malloc(c, (void**)&pb->d_img, pb->img_bytes + 64);
 	ok = ok && CU_OK(cudaEventRecord(c->ev[4], c->st));
 	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img, f + pb->file_off0, pb->img_bytes, cudaMemcpyHostToDevice, c->st));
 	ok = ok && CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st));
 	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st));
-	if (!ok || !pbf_finish_resident(pb, false) || !build_plane1_view(pb, f + pb->file_off0)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	if (!ok || !pbf_finish_resident(pb, false) || !build_plane1_view(pb)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
 	return pb;
@@ -924,7 +976,7 @@ extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cf
 	pb->file_off0 = 0;
 	uint8_t hdr[16];
 	{ const int32_t v[3] = {(int32_t)sc.m, 2, sc.shift}; memcpy(hdr, "PBF\1", 4); memcpy(hdr + 4, v, 12); } // pbwt.c:214-216
-	ok = CU_OK(cudaMalloc(&pb->d_img, pb->img_bytes + 64)) && CU_OK(cudaMalloc(&d_flat, sizeof(uint64_t) * (size_t)n));
+	ok = pool_malloc(c, (void**)&pb->d_img, pb->img_bytes + 64) && CU_OK(cudaMalloc(&d_flat, sizeof(uint64_t) * (size_t)n));
 	ok = ok && CU_OK(cudaMemsetAsync(pb->d_img, 0, pb->img_bytes + 64, c->st));
 	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img, hdr, 16, cudaMemcpyHostToDevice, c->st));
 	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img + ioff, tail.data(), tail.size(), cudaMemcpyHostToDevice, c->st));
@@ -937,8 +989,12 @@ extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cf
 	if (!ok || !pbf_finish_resident(pb, true)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	{ // the plane-1 view is built from a host copy of the generated image
 		uint8_t *h = (uint8_t*)b200_host_alloc(pb->img_bytes);
-		ok = h && CU_OK(cudaMemcpyAsync(h, pb->d_img, pb->img_bytes, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st)) &&
-		     build_plane1_view(pb, h);
+		ok = h && CU_OK(cudaMemcpyAsync(h, pb->d_img, pb->img_bytes, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+		if (ok) {
+			pb->p1blocks.assign(nb, P1Block());
+			for (int b = 0; b < nb; ++b) collect_plane1_block(h, pb->h_rowoff.data() + (size_t)b * (BS + 1), pb->rows_in_blk[b], sc.m, pb->p1blocks[b]);
+			ok = build_plane1_view(pb);
+		}
 		b200_host_free(h);
 		if (!ok) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	}
