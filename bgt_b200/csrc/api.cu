@@ -69,7 +69,7 @@ struct b200_ctx_s {
 	int64_t launches = 0;
 	int *d_err = nullptr;
 	unsigned long long *d_acc = nullptr; // [0..3] totals, [4] bad rows
-	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], qcol, qrow, qcount, blk_lists, blk_split;
+	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], qcol, qrow, qcount, blk_lists, blk_split, n0g;
 	int sm_count = 148;
 };
 
@@ -209,7 +209,7 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	if (c->st) cudaStreamSynchronize(c->st);
 	c->cnt_raw.release(); c->counts.release(); c->pass.release();
 	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
-	c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
+	c->n0g.release(); c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
 	for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
 	for (auto &b : c->pool_free_list) cudaFree(b.p);
@@ -811,7 +811,9 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	// from the RLE alone; only the columns that carry a missing / other-ALT code somewhere in the block (the set W,
 	// from the block's plane-1 rows) have to be walked to resolve the joint codes.  Blocks whose W would be large
 	// (pb->blk_sparse == 0) and every other kind of query take the general walk over all tracked columns.
-	const bool split = q->full && G == 1 && !emit && pb->p1_ready && !(flags & B200_SCAN_NO_SPLIT) && n_track > 0;
+	// (several groups: the per-group marginals come from marginal.cu -- one bit vector per group in shared memory)
+	const bool split = q->full && !emit && pb->p1_ready && !(flags & B200_SCAN_NO_SPLIT) && n_track > 0 &&
+	                   (G == 1 || (G <= 8 && marginal_smem_bytes(pb->m) <= 200 * 1024));
 	std::vector<int> lists;          // [general blocks..., split blocks...]
 	std::vector<uint8_t> split_flag(pb->n_blk, 0);
 	int n_gen = 0, n_split = 0;
@@ -852,6 +854,16 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : 8;
 		ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_QUERY, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
 		c->launches += 2;
+		if (G > 1) { // per-group plane-0 marginals for the first G-1 groups (the last one is the remainder)
+			if (!c->n0g.reserve(nr * (size_t)(G - 1) * sizeof(int32_t))) return -1;
+			MarginalParams M;
+			M.img = pb->d_img; M.rowoff = pb->d_rowoff; M.n1 = pb->d_n1; M.blkoff = pb->d_blkoff; M.rows_in_blk = pb->d_rows_in_blk;
+			M.blk_list = d_split_list; M.tgrp = q->d_tgrp; M.n0g = (int32_t*)c->n0g.p; M.m = pb->m; M.shift = pb->shift; M.n_vec = G - 1;
+			M.blk_row0 = P.blk_row0; M.row_lo = row_beg; M.row_hi = row_beg + n_rows;
+			ok = ok && CU_OK(launch_marginal(M, n_split, c->st));
+			++c->launches;
+			sp.n0g = (const int32_t*)c->n0g.p; sp.n_vec = G - 1;
+		}
 		sp.blk_split = (const uint8_t*)c->blk_split.p; sp.n1 = pb->d_n1; sp.row_lo = row_beg; sp.blk_row0 = P.blk_row0; sp.shift = pb->shift;
 	}
 	ok = ok && CU_OK(cudaEventRecord(c->ev[1], c->st));

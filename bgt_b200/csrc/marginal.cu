@@ -1,0 +1,242 @@
+// marginal.cu -- per-group plane-0 marginals for the split scan of grouped full-cohort queries (`-s A -s B -f ... -G`).
+//
+// With several sample groups the number of ALT codes per group is (ones of the plane-0 row inside the group) minus
+// (other-ALT codes inside the group).  The second term comes from the plane-1 queries (plane1.cu + WALK_QUERY); the
+// first one needs no per-column state either: keep, per checkpoint block and group, ONE BIT per rank -- "the column
+// at this rank belongs to the group" -- and push that bit vector through the same stable partition the PBWT applies
+// to the permutation (pbwt.c:79-88): the bits under the row's 0-runs move to the front, the bits under its 1-runs
+// behind them, both in order.  The popcount of the part that moved behind is the group's number of ones.
+// m/32 words per row instead of m rank updates.
+//
+// grid = (blocks, groups-1); one CTA of 1024 threads owns one bit vector (two buffers in shared memory).  Rows are
+// staged in tiles like in the walk kernel (plain cooperative loads here: this kernel is a few percent of the scan).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pbwt_kernels.cuh"
+
+namespace b200 {
+
+constexpr int MG_NT = 1024, MG_NW = MG_NT / 32, MG_RAW = 4096, MG_TMAX = 32;
+
+__device__ __forceinline__ uint32_t mg_rle_len(uint32_t c) { const uint32_t v = c >> 1; return (v & 15u) << ((v >> 4) << 2); }
+
+__device__ __forceinline__ uint32_t mg_ld_u32_unaligned(const uint8_t *p)
+{
+	const uintptr_t a = (uintptr_t)p;
+	const uint32_t *w = (const uint32_t*)(a & ~(uintptr_t)3);
+	const uint32_t sh = (uint32_t)(a & 3) * 8;
+	const uint32_t lo = w[0];
+	if (sh == 0) return lo;
+	return __funnelshift_r(lo, w[1], sh);
+}
+
+__global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalParams P)
+{
+	extern __shared__ __align__(16) uint8_t sm[];
+	const int words = (P.m + 31) / 32, wpad = (words + 3) & ~3;
+	uint32_t *V0 = (uint32_t*)sm, *V1 = V0 + wpad;
+	uint32_t *ts = V1 + wpad;                       // [MG_RAW] run starts (per RLE byte)
+	int32_t *td = (int32_t*)(ts + MG_RAW);          // [MG_RAW] rank shift of the run
+	uint8_t *raw = (uint8_t*)(td + MG_RAW);         // [MG_RAW + 16]
+	uint32_t *r_off = (uint32_t*)(raw + MG_RAW + 16); // [MG_TMAX] offset of the plane-0 RLE of the tile's rows in raw
+	uint32_t *r_len = r_off + MG_TMAX, *r_n1 = r_len + MG_TMAX;
+	int32_t *r_cnt = (int32_t*)(r_n1 + MG_TMAX);    // [MG_TMAX] ones of the group per row
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int blk = P.blk_list[blockIdx.x], g = blockIdx.y;
+	const int BS = 1 << P.shift;
+	const uint32_t m = (uint32_t)P.m;
+	const uint64_t *roff = P.rowoff + (size_t)blk * (BS + 1);
+	const long long blk_row = P.blk_row0 + ((long long)blk << P.shift);
+	int rows = P.rows_in_blk[blk];
+	if (blk_row + rows > P.row_hi) rows = (int)(P.row_hi - blk_row);
+
+	// ---- the block's start vector: bit i = group of the column at rank i under the plane-0 snapshot (pbwt.c:298-300)
+	const uint8_t *S0 = P.img + P.blkoff[blk] + 1;
+	for (int w = warp; w < wpad; w += MG_NW) {
+		const uint32_t i = (uint32_t)w * 32 + lane;
+		bool in = false;
+		if (i < m) { const uint32_t col = mg_ld_u32_unaligned(S0 + 4 * (size_t)i); in = col < m && P.tgrp[col] == g; }
+		const uint32_t bits = __ballot_sync(0xffffffffu, in);
+		if (lane == 0) { V0[w] = bits; V1[w] = 0; }
+	}
+	__syncthreads();
+	int total = 0;                                   // columns of the group (for all-ones rows)
+	for (int w = tid; w < words; w += MG_NT) total += __popc(V0[w]);
+	#pragma unroll
+	for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+	if (tid < MG_TMAX) r_cnt[tid] = 0;
+	__shared__ int s_total;
+	if (tid == 0) s_total = 0;
+	__syncthreads();
+	if (lane == 0 && total) atomicAdd(&s_total, total);
+	__syncthreads();
+	const int group_cols = s_total;
+
+	uint32_t *Vold = V0, *Vnew = V1;                 // Vnew is all zero here
+	for (int r0 = 0; r0 < rows;) {
+		// ---- tile: as many rows as fit MG_RAW bytes (a single larger row is staged piecewise below)
+		int nr = 1;
+		while (r0 + nr < rows && nr < MG_TMAX && roff[r0 + nr + 1] - roff[r0] <= (uint64_t)MG_RAW) ++nr;
+		const uint64_t t_beg = roff[r0];
+		const bool big = roff[r0 + 1] - t_beg > (uint64_t)MG_RAW;
+		if (!big) {
+			const uint32_t nbytes = (uint32_t)(roff[r0 + nr] - t_beg);
+			for (uint32_t i = tid; i < nbytes; i += MG_NT) raw[i] = P.img[t_beg + i];
+			__syncthreads();
+			if (tid < nr) {
+				const uint32_t o = (uint32_t)(roff[r0 + tid] - t_beg);
+				r_len[tid] = (uint32_t)raw[o + 1] | (uint32_t)raw[o + 2] << 8 | (uint32_t)raw[o + 3] << 16 | (uint32_t)raw[o + 4] << 24;
+				r_off[tid] = o + 5;
+				r_n1[tid] = P.n1[((size_t)blk * BS + r0 + tid) * 2];
+			}
+			__syncthreads();
+			for (int r = warp; r < nr; r += MG_NW) {     // per-byte run table of plane 0 (same arithmetic as parse_runs)
+				const uint32_t n1 = r_n1[r], len = r_len[r], off = r_off[r];
+				if (n1 == 0 || n1 == m) continue;
+				uint32_t tot = 0, ones = 0;
+				for (uint32_t base = 0; base < len; base += 32) {
+					const uint32_t i = base + lane;
+					const uint32_t c = i < len ? raw[off + i] : 0u;
+					const uint32_t L = mg_rle_len(c), b = c & 1u, L1 = b ? L : 0u;
+					uint32_t x = L, y = L1;
+					#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						const uint32_t tx = __shfl_up_sync(0xffffffffu, x, d), ty = __shfl_up_sync(0xffffffffu, y, d);
+						if (lane >= d) { x += tx; y += ty; }
+					}
+					const uint32_t start = tot + x - L, ones_before = ones + y - L1;
+					if (i < len) { ts[off + i] = start; td[off + i] = b ? (int32_t)((m - n1) - (start - ones_before)) : -(int32_t)ones_before; }
+					tot += __shfl_sync(0xffffffffu, x, 31);
+					ones += __shfl_sync(0xffffffffu, y, 31);
+				}
+			}
+			__syncthreads();
+		}
+		for (int r = 0; r < nr; ++r) {
+			uint32_t n1, n;
+			const uint32_t *rts; const int32_t *rtd;
+			if (!big) { n1 = r_n1[r]; n = r_len[r]; rts = ts + r_off[r]; rtd = td + r_off[r]; }
+			else { n1 = P.n1[((size_t)blk * BS + r0) * 2]; n = 0; rts = ts; rtd = td; }
+			int cnt = 0;
+			if (n1 == 0) { /* nothing moves, no ones */ }
+			else if (n1 == m) { if (tid == 0) r_cnt[r] = group_cols; }
+			else if (!big) {
+				const uint32_t zt = m - n1;
+				for (int w = tid; w < words; w += MG_NT) {
+					const uint32_t bits = Vold[w];
+					if (bits == 0) continue;                 // Vnew is pre-zeroed: only 1 bits have to be moved
+					const uint32_t pos = (uint32_t)w * 32;
+					uint32_t lo = 0;
+					for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; lo += rts[lo + half] <= pos ? half : 0u; len -= half; }
+					for (uint32_t j = lo; j < n; ++j) {
+						const uint32_t s = rts[j], e = j + 1 < n ? rts[j + 1] : m;
+						if (s >= pos + 32) break;
+						const uint32_t a = s > pos ? s : pos, b = e < pos + 32 ? e : pos + 32;
+						if (b <= a) continue;
+						const uint32_t piece = (bits >> (a - pos)) & (b - a == 32 ? 0xffffffffu : ((1u << (b - a)) - 1u));
+						if (piece == 0) continue;
+						const uint32_t dst = a + (uint32_t)rtd[j], dw = dst >> 5, db = dst & 31;
+						atomicOr(&Vnew[dw], piece << db);
+						if (db && (piece >> (32 - db))) atomicOr(&Vnew[dw + 1], piece >> (32 - db));
+						if (dst >= zt) cnt += __popc(piece);
+					}
+				}
+			} else {
+				// a row larger than the staging buffer: stream its plane-0 RLE in pieces; every piece covers a rank range
+				const uint8_t *rec = P.img + roff[r0];
+				const uint32_t l = mg_ld_u32_unaligned(rec + 1), zt = m - n1;
+				const uint8_t *rle = rec + 5;
+				__shared__ uint32_t carry[4];
+				if (tid == 0) { carry[0] = 0; carry[1] = 0; }
+				for (uint32_t cb = 0; cb < l; cb += MG_RAW) {
+					const uint32_t nn = l - cb < (uint32_t)MG_RAW ? l - cb : (uint32_t)MG_RAW;
+					for (uint32_t i = tid; i < nn; i += MG_NT) raw[i] = rle[cb + i];
+					__syncthreads();
+					const uint32_t cs = carry[0];
+					if (warp == 0) {
+						uint32_t tot = cs, ones = carry[1];
+						for (uint32_t base = 0; base < nn; base += 32) {
+							const uint32_t i = base + lane;
+							const uint32_t c = i < nn ? raw[i] : 0u;
+							const uint32_t L = mg_rle_len(c), b = c & 1u, L1 = b ? L : 0u;
+							uint32_t x = L, y = L1;
+							#pragma unroll
+							for (int d = 1; d < 32; d <<= 1) {
+								const uint32_t tx = __shfl_up_sync(0xffffffffu, x, d), ty = __shfl_up_sync(0xffffffffu, y, d);
+								if (lane >= d) { x += tx; y += ty; }
+							}
+							const uint32_t start = tot + x - L, ones_before = ones + y - L1;
+							if (i < nn) { ts[i] = start; td[i] = b ? (int32_t)(zt - (start - ones_before)) : -(int32_t)ones_before; }
+							tot += __shfl_sync(0xffffffffu, x, 31);
+							ones += __shfl_sync(0xffffffffu, y, 31);
+						}
+						if (lane == 0) { carry[2] = tot; carry[3] = ones; }
+					}
+					__syncthreads();
+					const uint32_t ce = carry[2];
+					// source words overlapping the rank range [cs, ce) of this piece
+					const int w_lo = (int)(cs >> 5), w_hi = (int)((ce + 31) >> 5);
+					for (int w = w_lo + tid; w < w_hi && w < words; w += MG_NT) {
+						const uint32_t bits = Vold[w];
+						if (bits == 0) continue;
+						const uint32_t pos = (uint32_t)w * 32;
+						uint32_t lo = 0;
+						for (uint32_t len = nn; len > 1;) { const uint32_t half = len >> 1; lo += ts[lo + half] <= pos ? half : 0u; len -= half; }
+						for (uint32_t j = lo; j < nn; ++j) {
+							const uint32_t s = ts[j], e = j + 1 < nn ? ts[j + 1] : ce;
+							if (s >= pos + 32) break;
+							const uint32_t a = s > pos ? s : pos, b = e < pos + 32 ? e : pos + 32;
+							if (b <= a) continue;
+							const uint32_t piece = (bits >> (a - pos)) & (b - a == 32 ? 0xffffffffu : ((1u << (b - a)) - 1u));
+							if (piece == 0) continue;
+							const uint32_t dst = a + (uint32_t)td[j], dw = dst >> 5, db = dst & 31;
+							atomicOr(&Vnew[dw], piece << db);
+							if (db && (piece >> (32 - db))) atomicOr(&Vnew[dw + 1], piece >> (32 - db));
+							if (dst >= zt) cnt += __popc(piece);
+						}
+					}
+					__syncthreads();
+					if (tid == 0) { carry[0] = carry[2]; carry[1] = carry[3]; }
+					__syncthreads();
+				}
+			}
+			if (n1 != 0 && n1 != m) {
+				#pragma unroll
+				for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+				if (lane == 0 && cnt) atomicAdd(&r_cnt[r], cnt);
+				__syncthreads();                             // all bits have landed in Vnew
+				uint32_t *t = Vold; Vold = Vnew; Vnew = t;
+				for (int w = tid; w < wpad; w += MG_NT) Vnew[w] = 0;
+				__syncthreads();
+			}
+		}
+		__syncthreads();
+		if (tid < nr) {
+			const long long arow = blk_row + r0 + tid;
+			if (arow >= P.row_lo && arow < P.row_hi) P.n0g[(size_t)(arow - P.row_lo) * P.n_vec + g] = r_cnt[tid];
+			r_cnt[tid] = 0;
+		}
+		__syncthreads();
+		r0 += nr;
+	}
+}
+
+size_t marginal_smem_bytes(int m)
+{
+	const int words = (m + 31) / 32, wpad = (words + 3) & ~3;
+	return (size_t)wpad * 8 + MG_RAW * 8 + MG_RAW + 16 + MG_TMAX * 16 + 64;
+}
+
+cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st)
+{
+	if (n_blk <= 0 || P.n_vec <= 0) return cudaSuccess;
+	const size_t smem = marginal_smem_bytes(P.m);
+	cudaError_t e = cudaFuncSetAttribute(pbwt_marginal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	dim3 grid(n_blk, P.n_vec, 1);
+	pbwt_marginal_kernel<<<grid, MG_NT, smem, st>>>(P);
+	return cudaGetLastError();
+}
+
+} // namespace b200

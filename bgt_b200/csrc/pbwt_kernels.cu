@@ -624,10 +624,18 @@ __global__ void __launch_bounds__(256) finalize_kernel(const int32_t *__restrict
 		for (int g = 0; g < G; ++g) {
 			int32_t c1 = c[g * 3];
 			const int32_t c2 = c[g * 3 + 1], c3 = c[g * 3 + 2];
-			if (sp.blk_split) { // split scan: the walk only counted the plane-1 codes; #ALT = (ones of plane 0) - #other-ALT
+			if (sp.blk_split) { // split scan: the walk only counted the plane-1 codes; #ALT = (plane-0 ones in the group) - #other-ALT
 				const long long arow = sp.row_lo + row;
 				const int blk = (int)((arow - sp.blk_row0) >> sp.shift);
-				if (sp.blk_split[blk]) c1 = (int32_t)sp.n1[((size_t)blk << sp.shift << 1) + (size_t)(arow - sp.blk_row0 - ((long long)blk << sp.shift)) * 2] - c3;
+				if (sp.blk_split[blk]) {
+					int32_t n0;
+					if (g < sp.n_vec) n0 = sp.n0g[(size_t)row * sp.n_vec + g];
+					else {
+						n0 = (int32_t)sp.n1[((size_t)blk << sp.shift << 1) + (size_t)(arow - sp.blk_row0 - ((long long)blk << sp.shift)) * 2];
+						for (int k = 0; k < sp.n_vec; ++k) n0 -= sp.n0g[(size_t)row * sp.n_vec + k];
+					}
+					c1 = n0 - c3;
+				}
 			}
 			const int32_t gan = gsize[g] - c2;            // c0 + c1 + c3
 			v[3 + 3 * g] = gan; v[4 + 3 * g] = c1; v[5 + 3 * g] = c3;

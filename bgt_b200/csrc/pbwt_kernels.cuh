@@ -73,8 +73,25 @@ struct SelectParams {
 constexpr int SELECT_MAX_ROWS = 4096, SELECT_MAX_BYTES = 48 * 1024;
 cudaError_t launch_plane1_select(const SelectParams &P, int n_blk, cudaStream_t st);
 
-// split scan: rows of blocks flagged in blk_split take #ALT from the plane-0 marginal n1[row][0] (all columns, one group)
-struct FinalizeSplit { const uint8_t *blk_split; const uint32_t *n1; long long row_lo, blk_row0; int shift; };
+// per-group plane-0 marginals (marginal.cu): n0g[row][g] = ones of the plane-0 row among the columns of group g
+struct MarginalParams {
+	const uint8_t  *img;
+	const uint64_t *rowoff;
+	const uint32_t *n1;
+	const uint64_t *blkoff;
+	const int      *rows_in_blk;
+	const int      *blk_list;
+	const uint8_t  *tgrp;      // 0-based group per column (full-cohort queries: tracked entry == column)
+	int32_t        *n0g;       // out [rows out][n_vec]
+	int m, shift, n_vec;
+	long long blk_row0, row_lo, row_hi;
+};
+size_t marginal_smem_bytes(int m);
+cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st);
+
+// split scan: rows of blocks flagged in blk_split take #ALT of group g from the plane-0 marginal -- n0g[row][g] for the
+// first n_vec groups, the rest of n1[row][0] for the last group -- minus the group's other-ALT count
+struct FinalizeSplit { const uint8_t *blk_split; const uint32_t *n1; const int32_t *n0g; int n_vec; long long row_lo, blk_row0; int shift; };
 
 cudaError_t launch_rowmeta(const uint8_t *img, const uint64_t *rowoff, int n_blk, int shift, long long n_rows_total_in_blocks,
                            const int *rows_in_blk, uint32_t m, uint32_t *n1, unsigned long long *bad, cudaStream_t st);
