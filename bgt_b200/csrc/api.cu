@@ -63,14 +63,15 @@ struct b200_ctx_s {
 	size_t pool_cached = 0;
 	int dev = 0;
 	cudaStream_t st = nullptr;
-	cudaEvent_t ev[8] = {};   // 0/1 walk, 2/3 scan, 4/5 h2d, 6/7 d2h
+	cudaEvent_t ev[12] = {};  // 0/1 walk phase(s), 2/3 scan, 4/5 h2d, 6/7 d2h, 8/9 plane1 select, 10/11 marginals
 	cudaEvent_t mark[4] = {};
-	double last_ms[4] = {0, 0, 0, 0};
+	double last_ms[6] = {0, 0, 0, 0, 0, 0};
 	int64_t launches = 0;
 	int *d_err = nullptr;
 	unsigned long long *d_acc = nullptr; // [0..3] totals, [4] bad rows
 	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], qcol, qrow, qcount, blk_lists, blk_split, n0g;
 	int sm_count = 148;
+	bool split_used = false, marginal_used = false;
 };
 
 struct P1Block { // rows of one checkpoint block whose plane 1 is not empty, re-framed (see build_plane1_view)
@@ -194,7 +195,7 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	b200_ctx_t *c = new b200_ctx_t();
 	c->dev = device; c->sm_count = prop.multiProcessorCount;
 	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-	for (int i = 0; ok && i < 8; ++i) ok = CU_OK(cudaEventCreate(&c->ev[i]));
+	for (int i = 0; ok && i < 12; ++i) ok = CU_OK(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; ok && i < 4; ++i) ok = CU_OK(cudaEventCreate(&c->mark[i]));
 	ok = ok && CU_OK(cudaMalloc(&c->d_err, sizeof(int))) && CU_OK(cudaMalloc(&c->d_acc, 8 * sizeof(unsigned long long)));
 	ok = ok && CU_OK(cudaMemset(c->d_err, 0, sizeof(int))) && CU_OK(cudaMemset(c->d_acc, 0, 8 * sizeof(unsigned long long)));
@@ -210,7 +211,7 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	c->cnt_raw.release(); c->counts.release(); c->pass.release();
 	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
 	c->n0g.release(); c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
-	for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
 	for (auto &b : c->pool_free_list) cudaFree(b.p);
 	for (auto &b : c->pool_live) cudaFree(b.p);
@@ -236,7 +237,7 @@ extern "C" void *b200_host_alloc(size_t bytes)
 
 extern "C" void b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
-extern "C" double b200_last_ms(b200_ctx_t *c, int which) { return (c && which >= 0 && which < 4) ? c->last_ms[which] : -1.0; }
+extern "C" double b200_last_ms(b200_ctx_t *c, int which) { return (c && which >= 0 && which < 6) ? c->last_ms[which] : -1.0; }
 extern "C" int64_t b200_kernel_launches(b200_ctx_t *c) { return c ? c->launches : 0; }
 
 extern "C" int b200_mark(b200_ctx_t *c, int slot)
@@ -754,6 +755,18 @@ static int pick_cols_per_thread(const b200_ctx_t *c, int n_track, int n_blk)
 	return 1;
 }
 
+// device times of the last scan: [0] all phases between the first and the last walk-type kernel, [1] whole scan,
+// [4] plane1_select_kernel, [5] pbwt_marginal_kernel; the rank-walk kernel alone is [0] - [4] - [5]
+static void read_scan_timings(b200_ctx_t *c)
+{
+	float ms;
+	c->last_ms[4] = c->last_ms[5] = 0;
+	if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->last_ms[0] = ms;
+	if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->last_ms[1] = ms;
+	if (c->split_used && cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]) == cudaSuccess) c->last_ms[4] = ms;
+	if (c->marginal_used && cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]) == cudaSuccess) c->last_ms[5] = ms;
+}
+
 extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_query_t *q, int64_t row_beg, int64_t n_rows,
                              unsigned flags, b200_scan_out_t *out)
 {
@@ -836,6 +849,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		ok = CU_OK(launch_walk(P, Cg, emit ? WALK_MODE_EMIT : WALK_MODE_COUNT, (n_track + WALK_NT * Cg - 1) / (WALK_NT * Cg), n_gen, c->st));
 		c->launches += (n_gen + 32767) / 32768;
 	}
+	c->split_used = n_split > 0; c->marginal_used = n_split > 0 && G > 1;
 	if (ok && n_split > 0) {
 		const int cap = pb->p1_cap;
 		if (!c->qcol.reserve((size_t)pb->n_blk * cap * sizeof(int32_t)) || !c->qrow.reserve((size_t)pb->n_blk * cap * sizeof(uint16_t)) ||
@@ -846,7 +860,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
 		A.m = pb->m; A.shift = pb->shift; A.cap = cap;
 		A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err;
-		ok = CU_OK(launch_plane1_select(A, n_split, c->st));
+		ok = CU_OK(cudaEventRecord(c->ev[8], c->st)) && CU_OK(launch_plane1_select(A, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[9], c->st));
 		// phase 2: walk those haplotypes through plane 0 up to their row and add code 3 (other-ALT) or 2 (missing) there
 		WalkParams B = P;
 		B.track = (const int32_t*)c->qcol.p; B.qrow = (const uint16_t*)c->qrow.p; B.track_stride = cap;
@@ -860,7 +874,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			M.img = pb->d_img; M.rowoff = pb->d_rowoff; M.n1 = pb->d_n1; M.blkoff = pb->d_blkoff; M.rows_in_blk = pb->d_rows_in_blk;
 			M.blk_list = d_split_list; M.tgrp = q->d_tgrp; M.n0g = (int32_t*)c->n0g.p; M.m = pb->m; M.shift = pb->shift; M.n_vec = G - 1;
 			M.blk_row0 = P.blk_row0; M.row_lo = row_beg; M.row_hi = row_beg + n_rows;
-			ok = ok && CU_OK(launch_marginal(M, n_split, c->st));
+			ok = ok && CU_OK(cudaEventRecord(c->ev[10], c->st)) && CU_OK(launch_marginal(M, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[11], c->st));
 			++c->launches;
 			sp.n0g = (const int32_t*)c->n0g.p; sp.n_vec = G - 1;
 		}
@@ -905,9 +919,8 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	if (err) { set_err("device error flags 0x%x during scan", err); return -1; }
 	out->totals[0] = (int64_t)dtot[0]; out->totals[1] = (int64_t)dtot[1]; out->totals[2] = (int64_t)dtot[2];
 	out->totals[3] = host_flt ? (int64_t)tot[3] : (int64_t)dtot[3];
+	read_scan_timings(c);
 	float ms;
-	if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->last_ms[0] = ms;
-	if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->last_ms[1] = ms;
 	if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->last_ms[3] = ms;
 	return n_rows;
 }
@@ -924,9 +937,7 @@ extern "C" int b200_scan_collect(b200_ctx_t *c, int64_t totals[4])
 	if (!ok) return -1;
 	if (err) { set_err("device error flags 0x%x during scan", err); return -1; }
 	if (totals) for (int i = 0; i < 4; ++i) totals[i] = (int64_t)dtot[i];
-	float ms;
-	if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->last_ms[0] = ms;
-	if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->last_ms[1] = ms;
+	read_scan_timings(c);
 	return 0;
 }
 

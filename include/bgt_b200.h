@@ -97,7 +97,9 @@ int64_t b200_scan(b200_ctx_t *ctx, const b200_pbf_t *pb, const b200_query_t *q, 
 int     b200_scan_collect(b200_ctx_t *ctx, int64_t totals[4]);
 
 /* device time (ms) of the kernels of the last b200_scan on this context, measured with CUDA events on the
- * context's stream: which = 0 rank-walk kernel, 1 whole scan (all kernels), 2 H2D of the last load, 3 D2H */
+ * context's stream: which = 0 all decode phases (plane-1 select + rank walk + group marginals), 1 whole scan (all
+ * kernels), 2 H2D of the last load, 3 D2H of the results, 4 plane1_select_kernel, 5 pbwt_marginal_kernel.
+ * The rank-walk kernel alone is [0] - [4] - [5]. */
 double  b200_last_ms(b200_ctx_t *ctx, int which);
 int64_t b200_kernel_launches(b200_ctx_t *ctx);      /* kernels launched by this context so far */
 /* user timing marks on the context's stream (slot 0..3): record now / device ms between two recorded marks (syncs) */
