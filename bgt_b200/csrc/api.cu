@@ -109,6 +109,12 @@ struct b200_pbf_s {
 	uint64_t *d_p1_rowoff = nullptr;
 	uint32_t *d_p1_n1 = nullptr;
 	uint16_t *d_p1_realrow = nullptr;
+	int *d_grp_tile_beg = nullptr;       // [n_blk][groups+1] first tile of every COMP_K-row group
+	// composite plane-0 maps of the row groups (compose.cu), built lazily by the first split scan and cached
+	mutable bool comp_ready = false;
+	mutable uint32_t *d_comp_start = nullptr;
+	mutable int32_t *d_comp_delta = nullptr;
+	mutable int *d_comp_n = nullptr;
 	int *d_p1_rows_in_blk = nullptr;
 	int64_t p1_rows = 0;
 };
@@ -272,6 +278,10 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_p1_rowoff);
 	pool_free(pb->ctx, pb->d_p1_n1);
 	pool_free(pb->ctx, pb->d_p1_realrow);
+	pool_free(pb->ctx, pb->d_grp_tile_beg);
+	pool_free(pb->ctx, pb->d_comp_start);
+	pool_free(pb->ctx, pb->d_comp_delta);
+	pool_free(pb->ctx, pb->d_comp_n);
 	pool_free(pb->ctx, pb->d_p1_rows_in_blk);
 }
 
@@ -299,7 +309,7 @@ static void plan_tiles_of(int n_blk, int BS, const std::vector<uint64_t> &rowoff
 		while (r < rows) {
 			if (ro[r + 1] - ro[r] > (uint64_t)RAW_CAP) { tiles.push_back(make_int2(r, (int)(1u | 0x80000000u))); ++r; continue; }
 			int e = r + 1;
-			while (e < rows && e - r < T_MAX && ro[e + 1] - ro[r] <= (uint64_t)RAW_CAP) ++e;
+			while (e < rows && e - r < T_MAX && (e % COMP_K) != 0 && ro[e + 1] - ro[r] <= (uint64_t)RAW_CAP) ++e;
 			tiles.push_back(make_int2(r, e - r));
 			r = e;
 		}
@@ -405,6 +415,17 @@ static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain)
 	std::vector<int> btb;
 	plan_tiles(pb, tiles, btb);
 	const size_t n_tiles = tiles.size();
+	const int n_grp = (BS + COMP_K - 1) / COMP_K;
+	std::vector<int> gtb((size_t)nb * (n_grp + 1));
+	for (int b = 0; b < nb; ++b) { // first tile of every row group (tiles never cross a multiple of COMP_K rows)
+		int t = btb[b];
+		for (int g = 0; g <= n_grp; ++g) {
+			while (t < btb[b + 1] && tiles[t].x < g * COMP_K) ++t;
+			gtb[(size_t)b * (n_grp + 1) + g] = t;
+		}
+	}
+	if (!pool_malloc(c, (void**)&pb->d_grp_tile_beg, gtb.size() * sizeof(int) + 16) ||
+	    !CU_OK(cudaMemcpyAsync(pb->d_grp_tile_beg, gtb.data(), gtb.size() * sizeof(int), cudaMemcpyHostToDevice, c->st))) return false;
 	bool ok = pool_malloc(c, (void**)&pb->d_rowoff, sizeof(uint64_t) * (size_t)nb * (BS + 1) + 8) &&
 	          pool_malloc(c, (void**)&pb->d_blkoff, sizeof(uint64_t) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_rows_in_blk, sizeof(int) * (nb + 1)) &&
@@ -862,7 +883,30 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err;
 		ok = CU_OK(cudaEventRecord(c->ev[8], c->st)) && CU_OK(launch_plane1_select(A, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[9], c->st));
 		// phase 2: walk those haplotypes through plane 0 up to their row and add code 3 (other-ALT) or 2 (missing) there
+		if (!pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) { // composite maps of the row groups: once per resident PBF
+			const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
+			std::vector<int> all;
+			for (int b = 0; b < pb->n_blk; ++b) if (pb->blk_sparse[b]) all.push_back(b);
+			int *d_all = nullptr;
+			const size_t slots = (size_t)pb->n_blk * n_grp;
+			bool okc = pool_malloc(c, (void**)&pb->d_comp_start, slots * COMP_CAP * sizeof(uint32_t)) &&
+			           pool_malloc(c, (void**)&pb->d_comp_delta, slots * COMP_CAP * sizeof(int32_t)) &&
+			           pool_malloc(c, (void**)&pb->d_comp_n, slots * sizeof(int) + 16) && pool_malloc(c, (void**)&d_all, all.size() * sizeof(int) + 16);
+			okc = okc && CU_OK(cudaMemsetAsync(pb->d_comp_n, 0, slots * sizeof(int), c->st)) &&
+			      CU_OK(cudaMemcpyAsync(d_all, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+			ComposeParams K;
+			K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rows_in_blk = pb->d_rows_in_blk; K.blk_list = d_all;
+			K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
+			okc = okc && CU_OK(launch_compose(K, (int)all.size(), c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+			pool_free(c, d_all);
+			if (!okc) return -1;
+			pb->comp_ready = true;
+			++c->launches;
+		}
 		WalkParams B = P;
+		if (pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) {
+			B.comp_start = pb->d_comp_start; B.comp_delta = pb->d_comp_delta; B.comp_n = pb->d_comp_n; B.grp_tile_beg = pb->d_grp_tile_beg;
+		}
 		B.track = (const int32_t*)c->qcol.p; B.qrow = (const uint16_t*)c->qrow.p; B.track_stride = cap;
 		B.n_track_blk = (const int*)c->qcount.p; B.n_track = cap; B.blk_list = d_split_list;
 		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : 8;

@@ -422,7 +422,36 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 				r1[c] = (uint32_t)P.rank0[((size_t)blk * 2 + 1) * m + col[c]];
 			}
 		}
-		const int t_beg = P.blk_tile_beg[blk], t_end = P.blk_tile_beg[blk + 1];
+		int t_beg = P.blk_tile_beg[blk];
+		const int t_end = P.blk_tile_beg[blk + 1];
+		if (QUERY && P.comp_n) {
+			// Row groups that lie entirely in front of this CTA's first target row are crossed with ONE look-up per
+			// entry in the group's composite map (compose.cu), staged by TMA straight into the run-table buffers.
+			const int n_grp = (BS + COMP_K - 1) / COMP_K;
+			const int g_mixed = (int)P.qrow[(size_t)blk_own * P.track_stride + slice_base] / COMP_K;
+			int g = 0;
+			for (; g < g_mixed; ++g) {
+				const size_t slot = (size_t)blk * n_grp + g;
+				const int np = P.comp_n[slot];
+				if (np == 0) break;                                 // not available: row by row from here on
+				if (tid == 0) {
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					mbar_expect_tx(S.mbar, (uint32_t)np * 8u);
+					tma_bulk_g2s(S.ts, P.comp_start + slot * COMP_CAP, (uint32_t)np * 4u, S.mbar);
+					tma_bulk_g2s(S.td, P.comp_delta + slot * COMP_CAP, (uint32_t)np * 4u, S.mbar);
+				}
+				{
+					uint32_t spins = 0;
+					while (!mbar_try_wait(S.mbar, parity))
+						if (++spins > (1u << 26)) { atomicOr(P.err, 8); __trap(); }
+					parity ^= 1;
+				}
+				uint32_t unused;
+				lookup_runs<C>(r0, ts_saddr, (uint32_t)np, 0u, unused);
+				__syncthreads();
+			}
+			t_beg = P.grp_tile_beg[(size_t)blk * (n_grp + 1) + g];
+		}
 
 		// thread 0: start the TMA bulk copy of tile t if it is an ordinary (not oversized) tile that will be used
 		auto prefetch = [&](int t) {

@@ -20,6 +20,8 @@ constexpr int WALK_NW   = WALK_NT / 32;
 constexpr int RAW_CAP   = 8192;         // RLE bytes staged per tile
 constexpr int RAW_BYTES = RAW_CAP + 32; // + 16-byte alignment slack at both ends
 constexpr int T_MAX     = 64;           // rows per tile
+constexpr int COMP_K    = 32;           // rows per composite map (compose.cu); tiles never cross a multiple of it
+constexpr int COMP_CAP  = 4096;         // pieces per composite map (<= RAW_BYTES: staged in the run-table buffers)
 constexpr int B200_MAX_GROUPS_K = 32;   // BGT_MAX_GROUPS, bgt.h:13
 
 struct RowMeta { uint32_t off[2], len[2], n1[2]; };
@@ -36,6 +38,10 @@ struct WalkParams {
 	int32_t        *cnt_raw;   // [rows out][G][3] = #ALT, #missing, #other-ALT per group (zero-initialised, accumulated)
 	uint32_t       *hap[2];    // [rows out][words] bit planes (EMIT only)
 	const uint16_t *qrow;      // QUERY only: target row (within the block) of every tracked entry, ascending per block
+	const uint32_t *comp_start; // QUERY only: composite maps (compose.cu) [blocks][groups][COMP_CAP], or nullptr
+	const int32_t  *comp_delta;
+	const int      *comp_n;     // [blocks][groups] pieces (padded to 4), 0 = not available
+	const int      *grp_tile_beg; // [blocks][groups+1] first tile of every row group
 	const int      *blk_list;  // resident-block indices handled by this launch (nullptr: blk_first + blockIdx.y)
 	const int      *n_track_blk; // per-block number of tracked columns (nullptr: n_track)
 	long long       track_stride; // > 0: track holds one list per resident block, this many entries apart
@@ -53,6 +59,21 @@ size_t walk_smem_bytes(int C, int G);
 // C = tracked columns per thread (1,2,4,8); mode = WALK_COUNT / WALK_EMIT / WALK_CHAIN / WALK_QUERY (pbwt_kernels.cu)
 enum { WALK_MODE_COUNT = 0, WALK_MODE_EMIT = 1, WALK_MODE_CHAIN = 2, WALK_MODE_QUERY = 3 };
 cudaError_t launch_walk(const WalkParams &P, int C, int mode, int slices, int n_blk, cudaStream_t st);
+
+// composite maps of row groups (compose.cu)
+struct ComposeParams {
+	const uint8_t  *img;
+	const uint64_t *rowoff;
+	const uint32_t *n1;
+	const int      *rows_in_blk;
+	const int      *blk_list;
+	int m, shift;
+	uint32_t *comp_start;
+	int32_t  *comp_delta;
+	int      *comp_n;
+};
+size_t compose_smem_bytes();
+cudaError_t launch_compose(const ComposeParams &P, int n_blk, cudaStream_t st);
 
 // plane-1 select (plane1.cu): per block, the (column, row) pairs that carry a plane-1 bit, in row order
 struct SelectParams {

@@ -284,7 +284,7 @@ def test_split_scan_equals_general_and_oracle(b200, ctx, oracle, case):
     want = oracle.Pbf(pbf).scan(0, n, flt="AC>0")
     pb = b200.Pbf.from_bytes(ctx, pbf)
     q = b200.Query(ctx, pb, flt="AC>0")
-    for kw in (dict(), dict(no_split=True), dict(cols_per_thread=1), dict(cols_per_thread=8)):
+    for kw in (dict(), dict(no_split=True), dict(no_compose=True), dict(cols_per_thread=1), dict(cols_per_thread=8)):
         got = b200.scan(ctx, pb, q, 0, n, **kw)
         assert (got["counts"] == want["counts"]).all(), (case, kw)
         assert (got["passed"] == want["passed"]).all()
