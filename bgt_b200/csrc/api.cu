@@ -115,6 +115,9 @@ struct b200_pbf_s {
 	mutable uint32_t *d_comp_start = nullptr;
 	mutable int32_t *d_comp_delta = nullptr;
 	mutable int *d_comp_n = nullptr;
+	mutable uint32_t *d_vcomp_start = nullptr;   // inverse composites of the plane-1 view rows (plane1_select_kernel)
+	mutable int32_t *d_vcomp_delta = nullptr;
+	mutable int *d_vcomp_n = nullptr;
 	int *d_p1_rows_in_blk = nullptr;
 	int64_t p1_rows = 0;
 };
@@ -282,6 +285,9 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_comp_start);
 	pool_free(pb->ctx, pb->d_comp_delta);
 	pool_free(pb->ctx, pb->d_comp_n);
+	pool_free(pb->ctx, pb->d_vcomp_start);
+	pool_free(pb->ctx, pb->d_vcomp_delta);
+	pool_free(pb->ctx, pb->d_vcomp_n);
 	pool_free(pb->ctx, pb->d_p1_rows_in_blk);
 }
 
@@ -875,14 +881,6 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		const int cap = pb->p1_cap;
 		if (!c->qcol.reserve((size_t)pb->n_blk * cap * sizeof(int32_t)) || !c->qrow.reserve((size_t)pb->n_blk * cap * sizeof(uint16_t)) ||
 		    !c->qcount.reserve((size_t)pb->n_blk * sizeof(int))) return -1;
-		// phase 1 (plane1.cu): the (column, row) pairs that carry a plane-1 bit, per block, in row order
-		SelectParams A;
-		A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow;
-		A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
-		A.m = pb->m; A.shift = pb->shift; A.cap = cap;
-		A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err;
-		ok = CU_OK(cudaEventRecord(c->ev[8], c->st)) && CU_OK(launch_plane1_select(A, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[9], c->st));
-		// phase 2: walk those haplotypes through plane 0 up to their row and add code 3 (other-ALT) or 2 (missing) there
 		if (!pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) { // composite maps of the row groups: once per resident PBF
 			const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
 			std::vector<int> all;
@@ -897,19 +895,42 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			ComposeParams K;
 			K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rows_in_blk = pb->d_rows_in_blk; K.blk_list = d_all;
 			K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
-			okc = okc && CU_OK(launch_compose(K, (int)all.size(), c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+			K.n_grp = n_grp; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0;
+			okc = okc && CU_OK(launch_compose(K, (int)all.size(), c->st));
+			// ... and the inverse composites of the plane-1 view rows for the select kernel
+			const size_t vslots = (size_t)pb->n_blk * SELECT_GROUPS;
+			okc = okc && pool_malloc(c, (void**)&pb->d_vcomp_start, vslots * SELECT_COMP_CAP * sizeof(uint32_t)) &&
+			      pool_malloc(c, (void**)&pb->d_vcomp_delta, vslots * SELECT_COMP_CAP * sizeof(int32_t)) &&
+			      pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16) &&
+			      CU_OK(cudaMemsetAsync(pb->d_vcomp_n, 0, vslots * sizeof(int), c->st));
+			ComposeParams V = K;
+			V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
+			V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
+			V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 1; V.inverse = 1;
+			okc = okc && CU_OK(launch_compose(V, (int)all.size(), c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+			++c->launches;
 			pool_free(c, d_all);
 			if (!okc) return -1;
 			pb->comp_ready = true;
 			++c->launches;
 		}
+		// phase 1 (plane1.cu): the (column, row) pairs that carry a plane-1 bit, per block, in row order
+		SelectParams A;
+		A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow;
+		A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
+		A.m = pb->m; A.shift = pb->shift; A.cap = cap;
+		const bool use_comp = pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE);
+		A.vcomp_start = use_comp ? pb->d_vcomp_start : nullptr; A.vcomp_delta = use_comp ? pb->d_vcomp_delta : nullptr; A.vcomp_n = use_comp ? pb->d_vcomp_n : nullptr;
+		A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err;
+		ok = CU_OK(cudaEventRecord(c->ev[8], c->st)) && CU_OK(launch_plane1_select(A, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[9], c->st));
+		// phase 2: walk those haplotypes through plane 0 up to their row and add code 3 (other-ALT) or 2 (missing) there
 		WalkParams B = P;
 		if (pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) {
 			B.comp_start = pb->d_comp_start; B.comp_delta = pb->d_comp_delta; B.comp_n = pb->d_comp_n; B.grp_tile_beg = pb->d_grp_tile_beg;
 		}
 		B.track = (const int32_t*)c->qcol.p; B.qrow = (const uint16_t*)c->qrow.p; B.track_stride = cap;
 		B.n_track_blk = (const int*)c->qcount.p; B.n_track = cap; B.blk_list = d_split_list;
-		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : 8;
+		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : (use_comp ? 2 : 8);
 		ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_QUERY, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
 		c->launches += 2;
 		if (G > 1) { // per-group plane-0 marginals for the first G-1 groups (the last one is the remainder)

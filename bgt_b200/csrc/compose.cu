@@ -9,7 +9,9 @@
 //
 // One CTA per (checkpoint block, row group); groups are independent of each other and of the query, so the tables
 // are built once per resident PBF (lazily, at the first scan that wants them) and cached with it.
-//   out: comp_start[blk][g][COMP_CAP] (piece starts, ascending, padded with 0xffffffff to a multiple of 4),
+// The same kernel also builds INVERSE composites (output coordinates -> input coordinates, rows composed in reverse)
+// of the plane-1 view rows for plane1_select_kernel: P.inverse = 1, records of the view (rle at +9, n1 of plane 1).
+//   out: comp_start[blk][g][cap] (piece starts, ascending, padded with 0xffffffff to a multiple of 4),
 //        comp_delta[blk][g][COMP_CAP], comp_n[blk][g] = number of pieces (padded), 0 = not available (too many
 //        pieces or runs for the staging buffers -> the walk falls back to row-by-row for that group).
 #include <cuda_runtime.h>
@@ -41,13 +43,13 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	uint32_t *A_c = A_s + COMP_CAP + 1;                    // [COMP_CAP] piece positions in current coordinates
 	uint32_t *B_s = A_c + COMP_CAP;                        // second list
 	uint32_t *B_c = B_s + COMP_CAP + 1;
-	__shared__ int row_beg[COMP_K + 1];                    // first run of every row in runs_s (row_beg[j+1]-row_beg[j] = runs; 0 runs = identity)
+	__shared__ int row_beg[COMP_K + 1], row_nz[COMP_K];                    // first run of every row in runs_s (row_beg[j+1]-row_beg[j] = runs; 0 runs = identity)
 	__shared__ int warp_tot[CP_NW];
 	__shared__ int s_fail, s_n;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int BS = 1 << P.shift;
-	const int n_grp = (BS + COMP_K - 1) / COMP_K;
+	const int n_grp = P.n_grp;
 	const int blk = P.blk_list[blockIdx.x / n_grp], g = blockIdx.x % n_grp;
 	const uint32_t m = (uint32_t)P.m;
 	const uint64_t *roff = P.rowoff + (size_t)blk * (BS + 1);
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	int nrow = P.rows_in_blk[blk] - r_lo;
 	if (nrow > COMP_K) nrow = COMP_K;
 	const size_t slot = ((size_t)blk * n_grp + g);
+	const int cap = P.cap;
 	if (nrow < COMP_K) { if (tid == 0) P.comp_n[slot] = 0; return; }   // partial last group: never crossed as a whole
 	if (tid == 0) { s_fail = 0; s_n = 0; }
 	__syncthreads();
@@ -63,12 +66,13 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	for (int pass = 0; pass < 2; ++pass) {
 		for (int j = warp; j < nrow; j += CP_NW) {
 			const uint8_t *rec = P.img + roff[r_lo + j];
-			const uint32_t l = cp_ld_u32_unaligned(rec + 1);
-			const uint8_t *rle = rec + 5;
-			const uint32_t n1 = P.n1[((size_t)blk * BS + r_lo + j) * 2];
+			const uint32_t l = cp_ld_u32_unaligned(rec + P.rle_off - 4);
+			const uint8_t *rle = rec + P.rle_off;
+			const uint32_t n1 = P.n1[((size_t)blk * BS + r_lo + j) * 2 + P.n1_plane];
 			const bool triv = (n1 == 0 || n1 == m);
-			uint32_t tot = 0, ones = 0, nrun = 0, prev_bit = 2;
+			uint32_t tot = 0, ones = 0, nrun = 0, nzr = 0, prev_bit = 2;
 			const int base_out = pass ? row_beg[j] : 0;
+			const int nz_row = pass ? row_nz[j] : 0;
 			if (!triv) {
 				for (uint32_t base = 0; base < l; base += 32) {
 					const uint32_t i = base + lane;
@@ -89,17 +93,26 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 					if (below) pb = (bitm >> (31 - __clz(below))) & 1u;
 					const bool is_start = L > 0 && pb != b;
 					const uint32_t sm_ = __ballot_sync(0xffffffffu, is_start);
+					const uint32_t zm_ = sm_ & ~bitm;                      // run starts of 0-runs
 					if (pass && is_start) {
-						const int k = base_out + (int)nrun + __popc(sm_ & ((1u << lane) - 1u));
-						if (k < CP_RUNS) { runs_s[k] = start; runs_d[k] = b ? (int32_t)((m - n1) - (start - ones_before)) : -(int32_t)ones_before; }
+						const int32_t delta = b ? (int32_t)((m - n1) - (start - ones_before)) : -(int32_t)ones_before;
+						if (!P.inverse) {
+							const int k = base_out + (int)nrun + __popc(sm_ & ((1u << lane) - 1u));
+							if (k < CP_RUNS) { runs_s[k] = start; runs_d[k] = delta; }
+						} else { // inverse map: runs ordered by where they land (0-runs, then 1-runs), translated back
+							const uint32_t lt = (1u << lane) - 1u;
+							const int k = b ? base_out + nz_row + (int)(nrun - nzr) + __popc(sm_ & bitm & lt) : base_out + (int)nzr + __popc(zm_ & lt);
+							if (k < CP_RUNS) { runs_s[k] = start + (uint32_t)delta; runs_d[k] = -delta; }
+						}
 					}
 					nrun += __popc(sm_);
+					nzr += __popc(zm_);
 					if (valid) prev_bit = (bitm >> (31 - __clz(valid))) & 1u;
 					tot += __shfl_sync(0xffffffffu, x, 31);
 					ones += __shfl_sync(0xffffffffu, y, 31);
 				}
 			}
-			if (!pass && lane == 0) row_beg[j + 1] = (int)nrun;   // counts for now
+			if (!pass && lane == 0) { row_beg[j + 1] = (int)nrun; row_nz[j] = (int)nzr; }   // counts for now
 		}
 		__syncthreads();
 		if (!pass) {
@@ -119,7 +132,8 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	int n = 1;
 	if (tid == 0) { Ls[0] = 0; Lc[0] = 0; Ls[1] = m; }
 	__syncthreads();
-	for (int j = 0; j < nrow; ++j) {
+	for (int jj = 0; jj < nrow; ++jj) {
+		const int j = P.inverse ? nrow - 1 - jj : jj;           // inverse composite: undo the last row first
 		const int rb = row_beg[j], nr = row_beg[j + 1] - rb;
 		if (nr == 0) continue;                                  // constant row: identity (pbwt.c:75-77)
 		const uint32_t *rs = runs_s + rb;
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 		__syncthreads();
 		int off = x - mine;
 		for (int w = 0; w < warp; ++w) off += warp_tot[w];
-		if (tid == CP_NT - 1) { s_n = off + mine; if (off + mine > COMP_CAP - 4) s_fail = 1; }
+		if (tid == CP_NT - 1) { s_n = off + mine; if (off + mine > cap - 4) s_fail = 1; }
 		__syncthreads();
 		if (s_fail) { if (tid == 0) P.comp_n[slot] = 0; return; }
 		for (int p = p0; p < p1; ++p) {
@@ -160,8 +174,8 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	}
 	// ---- write out, padded to a multiple of 4 entries (16-byte TMA granularity)
 	const int npad = (n + 3) & ~3;
-	uint32_t *os = P.comp_start + slot * COMP_CAP;
-	int32_t *od = P.comp_delta + slot * COMP_CAP;
+	uint32_t *os = P.comp_start + slot * cap;
+	int32_t *od = P.comp_delta + slot * cap;
 	for (int p = tid; p < npad; p += CP_NT) {
 		os[p] = p < n ? Ls[p] : 0xffffffffu;
 		od[p] = p < n ? (int32_t)(Lc[p] - Ls[p]) : 0;
@@ -174,7 +188,7 @@ size_t compose_smem_bytes() { return sizeof(uint32_t) * (2 * CP_RUNS + 4 * COMP_
 cudaError_t launch_compose(const ComposeParams &P, int n_blk, cudaStream_t st)
 {
 	if (n_blk <= 0) return cudaSuccess;
-	const int BS = 1 << P.shift, n_grp = (BS + COMP_K - 1) / COMP_K;
+	const int n_grp = P.n_grp;
 	const size_t smem = compose_smem_bytes();
 	cudaError_t e = cudaFuncSetAttribute(pbwt_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;

@@ -68,6 +68,11 @@ struct ComposeParams {
 	const int      *rows_in_blk;
 	const int      *blk_list;
 	int m, shift;
+	int n_grp;        // row groups per block (slots per block in the output arrays)
+	int cap;          // pieces per slot (<= COMP_CAP)
+	int rle_off;      // offset of the plane's RLE inside a row record: 5 = plane 0 of a .pbf row, 9 = plane 1 of a plane-1 view row
+	int n1_plane;     // which entry of n1[row][2] belongs to that plane
+	int inverse;      // 1: inverse composite (coordinates behind the group -> in front of it)
 	uint32_t *comp_start;
 	int32_t  *comp_delta;
 	int      *comp_n;
@@ -86,12 +91,16 @@ struct SelectParams {
 	const uint64_t *blkoff;
 	const int      *blk_list;
 	int m, shift, cap;
+	const uint32_t *vcomp_start;  // inverse composites of the view rows (compose.cu, inverse = 1) [blocks][SELECT_GROUPS][SELECT_COMP_CAP], or nullptr
+	const int32_t  *vcomp_delta;
+	const int      *vcomp_n;      // [blocks][SELECT_GROUPS]
 	int32_t  *qcol;               // out [blocks][cap]
 	uint16_t *qrow;               // out [blocks][cap]
 	int      *qcount;             // out [blocks]
 	int      *err;
 };
 constexpr int SELECT_MAX_ROWS = 4096, SELECT_MAX_BYTES = 48 * 1024;
+constexpr int SELECT_GROUPS = SELECT_MAX_ROWS / COMP_K, SELECT_COMP_CAP = 1024, SELECT_COMP_SMEM = 8192; // pieces of all groups of a block held in smem
 cudaError_t launch_plane1_select(const SelectParams &P, int n_blk, cudaStream_t st);
 
 // per-group plane-0 marginals (marginal.cu): n0g[row][g] = ones of the plane-0 row among the columns of group g

@@ -61,7 +61,10 @@ __global__ void __launch_bounds__(1024) plane1_select_kernel(const SelectParams 
 	uint32_t *roff = prefix + SELECT_MAX_ROWS + 1;                  // [SELECT_MAX_ROWS + 1] record offsets inside raw
 	uint32_t *n1v = roff + SELECT_MAX_ROWS + 1;                     // [SELECT_MAX_ROWS]
 	uint8_t *raw = (uint8_t*)(n1v + SELECT_MAX_ROWS);               // [SELECT_MAX_BYTES]
+	uint32_t *cs = (uint32_t*)(raw + SELECT_MAX_BYTES);             // [SELECT_COMP_SMEM] inverse composites of the block's row groups, packed
+	int32_t *cd = (int32_t*)(cs + SELECT_COMP_SMEM);                // [SELECT_COMP_SMEM]
 	__shared__ uint32_t warp_tot[32];
+	__shared__ int cg_off[SELECT_GROUPS + 1];                       // first piece of group g in cs/cd; cg_off[g+1]-cg_off[g] = 0: not available
 
 	const int blk = P.blk_list[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int BS = 1 << P.shift;
@@ -90,6 +93,24 @@ __global__ void __launch_bounds__(1024) plane1_select_kernel(const SelectParams 
 		for (int j = 0; j < 4; ++j) { const int v = tid * 4 + j; if (v <= nv) prefix[v] = before; before += x[j]; }
 	}
 	__syncthreads();
+	// inverse composite maps of the full COMP_K-row groups of the view (compose.cu), as many as fit
+	const int n_full = nv / COMP_K;
+	if (tid == 0) {
+		int acc = 0;
+		for (int g = 0; g < SELECT_GROUPS; ++g) {
+			cg_off[g] = acc;
+			const int np = (P.vcomp_n && g < n_full) ? P.vcomp_n[(size_t)blk * SELECT_GROUPS + g] : 0;
+			if (np > 0 && acc + np <= SELECT_COMP_SMEM) acc += np;
+		}
+		cg_off[SELECT_GROUPS] = acc;
+	}
+	__syncthreads();
+	for (int g = 0; g < n_full; ++g) {
+		const int o = cg_off[g], np = cg_off[g + 1] - o;
+		const size_t slot = ((size_t)blk * SELECT_GROUPS + g) * SELECT_COMP_CAP;
+		for (int i = tid; i < np; i += 1024) { cs[o + i] = P.vcomp_start[slot + i]; cd[o + i] = P.vcomp_delta[slot + i]; }
+	}
+	__syncthreads();
 	const uint32_t Q = prefix[nv];
 	if (Q > (uint32_t)P.cap) { if (tid == 0) { atomicOr(P.err, 32); P.qcount[blk] = 0; } return; }
 	const uint8_t *S1 = P.img + P.blkoff[blk] + 1 + 4 * (size_t)P.m;   // plane-1 snapshot of the block (pbwt.c:298-300)
@@ -100,8 +121,19 @@ __global__ void __launch_bounds__(1024) plane1_select_kernel(const SelectParams 
 		const int v = lo;
 		const uint8_t *rec = raw + roff[v];
 		uint32_t r = rank_of_one(rec + 9, (uint32_t)(roff[v + 1] - roff[v]) - 9u, q - prefix[v]);
-		for (int u = v - 1; u >= 0 && r < m; --u)
-			r = undo_row(raw + roff[u] + 9, (uint32_t)(roff[u + 1] - roff[u]) - 9u, m - n1v[u], r);
+		for (int u = v - 1; u >= 0 && r < m;) {
+			const int g = u / COMP_K;
+			const int o = cg_off[g], np = cg_off[g + 1] - o;
+			if ((u + 1) % COMP_K == 0 && np > 0) {          // a whole group lies behind: one look-up in its inverse composite
+				int lo2 = 0;
+				for (int len = np; len > 1;) { const int half = len >> 1; lo2 += cs[o + lo2 + half] <= r ? half : 0; len -= half; }
+				r += (uint32_t)cd[o + lo2];
+				u -= COMP_K;
+			} else {
+				r = undo_row(raw + roff[u] + 9, (uint32_t)(roff[u + 1] - roff[u]) - 9u, m - n1v[u], r);
+				--u;
+			}
+		}
 		const uint32_t col = r < m ? p1_ld_u32_unaligned(S1 + 4 * (size_t)r) : 0xffffffffu;
 		if (col >= m) { atomicOr(P.err, 64); continue; }
 		P.qcol[(size_t)blk * P.cap + q] = (int32_t)col;
@@ -113,7 +145,7 @@ __global__ void __launch_bounds__(1024) plane1_select_kernel(const SelectParams 
 cudaError_t launch_plane1_select(const SelectParams &P, int n_blk, cudaStream_t st)
 {
 	if (n_blk <= 0) return cudaSuccess;
-	const size_t smem = sizeof(uint32_t) * (3 * SELECT_MAX_ROWS + 2) + SELECT_MAX_BYTES;
+	const size_t smem = sizeof(uint32_t) * (3 * SELECT_MAX_ROWS + 2) + SELECT_MAX_BYTES + 8 * SELECT_COMP_SMEM;
 	cudaError_t e = cudaFuncSetAttribute(plane1_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	plane1_select_kernel<<<n_blk, 1024, smem, st>>>(P);
