@@ -6,6 +6,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <time.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -84,6 +85,8 @@ struct P1Block { // rows of one checkpoint block whose plane 1 is not empty, re-
 struct b200_pbf_s {
 	b200_ctx_t *ctx = nullptr;
 	std::vector<P1Block> p1blocks;
+	std::vector<uint64_t> h_idx;      // the file's block index (pbwt.c:268-276)
+	uint64_t ioff = 0;                // file offset of the 'I' record
 	int m = 0, g = 0, shift = 0, BS = 0;
 	int64_t n = 0;               // rows in the file
 	int blk0 = 0, n_blk = 0;     // resident checkpoint blocks [blk0, blk0+n_blk)
@@ -119,6 +122,7 @@ struct b200_pbf_s {
 	mutable int32_t *d_vcomp_delta = nullptr;
 	mutable int *d_vcomp_n = nullptr;
 	int *d_p1_rows_in_blk = nullptr;
+	long long *d_p1_vbase = nullptr;     // [n_blk+1] first view row of every block
 	int64_t p1_rows = 0;
 };
 
@@ -289,6 +293,7 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_vcomp_delta);
 	pool_free(pb->ctx, pb->d_vcomp_n);
 	pool_free(pb->ctx, pb->d_p1_rows_in_blk);
+	pool_free(pb->ctx, pb->d_p1_vbase);
 }
 
 extern "C" void b200_pbf_close(b200_pbf_t *pb)
@@ -375,38 +380,39 @@ static bool build_plane1_view(b200_pbf_t *pb)
 		pb->p1_rows_in_blk[b] = (int)o.n1s.size();
 	}
 	std::vector<P1Block> &rec_blocks = pb->p1blocks;
-	std::vector<uint64_t> rowoff((size_t)nb * (BS + 1), 0);
-	std::vector<uint32_t> n1((size_t)nb * BS * 2, 0);
-	std::vector<uint16_t> realrow((size_t)nb * BS, 0);
-	std::vector<uint8_t> img;
+	std::vector<long long> vbase(nb + 1, 0);
 	size_t total = 0;
-	for (int b = 0; b < nb; ++b) total += ((rec_blocks[b].rec.size() + 15) & ~(size_t)15);
+	for (int b = 0; b < nb; ++b) { vbase[b + 1] = vbase[b] + (long long)rec_blocks[b].n1s.size(); total += ((rec_blocks[b].rec.size() + 15) & ~(size_t)15); }
+	const size_t nrows = (size_t)vbase[nb];
+	std::vector<uint64_t> rowoff(nrows + nb + 1, 0);
+	std::vector<uint32_t> n1(nrows + 1, 0);
+	std::vector<uint16_t> realrow(nrows + 1, 0);
+	std::vector<uint8_t> img;
 	img.reserve(total + 64);
-	pb->p1_rows = 0;
+	pb->p1_rows = (int64_t)nrows;
 	for (int b = 0; b < nb; ++b) {
+		const P1Block &o = rec_blocks[b];
 		uint64_t pos = img.size();
-		uint64_t *ro = rowoff.data() + (size_t)b * (BS + 1);
-		for (size_t r = 0; r < rec_blocks[b].n1s.size(); ++r) {
-			ro[r] = pos; pos += rec_blocks[b].lens[r];
-			n1[((size_t)b * BS + r) * 2 + 1] = rec_blocks[b].n1s[r];
-			realrow[(size_t)b * BS + r] = (uint16_t)rec_blocks[b].rrow[r];
+		uint64_t *ro = rowoff.data() + vbase[b] + b;
+		for (size_t r = 0; r < o.n1s.size(); ++r) {
+			ro[r] = pos; pos += o.lens[r];
+			n1[vbase[b] + r] = o.n1s[r];
+			realrow[vbase[b] + r] = (uint16_t)o.rrow[r];
 		}
-		ro[rec_blocks[b].n1s.size()] = pos;
-		img.insert(img.end(), rec_blocks[b].rec.begin(), rec_blocks[b].rec.end());
+		ro[o.n1s.size()] = pos;
+		img.insert(img.end(), o.rec.begin(), o.rec.end());
 		img.resize((img.size() + 15) & ~(size_t)15, 0);
-		pb->p1_rows += (int64_t)rec_blocks[b].n1s.size();
 	}
 	img.resize(img.size() + 64, 0);
 	bool ok = pool_malloc(c, (void**)&pb->d_p1img, img.size()) && pool_malloc(c, (void**)&pb->d_p1_rowoff, rowoff.size() * 8 + 8) &&
-	          pool_malloc(c, (void**)&pb->d_p1_n1, n1.size() * 4 + 8) &&
-	          pool_malloc(c, (void**)&pb->d_p1_realrow, realrow.size() * 2 + 8) &&
-	          pool_malloc(c, (void**)&pb->d_p1_rows_in_blk, (nb + 1) * sizeof(int));
+	          pool_malloc(c, (void**)&pb->d_p1_n1, n1.size() * 4 + 8) && pool_malloc(c, (void**)&pb->d_p1_realrow, realrow.size() * 2 + 8) &&
+	          pool_malloc(c, (void**)&pb->d_p1_rows_in_blk, (nb + 1) * sizeof(int)) && pool_malloc(c, (void**)&pb->d_p1_vbase, (nb + 1) * sizeof(long long));
 	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_p1img, img.data(), img.size(), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_rowoff, rowoff.data(), rowoff.size() * 8, cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_n1, n1.data(), n1.size() * 4, cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_realrow, realrow.data(), realrow.size() * 2, cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_rows_in_blk, pb->p1_rows_in_blk.data(), nb * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaStreamSynchronize(c->st));
+	     CU_OK(cudaMemcpyAsync(pb->d_p1_vbase, vbase.data(), (nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->st));
 	pb->p1_ready = ok;
 	std::vector<P1Block>().swap(pb->p1blocks);
 	return ok;
@@ -507,7 +513,7 @@ static bool walk_block(const uint8_t *f, size_t flen, uint64_t off, int m, int g
 
 // Host half of making rows [row_beg,row_end) resident: header / index parse (pbwt.c:231-258), block range,
 // per-block row offsets (a few host threads).  Offsets are relative to pb->file_off0.
-static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
+static b200_pbf_t *pbf_index_prepare(const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
 {
 	if (!f) { set_err("null PBF image"); return nullptr; }
 	if (flen < 16 + 13 + 8 || memcmp(f, "PBF\1", 4) != 0) { set_err("not a PBF file (bad magic)"); return nullptr; } // pbwt.c:231-235
@@ -529,6 +535,8 @@ static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg
 	if (row_beg > row_end) row_beg = row_end;
 	std::vector<uint64_t> idx(n_idx);
 	memcpy(idx.data(), f + ioff + 13, 8ull * n_idx);
+	for (int32_t i = 0; i < n_idx; ++i)
+		if (idx[i] < 16 || idx[i] >= ioff || (i && idx[i] <= idx[i - 1])) { set_err("corrupt PBF: block index entry %d out of order", i); return nullptr; }
 
 	b200_pbf_t *pb = new b200_pbf_t();
 	pb->m = m; pb->g = g; pb->shift = shift; pb->BS = BS; pb->n = n; pb->n_blk_file = n_idx;
@@ -541,6 +549,19 @@ static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg
 	if (pb->blk0 == 0 && blk1 == n_idx) { pb->file_off0 = 0; pb->file_size = flen; }
 	const uint64_t copy_end = pb->file_size ? flen : byte_end;
 	pb->img_bytes = (size_t)(copy_end - pb->file_off0);
+	pb->h_idx.swap(idx);
+	pb->ioff = ioff;
+	return pb;
+}
+
+// second half: walk the length prefixes of every resident block (the file indexes only block starts, pbwt.c:297) and
+// collect the plane-1 rows; a few host threads, meant to run while the H2D copy of the image is in flight
+static bool pbf_index_walk(b200_pbf_t *pb, const uint8_t *f)
+{
+	const int nb = pb->n_blk, BS = pb->BS, shift = pb->shift, m = pb->m, g = pb->g;
+	const int64_t n = pb->n;
+	const std::vector<uint64_t> &idx = pb->h_idx;
+	const uint64_t ioff = pb->ioff;
 	pb->rows_in_blk.resize(nb);
 	pb->p1blocks.assign(nb, P1Block());
 	pb->h_rowoff.assign((size_t)nb * (BS + 1), 0);
@@ -569,17 +590,34 @@ static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg
 		for (auto &x : th) x.join();
 		for (int t = 0; t < nt; ++t) if (bad[t]) ok = false;
 	}
-	if (!ok) { set_err("corrupt PBF: record tags/lengths inside a checkpoint block do not parse"); delete pb; return nullptr; }
+	if (!ok) { set_err("corrupt PBF: record tags/lengths inside a checkpoint block do not parse"); return false; }
+	return true;
+}
+
+static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
+{
+	b200_pbf_t *pb = pbf_index_prepare(f, flen, row_beg, row_end);
+	if (pb && !pbf_index_walk(pb, f)) { delete pb; return nullptr; }
 	return pb;
+}
+
+
+static double now_ms()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
 extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
 {
 	if (!c || !f) { set_err("b200_pbf_load: null argument"); return nullptr; }
 	cudaSetDevice(c->dev);
+	const bool trace = getenv("BGT_B200_TRACE") != nullptr;
+	const double t0 = now_ms();
 	// the H2D copy of the block range is queued first (its extent only needs the header and the index record); the
 	// row walk below then overlaps it
-	b200_pbf_t *pb = pbf_index_host(f, flen, row_beg, row_end);
+	b200_pbf_t *pb = pbf_index_prepare(f, flen, row_beg, row_end);
 	if (!pb) return nullptr;
 	pb->ctx = c;
 	bool ok = pool_malloc(c, (void**)&pb->d_img, pb->img_bytes + 64);
@@ -587,7 +625,14 @@ extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t fle
 	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img, f + pb->file_off0, pb->img_bytes, cudaMemcpyHostToDevice, c->st));
 	ok = ok && CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st));
 	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st));
-	if (!ok || !pbf_finish_resident(pb, false) || !build_plane1_view(pb)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	const double t1 = now_ms();
+	ok = ok && pbf_index_walk(pb, f);            // overlaps the copy queued above
+	const double t2 = now_ms();
+	ok = ok && build_plane1_view(pb);
+	const double t3 = now_ms();
+	ok = ok && pbf_finish_resident(pb, false);
+	if (trace) fprintf(stderr, "[b200 trace] load: enqueue h2d %.2f ms, index walk %.2f ms, plane-1 view %.2f ms, finish_resident (+ wait for the copy) %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
+	if (!ok) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
 	return pb;
@@ -895,7 +940,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			ComposeParams K;
 			K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rows_in_blk = pb->d_rows_in_blk; K.blk_list = d_all;
 			K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
-			K.n_grp = n_grp; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0;
+			K.n_grp = n_grp; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0; K.row_base = nullptr; K.n1_step = 2;
 			okc = okc && CU_OK(launch_compose(K, (int)all.size(), c->st));
 			// ... and the inverse composites of the plane-1 view rows for the select kernel
 			const size_t vslots = (size_t)pb->n_blk * SELECT_GROUPS;
@@ -906,7 +951,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			ComposeParams V = K;
 			V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
 			V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
-			V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 1; V.inverse = 1;
+			V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
 			okc = okc && CU_OK(launch_compose(V, (int)all.size(), c->st)) && CU_OK(cudaStreamSynchronize(c->st));
 			++c->launches;
 			pool_free(c, d_all);
@@ -916,7 +961,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		}
 		// phase 1 (plane1.cu): the (column, row) pairs that carry a plane-1 bit, per block, in row order
 		SelectParams A;
-		A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow;
+		A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
 		A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
 		A.m = pb->m; A.shift = pb->shift; A.cap = cap;
 		const bool use_comp = pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE);

@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	const int n_grp = P.n_grp;
 	const int blk = P.blk_list[blockIdx.x / n_grp], g = blockIdx.x % n_grp;
 	const uint32_t m = (uint32_t)P.m;
-	const uint64_t *roff = P.rowoff + (size_t)blk * (BS + 1);
+	const long long rbase = P.row_base ? P.row_base[blk] : (long long)blk * BS;   // first row of the block in the per-row arrays
+	const uint64_t *roff = P.rowoff + (P.row_base ? rbase + blk : (long long)blk * (BS + 1));
 	const int r_lo = g * COMP_K;
 	int nrow = P.rows_in_blk[blk] - r_lo;
 	if (nrow > COMP_K) nrow = COMP_K;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 			const uint8_t *rec = P.img + roff[r_lo + j];
 			const uint32_t l = cp_ld_u32_unaligned(rec + P.rle_off - 4);
 			const uint8_t *rle = rec + P.rle_off;
-			const uint32_t n1 = P.n1[((size_t)blk * BS + r_lo + j) * 2 + P.n1_plane];
+			const uint32_t n1 = P.n1[(size_t)(rbase + r_lo + j) * P.n1_step + P.n1_plane];
 			const bool triv = (n1 == 0 || n1 == m);
 			uint32_t tot = 0, ones = 0, nrun = 0, nzr = 0, prev_bit = 2;
 			const int base_out = pass ? row_beg[j] : 0;

@@ -68,6 +68,8 @@ struct ComposeParams {
 	const int      *rows_in_blk;
 	const int      *blk_list;
 	int m, shift;
+	const long long *row_base; // per block: index of its first row in rowoff (with one extra end entry per block) / n1 / ...; nullptr: blk*(BS+1), blk*BS
+	int n1_step;      // entries of n1 per row (2 for a .pbf image: both planes; 1 for the plane-1 view)
 	int n_grp;        // row groups per block (slots per block in the output arrays)
 	int cap;          // pieces per slot (<= COMP_CAP)
 	int rle_off;      // offset of the plane's RLE inside a row record: 5 = plane 0 of a .pbf row, 9 = plane 1 of a plane-1 view row
@@ -83,9 +85,10 @@ cudaError_t launch_compose(const ComposeParams &P, int n_blk, cudaStream_t st);
 // plane-1 select (plane1.cu): per block, the (column, row) pairs that carry a plane-1 bit, in row order
 struct SelectParams {
 	const uint8_t  *p1img;        // plane-1 view: records 'B', l0 = 0, l1, bytes of the rows whose plane 1 is not empty
-	const uint64_t *p1_rowoff;    // [blocks][BS+1]
-	const uint32_t *p1_n1;        // [blocks][BS][2]
-	const uint16_t *p1_realrow;   // [blocks][BS] row (within the block) of every view row
+	const uint64_t *p1_rowoff;    // view rows of all blocks back to back, one extra end entry per block: index vbase[blk] + blk + v
+	const uint32_t *p1_n1;        // ones of plane 1 per view row: index vbase[blk] + v
+	const uint16_t *p1_realrow;   // row (within the block) of every view row: index vbase[blk] + v
+	const long long *p1_vbase;    // [blocks+1] first view row of every block
 	const int      *p1_rows_in_blk;
 	const uint8_t  *img;          // the real image (for the block's plane-1 snapshot)
 	const uint64_t *blkoff;

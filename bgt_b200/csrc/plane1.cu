@@ -67,14 +67,14 @@ __global__ void __launch_bounds__(1024) plane1_select_kernel(const SelectParams 
 	__shared__ int cg_off[SELECT_GROUPS + 1];                       // first piece of group g in cs/cd; cg_off[g+1]-cg_off[g] = 0: not available
 
 	const int blk = P.blk_list[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int BS = 1 << P.shift;
 	const int nv = P.p1_rows_in_blk[blk];
-	const uint64_t *ro = P.p1_rowoff + (size_t)blk * (BS + 1);
+	const long long vb = P.p1_vbase[blk];
+	const uint64_t *ro = P.p1_rowoff + vb + blk;
 	const uint64_t base = ro[0];
 	const uint32_t nbytes = (uint32_t)(ro[nv] - base);
 	if (nv >= SELECT_MAX_ROWS || nbytes > (uint32_t)SELECT_MAX_BYTES) { if (tid == 0) { atomicOr(P.err, 16); P.qcount[blk] = 0; } return; }
 	for (int v = tid; v <= nv; v += 1024) roff[v] = (uint32_t)(ro[v] - base);
-	for (int v = tid; v < nv; v += 1024) n1v[v] = P.p1_n1[((size_t)blk * BS + v) * 2 + 1];
+	for (int v = tid; v < nv; v += 1024) n1v[v] = P.p1_n1[vb + v];
 	for (uint32_t i = tid; i < nbytes; i += 1024) raw[i] = P.p1img[base + i];
 	__syncthreads();
 	// exclusive prefix of the per-row ones: 4 rows per thread, warp scan, cross-warp fix-up
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(1024) plane1_select_kernel(const SelectParams 
 		const uint32_t col = r < m ? p1_ld_u32_unaligned(S1 + 4 * (size_t)r) : 0xffffffffu;
 		if (col >= m) { atomicOr(P.err, 64); continue; }
 		P.qcol[(size_t)blk * P.cap + q] = (int32_t)col;
-		P.qrow[(size_t)blk * P.cap + q] = P.p1_realrow[(size_t)blk * BS + v];
+		P.qrow[(size_t)blk * P.cap + q] = P.p1_realrow[vb + v];
 	}
 	if (tid == 0) P.qcount[blk] = (int)Q;
 }
