@@ -7,6 +7,7 @@
 // then cross a whole group with ONE binary search instead of COMP_K -- the bits of the rows in between are not
 // needed by the count-only scan.
 //
+// The COMP_K row maps are composed pairwise in a tree (log2 COMP_K levels), each level one pass over all pieces.
 // One CTA per (checkpoint block, row group); groups are independent of each other and of the query, so the tables
 // are built once per resident PBF (lazily, at the first scan that wants them) and cached with it.
 // The same kernel also builds INVERSE composites (output coordinates -> input coordinates, rows composed in reverse)
@@ -34,16 +35,15 @@ __device__ __forceinline__ uint32_t cp_ld_u32_unaligned(const uint8_t *p)
 	return __funnelshift_r(lo, w[1], sh);
 }
 
+// Pieces of the maps of one level live back to back in (S, D): S = start of the piece in the map's input coordinates,
+// D = translation.  off[i] .. off[i+1] are the pieces of map i.
 __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams P)
 {
 	extern __shared__ __align__(16) uint8_t sm[];
-	uint32_t *runs_s = (uint32_t*)sm;                      // [CP_RUNS] run starts of all rows (row after row)
-	int32_t  *runs_d = (int32_t*)(runs_s + CP_RUNS);       // [CP_RUNS] run deltas
-	uint32_t *A_s = (uint32_t*)(runs_d + CP_RUNS);         // [COMP_CAP + 1] piece starts (input coordinates)
-	uint32_t *A_c = A_s + COMP_CAP + 1;                    // [COMP_CAP] piece positions in current coordinates
-	uint32_t *B_s = A_c + COMP_CAP;                        // second list
-	uint32_t *B_c = B_s + COMP_CAP + 1;
-	__shared__ int row_beg[COMP_K + 1], row_nz[COMP_K];                    // first run of every row in runs_s (row_beg[j+1]-row_beg[j] = runs; 0 runs = identity)
+	constexpr int CPX = CP_RUNS + COMP_K + 8;
+	uint32_t *S0 = (uint32_t*)sm;          int32_t *D0 = (int32_t*)(S0 + CPX);
+	uint32_t *S1 = (uint32_t*)(D0 + CPX);  int32_t *D1 = (int32_t*)(S1 + CPX);
+	__shared__ int offA[COMP_K + 1], offB[COMP_K + 1], row_nz[COMP_K];
 	__shared__ int warp_tot[CP_NW];
 	__shared__ int s_fail, s_n;
 
@@ -55,26 +55,30 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	const long long rbase = P.row_base ? P.row_base[blk] : (long long)blk * BS;   // first row of the block in the per-row arrays
 	const uint64_t *roff = P.rowoff + (P.row_base ? rbase + blk : (long long)blk * (BS + 1));
 	const int r_lo = g * COMP_K;
-	int nrow = P.rows_in_blk[blk] - r_lo;
-	if (nrow > COMP_K) nrow = COMP_K;
+	const int nrow = P.rows_in_blk[blk] - r_lo;
 	const size_t slot = ((size_t)blk * n_grp + g);
 	const int cap = P.cap;
 	if (nrow < COMP_K) { if (tid == 0) P.comp_n[slot] = 0; return; }   // partial last group: never crossed as a whole
 	if (tid == 0) { s_fail = 0; s_n = 0; }
 	__syncthreads();
 
-	// ---- per-row merged run tables: warps take rows round-robin; run counts first (to place the rows), then the tables
+	// ---- level 0: one map per row, in the order they are applied (inverse composite: last row first).  Warps take
+	// rows round-robin; run counts first (to place the maps), then the tables.  A constant row is the identity.
 	for (int pass = 0; pass < 2; ++pass) {
-		for (int j = warp; j < nrow; j += CP_NW) {
+		for (int j = warp; j < COMP_K; j += CP_NW) {
+			const int k_map = P.inverse ? COMP_K - 1 - j : j;
 			const uint8_t *rec = P.img + roff[r_lo + j];
 			const uint32_t l = cp_ld_u32_unaligned(rec + P.rle_off - 4);
 			const uint8_t *rle = rec + P.rle_off;
 			const uint32_t n1 = P.n1[(size_t)(rbase + r_lo + j) * P.n1_step + P.n1_plane];
 			const bool triv = (n1 == 0 || n1 == m);
 			uint32_t tot = 0, ones = 0, nrun = 0, nzr = 0, prev_bit = 2;
-			const int base_out = pass ? row_beg[j] : 0;
-			const int nz_row = pass ? row_nz[j] : 0;
-			if (!triv) {
+			const int base_out = pass ? offA[k_map] : 0;
+			const int nz_row = pass ? row_nz[k_map] : 0;
+			if (triv) {
+				if (pass && lane == 0) { S0[base_out] = 0; D0[base_out] = 0; }
+				nrun = 1;
+			} else {
 				for (uint32_t base = 0; base < l; base += 32) {
 					const uint32_t i = base + lane;
 					const uint32_t c = i < l ? rle[i] : 0u;
@@ -89,7 +93,8 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 					// a run starts at a byte of non-zero length whose bit differs from the previous non-empty byte
 					const uint32_t valid = __ballot_sync(0xffffffffu, L > 0);
 					const uint32_t bitm = __ballot_sync(0xffffffffu, b != 0);
-					const uint32_t below = valid & ((1u << lane) - 1u);
+					const uint32_t lt = (1u << lane) - 1u;
+					const uint32_t below = valid & lt;
 					uint32_t pb = prev_bit;
 					if (below) pb = (bitm >> (31 - __clz(below))) & 1u;
 					const bool is_start = L > 0 && pb != b;
@@ -98,12 +103,11 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 					if (pass && is_start) {
 						const int32_t delta = b ? (int32_t)((m - n1) - (start - ones_before)) : -(int32_t)ones_before;
 						if (!P.inverse) {
-							const int k = base_out + (int)nrun + __popc(sm_ & ((1u << lane) - 1u));
-							if (k < CP_RUNS) { runs_s[k] = start; runs_d[k] = delta; }
+							const int k = base_out + (int)nrun + __popc(sm_ & lt);
+							S0[k] = start; D0[k] = delta;
 						} else { // inverse map: runs ordered by where they land (0-runs, then 1-runs), translated back
-							const uint32_t lt = (1u << lane) - 1u;
 							const int k = b ? base_out + nz_row + (int)(nrun - nzr) + __popc(sm_ & bitm & lt) : base_out + (int)nzr + __popc(zm_ & lt);
-							if (k < CP_RUNS) { runs_s[k] = start + (uint32_t)delta; runs_d[k] = -delta; }
+							S0[k] = start + (uint32_t)delta; D0[k] = -delta;
 						}
 					}
 					nrun += __popc(sm_);
@@ -113,78 +117,96 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 					ones += __shfl_sync(0xffffffffu, y, 31);
 				}
 			}
-			if (!pass && lane == 0) { row_beg[j + 1] = (int)nrun; row_nz[j] = (int)nzr; }   // counts for now
+			if (!pass && lane == 0) { offA[k_map + 1] = (int)nrun; row_nz[k_map] = (int)nzr; }   // counts for now
 		}
 		__syncthreads();
 		if (!pass) {
 			if (tid == 0) {
 				int acc = 0;
-				row_beg[0] = 0;
-				for (int j = 0; j < nrow; ++j) { const int c = row_beg[j + 1]; acc += c; row_beg[j + 1] = acc; }
-				if (acc > CP_RUNS) s_fail = 1;
+				offA[0] = 0;
+				for (int k = 0; k < COMP_K; ++k) { const int c = offA[k + 1]; acc += c; offA[k + 1] = acc; }
+				if (acc > CP_RUNS + COMP_K) s_fail = 1;
 			}
 			__syncthreads();
 			if (s_fail) { if (tid == 0) P.comp_n[slot] = 0; return; }
 		}
 	}
 
-	// ---- compose row after row
-	uint32_t *Ls = A_s, *Lc = A_c, *Ns = B_s, *Nc = B_c;
-	int n = 1;
-	if (tid == 0) { Ls[0] = 0; Lc[0] = 0; Ls[1] = m; }
-	__syncthreads();
-	for (int jj = 0; jj < nrow; ++jj) {
-		const int j = P.inverse ? nrow - 1 - jj : jj;           // inverse composite: undo the last row first
-		const int rb = row_beg[j], nr = row_beg[j + 1] - rb;
-		if (nr == 0) continue;                                  // constant row: identity (pbwt.c:75-77)
-		const uint32_t *rs = runs_s + rb;
-		const int32_t *rd = runs_d + rb;
-		// pieces per thread: contiguous chunk, so that the output stays in input order
-		const int per = (n + CP_NT - 1) / CP_NT, p0 = tid * per, p1 = p0 + per < n ? p0 + per : n;
+	// ---- compose pairwise, level by level: result i = (map 2i+1) after (map 2i).  Every piece of map 2i is cut at the
+	// starts of map 2i+1 that fall inside its image; one scan over all pieces of the level places the results.
+	uint32_t *Sa = S0, *Sb = S1;
+	int32_t *Da = D0, *Db = D1;
+	int *off = offA, *noff = offB;
+	for (int nmaps = COMP_K; nmaps > 1; nmaps >>= 1) {
+		const int total = off[nmaps];
+		const int per = (total + CP_NT - 1) / CP_NT, p0 = tid * per, p1 = p0 + per < total ? p0 + per : total;
+		// owner map of my first piece
+		int om = 0;
+		for (int len = nmaps; len > 1;) { const int half = len >> 1; om += off[om + half] <= p0 ? half : 0; len -= half; }
 		int mine = 0;
-		for (int p = p0; p < p1; ++p) {
-			const uint32_t c = Lc[p], e = c + (Ls[p + 1] - Ls[p]);
-			int lo = 0, hi = 0;                                  // lo = last run with start <= c ; hi = last run with start < e
-			for (int len = nr; len > 1;) { const int half = len >> 1; lo += rs[lo + half] <= c ? half : 0; hi += rs[hi + half] < e ? half : 0; len -= half; }
-			mine += hi - lo + 1;
+		{
+			int o = om;
+			for (int p = p0; p < p1; ++p) {
+				while (p >= off[o + 1]) ++o;
+				if (o & 1) continue;                                   // pieces of the second map of a pair are only looked up
+				const uint32_t cur = Sa[p] + (uint32_t)Da[p];
+				const uint32_t e = cur + ((p + 1 < off[o + 1] ? Sa[p + 1] : m) - Sa[p]);
+				const uint32_t *rs = Sa + off[o + 1];
+				const int nr = off[o + 2] - off[o + 1];
+				int lo = 0, hi = 0;                                    // lo = last start <= cur ; hi = last start < e
+				for (int len = nr; len > 1;) { const int half = len >> 1; lo += rs[lo + half] <= cur ? half : 0; hi += rs[hi + half] < e ? half : 0; len -= half; }
+				mine += hi - lo + 1;
+			}
 		}
 		int x = mine;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += t; }
 		if (lane == 31) warp_tot[warp] = x;
 		__syncthreads();
-		int off = x - mine;
-		for (int w = 0; w < warp; ++w) off += warp_tot[w];
-		if (tid == CP_NT - 1) { s_n = off + mine; if (off + mine > cap - 4) s_fail = 1; }
+		int out = x - mine;
+		for (int w = 0; w < warp; ++w) out += warp_tot[w];
+		if (tid == CP_NT - 1) { s_n = out + mine; if (out + mine > CPX - 4 || (nmaps == 2 && out + mine > cap - 4)) s_fail = 1; }
 		__syncthreads();
 		if (s_fail) { if (tid == 0) P.comp_n[slot] = 0; return; }
-		for (int p = p0; p < p1; ++p) {
-			const uint32_t s0 = Ls[p], c = Lc[p], e = c + (Ls[p + 1] - s0);
-			int lo = 0, hi = 0;
-			for (int len = nr; len > 1;) { const int half = len >> 1; lo += rs[lo + half] <= c ? half : 0; hi += rs[hi + half] < e ? half : 0; len -= half; }
-			Ns[off] = s0; Nc[off] = c + (uint32_t)rd[lo]; ++off;
-			for (int k = lo + 1; k <= hi; ++k) { const uint32_t s = rs[k]; Ns[off] = s0 + (s - c); Nc[off] = s + (uint32_t)rd[k]; ++off; }
+		{
+			int o = om;
+			for (int p = p0; p < p1; ++p) {
+				while (p >= off[o + 1]) ++o;
+				if (o & 1) continue;
+				if (p == off[o]) noff[o >> 1] = out;                   // first piece of a pair's first map = start of the result map
+				const uint32_t s0 = Sa[p], cur = s0 + (uint32_t)Da[p];
+				const uint32_t e = cur + ((p + 1 < off[o + 1] ? Sa[p + 1] : m) - s0);
+				const uint32_t *rs = Sa + off[o + 1];
+				const int32_t *rd = Da + off[o + 1];
+				const int nr = off[o + 2] - off[o + 1];
+				int lo = 0, hi = 0;
+				for (int len = nr; len > 1;) { const int half = len >> 1; lo += rs[lo + half] <= cur ? half : 0; hi += rs[hi + half] < e ? half : 0; len -= half; }
+				Sb[out] = s0; Db[out] = (int32_t)(cur + (uint32_t)rd[lo] - s0); ++out;
+				for (int k = lo + 1; k <= hi; ++k) {
+					const uint32_t s = rs[k], in_s = s0 + (s - cur);
+					Sb[out] = in_s; Db[out] = (int32_t)(s + (uint32_t)rd[k] - in_s); ++out;
+				}
+			}
 		}
-		n = s_n;
+		if (tid == 0) noff[nmaps >> 1] = s_n;
 		__syncthreads();
-		if (tid == 0) Ns[n] = m;
-		uint32_t *t;
-		t = Ls; Ls = Ns; Ns = t;
-		t = Lc; Lc = Nc; Nc = t;
-		__syncthreads();
+		{ uint32_t *t = Sa; Sa = Sb; Sb = t; }
+		{ int32_t *t = Da; Da = Db; Db = t; }
+		{ int *t = off; off = noff; noff = t; }
 	}
 	// ---- write out, padded to a multiple of 4 entries (16-byte TMA granularity)
+	const int n = off[1];
 	const int npad = (n + 3) & ~3;
 	uint32_t *os = P.comp_start + slot * cap;
 	int32_t *od = P.comp_delta + slot * cap;
 	for (int p = tid; p < npad; p += CP_NT) {
-		os[p] = p < n ? Ls[p] : 0xffffffffu;
-		od[p] = p < n ? (int32_t)(Lc[p] - Ls[p]) : 0;
+		os[p] = p < n ? Sa[p] : 0xffffffffu;
+		od[p] = p < n ? Da[p] : 0;
 	}
 	if (tid == 0) P.comp_n[slot] = npad;
 }
 
-size_t compose_smem_bytes() { return sizeof(uint32_t) * (2 * CP_RUNS + 4 * COMP_CAP + 2) + 64; }
+size_t compose_smem_bytes() { return sizeof(uint32_t) * 4 * (CP_RUNS + COMP_K + 8) + 64; }
 
 cudaError_t launch_compose(const ComposeParams &P, int n_blk, cudaStream_t st)
 {
