@@ -261,7 +261,7 @@ def test_synth_generator_is_truthful_and_canonical(b200, ctx, oracle):
         q.close(); pb.close(); pb2.close()
 
 
-@pytest.mark.parametrize("case", ["sparse", "dense", "mixed", "allones", "wide"])
+@pytest.mark.parametrize("case", ["sparse", "dense", "mixed", "allones", "wide", "noisy0", "deep"])
 def test_split_scan_equals_general_and_oracle(b200, ctx, oracle, case):
     """Count-only full-cohort scans take the split path (plane-0 marginal + walk of the columns that carry plane-1 codes);
     it must agree with the general walk and with the oracle whatever the density of plane 1."""
@@ -276,9 +276,19 @@ def test_split_scan_equals_general_and_oracle(b200, ctx, oracle, case):
     elif case == "allones":
         mat = haplo_matrix(200, 4400, 9)
         mat[50] = 2; mat[51] = 3; mat[120] = 1; mat[121] = 0
+    elif case == "noisy0":
+        # plane 0 incompressible (thousands of runs per row: the composite maps overflow and the walk falls back to
+        # row-by-row), plane 1 sparse (so the split path is still taken)
+        mat = (rng.random((400, 4400)) < 0.5).astype(np.uint8)
+        for k in range(0, 400, 7):
+            mat[k, rng.integers(0, 4400, size=5)] = 2 + (k & 1)
+    elif case == "deep":
+        # long blocks (many 32-row groups per checkpoint) with plane-1 codes on most rows: exercises the composite
+        # maps of both planes and the per-group fallbacks at block ends
+        mat = haplo_matrix(2300, 1200, 11, p_missing_row=0.45, p_multi_row=0.45)
     else:
         mat = haplo_matrix(70, 70002, 10, p_missing_row=0.3, p_multi_row=0.3)
-    shift = 6 if case != "wide" else 4
+    shift = 4 if case == "wide" else 11 if case == "deep" else 8 if case == "noisy0" else 6
     pbf = oracle.encode_pbf(mat, shift=shift)
     n = mat.shape[0]
     want = oracle.Pbf(pbf).scan(0, n, flt="AC>0")
