@@ -299,7 +299,7 @@ def run_b200(args, rank, world, local_rank):
     ranges = [(i * per * 8192, min((i + 1) * per * 8192, n)) for i in range(n_chunks) if i * per * 8192 < n]
 
     def shard(cx, beg, end):
-        pb = bgt_b200.Pbf.from_bytes(cx, host_img, beg, end)
+        pb = bgt_b200.Pbf.from_bytes(cx, host_img, beg, end, prepare_count_scan=True)
         qq = bgt_b200.Query(cx, pb, flt=FILTER)
         bgt_b200.scan(cx, pb, qq, beg, end - beg, out={"counts": h_counts[beg:end], "passed": h_pass[beg:end]})
         qq.close()

@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200_host_alloc": (_vp, [C.c_size_t]),
     "b200_host_free": (None, [_vp]),
     "b200_pbf_load": (_vp, [_vp, _vp, C.c_size_t, _i64, _i64]),
+    "b200_pbf_load_ex": (_vp, [_vp, _vp, C.c_size_t, _i64, _i64, C.c_uint]),
     "b200_pbf_open": (_vp, [_vp, C.c_char_p, _i64, _i64]),
     "b200_pbf_close": (None, [_vp]),
     "b200_pbf_m": (_int, [_vp]),
@@ -152,9 +153,9 @@ class Pbf:
         self.bad_rows = L.b200_pbf_bad_rows(handle)
 
     @classmethod
-    def from_bytes(cls, ctx, data, row_beg=0, row_end=-1):
+    def from_bytes(cls, ctx, data, row_beg=0, row_end=-1, prepare_count_scan=False):
         buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
-        return cls(ctx, lib().b200_pbf_load(ctx.h, _ptr(buf), buf.size, row_beg, row_end))
+        return cls(ctx, lib().b200_pbf_load_ex(ctx.h, _ptr(buf), buf.size, row_beg, row_end, 1 if prepare_count_scan else 0))
 
     @classmethod
     def open(cls, ctx, fn, row_beg=0, row_end=-1):

@@ -32,6 +32,13 @@ static void set_err(const char *fmt, ...)
 	va_end(ap);
 }
 
+static double now_ms()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 #define CU_OK(call) cu_ok((call), #call, __LINE__)
 static bool cu_ok(cudaError_t e, const char *what, int line)
 {
@@ -64,6 +71,8 @@ struct b200_ctx_s {
 	size_t pool_cached = 0;
 	int dev = 0;
 	cudaStream_t st = nullptr;
+	cudaStream_t st_copy = nullptr;   // H2D of PBF images, so that per-chunk kernels on `st` overlap the rest of the copy
+	cudaEvent_t ev_chunk[8] = {};
 	cudaEvent_t ev[12] = {};  // 0/1 walk phase(s), 2/3 scan, 4/5 h2d, 6/7 d2h, 8/9 plane1 select, 10/11 marginals
 	cudaEvent_t mark[4] = {};
 	double last_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -86,6 +95,8 @@ struct b200_pbf_s {
 	b200_ctx_t *ctx = nullptr;
 	std::vector<P1Block> p1blocks;
 	std::vector<uint64_t> h_idx;      // the file's block index (pbwt.c:268-276)
+	std::vector<int> chunk_blk;       // load in flight: resident-block boundaries of the H2D chunks (events ctx->ev_chunk[k])
+	bool prepare_split = false;       // build the composite maps while loading (b200_pbf_load_ex)
 	uint64_t ioff = 0;                // file offset of the 'I' record
 	int m = 0, g = 0, shift = 0, BS = 0;
 	int64_t n = 0;               // rows in the file
@@ -207,7 +218,8 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	if (prop.major < 10) { set_err("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return nullptr; }
 	b200_ctx_t *c = new b200_ctx_t();
 	c->dev = device; c->sm_count = prop.multiProcessorCount;
-	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) && CU_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+	for (int i = 0; ok && i < 8; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
 	for (int i = 0; ok && i < 12; ++i) ok = CU_OK(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; ok && i < 4; ++i) ok = CU_OK(cudaEventCreate(&c->mark[i]));
 	ok = ok && CU_OK(cudaMalloc(&c->d_err, sizeof(int))) && CU_OK(cudaMalloc(&c->d_acc, 8 * sizeof(unsigned long long)));
@@ -221,6 +233,7 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	if (!c) return;
 	cudaSetDevice(c->dev);
 	if (c->st) cudaStreamSynchronize(c->st);
+	if (c->st_copy) cudaStreamSynchronize(c->st_copy);
 	c->cnt_raw.release(); c->counts.release(); c->pass.release();
 	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
 	c->n0g.release(); c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
@@ -230,6 +243,8 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	for (auto &b : c->pool_live) cudaFree(b.p);
 	if (c->d_err) cudaFree(c->d_err);
 	if (c->d_acc) cudaFree(c->d_acc);
+	for (int i = 0; i < 8; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+	if (c->st_copy) cudaStreamDestroy(c->st_copy);
 	if (c->st) cudaStreamDestroy(c->st);
 	delete c;
 }
@@ -369,6 +384,8 @@ static void collect_plane1_block(const uint8_t *img0, const uint64_t *ro, int ro
 static bool build_plane1_view(b200_pbf_t *pb)
 {
 	b200_ctx_t *c = pb->ctx;
+	const bool trace = getenv("BGT_B200_TRACE") != nullptr;
+	const double tv0 = now_ms();
 	const int nb = pb->n_blk, BS = pb->BS;
 	pb->p1_cap = (((pb->m / 4 > 4096 ? pb->m / 4 : 4096) + 2047) / 2048) * 2048;
 	pb->blk_sparse.assign(nb, 1);
@@ -404,6 +421,7 @@ static bool build_plane1_view(b200_pbf_t *pb)
 		img.resize((img.size() + 15) & ~(size_t)15, 0);
 	}
 	img.resize(img.size() + 64, 0);
+	const double tv1 = now_ms();
 	bool ok = pool_malloc(c, (void**)&pb->d_p1img, img.size()) && pool_malloc(c, (void**)&pb->d_p1_rowoff, rowoff.size() * 8 + 8) &&
 	          pool_malloc(c, (void**)&pb->d_p1_n1, n1.size() * 4 + 8) && pool_malloc(c, (void**)&pb->d_p1_realrow, realrow.size() * 2 + 8) &&
 	          pool_malloc(c, (void**)&pb->d_p1_rows_in_blk, (nb + 1) * sizeof(int)) && pool_malloc(c, (void**)&pb->d_p1_vbase, (nb + 1) * sizeof(long long));
@@ -414,12 +432,79 @@ static bool build_plane1_view(b200_pbf_t *pb)
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_rows_in_blk, pb->p1_rows_in_blk.data(), nb * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(pb->d_p1_vbase, vbase.data(), (nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->st));
 	pb->p1_ready = ok;
+	const double tv2 = now_ms();
 	std::vector<P1Block>().swap(pb->p1blocks);
+	if (trace) fprintf(stderr, "[b200 trace]   view: host assembly %.2f ms, alloc+upload %.2f ms, free %.2f ms\n", tv1 - tv0, tv2 - tv1, now_ms() - tv2);
 	return ok;
 }
 
-// Upload the row index, plan tiles, compute per-row n1, [generator: run the chain], invert the snapshots.
-static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain)
+// Composite maps of the row groups (compose.cu) for every sparse block: forward maps of plane 0 for the QUERY walk and
+// inverse maps of the plane-1 view for the select kernel.  Query independent, so they are built once per resident PBF:
+// lazily by the first split scan, or chunk by chunk while the image is still being copied (b200_pbf_load_ex).
+struct ComposeJob {
+	const b200_pbf_t *pb = nullptr;
+	std::vector<int> all;     // sparse blocks, ascending
+	int *d_all = nullptr;
+	size_t next = 0;          // first entry of `all` not launched yet
+	ComposeParams K;
+
+	bool begin(const b200_pbf_t *p) {
+		pb = p;
+		b200_ctx_t *c = pb->ctx;
+		const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
+		for (int b = 0; b < pb->n_blk; ++b) if (pb->blk_sparse[b]) all.push_back(b);
+		const size_t slots = (size_t)pb->n_blk * n_grp, vslots = (size_t)pb->n_blk * SELECT_GROUPS;
+		bool ok = pool_malloc(c, (void**)&pb->d_comp_start, slots * COMP_CAP * sizeof(uint32_t)) &&
+		          pool_malloc(c, (void**)&pb->d_comp_delta, slots * COMP_CAP * sizeof(int32_t)) &&
+		          pool_malloc(c, (void**)&pb->d_comp_n, slots * sizeof(int) + 16) && pool_malloc(c, (void**)&d_all, all.size() * sizeof(int) + 16) &&
+		          pool_malloc(c, (void**)&pb->d_vcomp_start, vslots * SELECT_COMP_CAP * sizeof(uint32_t)) &&
+		          pool_malloc(c, (void**)&pb->d_vcomp_delta, vslots * SELECT_COMP_CAP * sizeof(int32_t)) &&
+		          pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16);
+		ok = ok && CU_OK(cudaMemsetAsync(pb->d_comp_n, 0, slots * sizeof(int), c->st)) && CU_OK(cudaMemsetAsync(pb->d_vcomp_n, 0, vslots * sizeof(int), c->st)) &&
+		     CU_OK(cudaMemcpyAsync(d_all, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+		K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rows_in_blk = pb->d_rows_in_blk; K.blk_list = d_all;
+		K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
+		K.n_grp = n_grp; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0; K.row_base = nullptr; K.n1_step = 2;
+		return ok;
+	}
+	// forward composites of the sparse blocks below blk_end (their image bytes and row meta must be queued before)
+	bool upto(int blk_end) {
+		size_t i1 = next;
+		while (i1 < all.size() && all[i1] < blk_end) ++i1;
+		if (i1 == next) return true;
+		ComposeParams Kk = K;
+		Kk.blk_list = d_all + next;
+		const bool ok = CU_OK(launch_compose(Kk, (int)(i1 - next), pb->ctx->st));
+		++pb->ctx->launches;
+		next = i1;
+		return ok;
+	}
+	bool end() {
+		b200_ctx_t *c = pb->ctx;
+		bool ok = upto(pb->n_blk);
+		ComposeParams V = K;   // the plane-1 view is small and host-built: one launch
+		V.blk_list = d_all;
+		V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
+		V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
+		V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
+		ok = ok && CU_OK(launch_compose(V, (int)all.size(), c->st));
+		++c->launches;
+		ok = ok && CU_OK(cudaStreamSynchronize(c->st));   // d_all is read by the queued kernels
+		pool_free(c, d_all);
+		d_all = nullptr;
+		if (ok) pb->comp_ready = true;
+		return ok;
+	}
+};
+
+static bool build_composites(const b200_pbf_t *pb)
+{
+	ComposeJob job;
+	return job.begin(pb) && job.end();
+}
+
+// Plan tiles and upload the row index of the resident blocks.
+static bool pbf_upload_index(b200_pbf_t *pb)
 {
 	b200_ctx_t *c = pb->ctx;
 	const int BS = pb->BS, nb = pb->n_blk;
@@ -456,8 +541,35 @@ static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain)
 	     CU_OK(cudaMemsetAsync(c->d_acc + 4, 0, sizeof(unsigned long long), c->st)) &&
 	     CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
 	if (!ok) return false;
-	if (!CU_OK(launch_rowmeta(pb->d_img, pb->d_rowoff, nb, pb->shift, 0, pb->d_rows_in_blk, (uint32_t)pb->m, pb->d_n1, c->d_acc + 4, c->st))) return false;
-	++c->launches;
+	return true;
+}
+
+// Per-row n1, [generator: run the chain], snapshot inversion, [composite maps]; one sync at the end.
+static bool pbf_queue_kernels(b200_pbf_t *pb, bool synth_chain)
+{
+	b200_ctx_t *c = pb->ctx;
+	const int BS = pb->BS, nb = pb->n_blk;
+	bool ok = true;
+	ComposeJob cjob;
+	const bool eager = pb->prepare_split && pb->p1_ready && !synth_chain;
+	if (eager && !cjob.begin(pb)) return false;
+	const int n_chunks = pb->chunk_blk.size() > 1 ? (int)pb->chunk_blk.size() - 1 : 0;
+	if (n_chunks > 0) {
+		// the image is arriving in chunks of whole blocks on the copy stream: row meta, snapshot inversion and (if asked
+		// for) the composite maps of every chunk are queued behind that chunk's event, so they overlap the rest of the copy
+		for (int k = 0; k < n_chunks; ++k) {
+			const int b0 = pb->chunk_blk[k], b1 = pb->chunk_blk[k + 1];
+			if (!CU_OK(cudaStreamWaitEvent(c->st, c->ev_chunk[k], 0))) return false;
+			if (!CU_OK(launch_rowmeta(pb->d_img, pb->d_rowoff + (size_t)b0 * (BS + 1), b1 - b0, pb->shift, 0, pb->d_rows_in_blk + b0, (uint32_t)pb->m,
+			                          pb->d_n1 + (size_t)b0 * BS * 2, c->d_acc + 4, c->st))) return false;
+			if (!CU_OK(launch_invert_snapshots(pb->d_img, pb->d_blkoff + b0, b1 - b0, pb->m, pb->d_rank0 + (size_t)b0 * 2 * (size_t)pb->m, c->d_err, c->st))) return false;
+			c->launches += 2;
+			if (eager && !cjob.upto(b1)) return false;
+		}
+	} else {
+		if (!CU_OK(launch_rowmeta(pb->d_img, pb->d_rowoff, nb, pb->shift, 0, pb->d_rows_in_blk, (uint32_t)pb->m, pb->d_n1, c->d_acc + 4, c->st))) return false;
+		++c->launches;
+	}
 	if (synth_chain) {
 		WalkParams P;
 		memset(&P, 0, sizeof(P));
@@ -477,8 +589,12 @@ static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain)
 		cudaFree(d_zero);
 		if (!ok) return false;
 	}
-	if (!CU_OK(launch_invert_snapshots(pb->d_img, pb->d_blkoff, nb, pb->m, pb->d_rank0, c->d_err, c->st))) return false;
-	++c->launches;
+	if (n_chunks == 0) {
+		if (!CU_OK(launch_invert_snapshots(pb->d_img, pb->d_blkoff, nb, pb->m, pb->d_rank0, c->d_err, c->st))) return false;
+		++c->launches;
+		if (eager && !cjob.upto(nb)) return false;
+	}
+	if (eager && !cjob.end()) return false;
 	unsigned long long bad = 0;
 	int err = 0;
 	ok = CU_OK(cudaMemcpyAsync(&bad, c->d_acc + 4, sizeof(bad), cudaMemcpyDeviceToHost, c->st)) &&
@@ -490,6 +606,8 @@ static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain)
 	if (err & 8) { set_err("internal: TMA copy never completed"); return false; }
 	return true;
 }
+
+static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain) { return pbf_upload_index(pb) && pbf_queue_kernels(pb, synth_chain); }
 
 // the file indexes checkpoint blocks only (pbwt.c:297); walk the length prefixes of the rows inside
 static bool walk_block(const uint8_t *f, size_t flen, uint64_t off, int m, int g, int rows, uint64_t *roff)
@@ -602,40 +720,62 @@ static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg
 }
 
 
-static double now_ms()
-{
-	struct timespec ts;
-	clock_gettime(CLOCK_MONOTONIC, &ts);
-	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-}
-
-extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
+extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end, unsigned flags)
 {
 	if (!c || !f) { set_err("b200_pbf_load: null argument"); return nullptr; }
 	cudaSetDevice(c->dev);
 	const bool trace = getenv("BGT_B200_TRACE") != nullptr;
 	const double t0 = now_ms();
-	// the H2D copy of the block range is queued first (its extent only needs the header and the index record); the
-	// row walk below then overlaps it
 	b200_pbf_t *pb = pbf_index_prepare(f, flen, row_beg, row_end);
 	if (!pb) return nullptr;
 	pb->ctx = c;
+	pb->prepare_split = (flags & B200_LOAD_PREPARE_COUNT_SCAN) != 0;
+	// The H2D copy is queued first, in up to 8 chunks of whole checkpoint blocks on the copy stream (its extent only
+	// needs the header and the index record).  The row walk below runs meanwhile on the host; the per-block kernels
+	// are then queued chunk by chunk behind the chunks' events (pbf_finish_resident).
+	const int nb = pb->n_blk;
 	bool ok = pool_malloc(c, (void**)&pb->d_img, pb->img_bytes + 64);
-	ok = ok && CU_OK(cudaEventRecord(c->ev[4], c->st));
-	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_img, f + pb->file_off0, pb->img_bytes, cudaMemcpyHostToDevice, c->st));
-	ok = ok && CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st));
-	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st));
+	ok = ok && CU_OK(cudaStreamSynchronize(c->st));          // buffers from the pool may still be in use by queued work of this context
+	ok = ok && CU_OK(cudaEventRecord(c->ev[4], c->st_copy));
+	const int n_chunks = nb >= 16 ? 8 : (nb > 0 ? 1 : 0);
+	pb->chunk_blk.clear();
+	for (int k = 0; k <= n_chunks; ++k) pb->chunk_blk.push_back((int)((long long)nb * k / (n_chunks ? n_chunks : 1)));
+	size_t done = 0;
+	auto queue_chunks = [&](int k0, int k1) { // image bytes of the blocks of chunks [k0,k1) -> copy stream, one event per chunk
+		for (int k = k0; ok && k < k1; ++k) {
+			const int b1 = pb->chunk_blk[k + 1];
+			const size_t end = b1 < nb ? (size_t)(pb->h_idx[pb->blk0 + b1] - pb->file_off0) : pb->img_bytes;
+			ok = CU_OK(cudaMemcpyAsync(pb->d_img + done, f + pb->file_off0 + done, end - done, cudaMemcpyHostToDevice, c->st_copy));
+			if (ok && k == n_chunks - 1) ok = CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st_copy));
+			ok = ok && CU_OK(cudaEventRecord(c->ev_chunk[k], c->st_copy));
+			done = end;
+		}
+	};
+	// Small uploads share the H2D engine with the image: whatever is queued behind the whole image waits for all of it.
+	// So only the first chunks go out now (about as much copy time as the host walk takes); the index arrays follow
+	// them, then the rest of the image, then the per-chunk kernels.
+	const int k_first = n_chunks > 1 ? 4 : n_chunks;
+	queue_chunks(0, k_first);
+	if (n_chunks == 0) ok = ok && CU_OK(cudaMemsetAsync(pb->d_img, 0, 64, c->st_copy));
 	const double t1 = now_ms();
 	ok = ok && pbf_index_walk(pb, f);            // overlaps the copy queued above
 	const double t2 = now_ms();
-	ok = ok && build_plane1_view(pb);
+	ok = ok && build_plane1_view(pb) && pbf_upload_index(pb);
+	queue_chunks(k_first, n_chunks);
+	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st_copy));
 	const double t3 = now_ms();
-	ok = ok && pbf_finish_resident(pb, false);
-	if (trace) fprintf(stderr, "[b200 trace] load: enqueue h2d %.2f ms, index walk %.2f ms, plane-1 view %.2f ms, finish_resident (+ wait for the copy) %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
-	if (!ok) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	ok = ok && pbf_queue_kernels(pb, false);
+	pb->chunk_blk.clear();
+	if (trace) fprintf(stderr, "[b200 trace] load: first chunks %.2f ms, index walk %.2f ms, plane-1 view + index upload + rest of the image queued %.2f ms, kernels (+ wait for the copy) %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
+	if (!ok) { cudaStreamSynchronize(c->st_copy); cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
 	return pb;
+}
+
+extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
+{
+	return b200_pbf_load_ex(c, f, flen, row_beg, row_end, 0);
 }
 
 extern "C" int b200_pbf_plan(const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end, int64_t info[8])
@@ -927,37 +1067,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		if (!c->qcol.reserve((size_t)pb->n_blk * cap * sizeof(int32_t)) || !c->qrow.reserve((size_t)pb->n_blk * cap * sizeof(uint16_t)) ||
 		    !c->qcount.reserve((size_t)pb->n_blk * sizeof(int))) return -1;
 		if (!pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) { // composite maps of the row groups: once per resident PBF
-			const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
-			std::vector<int> all;
-			for (int b = 0; b < pb->n_blk; ++b) if (pb->blk_sparse[b]) all.push_back(b);
-			int *d_all = nullptr;
-			const size_t slots = (size_t)pb->n_blk * n_grp;
-			bool okc = pool_malloc(c, (void**)&pb->d_comp_start, slots * COMP_CAP * sizeof(uint32_t)) &&
-			           pool_malloc(c, (void**)&pb->d_comp_delta, slots * COMP_CAP * sizeof(int32_t)) &&
-			           pool_malloc(c, (void**)&pb->d_comp_n, slots * sizeof(int) + 16) && pool_malloc(c, (void**)&d_all, all.size() * sizeof(int) + 16);
-			okc = okc && CU_OK(cudaMemsetAsync(pb->d_comp_n, 0, slots * sizeof(int), c->st)) &&
-			      CU_OK(cudaMemcpyAsync(d_all, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
-			ComposeParams K;
-			K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rows_in_blk = pb->d_rows_in_blk; K.blk_list = d_all;
-			K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
-			K.n_grp = n_grp; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0; K.row_base = nullptr; K.n1_step = 2;
-			okc = okc && CU_OK(launch_compose(K, (int)all.size(), c->st));
-			// ... and the inverse composites of the plane-1 view rows for the select kernel
-			const size_t vslots = (size_t)pb->n_blk * SELECT_GROUPS;
-			okc = okc && pool_malloc(c, (void**)&pb->d_vcomp_start, vslots * SELECT_COMP_CAP * sizeof(uint32_t)) &&
-			      pool_malloc(c, (void**)&pb->d_vcomp_delta, vslots * SELECT_COMP_CAP * sizeof(int32_t)) &&
-			      pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16) &&
-			      CU_OK(cudaMemsetAsync(pb->d_vcomp_n, 0, vslots * sizeof(int), c->st));
-			ComposeParams V = K;
-			V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
-			V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
-			V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
-			okc = okc && CU_OK(launch_compose(V, (int)all.size(), c->st)) && CU_OK(cudaStreamSynchronize(c->st));
-			++c->launches;
-			pool_free(c, d_all);
-			if (!okc) return -1;
-			pb->comp_ready = true;
-			++c->launches;
+			if (!build_composites(pb)) return -1;
 		}
 		// phase 1 (plane1.cu): the (column, row) pairs that carry a plane-1 bit, per block, in row order
 		SelectParams A;

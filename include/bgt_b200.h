@@ -43,6 +43,10 @@ void        b200_host_free(void *p);
  * blocks are walked (the file only indexes block starts, pbwt.c:297) and the snapshots are inverted
  * into per-column start ranks.  Region sharding across GPUs = one call per rank with its own row range. */
 b200_pbf_t *b200_pbf_load(b200_ctx_t *ctx, const uint8_t *bytes, size_t n_bytes, int64_t row_beg, int64_t row_end);
+/* same, with B200_LOAD_* flags */
+#define B200_LOAD_PREPARE_COUNT_SCAN 0x1  /* the caller will run count-only scans (`view -G`): build the composite maps of the row
+                                            groups while the image is still being copied instead of at the first such scan */
+b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *ctx, const uint8_t *bytes, size_t n_bytes, int64_t row_beg, int64_t row_end, unsigned flags);
 b200_pbf_t *b200_pbf_open(b200_ctx_t *ctx, const char *fn, int64_t row_beg, int64_t row_end);
 void        b200_pbf_close(b200_pbf_t *pb);
 int         b200_pbf_m(const b200_pbf_t *pb);        /* pbf_get_m, pbwt.c:391 */

@@ -10,7 +10,7 @@ q0 = bgt_b200.Query(ctx, cohort, flt="AC>0")
 h_counts = bgt_b200.host_alloc(n*6*4).view(np.int32).reshape(n,6); h_pass = bgt_b200.host_alloc(n)
 for it in range(3):
     t0=time.perf_counter(); info = bgt_b200.pbf_plan(host); t1=time.perf_counter()
-    pb = bgt_b200.Pbf.from_bytes(ctx, host); t2=time.perf_counter()
+    pb = bgt_b200.Pbf.from_bytes(ctx, host, prepare_count_scan=True); t2=time.perf_counter()
     q = bgt_b200.Query(ctx, pb, flt="AC>0"); t3=time.perf_counter()
     r = bgt_b200.scan(ctx, pb, q, 0, n, out={"counts":h_counts,"passed":h_pass}); t4=time.perf_counter()
     q.close(); pb.close(); t5=time.perf_counter()
