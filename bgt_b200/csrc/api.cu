@@ -63,6 +63,8 @@ struct DevBuf { // grow-only device scratch
 };
 
 struct PoolBlock { void *p; size_t size; };
+constexpr int N_IDX_STREAMS = 8;
+constexpr int LOAD_CHUNKS = 16;   // a PBF image is copied in up to this many chunks of whole checkpoint blocks
 
 struct b200_ctx_s {
 	// device-memory pool: PBF windows are loaded and dropped repeatedly (seam A/B, end-to-end scans); cudaMalloc /
@@ -72,9 +74,12 @@ struct b200_ctx_s {
 	int dev = 0;
 	cudaStream_t st = nullptr;
 	cudaStream_t st_copy = nullptr;   // H2D of PBF images, so that per-chunk kernels on `st` overlap the rest of the copy
-	cudaEvent_t ev_chunk[8] = {};
+	cudaStream_t st_idx[N_IDX_STREAMS] = {};      // the row-index chase of a chunk is one long dependent chain per block (latency bound, a few
+	                                  // lanes): the chases of consecutive chunks overlap each other and the kernels of earlier chunks
+	cudaEvent_t ev_chunk[LOAD_CHUNKS] = {}, ev_idx[LOAD_CHUNKS] = {};
 	cudaEvent_t ev[12] = {};  // 0/1 walk phase(s), 2/3 scan, 4/5 h2d, 6/7 d2h, 8/9 plane1 select, 10/11 marginals
 	cudaEvent_t mark[4] = {};
+	cudaEvent_t ev_zero = nullptr;
 	double last_ms[6] = {0, 0, 0, 0, 0, 0};
 	int64_t launches = 0;
 	int *d_err = nullptr;
@@ -84,16 +89,8 @@ struct b200_ctx_s {
 	bool split_used = false, marginal_used = false;
 };
 
-struct P1Block { // rows of one checkpoint block whose plane 1 is not empty, re-framed (see build_plane1_view)
-	std::vector<uint8_t> rec;
-	std::vector<uint32_t> n1s, lens, rrow;
-	uint64_t ones_sum = 0;
-	bool all_ones = false;
-};
-
 struct b200_pbf_s {
 	b200_ctx_t *ctx = nullptr;
-	std::vector<P1Block> p1blocks;
 	std::vector<uint64_t> h_idx;      // the file's block index (pbwt.c:268-276)
 	std::vector<int> chunk_blk;       // load in flight: resident-block boundaries of the H2D chunks (events ctx->ev_chunk[k])
 	bool prepare_split = false;       // build the composite maps while loading (b200_pbf_load_ex)
@@ -103,12 +100,14 @@ struct b200_pbf_s {
 	int blk0 = 0, n_blk = 0;     // resident checkpoint blocks [blk0, blk0+n_blk)
 	int64_t n_blk_file = 0;
 	std::vector<int> rows_in_blk;
-	std::vector<uint64_t> h_rowoff;   // [n_blk][BS+1], relative to d_img
+	std::vector<uint64_t> h_rowoff;   // [n_blk][BS+1], relative to d_img: host copy of d_rowoff, fetched on demand (host_rowoff())
 	std::vector<uint64_t> h_blkoff;   // [n_blk] offset of the 'S' record, relative to d_img
+	std::vector<uint64_t> h_blkend;   // [n_blk] end of the block's records (next 'S' record or the 'I' record)
 	uint8_t *d_img = nullptr; size_t img_bytes = 0; uint64_t file_off0 = 0;
 	size_t file_size = 0;             // size of the complete file image (0 unless fully resident)
-	uint64_t *d_rowoff = nullptr, *d_blkoff = nullptr;
-	int *d_rows_in_blk = nullptr, *d_blk_tile_beg = nullptr;
+	uint64_t *d_rowoff = nullptr, *d_blkoff = nullptr, *d_blkend = nullptr;
+	int *d_rows_in_blk = nullptr, *d_blk_tile_beg = nullptr, *d_blk_tile_end = nullptr;
+	uint8_t *d_blk_sparse = nullptr;
 	int2 *d_tiles = nullptr;
 	uint32_t *d_n1 = nullptr;
 	int32_t *d_rank0 = nullptr;
@@ -118,7 +117,6 @@ struct b200_pbf_s {
 	bool p1_ready = false;
 	int p1_cap = 0;                      // capacity of the per-block column set W
 	std::vector<uint8_t> blk_sparse;     // [n_blk] 1 = the block's plane-1 ones fit p1_cap (split scan applies)
-	std::vector<int> p1_rows_in_blk;
 	uint8_t *d_p1img = nullptr;
 	uint64_t *d_p1_rowoff = nullptr;
 	uint32_t *d_p1_n1 = nullptr;
@@ -219,9 +217,11 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	b200_ctx_t *c = new b200_ctx_t();
 	c->dev = device; c->sm_count = prop.multiProcessorCount;
 	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) && CU_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
-	for (int i = 0; ok && i < 8; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+	for (int i = 0; ok && i < N_IDX_STREAMS; ++i) ok = CU_OK(cudaStreamCreateWithFlags(&c->st_idx[i], cudaStreamNonBlocking));
+	for (int i = 0; ok && i < LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming)) && CU_OK(cudaEventCreateWithFlags(&c->ev_idx[i], cudaEventDisableTiming));
 	for (int i = 0; ok && i < 12; ++i) ok = CU_OK(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; ok && i < 4; ++i) ok = CU_OK(cudaEventCreate(&c->mark[i]));
+	ok = ok && CU_OK(cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming));
 	ok = ok && CU_OK(cudaMalloc(&c->d_err, sizeof(int))) && CU_OK(cudaMalloc(&c->d_acc, 8 * sizeof(unsigned long long)));
 	ok = ok && CU_OK(cudaMemset(c->d_err, 0, sizeof(int))) && CU_OK(cudaMemset(c->d_acc, 0, 8 * sizeof(unsigned long long)));
 	if (!ok) { b200_ctx_destroy(c); return nullptr; }
@@ -234,17 +234,20 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	cudaSetDevice(c->dev);
 	if (c->st) cudaStreamSynchronize(c->st);
 	if (c->st_copy) cudaStreamSynchronize(c->st_copy);
+	for (int i = 0; i < N_IDX_STREAMS; ++i) if (c->st_idx[i]) cudaStreamSynchronize(c->st_idx[i]);
 	c->cnt_raw.release(); c->counts.release(); c->pass.release();
 	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
 	c->n0g.release(); c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
 	for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
+	if (c->ev_zero) cudaEventDestroy(c->ev_zero);
 	for (auto &b : c->pool_free_list) cudaFree(b.p);
 	for (auto &b : c->pool_live) cudaFree(b.p);
 	if (c->d_err) cudaFree(c->d_err);
 	if (c->d_acc) cudaFree(c->d_acc);
-	for (int i = 0; i < 8; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+	for (int i = 0; i < LOAD_CHUNKS; ++i) { if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]); if (c->ev_idx[i]) cudaEventDestroy(c->ev_idx[i]); }
 	if (c->st_copy) cudaStreamDestroy(c->st_copy);
+	for (int i = 0; i < N_IDX_STREAMS; ++i) if (c->st_idx[i]) cudaStreamDestroy(c->st_idx[i]);
 	if (c->st) cudaStreamDestroy(c->st);
 	delete c;
 }
@@ -293,6 +296,9 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_blkoff);
 	pool_free(pb->ctx, pb->d_rows_in_blk);
 	pool_free(pb->ctx, pb->d_blk_tile_beg);
+	pool_free(pb->ctx, pb->d_blk_tile_end);
+	pool_free(pb->ctx, pb->d_blkend);
+	pool_free(pb->ctx, pb->d_blk_sparse);
 	pool_free(pb->ctx, pb->d_tiles);
 	pool_free(pb->ctx, pb->d_n1);
 	pool_free(pb->ctx, pb->d_rank0);
@@ -348,266 +354,156 @@ static void plan_tiles(const b200_pbf_t *pb, std::vector<int2> &tiles, std::vect
 	plan_tiles_of(pb->n_blk, pb->BS, pb->h_rowoff, pb->rows_in_blk, tiles, blk_tile_beg);
 }
 
-// Collect, for one resident block, the rows whose plane 1 has at least one 1 bit (img0 = the byte that the row
-// offsets are relative to).  Called right after the block's length-prefix walk, while its records are cache-warm.
-static void collect_plane1_block(const uint8_t *img0, const uint64_t *ro, int rows, uint32_t m, P1Block &o)
-{
-	for (int r = 0; r < rows; ++r) {
-		const uint8_t *p = img0 + ro[r] + 1;
-		int32_t l0, l1;
-		memcpy(&l0, p, 4);
-		p += 4 + l0;
-		memcpy(&l1, p, 4);
-		p += 4;
-		uint64_t ones = 0, tot = 0;
-		for (int32_t i = 0; i < l1; ++i) {
-			const uint32_t v = p[i] >> 1, len = (v & 15u) << ((v >> 4) << 2);
-			tot += len;
-			if (p[i] & 1) ones += len;
-		}
-		if (ones == 0 || tot != m) continue;          // empty (or corrupt: decodes as empty, see rowmeta_kernel)
-		if (ones == m) o.all_ones = true;             // every column carries the code: the set would be everything
-		o.ones_sum += ones;
-		const int32_t zero = 0;
-		o.rec.push_back('B');
-		o.rec.insert(o.rec.end(), (const uint8_t*)&zero, (const uint8_t*)&zero + 4);
-		o.rec.insert(o.rec.end(), (const uint8_t*)&l1, (const uint8_t*)&l1 + 4);
-		o.rec.insert(o.rec.end(), p, p + l1);
-		o.n1s.push_back((uint32_t)ones);
-		o.lens.push_back(9u + (uint32_t)l1);
-		o.rrow.push_back((uint32_t)r);
-	}
-}
-
-// Assemble the plane-1 view of the resident blocks from pb->p1blocks: per block the rows whose plane 1 is not
-// empty, as records 'B', l0 = 0, l1, bytes (an empty plane 0), with their n1 and their row number in the block.
-static bool build_plane1_view(b200_pbf_t *pb)
-{
-	b200_ctx_t *c = pb->ctx;
-	const bool trace = getenv("BGT_B200_TRACE") != nullptr;
-	const double tv0 = now_ms();
-	const int nb = pb->n_blk, BS = pb->BS;
-	pb->p1_cap = (((pb->m / 4 > 4096 ? pb->m / 4 : 4096) + 2047) / 2048) * 2048;
-	pb->blk_sparse.assign(nb, 1);
-	pb->p1_rows_in_blk.assign(nb, 0);
-	for (int b = 0; b < nb; ++b) {
-		const P1Block &o = pb->p1blocks[b];
-		if (o.all_ones || o.ones_sum > (uint64_t)pb->p1_cap || o.n1s.size() >= (size_t)SELECT_MAX_ROWS || o.rec.size() > (size_t)SELECT_MAX_BYTES || BS > 65536)
-			pb->blk_sparse[b] = 0;
-		pb->p1_rows_in_blk[b] = (int)o.n1s.size();
-	}
-	std::vector<P1Block> &rec_blocks = pb->p1blocks;
-	std::vector<long long> vbase(nb + 1, 0);
-	size_t total = 0;
-	for (int b = 0; b < nb; ++b) { vbase[b + 1] = vbase[b] + (long long)rec_blocks[b].n1s.size(); total += ((rec_blocks[b].rec.size() + 15) & ~(size_t)15); }
-	const size_t nrows = (size_t)vbase[nb];
-	std::vector<uint64_t> rowoff(nrows + nb + 1, 0);
-	std::vector<uint32_t> n1(nrows + 1, 0);
-	std::vector<uint16_t> realrow(nrows + 1, 0);
-	std::vector<uint8_t> img;
-	img.reserve(total + 64);
-	pb->p1_rows = (int64_t)nrows;
-	for (int b = 0; b < nb; ++b) {
-		const P1Block &o = rec_blocks[b];
-		uint64_t pos = img.size();
-		uint64_t *ro = rowoff.data() + vbase[b] + b;
-		for (size_t r = 0; r < o.n1s.size(); ++r) {
-			ro[r] = pos; pos += o.lens[r];
-			n1[vbase[b] + r] = o.n1s[r];
-			realrow[vbase[b] + r] = (uint16_t)o.rrow[r];
-		}
-		ro[o.n1s.size()] = pos;
-		img.insert(img.end(), o.rec.begin(), o.rec.end());
-		img.resize((img.size() + 15) & ~(size_t)15, 0);
-	}
-	img.resize(img.size() + 64, 0);
-	const double tv1 = now_ms();
-	bool ok = pool_malloc(c, (void**)&pb->d_p1img, img.size()) && pool_malloc(c, (void**)&pb->d_p1_rowoff, rowoff.size() * 8 + 8) &&
-	          pool_malloc(c, (void**)&pb->d_p1_n1, n1.size() * 4 + 8) && pool_malloc(c, (void**)&pb->d_p1_realrow, realrow.size() * 2 + 8) &&
-	          pool_malloc(c, (void**)&pb->d_p1_rows_in_blk, (nb + 1) * sizeof(int)) && pool_malloc(c, (void**)&pb->d_p1_vbase, (nb + 1) * sizeof(long long));
-	ok = ok && CU_OK(cudaMemcpyAsync(pb->d_p1img, img.data(), img.size(), cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_p1_rowoff, rowoff.data(), rowoff.size() * 8, cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_p1_n1, n1.data(), n1.size() * 4, cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_p1_realrow, realrow.data(), realrow.size() * 2, cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_p1_rows_in_blk, pb->p1_rows_in_blk.data(), nb * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_p1_vbase, vbase.data(), (nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->st));
-	pb->p1_ready = ok;
-	const double tv2 = now_ms();
-	std::vector<P1Block>().swap(pb->p1blocks);
-	if (trace) fprintf(stderr, "[b200 trace]   view: host assembly %.2f ms, alloc+upload %.2f ms, free %.2f ms\n", tv1 - tv0, tv2 - tv1, now_ms() - tv2);
-	return ok;
-}
-
 // Composite maps of the row groups (compose.cu) for every sparse block: forward maps of plane 0 for the QUERY walk and
 // inverse maps of the plane-1 view for the select kernel.  Query independent, so they are built once per resident PBF:
 // lazily by the first split scan, or chunk by chunk while the image is still being copied (b200_pbf_load_ex).
-struct ComposeJob {
-	const b200_pbf_t *pb = nullptr;
-	std::vector<int> all;     // sparse blocks, ascending
-	int *d_all = nullptr;
-	size_t next = 0;          // first entry of `all` not launched yet
-	ComposeParams K;
+// Which blocks are sparse is decided on the device (index.cu: p1view_kernel -> d_blk_sparse); the kernels skip the others.
+static bool compose_alloc(const b200_pbf_t *pb)
+{
+	b200_ctx_t *c = pb->ctx;
+	const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
+	const size_t slots = (size_t)pb->n_blk * n_grp, vslots = (size_t)pb->n_blk * SELECT_GROUPS;
+	bool ok = pool_malloc(c, (void**)&pb->d_comp_start, slots * COMP_CAP * sizeof(uint32_t)) &&
+	          pool_malloc(c, (void**)&pb->d_comp_delta, slots * COMP_CAP * sizeof(int32_t)) &&
+	          pool_malloc(c, (void**)&pb->d_comp_n, slots * sizeof(int) + 16) &&
+	          pool_malloc(c, (void**)&pb->d_vcomp_start, vslots * SELECT_COMP_CAP * sizeof(uint32_t)) &&
+	          pool_malloc(c, (void**)&pb->d_vcomp_delta, vslots * SELECT_COMP_CAP * sizeof(int32_t)) &&
+	          pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16);
+	return ok && CU_OK(cudaMemsetAsync(pb->d_comp_n, 0, slots * sizeof(int), c->st)) && CU_OK(cudaMemsetAsync(pb->d_vcomp_n, 0, vslots * sizeof(int), c->st));
+}
 
-	bool begin(const b200_pbf_t *p) {
-		pb = p;
-		b200_ctx_t *c = pb->ctx;
-		const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
-		for (int b = 0; b < pb->n_blk; ++b) if (pb->blk_sparse[b]) all.push_back(b);
-		const size_t slots = (size_t)pb->n_blk * n_grp, vslots = (size_t)pb->n_blk * SELECT_GROUPS;
-		bool ok = pool_malloc(c, (void**)&pb->d_comp_start, slots * COMP_CAP * sizeof(uint32_t)) &&
-		          pool_malloc(c, (void**)&pb->d_comp_delta, slots * COMP_CAP * sizeof(int32_t)) &&
-		          pool_malloc(c, (void**)&pb->d_comp_n, slots * sizeof(int) + 16) && pool_malloc(c, (void**)&d_all, all.size() * sizeof(int) + 16) &&
-		          pool_malloc(c, (void**)&pb->d_vcomp_start, vslots * SELECT_COMP_CAP * sizeof(uint32_t)) &&
-		          pool_malloc(c, (void**)&pb->d_vcomp_delta, vslots * SELECT_COMP_CAP * sizeof(int32_t)) &&
-		          pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16);
-		ok = ok && CU_OK(cudaMemsetAsync(pb->d_comp_n, 0, slots * sizeof(int), c->st)) && CU_OK(cudaMemsetAsync(pb->d_vcomp_n, 0, vslots * sizeof(int), c->st)) &&
-		     CU_OK(cudaMemcpyAsync(d_all, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
-		K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rows_in_blk = pb->d_rows_in_blk; K.blk_list = d_all;
-		K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
-		K.n_grp = n_grp; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0; K.row_base = nullptr; K.n1_step = 2;
-		return ok;
-	}
-	// forward composites of the sparse blocks below blk_end (their image bytes and row meta must be queued before)
-	bool upto(int blk_end) {
-		size_t i1 = next;
-		while (i1 < all.size() && all[i1] < blk_end) ++i1;
-		if (i1 == next) return true;
-		ComposeParams Kk = K;
-		Kk.blk_list = d_all + next;
-		const bool ok = CU_OK(launch_compose(Kk, (int)(i1 - next), pb->ctx->st));
-		++pb->ctx->launches;
-		next = i1;
-		return ok;
-	}
-	bool end() {
-		b200_ctx_t *c = pb->ctx;
-		bool ok = upto(pb->n_blk);
-		ComposeParams V = K;   // the plane-1 view is small and host-built: one launch
-		V.blk_list = d_all;
-		V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
-		V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
-		V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
-		ok = ok && CU_OK(launch_compose(V, (int)all.size(), c->st));
-		++c->launches;
-		ok = ok && CU_OK(cudaStreamSynchronize(c->st));   // d_all is read by the queued kernels
-		pool_free(c, d_all);
-		d_all = nullptr;
-		if (ok) pb->comp_ready = true;
-		return ok;
-	}
-};
+// composites of resident blocks [b0,b1): their image bytes, row index, n1 and plane-1 view must be queued before on st
+static bool compose_queue(const b200_pbf_t *pb, int b0, int b1)
+{
+	if (b1 <= b0) return true;
+	b200_ctx_t *c = pb->ctx;
+	ComposeParams K;
+	memset(&K, 0, sizeof(K));
+	K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rows_in_blk = pb->d_rows_in_blk; K.blk_list = nullptr; K.blk_first = b0;
+	K.blk_ok = pb->d_blk_sparse;
+	K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
+	K.n_grp = (pb->BS + COMP_K - 1) / COMP_K; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0; K.row_base = nullptr; K.n1_step = 2;
+	ComposeParams V = K;   // inverse composites of the plane-1 view rows
+	V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
+	V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
+	V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
+	const bool ok = CU_OK(launch_compose(K, b1 - b0, c->st)) && CU_OK(launch_compose(V, b1 - b0, c->st));
+	c->launches += 2;
+	return ok;
+}
 
 static bool build_composites(const b200_pbf_t *pb)
 {
-	ComposeJob job;
-	return job.begin(pb) && job.end();
+	if (!compose_alloc(pb) || !compose_queue(pb, 0, pb->n_blk)) return false;
+	pb->comp_ready = true;
+	return true;
 }
 
-// Plan tiles and upload the row index of the resident blocks.
-static bool pbf_upload_index(b200_pbf_t *pb)
+// Device buffers of the row index and the plane-1 view (filled by index.cu), the block table and the zeroed outputs of
+// rowmeta / snapshot inversion.  The small uploads go on `up` (the copy stream when an image copy follows them).
+static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 {
 	b200_ctx_t *c = pb->ctx;
 	const int BS = pb->BS, nb = pb->n_blk;
-	std::vector<int2> tiles;
-	std::vector<int> btb;
-	plan_tiles(pb, tiles, btb);
-	const size_t n_tiles = tiles.size();
 	const int n_grp = (BS + COMP_K - 1) / COMP_K;
-	std::vector<int> gtb((size_t)nb * (n_grp + 1));
-	for (int b = 0; b < nb; ++b) { // first tile of every row group (tiles never cross a multiple of COMP_K rows)
-		int t = btb[b];
-		for (int g = 0; g <= n_grp; ++g) {
-			while (t < btb[b + 1] && tiles[t].x < g * COMP_K) ++t;
-			gtb[(size_t)b * (n_grp + 1) + g] = t;
-		}
-	}
-	if (!pool_malloc(c, (void**)&pb->d_grp_tile_beg, gtb.size() * sizeof(int) + 16) ||
-	    !CU_OK(cudaMemcpyAsync(pb->d_grp_tile_beg, gtb.data(), gtb.size() * sizeof(int), cudaMemcpyHostToDevice, c->st))) return false;
+	pb->p1_cap = (((pb->m / 4 > 4096 ? pb->m / 4 : 4096) + 2047) / 2048) * 2048;
 	bool ok = pool_malloc(c, (void**)&pb->d_rowoff, sizeof(uint64_t) * (size_t)nb * (BS + 1) + 8) &&
 	          pool_malloc(c, (void**)&pb->d_blkoff, sizeof(uint64_t) * (nb + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_blkend, sizeof(uint64_t) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_rows_in_blk, sizeof(int) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_blk_tile_beg, sizeof(int) * (nb + 1)) &&
-	          pool_malloc(c, (void**)&pb->d_tiles, sizeof(int2) * (n_tiles + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_blk_tile_end, sizeof(int) * (nb + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_grp_tile_beg, sizeof(int) * (size_t)nb * (n_grp + 1) + 16) &&
+	          pool_malloc(c, (void**)&pb->d_tiles, sizeof(int2) * ((size_t)nb * BS + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_n1, sizeof(uint32_t) * (size_t)nb * BS * 2 + 8) &&
-	          pool_malloc(c, (void**)&pb->d_rank0, sizeof(int32_t) * (size_t)nb * 2 * (size_t)pb->m + 8);
+	          pool_malloc(c, (void**)&pb->d_rank0, sizeof(int32_t) * (size_t)nb * 2 * (size_t)pb->m + 8) &&
+	          pool_malloc(c, (void**)&pb->d_p1img, (size_t)nb * P1_SLOT_BYTES + 64) &&
+	          pool_malloc(c, (void**)&pb->d_p1_rowoff, sizeof(uint64_t) * (size_t)nb * (SELECT_MAX_ROWS + 1) + 8) &&
+	          pool_malloc(c, (void**)&pb->d_p1_n1, sizeof(uint32_t) * (size_t)nb * SELECT_MAX_ROWS + 8) &&
+	          pool_malloc(c, (void**)&pb->d_p1_realrow, sizeof(uint16_t) * (size_t)nb * SELECT_MAX_ROWS + 8) &&
+	          pool_malloc(c, (void**)&pb->d_p1_rows_in_blk, sizeof(int) * (nb + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_p1_vbase, sizeof(long long) * (nb + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_blk_sparse, (size_t)nb + 16);
 	if (!ok) return false;
-	ok = CU_OK(cudaMemcpyAsync(pb->d_rowoff, pb->h_rowoff.data(), sizeof(uint64_t) * (size_t)nb * (BS + 1), cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_blkoff, pb->h_blkoff.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_rows_in_blk, pb->rows_in_blk.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_blk_tile_beg, btb.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(pb->d_tiles, tiles.data(), sizeof(int2) * n_tiles, cudaMemcpyHostToDevice, c->st)) &&
-	     CU_OK(cudaMemsetAsync(pb->d_n1, 0, sizeof(uint32_t) * (size_t)nb * BS * 2, c->st)) &&
-	     CU_OK(cudaMemsetAsync(pb->d_rank0, 0, sizeof(int32_t) * (size_t)nb * 2 * (size_t)pb->m, c->st)) &&
-	     CU_OK(cudaMemsetAsync(c->d_acc + 4, 0, sizeof(unsigned long long), c->st)) &&
-	     CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
-	if (!ok) return false;
-	return true;
+	return CU_OK(cudaMemsetAsync(c->d_acc + 4, 0, sizeof(unsigned long long), up)) &&
+	       CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), up)) &&
+	       CU_OK(cudaMemcpyAsync(pb->d_blkoff, pb->h_blkoff.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, up)) &&
+	       CU_OK(cudaMemcpyAsync(pb->d_blkend, pb->h_blkend.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, up)) &&
+	       CU_OK(cudaMemcpyAsync(pb->d_rows_in_blk, pb->rows_in_blk.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, up)) &&
+	       CU_OK(cudaMemsetAsync(pb->d_n1, 0, sizeof(uint32_t) * (size_t)nb * BS * 2, c->st)) &&
+	       CU_OK(cudaMemsetAsync(pb->d_rank0, 0, sizeof(int32_t) * (size_t)nb * 2 * (size_t)pb->m, c->st));
 }
 
-// Per-row n1, [generator: run the chain], snapshot inversion, [composite maps]; one sync at the end.
-static bool pbf_queue_kernels(b200_pbf_t *pb, bool synth_chain)
+static IndexParams index_params(const b200_pbf_t *pb, int b0)
+{
+	IndexParams X;
+	memset(&X, 0, sizeof(X));
+	X.img = pb->d_img; X.blkoff = pb->d_blkoff; X.blkend = pb->d_blkend; X.rows_in_blk = pb->d_rows_in_blk;
+	X.m = pb->m; X.shift = pb->shift; X.blk_first = b0; X.rowoff = pb->d_rowoff; X.tiles = pb->d_tiles;
+	X.blk_tile_beg = pb->d_blk_tile_beg; X.blk_tile_end = pb->d_blk_tile_end; X.grp_tile_beg = pb->d_grp_tile_beg; X.err = pb->ctx->d_err;
+	return X;
+}
+
+// blocks [b0,b1) whose row offsets are known (pbf_index_kernel): tiles and per-row n1
+static bool queue_tiles_rowmeta(b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
 {
 	b200_ctx_t *c = pb->ctx;
-	const int BS = pb->BS, nb = pb->n_blk;
-	bool ok = true;
-	ComposeJob cjob;
-	const bool eager = pb->prepare_split && pb->p1_ready && !synth_chain;
-	if (eager && !cjob.begin(pb)) return false;
-	const int n_chunks = pb->chunk_blk.size() > 1 ? (int)pb->chunk_blk.size() - 1 : 0;
-	if (n_chunks > 0) {
-		// the image is arriving in chunks of whole blocks on the copy stream: row meta, snapshot inversion and (if asked
-		// for) the composite maps of every chunk are queued behind that chunk's event, so they overlap the rest of the copy
-		for (int k = 0; k < n_chunks; ++k) {
-			const int b0 = pb->chunk_blk[k], b1 = pb->chunk_blk[k + 1];
-			if (!CU_OK(cudaStreamWaitEvent(c->st, c->ev_chunk[k], 0))) return false;
-			if (!CU_OK(launch_rowmeta(pb->d_img, pb->d_rowoff + (size_t)b0 * (BS + 1), b1 - b0, pb->shift, 0, pb->d_rows_in_blk + b0, (uint32_t)pb->m,
-			                          pb->d_n1 + (size_t)b0 * BS * 2, c->d_acc + 4, c->st))) return false;
-			if (!CU_OK(launch_invert_snapshots(pb->d_img, pb->d_blkoff + b0, b1 - b0, pb->m, pb->d_rank0 + (size_t)b0 * 2 * (size_t)pb->m, c->d_err, c->st))) return false;
-			c->launches += 2;
-			if (eager && !cjob.upto(b1)) return false;
-		}
-	} else {
-		if (!CU_OK(launch_rowmeta(pb->d_img, pb->d_rowoff, nb, pb->shift, 0, pb->d_rows_in_blk, (uint32_t)pb->m, pb->d_n1, c->d_acc + 4, c->st))) return false;
-		++c->launches;
-	}
-	if (synth_chain) {
-		WalkParams P;
-		memset(&P, 0, sizeof(P));
-		P.img = pb->d_img; P.rowoff = pb->d_rowoff; P.n1 = pb->d_n1; P.tiles = pb->d_tiles; P.blk_tile_beg = pb->d_blk_tile_beg;
-		P.snap_img = pb->d_img; P.blkoff = pb->d_blkoff;
-		P.m = pb->m; P.n_track = pb->m; P.G = 1; P.words = (pb->m + 31) / 32; P.shift = pb->shift;
-		P.n_blk_chain = nb; P.blk_row0 = 0; P.row_lo = 0; P.row_hi = pb->n; P.err = c->d_err;
-		// tgrp is read for valid entries: borrow the (zeroed) n1 buffer?  No: allocate a zero group map.
-		uint8_t *d_zero = nullptr;
-		if (!CU_OK(cudaMalloc(&d_zero, (size_t)pb->m + 16)) || !CU_OK(cudaMemsetAsync(d_zero, 0, (size_t)pb->m + 16, c->st))) return false;
-		P.tgrp = d_zero;
-		const int C = pb->m > 148 * 2 * WALK_NT * 4 ? 4 : pb->m > 148 * 2 * WALK_NT * 2 ? 2 : 1;
-		const int slices = (pb->m + WALK_NT * C - 1) / (WALK_NT * C);
-		ok = CU_OK(launch_walk(P, C, WALK_MODE_CHAIN, slices, nb, c->st));
-		++c->launches;
-		ok = ok && CU_OK(cudaStreamSynchronize(c->st));
-		cudaFree(d_zero);
-		if (!ok) return false;
-	}
-	if (n_chunks == 0) {
-		if (!CU_OK(launch_invert_snapshots(pb->d_img, pb->d_blkoff, nb, pb->m, pb->d_rank0, c->d_err, c->st))) return false;
-		++c->launches;
-		if (eager && !cjob.upto(nb)) return false;
-	}
-	if (eager && !cjob.end()) return false;
+	const int BS = pb->BS;
+	c->launches += 2;
+	return CU_OK(launch_plan_tiles(index_params(pb, b0), b1 - b0, st)) &&
+	       CU_OK(launch_rowmeta(pb->d_img, pb->d_rowoff + (size_t)b0 * (BS + 1), b1 - b0, pb->shift, 0, pb->d_rows_in_blk + b0, (uint32_t)pb->m,
+	                            pb->d_n1 + (size_t)b0 * BS * 2, c->d_acc + 4, st));
+}
+
+// blocks [b0,b1) whose snapshots are in place: start ranks (pbwt.c:343) and the plane-1 view
+static bool queue_ranks_view(b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
+{
+	b200_ctx_t *c = pb->ctx;
+	P1ViewParams V;
+	memset(&V, 0, sizeof(V));
+	V.img = pb->d_img; V.rowoff = pb->d_rowoff; V.n1 = pb->d_n1; V.rows_in_blk = pb->d_rows_in_blk;
+	V.m = pb->m; V.shift = pb->shift; V.blk_first = b0; V.p1_cap = pb->p1_cap;
+	V.p1img = pb->d_p1img; V.p1_rowoff = pb->d_p1_rowoff; V.p1_n1 = pb->d_p1_n1; V.p1_realrow = pb->d_p1_realrow;
+	V.p1_rows_in_blk = pb->d_p1_rows_in_blk; V.p1_vbase = pb->d_p1_vbase; V.blk_sparse = pb->d_blk_sparse;
+	c->launches += 2;
+	return CU_OK(launch_invert_snapshots(pb->d_img, pb->d_blkoff + b0, b1 - b0, pb->m, pb->d_rank0 + (size_t)b0 * 2 * (size_t)pb->m, c->d_err, st)) &&
+	       CU_OK(launch_p1view(V, b1 - b0, st));
+}
+
+// End of a load: fetch the per-block flags and the error state, wait for everything queued.
+static bool pbf_finish_load(b200_pbf_t *pb)
+{
+	b200_ctx_t *c = pb->ctx;
 	unsigned long long bad = 0;
 	int err = 0;
-	ok = CU_OK(cudaMemcpyAsync(&bad, c->d_acc + 4, sizeof(bad), cudaMemcpyDeviceToHost, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(err), cudaMemcpyDeviceToHost, c->st)) &&
-	     CU_OK(cudaStreamSynchronize(c->st));
+	pb->blk_sparse.assign(pb->n_blk ? pb->n_blk : 1, 0);
+	bool ok = CU_OK(cudaMemcpyAsync(&bad, c->d_acc + 4, sizeof(bad), cudaMemcpyDeviceToHost, c->st)) &&
+	          CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(err), cudaMemcpyDeviceToHost, c->st));
+	if (ok && pb->n_blk) ok = CU_OK(cudaMemcpyAsync(pb->blk_sparse.data(), pb->d_blk_sparse, (size_t)pb->n_blk, cudaMemcpyDeviceToHost, c->st));
+	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
 	if (!ok) return false;
 	pb->bad_rows = (int64_t)bad;
+	if (err & 2) { set_err("corrupt PBF: record tags/lengths inside a checkpoint block do not parse"); return false; }
 	if (err & 1) { set_err("corrupt PBF: an 'S' snapshot holds a column index >= m"); return false; }
 	if (err & 8) { set_err("internal: TMA copy never completed"); return false; }
+	pb->p1_ready = true;
 	return true;
 }
 
-static bool pbf_finish_resident(b200_pbf_t *pb, bool synth_chain) { return pbf_upload_index(pb) && pbf_queue_kernels(pb, synth_chain); }
+// host copy of the device-built row offsets, for the few host-side questions that need them (b200_pbf_row_bytes)
+static const std::vector<uint64_t> *host_rowoff(const b200_pbf_t *cpb)
+{
+	b200_pbf_t *pb = const_cast<b200_pbf_t*>(cpb);
+	if (pb->h_rowoff.empty() && pb->n_blk) {
+		pb->h_rowoff.assign((size_t)pb->n_blk * (pb->BS + 1), 0);
+		cudaSetDevice(pb->ctx->dev);
+		if (!CU_OK(cudaMemcpyAsync(pb->h_rowoff.data(), pb->d_rowoff, pb->h_rowoff.size() * 8, cudaMemcpyDeviceToHost, pb->ctx->st)) ||
+		    !CU_OK(cudaStreamSynchronize(pb->ctx->st))) { pb->h_rowoff.clear(); return nullptr; }
+	}
+	return &pb->h_rowoff;
+}
+
+
 
 // the file indexes checkpoint blocks only (pbwt.c:297); walk the length prefixes of the rows inside
 static bool walk_block(const uint8_t *f, size_t flen, uint64_t off, int m, int g, int rows, uint64_t *roff)
@@ -669,26 +565,30 @@ static b200_pbf_t *pbf_index_prepare(const uint8_t *f, size_t flen, int64_t row_
 	pb->img_bytes = (size_t)(copy_end - pb->file_off0);
 	pb->h_idx.swap(idx);
 	pb->ioff = ioff;
+	// block table: everything the device indexer needs comes from the header and the index record
+	pb->rows_in_blk.resize(nb);
+	pb->h_blkoff.resize(nb);
+	pb->h_blkend.resize(nb);
+	for (int b = 0; b < nb; ++b) {
+		const int64_t r0 = (int64_t)(pb->blk0 + b) << shift;
+		pb->rows_in_blk[b] = (int)(n - r0 < BS ? n - r0 : BS);
+		pb->h_blkoff[b] = pb->h_idx[pb->blk0 + b] - pb->file_off0;
+		pb->h_blkend[b] = (pb->blk0 + b + 1 < n_idx ? pb->h_idx[pb->blk0 + b + 1] : ioff) - pb->file_off0;
+		if (pb->h_blkoff[b] + 1 + (uint64_t)g * 4 * (uint64_t)m > pb->h_blkend[b]) { set_err("corrupt PBF: checkpoint block %d is shorter than its 'S' record", pb->blk0 + b); delete pb; return nullptr; }
+	}
 	return pb;
 }
 
-// second half: walk the length prefixes of every resident block (the file indexes only block starts, pbwt.c:297) and
-// collect the plane-1 rows; a few host threads, meant to run while the H2D copy of the image is in flight
+// Host mirror of index.cu's row index, for b200_pbf_plan only (planning / validation without a device): walk the
+// length prefixes of every resident block (the file indexes only block starts, pbwt.c:297).
 static bool pbf_index_walk(b200_pbf_t *pb, const uint8_t *f)
 {
 	const int nb = pb->n_blk, BS = pb->BS, shift = pb->shift, m = pb->m, g = pb->g;
 	const int64_t n = pb->n;
 	const std::vector<uint64_t> &idx = pb->h_idx;
 	const uint64_t ioff = pb->ioff;
-	pb->rows_in_blk.resize(nb);
-	pb->p1blocks.assign(nb, P1Block());
 	pb->h_rowoff.assign((size_t)nb * (BS + 1), 0);
-	pb->h_blkoff.resize(nb);
-	for (int b = 0; b < nb; ++b) {
-		const int64_t r0 = (int64_t)(pb->blk0 + b) << shift;
-		pb->rows_in_blk[b] = (int)(n - r0 < BS ? n - r0 : BS);
-		pb->h_blkoff[b] = idx[pb->blk0 + b] - pb->file_off0;
-	}
+	(void)shift; (void)n;
 	bool ok = true;
 	{
 		int hw = (int)std::thread::hardware_concurrency();
@@ -701,7 +601,6 @@ static bool pbf_index_walk(b200_pbf_t *pb, const uint8_t *f)
 				for (int b = t; b < nb; b += nt) {
 					uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
 					if (!walk_block(f, (size_t)ioff + 1, idx[pb->blk0 + b], m, g, pb->rows_in_blk[b], ro)) { bad[t] = 1; return; }
-					collect_plane1_block(f, ro, pb->rows_in_blk[b], (uint32_t)m, pb->p1blocks[b]);
 					for (int r = 0; r <= pb->rows_in_blk[b]; ++r) ro[r] -= pb->file_off0;
 				}
 			});
@@ -730,44 +629,62 @@ extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t 
 	if (!pb) return nullptr;
 	pb->ctx = c;
 	pb->prepare_split = (flags & B200_LOAD_PREPARE_COUNT_SCAN) != 0;
-	// The H2D copy is queued first, in up to 8 chunks of whole checkpoint blocks on the copy stream (its extent only
-	// needs the header and the index record).  The row walk below runs meanwhile on the host; the per-block kernels
-	// are then queued chunk by chunk behind the chunks' events (pbf_finish_resident).
+	// The host only parses the header and the block index (pbwt.c:231-258) and queues work; the rows inside the blocks
+	// are indexed on the device (index.cu).  The image goes out in up to LOAD_CHUNKS chunks of whole checkpoint blocks on the copy
+	// stream; behind every chunk's event: the length-prefix chase of its blocks (st_idx, latency bound, so it runs beside
+	// the previous chunk's kernels), then tiles, row meta, start ranks, the plane-1 view and -- if asked for -- the
+	// composite maps on st.  One synchronisation at the end.
 	const int nb = pb->n_blk;
 	bool ok = pool_malloc(c, (void**)&pb->d_img, pb->img_bytes + 64);
 	ok = ok && CU_OK(cudaStreamSynchronize(c->st));          // buffers from the pool may still be in use by queued work of this context
+	ok = ok && pbf_alloc_index(pb, c->st_copy);
+	const bool eager = pb->prepare_split;
+	const bool copy_only = getenv("BGT_B200_COPYONLY") != nullptr;   // diagnostics: time the bare H2D copy
+	if (eager) ok = ok && compose_alloc(pb);
+	// the zeroing memsets on st must be done before kernels on the index streams write n1 / rank0
+	ok = ok && CU_OK(cudaEventRecord(c->ev_zero, c->st));
+	for (int i = 0; ok && i < N_IDX_STREAMS; ++i) ok = CU_OK(cudaStreamWaitEvent(c->st_idx[i], c->ev_zero, 0));
 	ok = ok && CU_OK(cudaEventRecord(c->ev[4], c->st_copy));
-	const int n_chunks = nb >= 16 ? 8 : (nb > 0 ? 1 : 0);
-	pb->chunk_blk.clear();
-	for (int k = 0; k <= n_chunks; ++k) pb->chunk_blk.push_back((int)((long long)nb * k / (n_chunks ? n_chunks : 1)));
+	const int n_chunks = nb >= 2 * LOAD_CHUNKS ? LOAD_CHUNKS : (nb >= 16 ? 8 : (nb > 0 ? 1 : 0));
 	size_t done = 0;
-	auto queue_chunks = [&](int k0, int k1) { // image bytes of the blocks of chunks [k0,k1) -> copy stream, one event per chunk
-		for (int k = k0; ok && k < k1; ++k) {
-			const int b1 = pb->chunk_blk[k + 1];
-			const size_t end = b1 < nb ? (size_t)(pb->h_idx[pb->blk0 + b1] - pb->file_off0) : pb->img_bytes;
-			ok = CU_OK(cudaMemcpyAsync(pb->d_img + done, f + pb->file_off0 + done, end - done, cudaMemcpyHostToDevice, c->st_copy));
-			if (ok && k == n_chunks - 1) ok = CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st_copy));
-			ok = ok && CU_OK(cudaEventRecord(c->ev_chunk[k], c->st_copy));
-			done = end;
-		}
-	};
-	// Small uploads share the H2D engine with the image: whatever is queued behind the whole image waits for all of it.
-	// So only the first chunks go out now (about as much copy time as the host walk takes); the index arrays follow
-	// them, then the rest of the image, then the per-chunk kernels.
-	const int k_first = n_chunks > 1 ? 4 : n_chunks;
-	queue_chunks(0, k_first);
+	cudaEvent_t tev[LOAD_CHUNKS][4];
 	if (n_chunks == 0) ok = ok && CU_OK(cudaMemsetAsync(pb->d_img, 0, 64, c->st_copy));
-	const double t1 = now_ms();
-	ok = ok && pbf_index_walk(pb, f);            // overlaps the copy queued above
-	const double t2 = now_ms();
-	ok = ok && build_plane1_view(pb) && pbf_upload_index(pb);
-	queue_chunks(k_first, n_chunks);
+	for (int k = 0; ok && k < n_chunks; ++k) {
+		const int b0 = (int)((long long)nb * k / n_chunks), b1 = (int)((long long)nb * (k + 1) / n_chunks);
+		const size_t end = b1 < nb ? (size_t)(pb->h_idx[pb->blk0 + b1] - pb->file_off0) : pb->img_bytes;
+		ok = CU_OK(cudaMemcpyAsync(pb->d_img + done, f + pb->file_off0 + done, end - done, cudaMemcpyHostToDevice, c->st_copy));
+		if (ok && k == n_chunks - 1) ok = CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st_copy));
+		ok = ok && CU_OK(cudaEventRecord(c->ev_chunk[k], c->st_copy));
+		if (trace) { cudaEventCreate(&tev[k][3]); cudaEventRecord(tev[k][3], c->st_copy); }
+		done = end;
+		if (copy_only) continue;
+		// per chunk, on one of the index streams: chase -> tiles, n1, start ranks, plane-1 view (small latency-bound grids that
+		// overlap the previous chunks' composite maps, which are the only thing left on st)
+		cudaStream_t sx = c->st_idx[k % N_IDX_STREAMS];
+		ok = ok && CU_OK(cudaStreamWaitEvent(sx, c->ev_chunk[k], 0)) && CU_OK(launch_index(index_params(pb, b0), b1 - b0, sx));
+		++c->launches;
+		ok = ok && queue_tiles_rowmeta(pb, b0, b1, sx) && queue_ranks_view(pb, b0, b1, sx);
+		ok = ok && CU_OK(cudaEventRecord(c->ev_idx[k], sx)) && CU_OK(cudaStreamWaitEvent(c->st, c->ev_idx[k], 0));
+		if (eager) ok = ok && compose_queue(pb, b0, b1);
+		if (trace) {
+			for (int j = 0; j < 3; ++j) cudaEventCreate(&tev[k][j]);
+			cudaEventRecord(tev[k][1], sx); cudaEventRecord(tev[k][2], c->st);
+		}
+	}
 	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st_copy));
-	const double t3 = now_ms();
-	ok = ok && pbf_queue_kernels(pb, false);
-	pb->chunk_blk.clear();
-	if (trace) fprintf(stderr, "[b200 trace] load: first chunks %.2f ms, index walk %.2f ms, plane-1 view + index upload + rest of the image queued %.2f ms, kernels (+ wait for the copy) %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
-	if (!ok) { cudaStreamSynchronize(c->st_copy); cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	const double t1 = now_ms();
+	ok = ok && pbf_finish_load(pb);
+	if (ok && eager) pb->comp_ready = true;
+	if (trace) {
+		fprintf(stderr, "[b200 trace] load: queued in %.2f ms, device done after %.2f ms\n", t1 - t0, now_ms() - t0);
+		for (int k = 0; k < n_chunks && !copy_only; ++k) {
+			float a = 0, b = 0, d = 0;
+			cudaEventElapsedTime(&a, c->ev[4], tev[k][3]); cudaEventElapsedTime(&b, c->ev[4], tev[k][1]); cudaEventElapsedTime(&d, c->ev[4], tev[k][2]);
+			fprintf(stderr, "[b200 trace]   chunk %2d: copied at %.2f ms, indexed at %.2f, composites at %.2f\n", k, a, b, d);
+			for (int j = 0; j < 4; ++j) cudaEventDestroy(tev[k][j]);
+		}
+	}
+	if (!ok) { cudaStreamSynchronize(c->st_copy); for (int i = 0; i < N_IDX_STREAMS; ++i) cudaStreamSynchronize(c->st_idx[i]); cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
 	return pb;
@@ -849,11 +766,13 @@ extern "C" int64_t b200_pbf_row_bytes(const b200_pbf_t *pb, int64_t row_beg, int
 	if (row_beg < b200_pbf_row_beg(pb) || row_end > b200_pbf_row_end(pb) || row_beg > row_end) { set_err("row range not resident"); return -1; }
 	int64_t bytes = 0;
 	const int BS = pb->BS;
+	const std::vector<uint64_t> *hro = host_rowoff(pb);
+	if (!hro) return -1;
 	for (int64_t k = row_beg; k < row_end;) {
 		const int b = (int)(k >> pb->shift) - pb->blk0, r = (int)(k & (BS - 1));
 		const int64_t in_blk = pb->rows_in_blk[b] - r;
 		const int64_t take = row_end - k < in_blk ? row_end - k : in_blk;
-		const uint64_t *ro = pb->h_rowoff.data() + (size_t)b * (BS + 1);
+		const uint64_t *ro = hro->data() + (size_t)b * (BS + 1);
 		bytes += (int64_t)(ro[r + take] - ro[r]);
 		if (with_snapshots && r == 0) bytes += 1 + (int64_t)pb->g * 4 * pb->m;
 		k += take;
@@ -1025,7 +944,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	const int n_blk = b_last - b_first + 1;
 	WalkParams P;
 	memset(&P, 0, sizeof(P));
-	P.img = pb->d_img; P.rowoff = pb->d_rowoff; P.n1 = pb->d_n1; P.tiles = pb->d_tiles; P.blk_tile_beg = pb->d_blk_tile_beg;
+	P.img = pb->d_img; P.rowoff = pb->d_rowoff; P.n1 = pb->d_n1; P.tiles = pb->d_tiles; P.blk_tile_beg = pb->d_blk_tile_beg; P.blk_tile_end = pb->d_blk_tile_end;
 	P.rank0 = pb->d_rank0; P.track = q->full ? nullptr : q->d_track; P.tgrp = q->d_tgrp;
 	P.cnt_raw = (int32_t*)c->cnt_raw.p; P.hap[0] = d_bits[0]; P.hap[1] = d_bits[1];
 	P.m = pb->m; P.n_track = n_track; P.G = G; P.words = words; P.shift = pb->shift;
@@ -1192,6 +1111,7 @@ extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cf
 	pb->rows_in_blk.resize(nb);
 	pb->h_rowoff.assign((size_t)nb * (BS + 1), 0);
 	pb->h_blkoff.resize(nb);
+	pb->h_blkend.resize(nb);
 	uint64_t pos = 16;
 	for (int b = 0; b < nb; ++b) {
 		const int64_t r0 = (int64_t)b << sc.shift;
@@ -1205,6 +1125,7 @@ extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cf
 			pos += 9 + (uint64_t)len2[(r0 + r) * 2] + len2[(r0 + r) * 2 + 1];
 		}
 		ro[rows] = pos;
+		pb->h_blkend[b] = pos;
 	}
 	const uint64_t ioff = pos;
 	tail.resize(1 + 8 + 4 + 8 * (size_t)nb + 8);
@@ -1229,17 +1150,30 @@ extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cf
 	++c->launches;
 	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
 	if (d_flat) cudaFree(d_flat);
-	if (!ok || !pbf_finish_resident(pb, true)) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
-	{ // the plane-1 view is built from a host copy of the generated image
-		uint8_t *h = (uint8_t*)b200_host_alloc(pb->img_bytes);
-		ok = h && CU_OK(cudaMemcpyAsync(h, pb->d_img, pb->img_bytes, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
-		if (ok) {
-			pb->p1blocks.assign(nb, P1Block());
-			for (int b = 0; b < nb; ++b) collect_plane1_block(h, pb->h_rowoff.data() + (size_t)b * (BS + 1), pb->rows_in_blk[b], sc.m, pb->p1blocks[b]);
-			ok = build_plane1_view(pb);
-		}
-		b200_host_free(h);
-		if (!ok) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	// row index, tiles and n1 on the device (index.cu), then the running permutation: the walk kernel in CHAIN mode over
+	// all rows (identity start, pbwt.c:103) dumps S = rank^-1 in front of every block; then start ranks + plane-1 view
+	ok = ok && pbf_alloc_index(pb, c->st);
+	ok = ok && CU_OK(launch_index(index_params(pb, 0), nb, c->st));
+	++c->launches;
+	ok = ok && queue_tiles_rowmeta(pb, 0, nb, c->st);
+	if (ok) {
+		WalkParams P;
+		memset(&P, 0, sizeof(P));
+		P.img = pb->d_img; P.rowoff = pb->d_rowoff; P.n1 = pb->d_n1; P.tiles = pb->d_tiles; P.blk_tile_beg = pb->d_blk_tile_beg; P.blk_tile_end = pb->d_blk_tile_end;
+		P.snap_img = pb->d_img; P.blkoff = pb->d_blkoff;
+		P.m = pb->m; P.n_track = pb->m; P.G = 1; P.words = (pb->m + 31) / 32; P.shift = pb->shift;
+		P.n_blk_chain = nb; P.blk_row0 = 0; P.row_lo = 0; P.row_hi = pb->n; P.err = c->d_err;
+		uint8_t *d_zero = nullptr;   // group map of the (unused) counters
+		ok = CU_OK(cudaMalloc(&d_zero, (size_t)pb->m + 16)) && CU_OK(cudaMemsetAsync(d_zero, 0, (size_t)pb->m + 16, c->st));
+		P.tgrp = d_zero;
+		const int C = pb->m > 148 * 2 * WALK_NT * 4 ? 4 : pb->m > 148 * 2 * WALK_NT * 2 ? 2 : 1;
+		const int slices = (pb->m + WALK_NT * C - 1) / (WALK_NT * C);
+		ok = ok && CU_OK(launch_walk(P, C, WALK_MODE_CHAIN, slices, nb, c->st));
+		++c->launches;
+		ok = ok && CU_OK(cudaStreamSynchronize(c->st));
+		if (d_zero) cudaFree(d_zero);
 	}
+	ok = ok && queue_ranks_view(pb, 0, nb, c->st) && pbf_finish_load(pb);
+	if (!ok) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	return pb;
 }

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int BS = 1 << P.shift;
 	const int n_grp = P.n_grp;
-	const int blk = P.blk_list[blockIdx.x / n_grp], g = blockIdx.x % n_grp;
+	const int blk = P.blk_list ? P.blk_list[blockIdx.x / n_grp] : P.blk_first + (int)(blockIdx.x / n_grp), g = blockIdx.x % n_grp;
 	const uint32_t m = (uint32_t)P.m;
 	const long long rbase = P.row_base ? P.row_base[blk] : (long long)blk * BS;   // first row of the block in the per-row arrays
 	const uint64_t *roff = P.rowoff + (P.row_base ? rbase + blk : (long long)blk * (BS + 1));
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	const int nrow = P.rows_in_blk[blk] - r_lo;
 	const size_t slot = ((size_t)blk * n_grp + g);
 	const int cap = P.cap;
-	if (nrow < COMP_K) { if (tid == 0) P.comp_n[slot] = 0; return; }   // partial last group: never crossed as a whole
+	if (nrow < COMP_K || (P.blk_ok && !P.blk_ok[blk])) { if (tid == 0) P.comp_n[slot] = 0; return; }   // partial last group: never crossed as a whole
 	if (tid == 0) { s_fail = 0; s_n = 0; }
 	__syncthreads();
 

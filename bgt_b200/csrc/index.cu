@@ -1,0 +1,322 @@
+// index.cu -- the row index of a resident PBF, built on the device.
+//
+// The .pbf only indexes checkpoint blocks (one file offset per 'S' record, pbwt.c:268-276,297); the rows inside a
+// block are length-prefixed records ('B', then per plane int32 l + l bytes, pbwt.c:302-308) that pbf_read
+// (pbwt.c:313-337) steps through one fread at a time.  Everything per-row that the scan kernels need is derived here
+// from the image bytes as they arrive in HBM, so the host only queues the copy:
+//   pbf_index_kernel   one CTA (a single running thread) per block chases the length prefixes through a shared-memory
+//                      ring that is kept full by TMA bulk copies -> rowoff[blk][0..rows]; validates tags and lengths.
+//   plan_tiles_kernel  groups rows into the walk kernel's tiles (<= RAW_CAP bytes, never across a COMP_K boundary).
+//   p1view_kernel      compacts the rows whose second bit plane is not empty into the "plane-1 view" (a miniature
+//                      PBF image per block in fixed-size slots) and decides whether the block qualifies for the split
+//                      scan (plane1.cu).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pbwt_kernels.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------ row offsets
+
+constexpr int IX_STAGE = 2048, IX_SLOTS = 4, IX_RING = IX_STAGE * IX_SLOTS;   // small on purpose: a chase CTA (16 KB) must fit
+                                                                            // beside the resident CTAs of the kernels it overlaps
+constexpr int IX_LANES = 2;   // checkpoint blocks chased per CTA, one lane each (see pbf_index_kernel)
+
+__device__ __forceinline__ uint32_t ix_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct IxRing {
+	uint8_t  *ring;
+	uint64_t *bar;          // [IX_SLOTS]
+	const uint8_t *img;
+	uint64_t base, end16;   // ring stage k covers image bytes [base + k*IX_STAGE, ...); end16 = end of the copyable range
+	long long stage[IX_SLOTS];
+	uint32_t parity[IX_SLOTS];
+	bool inflight[IX_SLOTS];
+	int *err;
+
+	__device__ __forceinline__ void wait(int s)
+	{
+		uint32_t spins = 0, ok = 0;
+		while (true) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			             : "=r"(ok) : "r"(ix_smem_u32(bar + s)), "r"(parity[s]) : "memory");
+			if (ok) break;
+			if (++spins > (1u << 26)) { atomicOr(err, 8); __trap(); }
+		}
+		parity[s] ^= 1u;
+		inflight[s] = false;
+	}
+	__device__ __forceinline__ void issue(int s, long long k)
+	{
+		if (inflight[s]) wait(s);
+		const uint64_t beg = base + (uint64_t)k * IX_STAGE;
+		uint64_t stop = beg + IX_STAGE;
+		if (stop > end16) stop = end16;
+		stage[s] = k;
+		if (beg >= stop) return;
+		const uint32_t bytes = (uint32_t)(stop - beg);
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ix_smem_u32(bar + s)), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		             :: "r"(ix_smem_u32(ring + (size_t)s * IX_STAGE)), "l"(img + beg), "r"(bytes), "r"(ix_smem_u32(bar + s)) : "memory");
+		inflight[s] = true;
+	}
+	// make stage k resident and complete; top up the stages behind it
+	__device__ void need(long long k)
+	{
+		const int s = (int)(k % IX_SLOTS);
+		if (stage[s] != k) issue(s, k);
+		#pragma unroll 1
+		for (int j = 1; j < IX_SLOTS - 1; ++j) {   // one slot of slack: a read may straddle stages k-1 and k
+			const long long kk = k + j;
+			const int s2 = (int)(kk % IX_SLOTS);
+			if (stage[s2] < kk && base + (uint64_t)kk * IX_STAGE < end16) issue(s2, kk);
+		}
+		if (inflight[s]) wait(s);
+	}
+};
+
+// 8 bytes of the image at ring-relative offset o (o..o+7; only the first 5 are used by the callers' checks).  o is
+// relative to the ring base; two aligned words cover 5 bytes at any alignment.
+__device__ __forceinline__ uint64_t ix_read5(uint32_t ring_saddr, uint32_t o)
+{
+	const uint32_t i0 = o & (uint32_t)(IX_RING - 4), i1 = (i0 + 4) & (uint32_t)(IX_RING - 1);
+	uint32_t w0, w1;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ring_saddr + i0));
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(ring_saddr + i1));
+	return ((uint64_t)w1 << 32 | w0) >> ((o & 3u) * 8u);
+}
+
+// One LANE per checkpoint block, IX_LANES blocks per CTA, each with its own ring.  (A CTA with a single running thread
+// is compiled onto the uniform datapath, whose register round trips more than double the latency of every hop; lanes
+// that chase different blocks are genuinely divergent and stay in vector registers.)
+__global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
+{
+	extern __shared__ __align__(128) uint8_t ix_sm_all[];
+	const int lane = threadIdx.x;
+	if (lane >= IX_LANES || (int)blockIdx.x * IX_LANES + lane >= P.blk_count) return;
+	uint8_t *ix_sm = ix_sm_all + (size_t)lane * (IX_RING + 64);
+	const int blk = P.blk_first + (int)blockIdx.x * IX_LANES + lane;
+	const int BS = 1 << P.shift;
+	uint64_t *ro = P.rowoff + (size_t)blk * (BS + 1);
+	const int rows = P.rows_in_blk[blk];
+	const uint64_t first = P.blkoff[blk] + 1 + 8ull * (uint64_t)P.m;  // behind the 'S' record (pbwt.c:298-300)
+	const uint64_t base = first & ~15ull;
+
+	IxRing R;   // slow-path state (local memory); the chase itself keeps its cursor in registers
+	R.ring = ix_sm; R.bar = (uint64_t*)(ix_sm + IX_RING); R.img = P.img; R.err = P.err;
+	R.base = base; R.end16 = (P.blkend[blk] + 15) & ~15ull;
+	#pragma unroll
+	for (int s = 0; s < IX_SLOTS; ++s) {
+		R.stage[s] = -1; R.parity[s] = 0; R.inflight[s] = false;
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ix_smem_u32(R.bar + s)), "r"(1));
+	}
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+
+	// all offsets below are relative to `base` (the chase needs no 64-bit image addresses)
+	const uint64_t end = P.blkend[blk] - base;
+	uint64_t pos = first - base;
+	const uint32_t ring_saddr = ix_smem_u32(ix_sm);
+	bool bad = P.img[P.blkoff[blk]] != 'S' || first > P.blkend[blk];
+	uint64_t cur_lo = 1, cur_hi = 0;       // a complete stage holds [cur_lo, cur_hi)
+	auto fetch = [&](uint64_t a) {         // slow path: make the stage(s) of bytes a..a+7 resident
+		const long long k0 = (long long)(a / IX_STAGE), k1 = (long long)((a + 7) / IX_STAGE);
+		R.need(k0);
+		if (k1 != k0 && base + (uint64_t)k1 * IX_STAGE < R.end16) R.need(k1);
+		cur_lo = (uint64_t)k0 * IX_STAGE; cur_hi = cur_lo + IX_STAGE;
+	};
+	int r = 0;
+	for (; r < rows && !bad; ++r) {
+		// 'B' + l0 (5 bytes at pos), then l1 (4 bytes behind the plane-0 bytes)
+		if (pos + 9 > end) { bad = true; break; }
+		if (pos < cur_lo || pos + 8 > cur_hi) fetch(pos);
+		const uint64_t v = ix_read5(ring_saddr, (uint32_t)pos);
+		const int32_t l0 = (int32_t)(uint32_t)(v >> 8);
+		const uint64_t p1 = pos + 5 + (uint64_t)(uint32_t)l0;
+		if ((uint8_t)v != 'B' || l0 < 0 || p1 + 4 > end) { bad = true; break; }
+		if (p1 < cur_lo || p1 + 8 > cur_hi) fetch(p1);
+		const int32_t l1 = (int32_t)(uint32_t)ix_read5(ring_saddr, (uint32_t)p1);
+		const uint64_t nxt = p1 + 4 + (uint64_t)(uint32_t)l1;
+		if (l1 < 0 || nxt > end) { bad = true; break; }
+		ro[r] = base + pos;
+		pos = nxt;
+	}
+	#pragma unroll 1
+	for (int s = 0; s < IX_SLOTS; ++s) if (R.inflight[s]) R.wait(s);   // no copy may be in flight when the CTA exits
+	if (bad) {
+		// the records of this block do not parse: it decodes as an empty block and the load reports the corruption
+		atomicOr(P.err, 2);
+		P.rows_in_blk[blk] = 0;
+		ro[0] = P.blkoff[blk];
+		return;
+	}
+	ro[rows] = base + pos;
+}
+
+cudaError_t launch_index(const IndexParams &P, int n_blk, cudaStream_t st)
+{
+	if (n_blk <= 0) return cudaSuccess;
+	const size_t smem = (size_t)IX_LANES * (IX_RING + 64);
+	cudaError_t e = cudaFuncSetAttribute(pbf_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	IndexParams Q = P;
+	Q.blk_count = n_blk;
+	pbf_index_kernel<<<(n_blk + IX_LANES - 1) / IX_LANES, 32, smem, st>>>(Q);
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ tiles
+
+// Tiles: maximal groups of consecutive rows with <= T_MAX rows and <= RAW_CAP bytes that do not cross a multiple of
+// COMP_K rows; a row larger than RAW_CAP on its own is a single-row "big" tile (streamed in pieces by the walk).
+// Tiles of different COMP_K-row groups are independent: one thread per group, two passes (count, place).
+__device__ __forceinline__ int tiles_of_group(const uint64_t *ro, int r, int r_end, int2 *out)
+{
+	int n = 0;
+	while (r < r_end) {
+		if (ro[r + 1] - ro[r] > (uint64_t)RAW_CAP) { if (out) out[n] = make_int2(r, (int)(1u | 0x80000000u)); ++n; ++r; continue; }
+		int e = r + 1;
+		while (e < r_end && e - r < T_MAX && ro[e + 1] - ro[r] <= (uint64_t)RAW_CAP) ++e;
+		if (out) out[n] = make_int2(r, e - r);
+		++n;
+		r = e;
+	}
+	return n;
+}
+
+__global__ void __launch_bounds__(256) plan_tiles_kernel(const IndexParams P)
+{
+	__shared__ int warp_tot[8];
+	__shared__ int s_base;
+	const int blk = P.blk_first + (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int BS = 1 << P.shift;
+	const int n_grp = (BS + COMP_K - 1) / COMP_K;
+	const uint64_t *ro = P.rowoff + (size_t)blk * (BS + 1);
+	const int rows = P.rows_in_blk[blk];
+	const int t0 = blk * BS;                       // the block's tiles live in a fixed slot of BS entries
+	int *gtb = P.grp_tile_beg + (size_t)blk * (n_grp + 1);
+	if (tid == 0) s_base = 0;
+	__syncthreads();
+	for (int g0 = 0; g0 < n_grp; g0 += 256) {
+		const int g = g0 + tid;
+		int r_lo = g * COMP_K, r_hi = r_lo + COMP_K;
+		if (r_hi > rows) r_hi = rows;
+		const int mine = (g < n_grp && r_lo < rows) ? tiles_of_group(ro, r_lo, r_hi, nullptr) : 0;
+		int x = mine;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += t; }
+		if (lane == 31) warp_tot[warp] = x;
+		__syncthreads();
+		int before = s_base + x - mine;
+		for (int w = 0; w < warp; ++w) before += warp_tot[w];
+		if (g < n_grp) {
+			gtb[g] = t0 + before;
+			if (mine) tiles_of_group(ro, r_lo, r_hi, P.tiles + t0 + before);
+		}
+		__syncthreads();
+		if (tid == 255) s_base = before + mine;
+		__syncthreads();
+	}
+	if (tid == 0) { gtb[n_grp] = t0 + s_base; P.blk_tile_beg[blk] = t0; P.blk_tile_end[blk] = t0 + s_base; }
+}
+
+cudaError_t launch_plan_tiles(const IndexParams &P, int n_blk, cudaStream_t st)
+{
+	if (n_blk <= 0) return cudaSuccess;
+	plan_tiles_kernel<<<n_blk, 256, 0, st>>>(P);
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ plane-1 view
+
+__device__ __forceinline__ uint32_t ix_ld_u32_unaligned(const uint8_t *p)
+{
+	const uintptr_t a = (uintptr_t)p;
+	const uint32_t *w = (const uint32_t*)(a & ~(uintptr_t)3);
+	const uint32_t sh = (uint32_t)(a & 3) * 8;
+	const uint32_t lo = w[0];
+	if (sh == 0) return lo;
+	return __funnelshift_r(lo, w[1], sh);
+}
+
+// Per block: the rows whose plane 1 has at least one 1 bit (n1 from rowmeta_kernel; a corrupt row counts as empty),
+// re-framed as records 'B', l0 = 0, l1, bytes -- an empty plane 0 -- in the block's slot of the view image, with their
+// n1 and row number.  A block is "sparse" (split scan applies) if its view fits the select kernel's staging buffers.
+__global__ void __launch_bounds__(1024) p1view_kernel(const P1ViewParams P)
+{
+	__shared__ uint32_t wrow[32], wbyte[32];
+	__shared__ uint32_t s_rows, s_bytes, s_allones;
+	__shared__ unsigned long long s_ones;
+	const int blk = P.blk_first + (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int BS = 1 << P.shift;
+	const uint64_t *ro = P.rowoff + (size_t)blk * (BS + 1);
+	const int rows = P.rows_in_blk[blk];
+	const uint32_t m = (uint32_t)P.m;
+	const size_t vb = (size_t)blk * SELECT_MAX_ROWS;
+	const uint64_t slot = (uint64_t)blk * P1_SLOT_BYTES;
+	uint64_t *vro = P.p1_rowoff + vb + blk;
+	if (tid == 0) { s_rows = 0; s_bytes = 0; s_allones = 0; s_ones = 0; }
+	__syncthreads();
+	for (int r0 = 0; r0 < rows; r0 += 1024) {
+		const int r = r0 + tid;
+		uint32_t n1 = 0, l1 = 0;
+		const uint8_t *rle = nullptr;
+		if (r < rows) {
+			n1 = P.n1[((size_t)blk * BS + r) * 2 + 1];
+			if (n1) {
+				const uint8_t *rec = P.img + ro[r];
+				const uint32_t l0 = ix_ld_u32_unaligned(rec + 1);
+				l1 = ix_ld_u32_unaligned(rec + 5 + l0);
+				rle = rec + 9 + l0;
+			}
+		}
+		const uint32_t f = n1 ? 1u : 0u, sz = n1 ? 9u + l1 : 0u;
+		uint32_t x = f, y = sz;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t tx = __shfl_up_sync(0xffffffffu, x, d), ty = __shfl_up_sync(0xffffffffu, y, d);
+			if (lane >= d) { x += tx; y += ty; }
+		}
+		if (lane == 31) { wrow[warp] = x; wbyte[warp] = y; }
+		__syncthreads();
+		uint32_t v = s_rows + x - f, off = s_bytes + y - sz;
+		for (int w = 0; w < warp; ++w) { v += wrow[w]; off += wbyte[w]; }
+		if (n1) {
+			if (n1 == m) s_allones = 1;
+			atomicAdd(&s_ones, (unsigned long long)n1);
+			if (v < (uint32_t)SELECT_MAX_ROWS && off + sz <= (uint32_t)SELECT_MAX_BYTES) {
+				vro[v] = slot + off;
+				P.p1_n1[vb + v] = n1;
+				P.p1_realrow[vb + v] = (uint16_t)r;
+				uint8_t *dst = P.p1img + slot + off;
+				dst[0] = 'B'; dst[1] = dst[2] = dst[3] = dst[4] = 0;
+				dst[5] = (uint8_t)l1; dst[6] = (uint8_t)(l1 >> 8); dst[7] = (uint8_t)(l1 >> 16); dst[8] = (uint8_t)(l1 >> 24);
+				for (uint32_t i = 0; i < l1; ++i) dst[9 + i] = rle[i];
+			}
+		}
+		__syncthreads();
+		if (tid == 1023) { s_rows = v + f; s_bytes = off + sz; }
+		__syncthreads();
+	}
+	if (tid == 0) {
+		const bool fits = s_rows < (uint32_t)SELECT_MAX_ROWS && s_bytes <= (uint32_t)SELECT_MAX_BYTES;
+		const bool sparse = fits && !s_allones && s_ones <= (unsigned long long)P.p1_cap && BS <= 65536;
+		P.blk_sparse[blk] = sparse ? 1 : 0;
+		P.p1_rows_in_blk[blk] = fits ? (int)s_rows : 0;
+		P.p1_vbase[blk] = (long long)vb;
+		vro[fits ? s_rows : 0] = slot + (fits ? s_bytes : 0);
+		if (fits) { // zero padding behind the records (the view is read in aligned words)
+			uint8_t *dst = P.p1img + slot + s_bytes;
+			for (int i = 0; i < 16; ++i) dst[i] = 0;
+		} else vro[0] = slot;
+	}
+}
+
+cudaError_t launch_p1view(const P1ViewParams &P, int n_blk, cudaStream_t st)
+{
+	if (n_blk <= 0) return cudaSuccess;
+	p1view_kernel<<<n_blk, 1024, 0, st>>>(P);
+	return cudaGetLastError();
+}
+
+} // namespace b200

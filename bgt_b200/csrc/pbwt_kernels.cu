@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 			}
 		}
 		int t_beg = P.blk_tile_beg[blk];
-		const int t_end = P.blk_tile_beg[blk + 1];
+		const int t_end = P.blk_tile_end[blk];
 		if (QUERY && P.comp_n) {
 			// Row groups that lie entirely in front of this CTA's first target row are crossed with ONE look-up per
 			// entry in the group's composite map (compose.cu), staged by TMA straight into the run-table buffers.

@@ -31,7 +31,8 @@ struct WalkParams {
 	const uint64_t *rowoff;
 	const uint32_t *n1;
 	const int2     *tiles;
-	const int      *blk_tile_beg;
+	const int      *blk_tile_beg;   // [blocks] first tile of every block ...
+	const int      *blk_tile_end;   // ... and one past its last tile (index.cu: the tiles of a block live in a fixed slot)
 	const int32_t  *rank0;
 	const int32_t  *track;     // tracked column ids [n_track] or nullptr (identity: every column)
 	const uint8_t  *tgrp;      // 0-based group of every tracked column
@@ -66,7 +67,9 @@ struct ComposeParams {
 	const uint64_t *rowoff;
 	const uint32_t *n1;
 	const int      *rows_in_blk;
-	const int      *blk_list;
+	const int      *blk_list;   // blocks handled by this launch; nullptr: blk_first + index
+	const uint8_t  *blk_ok;     // nullptr, or per block 1 = build (the device-side "sparse" flag of index.cu)
+	int blk_first;
 	int m, shift;
 	const long long *row_base; // per block: index of its first row in rowoff (with one extra end entry per block) / n1 / ...; nullptr: blk*(BS+1), blk*BS
 	int n1_step;      // entries of n1 per row (2 for a .pbf image: both planes; 1 for the plane-1 view)
@@ -103,8 +106,40 @@ struct SelectParams {
 	int      *err;
 };
 constexpr int SELECT_MAX_ROWS = 4096, SELECT_MAX_BYTES = 48 * 1024;
+constexpr int P1_SLOT_BYTES = SELECT_MAX_BYTES + 64;   // one block's slot in the plane-1 view image (index.cu)
 constexpr int SELECT_GROUPS = SELECT_MAX_ROWS / COMP_K, SELECT_COMP_CAP = 1024, SELECT_COMP_SMEM = 8192; // pieces of all groups of a block held in smem
 cudaError_t launch_plane1_select(const SelectParams &P, int n_blk, cudaStream_t st);
+
+// row index of a resident PBF, built on the device (index.cu)
+struct IndexParams {
+	const uint8_t  *img;
+	const uint64_t *blkoff;       // [blocks] offset of the 'S' record of every resident block, relative to img
+	const uint64_t *blkend;       // [blocks] end of the block's records (next 'S' record or the 'I' record)
+	int            *rows_in_blk;  // [blocks] rows per block; set to 0 by the index kernel if the block's records do not parse
+	int m, shift, blk_first, blk_count;
+	uint64_t *rowoff;             // out [blocks][BS+1]
+	int2     *tiles;              // out [blocks][BS]
+	int      *blk_tile_beg, *blk_tile_end, *grp_tile_beg;  // out [blocks], [blocks], [blocks][groups+1]
+	int      *err;
+};
+cudaError_t launch_index(const IndexParams &P, int n_blk, cudaStream_t st);
+cudaError_t launch_plan_tiles(const IndexParams &P, int n_blk, cudaStream_t st);
+
+struct P1ViewParams {
+	const uint8_t  *img;
+	const uint64_t *rowoff;
+	const uint32_t *n1;
+	const int      *rows_in_blk;
+	int m, shift, blk_first, p1_cap;
+	uint8_t   *p1img;             // out [blocks][P1_SLOT_BYTES]
+	uint64_t  *p1_rowoff;         // out [blocks][SELECT_MAX_ROWS+1]
+	uint32_t  *p1_n1;             // out [blocks][SELECT_MAX_ROWS]
+	uint16_t  *p1_realrow;        // out [blocks][SELECT_MAX_ROWS]
+	int       *p1_rows_in_blk;    // out [blocks]
+	long long *p1_vbase;          // out [blocks] = blk * SELECT_MAX_ROWS
+	uint8_t   *blk_sparse;        // out [blocks] 1 = the split scan applies to the block
+};
+cudaError_t launch_p1view(const P1ViewParams &P, int n_blk, cudaStream_t st);
 
 // per-group plane-0 marginals (marginal.cu): n0g[row][g] = ones of the plane-0 row among the columns of group g
 struct MarginalParams {
