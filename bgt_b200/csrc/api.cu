@@ -217,7 +217,11 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	b200_ctx_t *c = new b200_ctx_t();
 	c->dev = device; c->sm_count = prop.multiProcessorCount;
 	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) && CU_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
-	for (int i = 0; ok && i < N_IDX_STREAMS; ++i) ok = CU_OK(cudaStreamCreateWithFlags(&c->st_idx[i], cudaStreamNonBlocking));
+	{ // the small latency-bound index kernels must not queue behind the wide kernels they overlap: highest priority
+		int prio_lo = 0, prio_hi = 0;
+		cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+		for (int i = 0; ok && i < N_IDX_STREAMS; ++i) ok = CU_OK(cudaStreamCreateWithPriority(&c->st_idx[i], cudaStreamNonBlocking, prio_hi));
+	}
 	for (int i = 0; ok && i < LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming)) && CU_OK(cudaEventCreateWithFlags(&c->ev_idx[i], cudaEventDisableTiming));
 	for (int i = 0; ok && i < 12; ++i) ok = CU_OK(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; ok && i < 4; ++i) ok = CU_OK(cudaEventCreate(&c->mark[i]));

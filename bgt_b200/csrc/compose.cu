@@ -23,6 +23,7 @@ namespace b200 {
 
 constexpr int CP_NT = 256, CP_NW = CP_NT / 32;
 constexpr int CP_RUNS = 4096;      // merged runs of all rows of a group held in shared memory
+constexpr int CP_CACHE = 10;       // look-ups per thread kept in registers between the two passes of a level (total/2/CP_NT ~ 8)
 
 __device__ __forceinline__ uint32_t cp_rle_len(uint32_t c) { const uint32_t v = c >> 1; return (v & 15u) << ((v >> 4) << 2); }
 __device__ __forceinline__ uint32_t cp_ld_u32_unaligned(const uint8_t *p)
@@ -134,28 +135,54 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 
 	// ---- compose pairwise, level by level: result i = (map 2i+1) after (map 2i).  Every piece of map 2i is cut at the
 	// starts of map 2i+1 that fall inside its image; one scan over all pieces of the level places the results.
+	// Work items are the pieces of the FIRST maps of the pairs only (those of the second maps are just looked up), dealt
+	// out evenly; the look-up of a piece (first cut + number of cuts) is kept in registers between the counting and the
+	// placing pass.
 	uint32_t *Sa = S0, *Sb = S1;
 	int32_t *Da = D0, *Db = D1;
 	int *off = offA, *noff = offB;
 	for (int nmaps = COMP_K; nmaps > 1; nmaps >>= 1) {
-		const int total = off[nmaps];
-		const int per = (total + CP_NT - 1) / CP_NT, p0 = tid * per, p1 = p0 + per < total ? p0 + per : total;
-		// owner map of my first piece
-		int om = 0;
-		for (int len = nmaps; len > 1;) { const int half = len >> 1; om += off[om + half] <= p0 ? half : 0; len -= half; }
+		int total_even = 0;
+		for (int j = 0; j < nmaps; j += 2) total_even += off[j + 1] - off[j];
+		const int per = (total_even + CP_NT - 1) / CP_NT;
+		const int w0 = tid * per, w1 = w0 + per < total_even ? w0 + per : total_even;
+		// first item: pair j0 and piece p_first
+		int j0 = 0, p_first = 0;
+		{
+			int acc = 0;
+			for (; j0 < nmaps; j0 += 2) { const int c = off[j0 + 1] - off[j0]; if (w0 < acc + c) break; acc += c; }
+			p_first = j0 < nmaps ? off[j0] + (w0 - acc) : 0;
+		}
+		// piece p of map o against map o+1: lo = last start <= image start, cnt = pieces of the result
+		auto cut = [&](int p, int o, int &lo, int &cnt) {
+			const uint32_t s0 = Sa[p], cur = s0 + (uint32_t)Da[p];
+			const uint32_t e = cur + ((p + 1 < off[o + 1] ? Sa[p + 1] : m) - s0);
+			const uint32_t *rs = Sa + off[o + 1];
+			const int nr = off[o + 2] - off[o + 1];
+			int l = 0;
+			for (int len = nr; len > 1;) { const int half = len >> 1; l += rs[l + half] <= cur ? half : 0; len -= half; }
+			int h = l;
+			while (h + 1 < nr && rs[h + 1] < e) ++h;
+			lo = l; cnt = h - l + 1;
+		};
+		int lo_c[CP_CACHE], cnt_c[CP_CACHE];
 		int mine = 0;
 		{
-			int o = om;
-			for (int p = p0; p < p1; ++p) {
-				while (p >= off[o + 1]) ++o;
-				if (o & 1) continue;                                   // pieces of the second map of a pair are only looked up
-				const uint32_t cur = Sa[p] + (uint32_t)Da[p];
-				const uint32_t e = cur + ((p + 1 < off[o + 1] ? Sa[p + 1] : m) - Sa[p]);
-				const uint32_t *rs = Sa + off[o + 1];
-				const int nr = off[o + 2] - off[o + 1];
-				int lo = 0, hi = 0;                                    // lo = last start <= cur ; hi = last start < e
-				for (int len = nr; len > 1;) { const int half = len >> 1; lo += rs[lo + half] <= cur ? half : 0; hi += rs[hi + half] < e ? half : 0; len -= half; }
-				mine += hi - lo + 1;
+			int o = j0, p = p_first;
+			#pragma unroll
+			for (int q = 0; q < CP_CACHE; ++q) {
+				lo_c[q] = 0; cnt_c[q] = 0;
+				if (w0 + q < w1) {
+					cut(p, o, lo_c[q], cnt_c[q]);
+					mine += cnt_c[q];
+					if (++p == off[o + 1]) { o += 2; p = off[o < nmaps ? o : 0]; }
+				}
+			}
+			for (int w = w0 + CP_CACHE; w < w1; ++w) {
+				int l, c;
+				cut(p, o, l, c);
+				mine += c;
+				if (++p == off[o + 1]) { o += 2; p = off[o < nmaps ? o : 0]; }
 			}
 		}
 		int x = mine;
@@ -169,23 +196,26 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 		__syncthreads();
 		if (s_fail) { if (tid == 0) P.comp_n[slot] = 0; return; }
 		{
-			int o = om;
-			for (int p = p0; p < p1; ++p) {
-				while (p >= off[o + 1]) ++o;
-				if (o & 1) continue;
+			int o = j0, p = p_first;
+			auto place = [&](int lo, int cnt) {
 				if (p == off[o]) noff[o >> 1] = out;                   // first piece of a pair's first map = start of the result map
 				const uint32_t s0 = Sa[p], cur = s0 + (uint32_t)Da[p];
-				const uint32_t e = cur + ((p + 1 < off[o + 1] ? Sa[p + 1] : m) - s0);
 				const uint32_t *rs = Sa + off[o + 1];
 				const int32_t *rd = Da + off[o + 1];
-				const int nr = off[o + 2] - off[o + 1];
-				int lo = 0, hi = 0;
-				for (int len = nr; len > 1;) { const int half = len >> 1; lo += rs[lo + half] <= cur ? half : 0; hi += rs[hi + half] < e ? half : 0; len -= half; }
 				Sb[out] = s0; Db[out] = (int32_t)(cur + (uint32_t)rd[lo] - s0); ++out;
-				for (int k = lo + 1; k <= hi; ++k) {
-					const uint32_t s = rs[k], in_s = s0 + (s - cur);
-					Sb[out] = in_s; Db[out] = (int32_t)(s + (uint32_t)rd[k] - in_s); ++out;
+				for (int k = lo + 1; k < lo + cnt; ++k) {
+					const uint32_t st = rs[k], in_s = s0 + (st - cur);
+					Sb[out] = in_s; Db[out] = (int32_t)(st + (uint32_t)rd[k] - in_s); ++out;
 				}
+				if (++p == off[o + 1]) { o += 2; p = off[o < nmaps ? o : 0]; }
+			};
+			#pragma unroll
+			for (int q = 0; q < CP_CACHE; ++q)
+				if (w0 + q < w1) place(lo_c[q], cnt_c[q]);
+			for (int w = w0 + CP_CACHE; w < w1; ++w) {
+				int l, c;
+				cut(p, o, l, c);
+				place(l, c);
 			}
 		}
 		if (tid == 0) noff[nmaps >> 1] = s_n;

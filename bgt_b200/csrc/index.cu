@@ -239,12 +239,14 @@ __device__ __forceinline__ uint32_t ix_ld_u32_unaligned(const uint8_t *p)
 	return __funnelshift_r(lo, w[1], sh);
 }
 
+constexpr int P1V_NT = 256;
+
 // Per block: the rows whose plane 1 has at least one 1 bit (n1 from rowmeta_kernel; a corrupt row counts as empty),
 // re-framed as records 'B', l0 = 0, l1, bytes -- an empty plane 0 -- in the block's slot of the view image, with their
 // n1 and row number.  A block is "sparse" (split scan applies) if its view fits the select kernel's staging buffers.
-__global__ void __launch_bounds__(1024) p1view_kernel(const P1ViewParams P)
+__global__ void __launch_bounds__(P1V_NT) p1view_kernel(const P1ViewParams P)
 {
-	__shared__ uint32_t wrow[32], wbyte[32];
+	__shared__ uint32_t wrow[P1V_NT / 32], wbyte[P1V_NT / 32];
 	__shared__ uint32_t s_rows, s_bytes, s_allones;
 	__shared__ unsigned long long s_ones;
 	const int blk = P.blk_first + (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(1024) p1view_kernel(const P1ViewParams P)
 	uint64_t *vro = P.p1_rowoff + vb + blk;
 	if (tid == 0) { s_rows = 0; s_bytes = 0; s_allones = 0; s_ones = 0; }
 	__syncthreads();
-	for (int r0 = 0; r0 < rows; r0 += 1024) {
+	for (int r0 = 0; r0 < rows; r0 += P1V_NT) {
 		const int r = r0 + tid;
 		uint32_t n1 = 0, l1 = 0;
 		const uint8_t *rle = nullptr;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(1024) p1view_kernel(const P1ViewParams P)
 			}
 		}
 		__syncthreads();
-		if (tid == 1023) { s_rows = v + f; s_bytes = off + sz; }
+		if (tid == P1V_NT - 1) { s_rows = v + f; s_bytes = off + sz; }
 		__syncthreads();
 	}
 	if (tid == 0) {
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(1024) p1view_kernel(const P1ViewParams P)
 cudaError_t launch_p1view(const P1ViewParams &P, int n_blk, cudaStream_t st)
 {
 	if (n_blk <= 0) return cudaSuccess;
-	p1view_kernel<<<n_blk, 1024, 0, st>>>(P);
+	p1view_kernel<<<n_blk, P1V_NT, 0, st>>>(P);
 	return cudaGetLastError();
 }
 

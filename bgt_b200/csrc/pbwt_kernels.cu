@@ -200,6 +200,8 @@ constexpr uint32_t TD_MINUS_TS = sizeof(uint32_t) * RAW_BYTES;
 template<int C>
 __device__ __forceinline__ void lookup_runs(uint32_t (&r)[C], uint32_t ts_saddr, uint32_t n, uint32_t zeros_total, uint32_t &bits)
 {
+	// (the window halves as len - len/2, not by powers of two: power-of-two strides put the probes of all lanes into the
+	// same shared-memory bank from the sixth level on -- measured 1.45x slower)
 	uint32_t a[C];
 	#pragma unroll
 	for (int c = 0; c < C; ++c) a[c] = ts_saddr;
@@ -217,6 +219,28 @@ __device__ __forceinline__ void lookup_runs(uint32_t (&r)[C], uint32_t ts_saddr,
 	for (int c = 0; c < C; ++c) {
 		r[c] += lds_u32(a[c] + TD_MINUS_TS);
 		b |= (r[c] >= zeros_total ? 1u : 0u) << c;
+	}
+	bits = b;
+}
+
+// QUERY mode: only the slots in `act` advance (bit c = slot c); a warp in which no lane has slot c active skips its search
+template<int C>
+__device__ __forceinline__ void lookup_runs_masked(uint32_t (&r)[C], uint32_t ts_saddr, uint32_t n, uint32_t zeros_total, uint32_t act, uint32_t &bits)
+{
+	if (__all_sync(FULL_MASK, act == (1u << C) - 1u)) { lookup_runs<C>(r, ts_saddr, n, zeros_total, bits); return; }
+	uint32_t b = 0;
+	#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		const bool on = (act >> c) & 1u;
+		if (!__any_sync(FULL_MASK, on)) continue;
+		uint32_t a = ts_saddr;
+		for (uint32_t len = n; len > 1;) {
+			const uint32_t half = len >> 1, t = a + (half << 2);
+			a = lds_u32(t) <= r[c] ? t : a;
+			len -= half;
+		}
+		const uint32_t nr = r[c] + lds_u32(a + TD_MINUS_TS);
+		if (on) { r[c] = nr; b |= (nr >= zeros_total ? 1u : 0u) << c; }
 	}
 	bits = b;
 }
@@ -387,7 +411,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 		r0[c] = r1[c] = CHAIN ? (uint32_t)col[c] : 0u; // generator: identity before row 0 (pbwt.c:103)
 	}
 	for (int i = tid; i < T_MAX * P.G * 3; i += WALK_NT) S.rowcnt[i] = 0;
-	if (tid == 0) mbar_init(S.mbar, 1);
+	if (tid == 0) { mbar_init(S.mbar, 1); mbar_init(S.mbar + 1, 1); }
 	__syncthreads();
 
 	uint32_t parity = 0;
@@ -424,33 +448,67 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 		}
 		int t_beg = P.blk_tile_beg[blk];
 		const int t_end = P.blk_tile_end[blk];
+		uint32_t from_row[C];     // QUERY: first row (within the block) that the entry walks row by row
+		#pragma unroll
+		for (int c = 0; c < C; ++c) from_row[c] = 0;
 		if (QUERY && P.comp_n) {
-			// Row groups that lie entirely in front of this CTA's first target row are crossed with ONE look-up per
-			// entry in the group's composite map (compose.cu), staged by TMA straight into the run-table buffers.
+			// Every entry crosses the row groups that lie entirely in front of ITS target row with ONE look-up per group in
+			// the group's composite map (compose.cu), staged by TMA straight into the run-table buffers; it then walks row by
+			// row only inside its own group (below).  Entries are sorted by target row, so a group is live for a suffix of
+			// the CTA's entries and warps without a live entry skip the search.
 			const int n_grp = (BS + COMP_K - 1) / COMP_K;
 			const int g_mixed = (int)P.qrow[(size_t)blk_own * P.track_stride + slice_base] / COMP_K;
+			const int g_last = (q_stop - 1) / COMP_K;            // group of the CTA's last target row
+			// two composites fit the run-table buffers side by side: while group g is searched in one half, thread 0 has the
+			// copy of group g+1 in flight into the other half (its own mbarrier)
+			auto fetch_comp = [&](int gg) {
+				const size_t slot = (size_t)blk * n_grp + gg;
+				const uint32_t np = (uint32_t)P.comp_n[slot];
+				if (np == 0) return;
+				uint64_t *bar = S.mbar + (gg & 1);
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				mbar_expect_tx(bar, np * 8u);
+				tma_bulk_g2s(S.ts + (gg & 1) * COMP_CAP, P.comp_start + slot * COMP_CAP, np * 4u, bar);
+				tma_bulk_g2s(S.td + (gg & 1) * COMP_CAP, P.comp_delta + slot * COMP_CAP, np * 4u, bar);
+			};
+			uint32_t parity1 = 0;
 			int g = 0;
-			for (; g < g_mixed; ++g) {
-				const size_t slot = (size_t)blk * n_grp + g;
-				const int np = P.comp_n[slot];
-				if (np == 0) break;                                 // not available: row by row from here on
-				if (tid == 0) {
-					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-					mbar_expect_tx(S.mbar, (uint32_t)np * 8u);
-					tma_bulk_g2s(S.ts, P.comp_start + slot * COMP_CAP, (uint32_t)np * 4u, S.mbar);
-					tma_bulk_g2s(S.td, P.comp_delta + slot * COMP_CAP, (uint32_t)np * 4u, S.mbar);
-				}
+			if (tid == 0 && g_last > 0) fetch_comp(0);
+			for (; g < g_last; ++g) {
+				const int np = P.comp_n[(size_t)blk * n_grp + g];
+				if (np == 0) break;                                 // not available: row by row from here on (nothing is in flight)
+				if (tid == 0 && g + 1 < g_last) fetch_comp(g + 1);  // the other half was released by the barrier below
 				{
 					uint32_t spins = 0;
-					while (!mbar_try_wait(S.mbar, parity))
+					while (!mbar_try_wait(S.mbar + (g & 1), (g & 1) ? parity1 : parity))
 						if (++spins > (1u << 26)) { atomicOr(P.err, 8); __trap(); }
-					parity ^= 1;
+					if (g & 1) parity1 ^= 1; else parity ^= 1;
 				}
-				uint32_t unused;
-				lookup_runs<C>(r0, ts_saddr, (uint32_t)np, 0u, unused);
+				uint32_t act = 0, unused;
+				#pragma unroll
+				for (int c = 0; c < C; ++c) act |= (tgt[c] != 0xffffffffu && (int)(tgt[c] / COMP_K) > g ? 1u : 0u) << c;
+				const uint32_t tab = ts_saddr + (uint32_t)(g & 1) * (COMP_CAP * 4u);
+				if (g < g_mixed) lookup_runs<C>(r0, tab, (uint32_t)np, 0u, unused);
+				else lookup_runs_masked<C>(r0, tab, (uint32_t)np, 0u, act, unused);
 				__syncthreads();
 			}
-			t_beg = P.grp_tile_beg[(size_t)blk * (n_grp + 1) + g];
+			// g = first group without a usable composite (or the last group): entries with a later target walk from there
+			#pragma unroll
+			for (int c = 0; c < C; ++c) {
+				const uint32_t tg = tgt[c] / COMP_K;
+				from_row[c] = (tg < (uint32_t)g ? tg : (uint32_t)g) * COMP_K;
+			}
+			t_beg = P.grp_tile_beg[(size_t)blk * (n_grp + 1) + (g_mixed < g ? g_mixed : g)];
+		}
+
+		// QUERY: the rows at which some entry of this warp is live, per slot (warp-uniform; entries are sorted by target row,
+		// so the 32 entries of a slot are neighbours) -- lets the row loop skip dead rows before touching anything
+		uint32_t wlo[C], whi[C];
+		#pragma unroll
+		for (int c = 0; c < C; ++c) {
+			const bool v = QUERY && tgt[c] != 0xffffffffu;
+			wlo[c] = QUERY ? __reduce_min_sync(FULL_MASK, v ? from_row[c] : 0xffffffffu) : 0u;
+			whi[c] = QUERY ? __reduce_max_sync(FULL_MASK, v ? tgt[c] : 0u) : 0xffffffffu;
 		}
 
 		// thread 0: start the TMA bulk copy of tile t if it is an ordinary (not oversized) tile that will be used
@@ -508,10 +566,25 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 				for (int r = 0; r < nr; ++r) {
 					const long long arow = blk_row + r_first + r;
 					if (arow >= row_hi) break;
+					if (QUERY) { // warp-uniform: no entry of this warp is live at this row
+						const uint32_t rb = (uint32_t)(r_first + r);
+						bool live = false;
+						#pragma unroll
+						for (int c = 0; c < C; ++c) live = live || (rb >= wlo[c] && rb <= whi[c]);
+						if (!live) continue;
+					}
 					const RowMeta mt = S.meta[r];
 					uint32_t bits0 = 0, bits1 = 0;
 					const bool triv0 = mt.n1[0] == 0 || mt.n1[0] == m, triv1 = mt.n1[1] == 0 || mt.n1[1] == m;
-					if (!triv0) lookup_runs<C>(r0, ts_saddr + 4u * mt.off[0], mt.len[0], m - mt.n1[0], bits0);
+					if (QUERY) {
+						// an entry is live from the start of its own group (or of the first group without a composite) to its target row
+						const uint32_t rb = (uint32_t)(r_first + r);
+						uint32_t act = 0;
+						#pragma unroll
+						for (int c = 0; c < C; ++c) act |= (rb >= from_row[c] && rb <= tgt[c] && tgt[c] != 0xffffffffu ? 1u : 0u) << c;
+						if (!triv0) lookup_runs_masked<C>(r0, ts_saddr + 4u * mt.off[0], mt.len[0], m - mt.n1[0], act, bits0);
+						else if (mt.n1[0]) bits0 = 0xffffffffu;
+					} else if (!triv0) lookup_runs<C>(r0, ts_saddr + 4u * mt.off[0], mt.len[0], m - mt.n1[0], bits0);
 					else if (mt.n1[0]) bits0 = 0xffffffffu;
 					if (!QUERY) {
 						if (!triv1) lookup_runs<C>(r1, ts_saddr + 4u * mt.off[1], mt.len[1], m - mt.n1[1], bits1);
@@ -544,6 +617,11 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 					if (QUERY && p == 1) continue;
 					if (n1 == 0 || n1 == m) { bits[p] = n1 ? 0xffffffffu : 0u; continue; }
 					uint32_t done = 0;
+					if (QUERY) { // entries that are not live at this row (see the tile path) must not move
+						#pragma unroll
+						for (int c = 0; c < C; ++c)
+							done |= ((uint32_t)r_first >= from_row[c] && (uint32_t)r_first <= tgt[c] && tgt[c] != 0xffffffffu ? 0u : 1u) << c;
+					}
 					if (tid == 0) { S.scratch[0] = 0; S.scratch[1] = 0; }
 					for (uint32_t cb = 0; cb < l; cb += RAW_CAP) {
 						const uint32_t n = l - cb < (uint32_t)RAW_CAP ? l - cb : (uint32_t)RAW_CAP;
