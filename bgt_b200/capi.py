@@ -69,6 +69,12 @@ SIGNATURES = {
     "b200_synth_generate": (_vp, [_vp, C.POINTER(SynthCfg)]),
     "b200_pbf_image_size": (C.c_size_t, [_vp]),
     "b200_pbf_image_download": (_int, [_vp, _vp, C.c_size_t]),
+    "b200_enc_create": (_vp, [_vp, _int, _int]),
+    "b200_enc_write_bytes": (_int, [_vp, _vp, _vp, _i64]),
+    "b200_enc_write_bits": (_int, [_vp, _vp, _i64]),
+    "b200_enc_rows": (_i64, [_vp]),
+    "b200_enc_finish": (_i64, [_vp, C.POINTER(_vp)]),
+    "b200_enc_destroy": (None, [_vp]),
 }
 
 
@@ -181,6 +187,42 @@ class Pbf:
     def close(self):
         if self.h:
             lib().b200_pbf_close(self.h)
+            self.h = None
+
+
+class Encoder:
+    """The PBWT encoder on the device (b200_enc_t): pbf_open_w / pbf_write / pbf_close (pbwt.c:199-219, 288-311, 264-286)."""
+
+    def __init__(self, ctx, m, shift=13):
+        self.h = lib().b200_enc_create(ctx.h, m, shift)
+        if not self.h:
+            raise B200Error(_err())
+        self.m, self.shift = m, shift
+
+    def write(self, a0, a1):
+        """rows as pbf_write takes them: two [n_rows][m] uint8 matrices (bit planes 0 and 1, one byte per haplotype)."""
+        a0 = np.ascontiguousarray(a0, dtype=np.uint8).reshape(-1, self.m)
+        a1 = np.ascontiguousarray(a1, dtype=np.uint8).reshape(-1, self.m)
+        if lib().b200_enc_write_bytes(self.h, _ptr(a0), _ptr(a1), a0.shape[0]) != 0:
+            raise B200Error(_err())
+
+    def write_bits(self, bits):
+        """rows as bit planes in column order: uint32 [n_rows][2][(m+31)//32]."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        if lib().b200_enc_write_bits(self.h, _ptr(bits), bits.shape[0]) != 0:
+            raise B200Error(_err())
+
+    def finish(self):
+        """The complete .pbf image as bytes."""
+        p = C.c_void_p()
+        n = lib().b200_enc_finish(self.h, C.byref(p))
+        if n < 0:
+            raise B200Error(_err())
+        return C.string_at(p, n)
+
+    def close(self):
+        if self.h:
+            lib().b200_enc_destroy(self.h)
             self.h = None
 
 

@@ -487,6 +487,7 @@ static bool pbf_finish_load(b200_pbf_t *pb)
 	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
 	if (!ok) return false;
 	pb->bad_rows = (int64_t)bad;
+	if (err & 128) { set_err("the records of one checkpoint block exceed 4 GiB; not supported"); return false; }
 	if (err & 2) { set_err("corrupt PBF: record tags/lengths inside a checkpoint block do not parse"); return false; }
 	if (err & 1) { set_err("corrupt PBF: an 'S' snapshot holds a column index >= m"); return false; }
 	if (err & 8) { set_err("internal: TMA copy never completed"); return false; }
@@ -1180,4 +1181,168 @@ extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cf
 	ok = ok && queue_ranks_view(pb, 0, nb, c->st) && pbf_finish_load(pb);
 	if (!ok) { cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
 	return pb;
+}
+
+// ------------------------------------------------------------------------------------------------ encoder (pbf_open_w / pbf_write / pbf_close)
+
+struct b200_enc_s {
+	b200_ctx_t *ctx = nullptr;
+	int m = 0, shift = 0, words = 0;
+	int64_t n = 0;                       // rows written so far (pbf_t.n, pbwt.c:309)
+	int32_t *d_rank = nullptr;
+	uint32_t *d_bitvec = nullptr;
+	unsigned long long *d_pos = nullptr; // [4]: stream offsets in / out
+	DevBuf in_bits, bytes[2], snap, out[2], row_len;
+	std::vector<uint8_t> image;          // the file so far
+	std::vector<uint64_t> idx;           // offsets of the 'S' records (pbwt.c:297)
+	std::vector<uint8_t> h_out[2];
+	std::vector<uint32_t> h_len;
+	std::vector<int32_t> h_snap;
+	bool finished = false;
+	int batch_rows = 0;
+};
+
+extern "C" void b200_enc_destroy(b200_enc_t *e)
+{
+	if (!e) return;
+	cudaSetDevice(e->ctx->dev);
+	cudaStreamSynchronize(e->ctx->st);
+	if (e->d_rank) cudaFree(e->d_rank);
+	if (e->d_bitvec) cudaFree(e->d_bitvec);
+	if (e->d_pos) cudaFree(e->d_pos);
+	e->in_bits.release(); e->bytes[0].release(); e->bytes[1].release(); e->snap.release(); e->out[0].release(); e->out[1].release(); e->row_len.release();
+	delete e;
+}
+
+extern "C" b200_enc_t *b200_enc_create(b200_ctx_t *c, int m, int shift)
+{
+	if (!c) { set_err("b200_enc_create: null context"); return nullptr; }
+	if (m <= 0 || m >= (1 << 30) || shift < 0 || shift > 24) { set_err("b200_enc_create: m=%d shift=%d out of range", m, shift); return nullptr; }
+	if (encode_smem_bytes(m) > 220 * 1024) { set_err("b200_enc_create: m=%d needs more shared memory than one SM has (limit about 1.2 M columns)", m); return nullptr; }
+	cudaSetDevice(c->dev);
+	b200_enc_t *e = new b200_enc_t();
+	e->ctx = c; e->m = m; e->shift = shift; e->words = (m + 31) / 32;
+	long long br = (256LL << 20) / m;
+	e->batch_rows = (int)(br < 16 ? 16 : (br > 4096 ? 4096 : br));
+	std::vector<int32_t> ident(2 * (size_t)m);
+	for (int p = 0; p < 2; ++p) for (int i = 0; i < m; ++i) ident[(size_t)p * m + i] = i;   // pbwt.c:103: S starts as the identity
+	bool ok = CU_OK(cudaMalloc(&e->d_rank, sizeof(int32_t) * 2 * (size_t)m)) && CU_OK(cudaMalloc(&e->d_bitvec, sizeof(uint32_t) * 6 * (size_t)e->words + 16)) &&
+	          CU_OK(cudaMalloc(&e->d_pos, 4 * sizeof(unsigned long long)));
+	ok = ok && CU_OK(cudaMemcpyAsync(e->d_rank, ident.data(), sizeof(int32_t) * 2 * (size_t)m, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemsetAsync(e->d_bitvec, 0, sizeof(uint32_t) * 6 * (size_t)e->words, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+	if (!ok) { b200_enc_destroy(e); return nullptr; }
+	// file header (pbwt.c:214-216)
+	e->image.resize(16);
+	const int32_t v[3] = {m, 2, shift};
+	memcpy(e->image.data(), "PBF\1", 4);
+	memcpy(e->image.data() + 4, v, 12);
+	return e;
+}
+
+// rows [e->n, e->n + R) are in e->in_bits (device): encode them and append their records to the image
+static bool enc_batch(b200_enc_t *e, int R)
+{
+	b200_ctx_t *c = e->ctx;
+	const int m = e->m, words = e->words;
+	const int64_t BS = 1LL << e->shift, row0 = e->n;
+	const int64_t k0 = (row0 + BS - 1) >> e->shift, k1 = (row0 + R - 1) >> e->shift;   // checkpoints inside the batch: k0..k1
+	const int n_snap = (int)(k1 >= k0 ? k1 - k0 + 1 : 0);
+	if (!e->snap.reserve(sizeof(int32_t) * 2 * (size_t)m * (size_t)(n_snap ? n_snap : 1)) || !e->row_len.reserve(sizeof(uint32_t) * 2 * (size_t)R)) return false;
+	for (int p = 0; p < 2; ++p) if (!e->out[p].reserve((size_t)R * (size_t)m + 64)) return false;   // a row's code never exceeds m bytes per plane
+	EncodeParams P;
+	memset(&P, 0, sizeof(P));
+	P.in_bits = (const uint32_t*)e->in_bits.p; P.m = m; P.words = words; P.shift = e->shift; P.n_rows = R; P.row0 = row0;
+	P.rank = e->d_rank; P.bitvec = e->d_bitvec; P.snap = (int32_t*)e->snap.p; P.out[0] = (uint8_t*)e->out[0].p; P.out[1] = (uint8_t*)e->out[1].p;
+	P.row_len = (uint32_t*)e->row_len.p; P.out_pos0 = e->d_pos; P.out_pos1 = e->d_pos + 2;
+	unsigned long long pos[2] = {0, 0};
+	bool ok = CU_OK(cudaMemsetAsync(e->d_pos, 0, 4 * sizeof(unsigned long long), c->st)) && CU_OK(launch_encode(P, c->sm_count, c->st));
+	++c->launches;
+	e->h_len.resize(2 * (size_t)R);
+	ok = ok && CU_OK(cudaMemcpyAsync(pos, e->d_pos + 2, sizeof(pos), cudaMemcpyDeviceToHost, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(e->h_len.data(), e->row_len.p, sizeof(uint32_t) * 2 * (size_t)R, cudaMemcpyDeviceToHost, c->st)) &&
+	     CU_OK(cudaStreamSynchronize(c->st));
+	if (!ok) return false;
+	for (int p = 0; p < 2; ++p) {
+		e->h_out[p].resize((size_t)pos[p] + 1);
+		if (pos[p] && !CU_OK(cudaMemcpyAsync(e->h_out[p].data(), e->out[p].p, (size_t)pos[p], cudaMemcpyDeviceToHost, c->st))) return false;
+	}
+	e->h_snap.resize(2 * (size_t)m * (size_t)(n_snap ? n_snap : 1));
+	if (n_snap && !CU_OK(cudaMemcpyAsync(e->h_snap.data(), e->snap.p, sizeof(int32_t) * 2 * (size_t)m * n_snap, cudaMemcpyDeviceToHost, c->st))) return false;
+	if (!CU_OK(cudaStreamSynchronize(c->st))) return false;
+	// file assembly, as pbf_write does it row by row (pbwt.c:288-311)
+	size_t o[2] = {0, 0};
+	for (int r = 0; r < R; ++r) {
+		const int64_t arow = row0 + r;
+		if ((arow & (BS - 1)) == 0) {
+			e->idx.push_back((uint64_t)e->image.size());
+			e->image.push_back('S');
+			const uint8_t *s = (const uint8_t*)(e->h_snap.data() + 2 * (size_t)m * (size_t)((arow >> e->shift) - k0));
+			e->image.insert(e->image.end(), s, s + 8 * (size_t)m);
+		}
+		e->image.push_back('B');
+		for (int p = 0; p < 2; ++p) {
+			const uint32_t l = e->h_len[2 * (size_t)r + p];
+			const uint8_t *lb = (const uint8_t*)&l;
+			e->image.insert(e->image.end(), lb, lb + 4);
+			e->image.insert(e->image.end(), e->h_out[p].data() + o[p], e->h_out[p].data() + o[p] + l);
+			o[p] += l;
+		}
+	}
+	e->n += R;
+	return true;
+}
+
+extern "C" int b200_enc_write_bits(b200_enc_t *e, const uint32_t *bits, int64_t n_rows)
+{
+	if (!e || (!bits && n_rows > 0) || n_rows < 0) { set_err("b200_enc_write_bits: bad argument"); return -1; }
+	if (e->finished) { set_err("b200_enc_write_bits: the image was already finished"); return -1; }
+	cudaSetDevice(e->ctx->dev);
+	const size_t row_words = 2 * (size_t)e->words;
+	for (int64_t done = 0; done < n_rows;) {
+		const int R = (int)(n_rows - done < e->batch_rows ? n_rows - done : e->batch_rows);
+		if (!e->in_bits.reserve(sizeof(uint32_t) * row_words * (size_t)R)) return -1;
+		if (!CU_OK(cudaMemcpyAsync(e->in_bits.p, bits + (size_t)done * row_words, sizeof(uint32_t) * row_words * (size_t)R, cudaMemcpyHostToDevice, e->ctx->st))) return -1;
+		if (!enc_batch(e, R)) return -1;
+		done += R;
+	}
+	return 0;
+}
+
+extern "C" int b200_enc_write_bytes(b200_enc_t *e, const uint8_t *a0, const uint8_t *a1, int64_t n_rows)
+{
+	if (!e || ((!a0 || !a1) && n_rows > 0) || n_rows < 0) { set_err("b200_enc_write_bytes: bad argument"); return -1; }
+	if (e->finished) { set_err("b200_enc_write_bytes: the image was already finished"); return -1; }
+	cudaSetDevice(e->ctx->dev);
+	const size_t m = (size_t)e->m, row_words = 2 * (size_t)e->words;
+	for (int64_t done = 0; done < n_rows;) {
+		const int R = (int)(n_rows - done < e->batch_rows ? n_rows - done : e->batch_rows);
+		if (!e->in_bits.reserve(sizeof(uint32_t) * row_words * (size_t)R) || !e->bytes[0].reserve(m * R) || !e->bytes[1].reserve(m * R)) return -1;
+		bool ok = CU_OK(cudaMemcpyAsync(e->bytes[0].p, a0 + (size_t)done * m, m * R, cudaMemcpyHostToDevice, e->ctx->st)) &&
+		          CU_OK(cudaMemcpyAsync(e->bytes[1].p, a1 + (size_t)done * m, m * R, cudaMemcpyHostToDevice, e->ctx->st)) &&
+		          CU_OK(launch_pack_rows((const uint8_t*)e->bytes[0].p, (const uint8_t*)e->bytes[1].p, R, e->m, (uint32_t*)e->in_bits.p, e->ctx->st));
+		++e->ctx->launches;
+		if (!ok || !enc_batch(e, R)) return -1;
+		done += R;
+	}
+	return 0;
+}
+
+extern "C" int64_t b200_enc_rows(const b200_enc_t *e) { return e ? e->n : -1; }
+
+extern "C" int64_t b200_enc_finish(b200_enc_t *e, const uint8_t **image)
+{
+	if (!e) { set_err("b200_enc_finish: null encoder"); return -1; }
+	if (!e->finished) { // the index record (pbwt.c:268-276)
+		const uint64_t off = (uint64_t)e->image.size();
+		const int64_t n = e->n;
+		const int32_t n_idx = (int32_t)e->idx.size();
+		e->image.push_back('I');
+		e->image.insert(e->image.end(), (const uint8_t*)&n, (const uint8_t*)&n + 8);
+		e->image.insert(e->image.end(), (const uint8_t*)&n_idx, (const uint8_t*)&n_idx + 4);
+		e->image.insert(e->image.end(), (const uint8_t*)e->idx.data(), (const uint8_t*)e->idx.data() + 8 * (size_t)n_idx);
+		e->image.insert(e->image.end(), (const uint8_t*)&off, (const uint8_t*)&off + 8);
+		e->finished = true;
+	}
+	if (image) *image = e->image.data();
+	return (int64_t)e->image.size();
 }

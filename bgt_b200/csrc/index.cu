@@ -18,9 +18,9 @@ namespace b200 {
 
 // ------------------------------------------------------------------------------------------------ row offsets
 
-constexpr int IX_STAGE = 2048, IX_SLOTS = 4, IX_RING = IX_STAGE * IX_SLOTS;   // small on purpose: a chase CTA (16 KB) must fit
+constexpr int IX_STAGE = 2048, IX_SLOTS = 8, IX_RING = IX_STAGE * IX_SLOTS;   // small on purpose: a chase CTA (16 KB) must fit
                                                                             // beside the resident CTAs of the kernels it overlaps
-constexpr int IX_LANES = 2;   // checkpoint blocks chased per CTA, one lane each (see pbf_index_kernel)
+constexpr int IX_LANES = 1;   // checkpoint blocks chased per CTA, one lane each (see pbf_index_kernel)
 
 __device__ __forceinline__ uint32_t ix_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,49 +61,52 @@ struct IxRing {
 		             :: "r"(ix_smem_u32(ring + (size_t)s * IX_STAGE)), "l"(img + beg), "r"(bytes), "r"(ix_smem_u32(bar + s)) : "memory");
 		inflight[s] = true;
 	}
-	// make stage k resident and complete; top up the stages behind it
-	__device__ void need(long long k)
+	__device__ __forceinline__ void want(long long k)
 	{
 		const int s = (int)(k % IX_SLOTS);
-		if (stage[s] != k) issue(s, k);
+		if (stage[s] != k && base + (uint64_t)k * IX_STAGE < end16) issue(s, k);
+	}
+	// make stages k and k+1 resident and complete (the chase's window), with the following ones in flight (TMA latency is
+	// several stages' worth of chasing); the last slot still holds k-1
+	__device__ void window(long long k)
+	{
 		#pragma unroll 1
-		for (int j = 1; j < IX_SLOTS - 1; ++j) {   // one slot of slack: a read may straddle stages k-1 and k
-			const long long kk = k + j;
-			const int s2 = (int)(kk % IX_SLOTS);
-			if (stage[s2] < kk && base + (uint64_t)kk * IX_STAGE < end16) issue(s2, kk);
-		}
-		if (inflight[s]) wait(s);
+		for (int j = 0; j < IX_SLOTS - 1; ++j) want(k + j);
+		if (inflight[(int)(k % IX_SLOTS)]) wait((int)(k % IX_SLOTS));
+		if (inflight[(int)((k + 1) % IX_SLOTS)]) wait((int)((k + 1) % IX_SLOTS));
 	}
 };
 
-// 8 bytes of the image at ring-relative offset o (o..o+7; only the first 5 are used by the callers' checks).  o is
-// relative to the ring base; two aligned words cover 5 bytes at any alignment.
-__device__ __forceinline__ uint64_t ix_read5(uint32_t ring_saddr, uint32_t o)
+// the 32-bit little-endian word at ring-relative offset o, any alignment
+__device__ __forceinline__ uint32_t ix_read4(uint32_t ring_saddr, uint32_t o)
 {
 	const uint32_t i0 = o & (uint32_t)(IX_RING - 4), i1 = (i0 + 4) & (uint32_t)(IX_RING - 1);
 	uint32_t w0, w1;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ring_saddr + i0));
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(ring_saddr + i1));
-	return ((uint64_t)w1 << 32 | w0) >> ((o & 3u) * 8u);
+	return __funnelshift_r(w0, w1, (o & 3u) * 8u);
 }
 
-// One LANE per checkpoint block, IX_LANES blocks per CTA, each with its own ring.  (A CTA with a single running thread
-// is compiled onto the uniform datapath, whose register round trips more than double the latency of every hop; lanes
-// that chase different blocks are genuinely divergent and stay in vector registers.)
+// One LANE per checkpoint block, IX_LANES blocks per CTA, each with its own ring.  The chain of a block is
+// rows x 2 dependent hops ('B', l0 | plane-0 bytes | l1 | plane-1 bytes), so the loop is written for latency: offsets are
+// 32-bit and relative to the ring base, both length words are read speculatively from the ring (always safe: it is
+// shared memory) and ONE combined test per row decides whether they were resident and valid; only rows at the edge of
+// the two-stage window take the careful path.
 __global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
 {
 	extern __shared__ __align__(128) uint8_t ix_sm_all[];
 	const int lane = threadIdx.x;
-	if (lane >= IX_LANES || (int)blockIdx.x * IX_LANES + lane >= P.blk_count) return;
+	if (lane >= P.lanes || (int)blockIdx.x * P.lanes + lane >= P.blk_count) return;   // P.lanes == IX_LANES, but a run-time value:
+	// with a compile-time single lane the whole chase lands on the uniform datapath (R2UR after every shared-memory load)
 	uint8_t *ix_sm = ix_sm_all + (size_t)lane * (IX_RING + 64);
-	const int blk = P.blk_first + (int)blockIdx.x * IX_LANES + lane;
+	const int blk = P.blk_first + (int)blockIdx.x * P.lanes + lane;
 	const int BS = 1 << P.shift;
 	uint64_t *ro = P.rowoff + (size_t)blk * (BS + 1);
 	const int rows = P.rows_in_blk[blk];
 	const uint64_t first = P.blkoff[blk] + 1 + 8ull * (uint64_t)P.m;  // behind the 'S' record (pbwt.c:298-300)
 	const uint64_t base = first & ~15ull;
 
-	IxRing R;   // slow-path state (local memory); the chase itself keeps its cursor in registers
+	IxRing R;   // ring bookkeeping (local memory, touched only on the careful path)
 	R.ring = ix_sm; R.bar = (uint64_t*)(ix_sm + IX_RING); R.img = P.img; R.err = P.err;
 	R.base = base; R.end16 = (P.blkend[blk] + 15) & ~15ull;
 	#pragma unroll
@@ -113,33 +116,41 @@ __global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
 	}
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
-	// all offsets below are relative to `base` (the chase needs no 64-bit image addresses)
-	const uint64_t end = P.blkend[blk] - base;
-	uint64_t pos = first - base;
+	const uint64_t end64 = P.blkend[blk] - base;
 	const uint32_t ring_saddr = ix_smem_u32(ix_sm);
 	bool bad = P.img[P.blkoff[blk]] != 'S' || first > P.blkend[blk];
-	uint64_t cur_lo = 1, cur_hi = 0;       // a complete stage holds [cur_lo, cur_hi)
-	auto fetch = [&](uint64_t a) {         // slow path: make the stage(s) of bytes a..a+7 resident
-		const long long k0 = (long long)(a / IX_STAGE), k1 = (long long)((a + 7) / IX_STAGE);
-		R.need(k0);
-		if (k1 != k0 && base + (uint64_t)k1 * IX_STAGE < R.end16) R.need(k1);
-		cur_lo = (uint64_t)k0 * IX_STAGE; cur_hi = cur_lo + IX_STAGE;
-	};
+	if (end64 > 0xfff00000ull) { atomicOr(P.err, 128); bad = true; }   // the records of one block must fit 32-bit offsets
+	const uint32_t end = (uint32_t)end64;
+	uint32_t o = (uint32_t)(first - base);
+	uint32_t wlo = 1, whi = 0;              // complete stages hold [wlo, whi)
 	int r = 0;
-	for (; r < rows && !bad; ++r) {
-		// 'B' + l0 (5 bytes at pos), then l1 (4 bytes behind the plane-0 bytes)
-		if (pos + 9 > end) { bad = true; break; }
-		if (pos < cur_lo || pos + 8 > cur_hi) fetch(pos);
-		const uint64_t v = ix_read5(ring_saddr, (uint32_t)pos);
-		const int32_t l0 = (int32_t)(uint32_t)(v >> 8);
-		const uint64_t p1 = pos + 5 + (uint64_t)(uint32_t)l0;
-		if ((uint8_t)v != 'B' || l0 < 0 || p1 + 4 > end) { bad = true; break; }
-		if (p1 < cur_lo || p1 + 8 > cur_hi) fetch(p1);
-		const int32_t l1 = (int32_t)(uint32_t)ix_read5(ring_saddr, (uint32_t)p1);
-		const uint64_t nxt = p1 + 4 + (uint64_t)(uint32_t)l1;
-		if (l1 < 0 || nxt > end) { bad = true; break; }
-		ro[r] = base + pos;
-		pos = nxt;
+	while (r < rows && !bad) {
+		// speculative: 'B' + l0 at o, l1 behind the plane-0 bytes
+		const uint32_t w0 = ix_read4(ring_saddr, o), w1 = ix_read4(ring_saddr, o + 4);
+		const uint32_t l0 = __funnelshift_r(w0, w1, 8);
+		const uint32_t p1 = o + 5u + l0;
+		const uint32_t l1 = ix_read4(ring_saddr, p1);
+		const uint32_t nxt = p1 + 4u + l1;
+		const bool resident = o >= wlo && o + 8u <= whi && p1 >= wlo && p1 + 8u <= whi;
+		const bool valid = (w0 & 0xffu) == 'B' && (l0 | l1) < 0x80000000u && nxt >= p1 && nxt <= end;   // (resident => p1 did not wrap)
+		if (resident && valid) { ro[r++] = base + o; o = nxt; continue; }
+		// careful path for this one row
+		if ((uint64_t)o + 9 > end64) { bad = true; break; }
+		R.window((long long)(o / IX_STAGE));
+		wlo = (o / IX_STAGE) * IX_STAGE; whi = wlo + 2 * IX_STAGE;
+		const uint32_t c0 = ix_read4(ring_saddr, o), c1 = ix_read4(ring_saddr, o + 4);
+		const uint32_t cl0 = __funnelshift_r(c0, c1, 8);
+		const uint64_t cp1 = (uint64_t)o + 5 + cl0;
+		if ((c0 & 0xffu) != 'B' || cl0 >= 0x80000000u || cp1 + 4 > end64) { bad = true; break; }
+		if (!((uint32_t)cp1 >= wlo && (uint32_t)cp1 + 8u <= whi)) {
+			R.window((long long)(cp1 / IX_STAGE));
+			wlo = (uint32_t)(cp1 / IX_STAGE) * IX_STAGE; whi = wlo + 2 * IX_STAGE;
+		}
+		const uint32_t cl1 = ix_read4(ring_saddr, (uint32_t)cp1);
+		const uint64_t cn = cp1 + 4 + cl1;
+		if (cl1 >= 0x80000000u || cn > end64) { bad = true; break; }
+		ro[r++] = base + o;
+		o = (uint32_t)cn;
 	}
 	#pragma unroll 1
 	for (int s = 0; s < IX_SLOTS; ++s) if (R.inflight[s]) R.wait(s);   // no copy may be in flight when the CTA exits
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
 		ro[0] = P.blkoff[blk];
 		return;
 	}
-	ro[rows] = base + pos;
+	ro[rows] = base + o;
 }
 
 cudaError_t launch_index(const IndexParams &P, int n_blk, cudaStream_t st)
@@ -161,6 +172,7 @@ cudaError_t launch_index(const IndexParams &P, int n_blk, cudaStream_t st)
 	if (e != cudaSuccess) return e;
 	IndexParams Q = P;
 	Q.blk_count = n_blk;
+	Q.lanes = IX_LANES;
 	pbf_index_kernel<<<(n_blk + IX_LANES - 1) / IX_LANES, 32, smem, st>>>(Q);
 	return cudaGetLastError();
 }

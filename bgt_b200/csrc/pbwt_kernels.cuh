@@ -116,7 +116,7 @@ struct IndexParams {
 	const uint64_t *blkoff;       // [blocks] offset of the 'S' record of every resident block, relative to img
 	const uint64_t *blkend;       // [blocks] end of the block's records (next 'S' record or the 'I' record)
 	int            *rows_in_blk;  // [blocks] rows per block; set to 0 by the index kernel if the block's records do not parse
-	int m, shift, blk_first, blk_count;
+	int m, shift, blk_first, blk_count, lanes;
 	uint64_t *rowoff;             // out [blocks][BS+1]
 	int2     *tiles;              // out [blocks][BS]
 	int      *blk_tile_beg, *blk_tile_end, *grp_tile_beg;  // out [blocks], [blocks], [blocks][groups+1]
@@ -167,6 +167,23 @@ cudaError_t launch_invert_snapshots(const uint8_t *img, const uint64_t *blkoff, 
 cudaError_t launch_finalize(const int32_t *cnt_raw, long long n_rows, int G, const int32_t *gsize, const flt_prog_t *prog, int use_flt,
                             int32_t *counts, uint8_t *pass, unsigned long long *totals, const FinalizeSplit &sp, cudaStream_t st);
 cudaError_t launch_unpack_bits(const uint32_t *bits, long long n_rows, int words, int n_track, uint8_t *bytes, cudaStream_t st);
+
+// PBWT encoder (encode.cu)
+struct EncodeParams {
+	const uint32_t *in_bits;       // [n_rows][2][words] the batch's rows as bit planes in column order
+	int m, words, shift, n_rows;
+	long long row0;                // absolute index of the batch's first row
+	int32_t  *rank;                // [2][m] rank of every column per plane: encoder state, carried from batch to batch
+	uint32_t *bitvec;              // [3][2][words] rotating scatter targets (all zero before the first row)
+	int32_t  *snap;                // out: 'S' snapshots of the checkpoints inside the batch, [k][2][m]
+	uint8_t  *out[2];              // out: run-length bytes of the rows, one stream per plane
+	uint32_t *row_len;             // out [n_rows][2]: bytes per (row, plane)
+	const unsigned long long *out_pos0;   // [2] stream offsets at the start of the batch ...
+	unsigned long long *out_pos1;         // ... and at its end
+};
+size_t encode_smem_bytes(int m);
+cudaError_t launch_encode(const EncodeParams &P, int sm_count, cudaStream_t st);
+cudaError_t launch_pack_rows(const uint8_t *a0, const uint8_t *a1, long long n_rows, int m, uint32_t *bits, cudaStream_t st);
 
 // synthetic cohort generator (synth.cu)
 struct SynthCfg { uint32_t m; long long n_rows; int shift; uint64_t seed; int r_max; int p1_one_in; };

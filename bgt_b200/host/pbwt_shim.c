@@ -1,8 +1,10 @@
 /*
  * pbwt_shim.c -- seam A (include/pbwt_b200.h): pbf_open_r / pbf_read / pbf_seek / pbf_subset of the reference
- * (pbwt.c:221-262, 313-388) implemented over the C ABI of libbgt_b200.so.  Host logic in C, as in the reference;
- * every row is decoded on the GPU.  A window of checkpoint blocks is resident in HBM at a time and rows are
- * decoded in batches sized by the output width; pbf_read hands out pointers into the current batch.
+ * (pbwt.c:221-262, 313-388) and its write side pbf_open_w / pbf_write (pbwt.c:199-219, 288-311) implemented over
+ * the C ABI of libbgt_b200.so.  Host logic in C, as in the reference; every row is decoded / encoded on the GPU.
+ * Reading: a window of checkpoint blocks is resident in HBM at a time and rows are decoded in batches sized by the
+ * output width; pbf_read hands out pointers into the current batch.  Writing: rows are collected into batches and
+ * encoded by b200_enc_write_bytes; the file is written when the handle is closed.
  */
 #include <fcntl.h>
 #include <stdio.h>
@@ -28,6 +30,11 @@ struct pbf_s {
 	int64_t bat_beg, bat_end;   /* decoded batch [bat_beg, bat_end) */
 	uint8_t *bat[2]; size_t bat_cap;
 	const uint8_t *ret[2];
+	/* writer */
+	int is_writing;
+	FILE *fp;
+	b200_enc_t *enc;
+	uint8_t *wrow[2]; int64_t w_n, w_cap;  /* rows collected for the next encoder batch */
 };
 
 static b200_ctx_t *g_ctx;
@@ -89,6 +96,49 @@ pbf_t *pbf_open_r(const char *fn)
 	return pb;
 }
 
+/* pbwt.c:199-219.  g must be 2 (what BGT writes, import.c:68); NULL/"-" = stdout like the reference. */
+pbf_t *pbf_open_w(const char *fn, int m, int g, int shift)
+{
+	pbf_t *pb;
+	FILE *fp;
+	if (g != 2) { fprintf(stderr, "[E::bgt_b200] pbf_open_w: %d bit planes; the B200 encoder writes BGT's 2 (import.c:68)\n", g); return 0; }
+	if (fn && strcmp(fn, "-") != 0) {
+		if ((fp = fopen(fn, "wb")) == NULL) return 0;
+	} else fp = stdout;
+	pb = (pbf_t*)calloc(1, sizeof(pbf_t));
+	pb->magic = SHIM_MAGIC; pb->is_writing = 1; pb->fp = fp;
+	pb->m = m; pb->g = g; pb->shift = shift;
+	pb->enc = b200_enc_create(shim_ctx(), m, shift);
+	if (pb->enc == 0) { fprintf(stderr, "[E::bgt_b200] %s\n", b200_strerror()); exit(1); } /* no CPU fallback */
+	pb->w_cap = (64LL << 20) / (m > 0 ? m : 1);
+	if (pb->w_cap < 16) pb->w_cap = 16;
+	if (pb->w_cap > 4096) pb->w_cap = 4096;
+	pb->wrow[0] = (uint8_t*)b200_host_alloc((size_t)pb->w_cap * m);
+	pb->wrow[1] = (uint8_t*)b200_host_alloc((size_t)pb->w_cap * m);
+	if (!pb->wrow[0] || !pb->wrow[1]) { fprintf(stderr, "[E::bgt_b200] %s\n", b200_strerror()); exit(1); }
+	return pb;
+}
+
+static void flush_rows(pbf_t *pb)
+{
+	if (pb->w_n && b200_enc_write_bytes(pb->enc, pb->wrow[0], pb->wrow[1], pb->w_n) != 0) {
+		fprintf(stderr, "[E::bgt_b200] %s\n", b200_strerror());
+		exit(1);
+	}
+	pb->w_n = 0;
+}
+
+/* pbwt.c:288-311: one row, a[g][m] bytes */
+int pbf_write(pbf_t *pb, uint8_t *const*a)
+{
+	if (pb == 0 || pb->magic != SHIM_MAGIC || !pb->is_writing) return -1;   /* pbwt.c:291 */
+	memcpy(pb->wrow[0] + (size_t)pb->w_n * pb->m, a[0], (size_t)pb->m);
+	memcpy(pb->wrow[1] + (size_t)pb->w_n * pb->m, a[1], (size_t)pb->m);
+	if (++pb->w_n == pb->w_cap) flush_rows(pb);
+	++pb->n;
+	return 0;
+}
+
 static void drop_window(pbf_t *pb)
 {
 	if (pb->q) { b200_query_destroy(pb->q); pb->q = 0; }
@@ -100,6 +150,19 @@ int pbf_close(pbf_t *pb)
 {
 	if (pb == 0) return 0;
 	if (pb->magic != SHIM_MAGIC) return g_foreign_close ? g_foreign_close(pb) : -1;
+	if (pb->is_writing) { /* pbwt.c:268-276: the index goes out with the rest of the file */
+		const uint8_t *img = 0;
+		int64_t len;
+		flush_rows(pb);
+		len = b200_enc_finish(pb->enc, &img);
+		if (len < 0 || fwrite(img, 1, (size_t)len, pb->fp) != (size_t)len) { fprintf(stderr, "[E::bgt_b200] writing the PBF failed\n"); exit(1); }
+		b200_enc_destroy(pb->enc);
+		b200_host_free(pb->wrow[0]); b200_host_free(pb->wrow[1]);
+		fclose(pb->fp);
+		pb->magic = 0;
+		free(pb);
+		return 0;
+	}
 	drop_window(pb);
 	b200_host_free(pb->bat[0]); b200_host_free(pb->bat[1]);
 	free(pb->sub);
@@ -126,7 +189,7 @@ int pbf_subset(pbf_t *pb, int n_sub, int *sub)
 
 int pbf_seek(pbf_t *pb, uint64_t k)
 {
-	if (pb == 0 || pb->magic != SHIM_MAGIC) return -1;                      /* pbwt.c:353 */
+	if (pb == 0 || pb->magic != SHIM_MAGIC || pb->is_writing) return -1;    /* pbwt.c:353 */
 	if ((int64_t)k > pb->n) return -1;                                      /* pbwt.c:359 */
 	pb->k = (int64_t)k;                                                     /* "next row to read", pbwt.c:334,354 */
 	return 0;
@@ -135,7 +198,7 @@ int pbf_seek(pbf_t *pb, uint64_t k)
 const uint8_t **pbf_read(pbf_t *pb)
 {
 	int width;
-	if (pb == 0 || pb->magic != SHIM_MAGIC) return 0;                       /* pbwt.c:317 */
+	if (pb == 0 || pb->magic != SHIM_MAGIC || pb->is_writing) return 0;     /* pbwt.c:317 */
 	if (pb->k >= pb->n) return 0;                                           /* 'I' record reached, pbwt.c:335 */
 	width = pb->n_sub ? pb->n_sub : pb->m;
 	if (pb->k < pb->bat_beg || pb->k >= pb->bat_end) {

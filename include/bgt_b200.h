@@ -135,6 +135,22 @@ b200_pbf_t *b200_synth_generate(b200_ctx_t *ctx, const b200_synth_t *cfg);
 size_t      b200_pbf_image_size(const b200_pbf_t *pb);             /* bytes of the complete file image, 0 if only a shard is held */
 int         b200_pbf_image_download(const b200_pbf_t *pb, uint8_t *dst, size_t n_bytes); /* device image -> host */
 
+/* ---------------------------------------------------------------- encoder (pbwt.c:199-219 pbf_open_w, :288-311 pbf_write, :264-286 pbf_close) */
+/* The PBWT encoder on the device: the column-owned rank walk run forward (pbc_enc_core, pbwt.c:57-66) + the run-length
+ * byte code (pbr_enc, pbwt.c:24-50).  g = 2 bit planes.  The .pbf image is assembled in host memory like pbf_write
+ * assembles the file: header, an 'S' snapshot before every 2^shift rows, one 'B' record per row, the index at finish. */
+typedef struct b200_enc_s b200_enc_t;
+b200_enc_t *b200_enc_create(b200_ctx_t *ctx, int m, int shift);
+/* rows as pbf_write takes them (uint8_t *const *a, pbwt.c:288): a0/a1 = [n_rows][m], one byte per haplotype per plane, non-zero = 1 (pbwt.c:61) */
+int         b200_enc_write_bytes(b200_enc_t *e, const uint8_t *a0, const uint8_t *a1, int64_t n_rows);
+/* the same rows as bit planes in column order: bits[row][plane][(m+31)/32], bit c of word w = haplotype 32w+c */
+int         b200_enc_write_bits(b200_enc_t *e, const uint32_t *bits, int64_t n_rows);
+int64_t     b200_enc_rows(const b200_enc_t *e);
+/* writes the index record (pbf_close, pbwt.c:268-276); *image = the complete file image (owned by the encoder, valid until
+ * b200_enc_destroy); returns its size */
+int64_t     b200_enc_finish(b200_enc_t *e, const uint8_t **image);
+void        b200_enc_destroy(b200_enc_t *e);
+
 #ifdef __cplusplus
 }
 #endif

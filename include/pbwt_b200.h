@@ -13,9 +13,12 @@
  *   pbf_get_*    pbwt.c:390-393
  *   pbf_close    pbwt.c:264-286
  *
- * The write side (pbf_open_w / pbf_write, pbwt.c:199-219,288-311) and the in-memory codec entry points
- * (pbc_*, pbs_dec) are not part of the accelerated path; INTEGRATION.md shows how a host application keeps
- * its own objects for them.
+ *   pbf_open_w   pbwt.c:199-219   g must be 2 (import.c:68); NULL/"-" = stdout.  NULL if the file cannot be created.
+ *   pbf_write    pbwt.c:288-311   one row, a[g] = m bytes per plane (non-zero = 1, pbwt.c:61); rows are batched and encoded
+ *                                 on the GPU (b200_enc_*); the file (header, 'S'/'B' records, index) is written at pbf_close.
+ *
+ * The in-memory codec entry points (pbc_*, pbs_dec) are not part of the seam; INTEGRATION.md shows how a host
+ * application keeps its own objects for them.
  */
 #ifndef PBWT_B200_H
 #define PBWT_B200_H
@@ -30,6 +33,8 @@ struct pbf_s;
 typedef struct pbf_s pbf_t;
 
 pbf_t *pbf_open_r(const char *fn);
+pbf_t *pbf_open_w(const char *fn, int m, int g, int shift);
+int pbf_write(pbf_t *pb, uint8_t *const*a);
 int pbf_close(pbf_t *pb);
 const uint8_t **pbf_read(pbf_t *pb);
 int pbf_seek(pbf_t *pb, uint64_t k);

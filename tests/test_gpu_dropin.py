@@ -106,7 +106,7 @@ def test_view_multiallelic_import(tools, tmp_path):
     run(tools.REF_BGT, ["import", "-S", prefix, str(vcf)])
     for args in (["-C"], ["-f", "AC>0", "-G"], ["-s", ",S0000001,S0000005", "-C"]):
         assert run(NEW_BGT, ["view"] + args + [prefix]) == run(tools.REF_BGT, ["view"] + args + [prefix])
-    # the same import through the drop-in binary (its writer is the host application's own)
+    # the same import through the drop-in binary: pbf_open_w / pbf_write of seam A, i.e. the GPU encoder (encode.cu)
     prefix2 = str(tmp_path / "imp2.bgt")
     run(NEW_BGT, ["import", "-S", prefix2, str(vcf)])
     for ext in (".pbf", ".spl"):
@@ -123,10 +123,26 @@ def test_pbfview_matches_reference(tools, cohort_small, tmp_path):
         want = run(tools.REF_PBFVIEW, args + [pbf])
         got = run(NEW_PBFVIEW, args + [pbf])
         assert got == want, args
-    # PBF -> PBF re-encode through the drop-in (GPU decode + the host application's own writer)
+    # PBF -> PBF re-encode through the drop-in (GPU decode + GPU encode through seam A)
     a, b = tmp_path / "a.pbf", tmp_path / "b.pbf"
     with open(a, "wb") as f:
         subprocess.run([tools.REF_PBFVIEW, "-b", "-r", "100", "-n", "300", pbf], stdout=f, check=True)
     with open(b, "wb") as f:
         subprocess.run([NEW_PBFVIEW, "-b", "-r", "100", "-n", "300", pbf], stdout=f, check=True)
     assert a.read_bytes() == b.read_bytes()
+
+
+def test_pbfview_pim_to_pbf_on_the_gpu_encoder(tools, tmp_path):
+    """PIM text -> PBF (`pbfview -Sb [-s shift]`, pbfview.c:40-71): the drop-in writes through seam A's pbf_open_w /
+    pbf_write (device encoder); files must equal the reference's byte for byte, and decode back to the same text."""
+    mat = haplo_matrix(700, 150, 31)
+    pim = tmp_path / "x.pim"
+    pim.write_bytes(tools.pim_text(mat))
+    for shift in ("1", "2", "6", "13"):
+        a, b = tmp_path / ("ref%s.pbf" % shift), tmp_path / ("new%s.pbf" % shift)
+        with open(a, "wb") as f:
+            subprocess.run([tools.REF_PBFVIEW, "-Sb", "-s", shift, str(pim)], stdout=f, check=True)
+        with open(b, "wb") as f:
+            subprocess.run([NEW_PBFVIEW, "-Sb", "-s", shift, str(pim)], stdout=f, check=True)
+        assert a.read_bytes() == b.read_bytes(), shift
+        assert run(NEW_PBFVIEW, [str(b)]) == run(tools.REF_PBFVIEW, [str(a)])
