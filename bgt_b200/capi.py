@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200_enc_rows": (_i64, [_vp]),
     "b200_enc_finish": (_i64, [_vp, C.POINTER(_vp)]),
     "b200_enc_destroy": (None, [_vp]),
+    "b200_bgzf_inflate": (_i64, [_vp, _vp, C.c_size_t, _vp, C.c_size_t]),
 }
 
 
@@ -224,6 +225,19 @@ class Encoder:
         if self.h:
             lib().b200_enc_destroy(self.h)
             self.h = None
+
+
+def bgzf_inflate(ctx, data):
+    """Inflate a BGZF file image on the device (b200_bgzf_inflate); returns bytes."""
+    buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    n = lib().b200_bgzf_inflate(ctx.h, _ptr(buf), buf.size, None, 0)
+    if n < 0:
+        raise B200Error(_err())
+    out = np.empty(max(n, 1), dtype=np.uint8)
+    got = lib().b200_bgzf_inflate(ctx.h, _ptr(buf), buf.size, _ptr(out), out.size)
+    if got < 0:
+        raise B200Error(_err())
+    return out[:got].tobytes()
 
 
 def synth_cohort(ctx, n_samples, n_rows, seed=1, shift=13, r_max=64, p1_one_in=16):

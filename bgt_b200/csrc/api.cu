@@ -1346,3 +1346,85 @@ extern "C" int64_t b200_enc_finish(b200_enc_t *e, const uint8_t **image)
 	if (image) *image = e->image.data();
 	return (int64_t)e->image.size();
 }
+
+// ------------------------------------------------------------------------------------------------ BGZF (bgzf.c)
+
+struct BgzfIndex { std::vector<uint64_t> coff, uoff; std::vector<uint32_t> csize, usize; uint64_t total = 0; uint32_t max_csize = 0; };
+
+// walk the block headers of a BGZF image (bgzf.c:259-281 check_header, :318-351 bgzf_read_block); ISIZE gives the output layout
+static bool bgzf_index(const uint8_t *f, size_t n, BgzfIndex &ix)
+{
+	size_t pos = 0;
+	while (pos < n) {
+		if (pos + 18 > n || f[pos] != 31 || f[pos + 1] != 139 || f[pos + 2] != 8 || !(f[pos + 3] & 4)) { set_err("not a BGZF file (block header at offset %zu)", pos); return false; }
+		const uint32_t xlen = f[pos + 10] | (uint32_t)f[pos + 11] << 8;
+		if (pos + 12 + xlen > n) { set_err("truncated BGZF block header"); return false; }
+		uint32_t bsize = 0; bool found = false;
+		for (uint32_t x = 0; x + 4 <= xlen;) { // extra subfields: SI1 SI2 SLEN data
+			const uint8_t *e = f + pos + 12 + x;
+			const uint32_t slen = e[2] | (uint32_t)e[3] << 8;
+			if (e[0] == 'B' && e[1] == 'C' && slen == 2 && x + 6 <= xlen) { bsize = (e[4] | (uint32_t)e[5] << 8) + 1; found = true; }
+			x += 4 + slen;
+		}
+		if (!found || bsize < 12 + xlen + 8 || pos + bsize > n) { set_err("corrupt BGZF block at offset %zu", pos); return false; }
+		const uint32_t csz = bsize - 12 - xlen - 8;
+		uint32_t isize;
+		memcpy(&isize, f + pos + bsize - 4, 4);
+		if (isize > 65536) { set_err("BGZF block at offset %zu claims %u uncompressed bytes", pos, isize); return false; }
+		if (isize) { // the empty EOF block (bgzf.c:51-57) carries nothing
+			ix.coff.push_back((uint64_t)pos + 12 + xlen); ix.csize.push_back(csz); ix.usize.push_back(isize); ix.uoff.push_back(ix.total);
+			ix.total += isize;
+			if (csz > ix.max_csize) ix.max_csize = csz;
+		}
+		pos += bsize;
+	}
+	return true;
+}
+
+// inflate a BGZF image into a device buffer (from the pool; caller frees with pool_free).  No sync.
+static bool bgzf_inflate_device(b200_ctx_t *c, const uint8_t *f, size_t n, uint8_t **d_out, uint64_t *out_len)
+{
+	BgzfIndex ix;
+	if (!bgzf_index(f, n, ix)) return false;
+	const size_t nb = ix.coff.size();
+	uint8_t *d_in = nullptr, *d_o = nullptr, *d_tab = nullptr;
+	const size_t tab_bytes = nb * (8 + 8 + 4 + 4) + 64;
+	bool ok = pool_malloc(c, (void**)&d_in, n + 64) && pool_malloc(c, (void**)&d_o, (size_t)ix.total + 64) && pool_malloc(c, (void**)&d_tab, tab_bytes);
+	if (!ok) return false;
+	uint64_t *d_coff = (uint64_t*)d_tab, *d_uoff = d_coff + nb;
+	uint32_t *d_csize = (uint32_t*)(d_uoff + nb), *d_usize = d_csize + nb;
+	ok = CU_OK(cudaMemcpyAsync(d_in, f, n, cudaMemcpyHostToDevice, c->st));
+	if (nb) ok = ok && CU_OK(cudaMemcpyAsync(d_coff, ix.coff.data(), nb * 8, cudaMemcpyHostToDevice, c->st)) && CU_OK(cudaMemcpyAsync(d_uoff, ix.uoff.data(), nb * 8, cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(d_csize, ix.csize.data(), nb * 4, cudaMemcpyHostToDevice, c->st)) && CU_OK(cudaMemcpyAsync(d_usize, ix.usize.data(), nb * 4, cudaMemcpyHostToDevice, c->st));
+	InflateParams P;
+	memset(&P, 0, sizeof(P));
+	P.in = d_in; P.blk_coff = d_coff; P.blk_csize = d_csize; P.blk_usize = d_usize; P.blk_uoff = d_uoff; P.out = d_o; P.max_csize = ix.max_csize; P.err = c->d_err;
+	ok = ok && CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st)) && CU_OK(launch_bgzf_inflate(P, (int)nb, c->st));
+	++c->launches;
+	// the tables and the compressed image are read by the queued kernel: released after the stream has passed it
+	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
+	pool_free(c, d_in); pool_free(c, d_tab);
+	if (!ok) { pool_free(c, d_o); return false; }
+	int err = 0;
+	if (!CU_OK(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost))) { pool_free(c, d_o); return false; }
+	if (err & 256) { set_err("corrupt BGZF file: a block does not inflate to its ISIZE"); pool_free(c, d_o); return false; }
+	*d_out = d_o; *out_len = ix.total;
+	return true;
+}
+
+extern "C" int64_t b200_bgzf_inflate(b200_ctx_t *c, const uint8_t *bytes, size_t n_bytes, uint8_t *out, size_t out_cap)
+{
+	if (!c || !bytes) { set_err("b200_bgzf_inflate: null argument"); return -1; }
+	cudaSetDevice(c->dev);
+	if (!out) { // size query: headers only
+		BgzfIndex ix;
+		return bgzf_index(bytes, n_bytes, ix) ? (int64_t)ix.total : -1;
+	}
+	uint8_t *d = nullptr; uint64_t len = 0;
+	if (!bgzf_inflate_device(c, bytes, n_bytes, &d, &len)) return -1;
+	bool ok = true;
+	if (len > out_cap) { set_err("b200_bgzf_inflate: output needs %llu bytes", (unsigned long long)len); ok = false; }
+	ok = ok && (len == 0 || (CU_OK(cudaMemcpyAsync(out, d, (size_t)len, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st))));
+	pool_free(c, d);
+	return ok ? (int64_t)len : -1;
+}

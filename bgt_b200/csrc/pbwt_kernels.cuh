@@ -185,6 +185,19 @@ size_t encode_smem_bytes(int m);
 cudaError_t launch_encode(const EncodeParams &P, int sm_count, cudaStream_t st);
 cudaError_t launch_pack_rows(const uint8_t *a0, const uint8_t *a1, long long n_rows, int m, uint32_t *bits, cudaStream_t st);
 
+// BGZF inflate (inflate.cu)
+struct InflateParams {
+	const uint8_t  *in;         // the compressed file image
+	const uint64_t *blk_coff;   // [blocks] offset of the block's DEFLATE stream in `in`
+	const uint32_t *blk_csize;  // [blocks] bytes of that stream
+	const uint32_t *blk_usize;  // [blocks] uncompressed size (ISIZE, bgzf.c:251-257)
+	const uint64_t *blk_uoff;   // [blocks] offset of the block's bytes in `out`
+	uint8_t *out;
+	uint32_t max_csize;
+	int *err;
+};
+cudaError_t launch_bgzf_inflate(const InflateParams &P, int n_blk, cudaStream_t st);
+
 // synthetic cohort generator (synth.cu)
 struct SynthCfg { uint32_t m; long long n_rows; int shift; uint64_t seed; int r_max; int p1_one_in; };
 cudaError_t launch_synth_lengths(const SynthCfg &c, uint32_t *len2 /*[n_rows][2]*/, cudaStream_t st);

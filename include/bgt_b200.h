@@ -151,6 +151,12 @@ int64_t     b200_enc_rows(const b200_enc_t *e);
 int64_t     b200_enc_finish(b200_enc_t *e, const uint8_t **image);
 void        b200_enc_destroy(b200_enc_t *e);
 
+/* ---------------------------------------------------------------- BGZF (bgzf.c:225-249 inflate_block, :318-351 bgzf_read_block, :353-379 bgzf_read) */
+/* Inflate a whole BGZF file image (the site-only .bcf / .csi of a BGT database) on the device: one warp per block, raw
+ * DEFLATE (RFC 1951), the CRC is not checked (like the reference's reader).  out == NULL: returns the uncompressed size
+ * (block headers only).  Returns the number of bytes written, <0 on a malformed file. */
+int64_t     b200_bgzf_inflate(b200_ctx_t *ctx, const uint8_t *bytes, size_t n_bytes, uint8_t *out, size_t out_cap);
+
 #ifdef __cplusplus
 }
 #endif
