@@ -76,6 +76,12 @@ SIGNATURES = {
     "b200_enc_finish": (_i64, [_vp, C.POINTER(_vp)]),
     "b200_enc_destroy": (None, [_vp]),
     "b200_bgzf_inflate": (_i64, [_vp, _vp, C.c_size_t, _vp, C.c_size_t]),
+    "b200_sites_load": (_vp, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _int]),
+    "b200_sites_n": (_i64, [_vp]),
+    "b200_sites_header": (C.c_void_p, [_vp, C.POINTER(_i64)]),
+    "b200_sites_rows": (_int, [_vp, _vp, _vp]),
+    "b200_sites_destroy": (None, [_vp]),
+    "b200_view_text": (_i64, [_vp, _vp, _vp, _vp, _int, _vp, _int, C.POINTER(_vp), C.POINTER(_i64)]),
 }
 
 
@@ -224,6 +230,42 @@ class Encoder:
     def close(self):
         if self.h:
             lib().b200_enc_destroy(self.h)
+            self.h = None
+
+
+class Sites:
+    """The site side of a BGT database on the device (b200_sites_t): .bcf (+ .csi) inflated, indexed and parsed by kernels."""
+
+    def __init__(self, ctx, bcf, csi=None, row_key=-1):
+        b = bcf if isinstance(bcf, np.ndarray) else np.frombuffer(bcf, dtype=np.uint8)
+        c = None if csi is None else (csi if isinstance(csi, np.ndarray) else np.frombuffer(csi, dtype=np.uint8))
+        self.h = lib().b200_sites_load(ctx.h, _ptr(b), b.size, _ptr(c), 0 if c is None else c.size, row_key)
+        if not self.h:
+            raise B200Error(_err())
+        self.ctx, self.n = ctx, lib().b200_sites_n(self.h)
+
+    def header(self):
+        n = C.c_int64(0)
+        p = lib().b200_sites_header(self.h, C.byref(n))
+        return C.string_at(p, n.value)
+
+    def rows(self):
+        rows, pos = np.empty(self.n, np.int64), np.empty(self.n, np.int32)
+        if lib().b200_sites_rows(self.h, _ptr(rows), _ptr(pos)) != 0:
+            raise B200Error(_err())
+        return rows, pos
+
+    def view_text(self, pbf, query, with_counts=False):
+        """The record lines of `bgt view -G [-C] [-f ..] [-s ..]` (b200_view_text); returns (bytes, n_lines)."""
+        p, nl = C.c_void_p(), C.c_int64(0)
+        n = lib().b200_view_text(self.ctx.h, self.h, pbf.h, query.h, int(with_counts), None, 0, C.byref(p), C.byref(nl))
+        if n < 0:
+            raise B200Error(_err())
+        return C.string_at(p, n), nl.value
+
+    def close(self):
+        if self.h:
+            lib().b200_sites_destroy(self.h)
             self.h = None
 
 

@@ -14,6 +14,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <algorithm>
+#include <string>
 #include "../../include/bgt_b200.h"
 #include "pbwt_kernels.cuh"
 #include "flt.h"
@@ -1427,4 +1429,263 @@ extern "C" int64_t b200_bgzf_inflate(b200_ctx_t *c, const uint8_t *bytes, size_t
 	ok = ok && (len == 0 || (CU_OK(cudaMemcpyAsync(out, d, (size_t)len, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st))));
 	pool_free(c, d);
 	return ok ? (int64_t)len : -1;
+}
+
+// ------------------------------------------------------------------------------------------------ sites (.bcf / .csi) and the text of `view -G`
+
+struct b200_sites_s {
+	b200_ctx_t *ctx = nullptr;
+	uint8_t *d_bcf = nullptr; uint64_t bcf_len = 0;
+	SiteRec *d_sites = nullptr;
+	int64_t n = 0;
+	std::string header;                 // BCF header text (vcf.c:263-288)
+	std::vector<std::string> contigs;   // BCF_DT_CTG in id order (vcf.c:121-133)
+	char *d_ctg = nullptr; int *d_ctg_off = nullptr;
+	int row_key = -1;
+	DevBuf len, off, temp, text;
+	char *h_text = nullptr; size_t h_text_cap = 0;
+	unsigned long long *d_nlines = nullptr;
+};
+
+extern "C" void b200_sites_destroy(b200_sites_t *s)
+{
+	if (!s) return;
+	cudaSetDevice(s->ctx->dev);
+	cudaStreamSynchronize(s->ctx->st);
+	pool_free(s->ctx, s->d_bcf);
+	if (s->d_sites) cudaFree(s->d_sites);
+	if (s->d_ctg) cudaFree(s->d_ctg);
+	if (s->d_ctg_off) cudaFree(s->d_ctg_off);
+	if (s->d_nlines) cudaFree(s->d_nlines);
+	s->len.release(); s->off.release(); s->temp.release(); s->text.release();
+	if (s->h_text) cudaFreeHost(s->h_text);
+	delete s;
+}
+
+// ID of a "##KIND=<...ID=xxx...>" header line, or empty
+static std::string hdr_line_id(const std::string &ln)
+{
+	size_t p = ln.find('<');
+	if (p == std::string::npos) return "";
+	size_t q = ln.find("ID=", p);
+	while (q != std::string::npos && !(ln[q - 1] == '<' || ln[q - 1] == ',')) q = ln.find("ID=", q + 1);
+	if (q == std::string::npos) return "";
+	size_t e = ln.find_first_of(",>", q + 3);
+	return ln.substr(q + 3, e == std::string::npos ? std::string::npos : e - q - 3);
+}
+
+// record-number index at the tail of an inflated .csi (hts.c:536-542): "RNI\1", n_rec, rec_shift, n, voff[n]
+static bool csi_rni(const std::vector<uint8_t> &csi, uint64_t *n_rec, int *rec_shift, std::vector<uint64_t> &voff)
+{
+	if (csi.size() < 16 || memcmp(csi.data(), "CSI\1", 4) != 0) return false;
+	size_t p = 4;
+	int32_t v[3];
+	memcpy(v, csi.data() + p, 12); p += 12;                       // min_shift, n_lvls, l_meta (hts.c:529-533)
+	if (v[2] < 0 || p + (size_t)v[2] + 4 > csi.size()) return false;
+	p += (size_t)v[2];
+	int32_t n_ref;
+	memcpy(&n_ref, csi.data() + p, 4); p += 4;
+	for (int32_t r = 0; r < n_ref; ++r) {                         // hts_idx_save_core, CSI flavour (hts.c:470-510)
+		int32_t n_bin;
+		if (p + 4 > csi.size()) return false;
+		memcpy(&n_bin, csi.data() + p, 4); p += 4;
+		for (int32_t b = 0; b < n_bin; ++b) {
+			int32_t n_chunk;
+			if (p + 16 > csi.size()) return false;
+			memcpy(&n_chunk, csi.data() + p + 12, 4);             // bin u32, loff u64, n_chunk i32
+			p += 16;
+			if (n_chunk < 0 || p + 16ull * (size_t)n_chunk > csi.size()) return false;
+			p += 16ull * (size_t)n_chunk;
+		}
+	}
+	p += 8;                                                       // n_no_coor
+	if (p + 20 > csi.size() || memcmp(csi.data() + p, "RNI\1", 4) != 0) return false;
+	int32_t n;
+	memcpy(n_rec, csi.data() + p + 4, 8); memcpy(rec_shift, csi.data() + p + 12, 4); memcpy(&n, csi.data() + p + 16, 4);
+	p += 20;
+	if (n < 0 || *rec_shift <= 0 || *rec_shift > 30 || p + 8ull * (size_t)n > csi.size()) return false;
+	voff.resize((size_t)n);
+	memcpy(voff.data(), csi.data() + p, 8ull * (size_t)n);
+	return true;
+}
+
+extern "C" b200_sites_t *b200_sites_load(b200_ctx_t *c, const uint8_t *bcf, size_t n_bcf, const uint8_t *csi, size_t n_csi, int row_key)
+{
+	if (!c || !bcf) { set_err("b200_sites_load: null argument"); return nullptr; }
+	cudaSetDevice(c->dev);
+	b200_sites_t *s = new b200_sites_t();
+	s->ctx = c;
+	BgzfIndex ix;
+	if (!bgzf_index(bcf, n_bcf, ix) || !bgzf_inflate_device(c, bcf, n_bcf, &s->d_bcf, &s->bcf_len)) { b200_sites_destroy(s); return nullptr; }
+	// ---- header: "BCF\2\2", l_text, text (vcf.c:263-288)
+	uint8_t h9[9];
+	uint32_t l_text = 0;
+	bool ok = s->bcf_len >= 9 && CU_OK(cudaMemcpy(h9, s->d_bcf, 9, cudaMemcpyDeviceToHost)) && memcmp(h9, "BCF\2\2", 5) == 0;
+	if (ok) { memcpy(&l_text, h9 + 5, 4); ok = 9ull + l_text <= s->bcf_len; }
+	if (!ok) { set_err("not a BCF2 file"); b200_sites_destroy(s); return nullptr; }
+	s->header.resize(l_text);
+	if (l_text && !CU_OK(cudaMemcpy(&s->header[0], s->d_bcf + 9, l_text, cudaMemcpyDeviceToHost))) { b200_sites_destroy(s); return nullptr; }
+	while (!s->header.empty() && s->header.back() == 0) s->header.pop_back();
+	{ // dictionaries as bcf_hdr_parse builds them (vcf.c:193-208): PASS first, then IDs / contigs in order of first appearance
+		std::vector<std::string> ids(1, "PASS");
+		size_t a = 0;
+		while (a < s->header.size()) {
+			size_t e = s->header.find('\n', a);
+			if (e == std::string::npos) e = s->header.size();
+			const std::string ln = s->header.substr(a, e - a);
+			a = e + 1;
+			if (ln.compare(0, 2, "##") != 0) continue;
+			const std::string id = hdr_line_id(ln);
+			if (id.empty()) continue;
+			if (ln.compare(0, 9, "##contig=") == 0) { if (std::find(s->contigs.begin(), s->contigs.end(), id) == s->contigs.end()) s->contigs.push_back(id); }
+			else if (ln.compare(0, 9, "##FILTER=") == 0 || ln.compare(0, 7, "##INFO=") == 0 || ln.compare(0, 9, "##FORMAT=") == 0) {
+				if (std::find(ids.begin(), ids.end(), id) == ids.end()) ids.push_back(id);
+			}
+		}
+		if (row_key < 0) { for (size_t i = 0; i < ids.size(); ++i) if (ids[i] == "_row") row_key = (int)i; }
+		s->row_key = row_key;
+	}
+	// ---- record offsets: stretches from the RNI of the .csi, or one stretch from the first record
+	const uint64_t first = 9ull + l_text;
+	std::vector<unsigned long long> seg;
+	int seg_len = 0;
+	int64_t n_rec = -1;
+	if (csi && n_csi) {
+		const int64_t clen = b200_bgzf_inflate(c, csi, n_csi, nullptr, 0);
+		std::vector<uint8_t> raw(clen > 0 ? (size_t)clen : 1);
+		std::vector<uint64_t> voff;
+		uint64_t nr = 0; int shift = 0;
+		if (clen > 0 && b200_bgzf_inflate(c, csi, n_csi, raw.data(), raw.size()) == clen && (raw.resize((size_t)clen), csi_rni(raw, &nr, &shift, voff))) {
+			// virtual offset = file offset of the BGZF block << 16 | offset inside it (bgzf.h); blocks are in ix by their DEFLATE start
+			std::vector<uint64_t> blk_start(ix.coff.size());
+			for (size_t b = 0; b < ix.coff.size(); ++b) blk_start[b] = ix.coff[b];
+			bool good = (uint64_t)voff.size() == ((nr + (1ull << shift) - 1) >> shift);
+			for (size_t k = 0; good && k < voff.size(); ++k) {
+				const uint64_t co = voff[k] >> 16, uo = voff[k] & 0xffff;
+				// the block whose header starts at co: its DEFLATE stream starts 12 + xlen bytes later -> last block with start > co is the one behind it
+				size_t b = std::upper_bound(blk_start.begin(), blk_start.end(), co) - blk_start.begin();
+				if (b >= blk_start.size() || blk_start[b] - co > 12 + 65535) { // co may point at the EOF block / end of file: position = end of stream
+					if (co >= n_bcf - 28 || b >= blk_start.size()) { seg.push_back(s->bcf_len); continue; }
+					good = false; break;
+				}
+				seg.push_back(ix.uoff[b] + uo);
+			}
+			if (good) { n_rec = (int64_t)nr; seg_len = 1 << shift; } else seg.clear();
+		}
+	}
+	unsigned long long *d_seg = nullptr, *d_off = nullptr, *d_cnt = nullptr;
+	ok = CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
+	if (n_rec < 0) { // no usable RNI: count, then chase, from the first record with one thread
+		seg.assign(1, first);
+		ok = ok && CU_OK(cudaMalloc(&d_seg, 8)) && CU_OK(cudaMalloc(&d_cnt, 8)) && CU_OK(cudaMemcpyAsync(d_seg, seg.data(), 8, cudaMemcpyHostToDevice, c->st)) &&
+		     CU_OK(launch_bcf_chase(s->d_bcf, s->bcf_len, d_seg, 1, 0, 0, nullptr, d_cnt, c->d_err, c->st));
+		unsigned long long cnt = 0;
+		ok = ok && CU_OK(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+		++c->launches;
+		n_rec = (int64_t)cnt; seg_len = n_rec > 0 ? (int)(n_rec < (1LL << 30) ? n_rec : (1LL << 30)) : 1;
+	} else {
+		ok = ok && CU_OK(cudaMalloc(&d_seg, 8 * (seg.size() + 1))) && CU_OK(cudaMemcpyAsync(d_seg, seg.data(), 8 * seg.size(), cudaMemcpyHostToDevice, c->st));
+	}
+	s->n = n_rec;
+	ok = ok && CU_OK(cudaMalloc(&d_off, 8 * (size_t)(n_rec + 1))) && CU_OK(cudaMalloc(&s->d_sites, sizeof(SiteRec) * (size_t)(n_rec + 1)));
+	ok = ok && CU_OK(launch_bcf_chase(s->d_bcf, s->bcf_len, d_seg, (int)seg.size(), seg_len, n_rec, d_off, nullptr, c->d_err, c->st)) &&
+	     CU_OK(launch_bcf_parse(s->d_bcf, s->bcf_len, d_off, n_rec, s->row_key, s->d_sites, c->d_err, c->st));
+	c->launches += 2;
+	// contig names for the text kernels
+	std::string names; std::vector<int> coff(1, 0);
+	for (const std::string &nm : s->contigs) { names += nm; coff.push_back((int)names.size()); }
+	if (s->contigs.empty()) { names = "."; coff.push_back(1); }
+	ok = ok && CU_OK(cudaMalloc(&s->d_ctg, names.size() + 16)) && CU_OK(cudaMalloc(&s->d_ctg_off, coff.size() * sizeof(int))) && CU_OK(cudaMalloc(&s->d_nlines, 8)) &&
+	     CU_OK(cudaMemcpyAsync(s->d_ctg, names.data(), names.size(), cudaMemcpyHostToDevice, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(s->d_ctg_off, coff.data(), coff.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
+	int err = 0;
+	ok = ok && CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+	if (d_seg) cudaFree(d_seg);
+	if (d_off) cudaFree(d_off);
+	if (d_cnt) cudaFree(d_cnt);
+	if (ok && (err & 512)) { set_err("corrupt BCF: record lengths do not chain to the end of the stream"); ok = false; }
+	if (ok && (err & 1024)) { set_err("BCF record without INFO/_row or with fewer than two alleles (not the site side of a BGT database)"); ok = false; }
+	if (!ok) { b200_sites_destroy(s); return nullptr; }
+	return s;
+}
+
+extern "C" int64_t b200_sites_n(const b200_sites_t *s) { return s ? s->n : -1; }
+extern "C" const char *b200_sites_header(const b200_sites_t *s, int64_t *len) { if (!s) return nullptr; if (len) *len = (int64_t)s->header.size(); return s->header.c_str(); }
+
+// (site, row) table to the host: for callers that keep assembling records themselves
+extern "C" int b200_sites_rows(const b200_sites_t *s, int64_t *rows, int32_t *pos)
+{
+	if (!s) return -1;
+	cudaSetDevice(s->ctx->dev);
+	std::vector<SiteRec> h((size_t)s->n + 1);
+	if (s->n && !CU_OK(cudaMemcpy(h.data(), s->d_sites, sizeof(SiteRec) * (size_t)s->n, cudaMemcpyDeviceToHost))) return -1;
+	for (int64_t i = 0; i < s->n; ++i) { if (rows) rows[i] = h[(size_t)i].row; if (pos) pos[i] = h[(size_t)i].pos; }
+	return 0;
+}
+
+extern "C" int64_t b200_view_text(b200_ctx_t *c, b200_sites_t *s, const b200_pbf_t *pb, const b200_query_t *q, int with_counts,
+                                  const char *const *contig_names, int n_contigs, const char **text, int64_t *n_lines)
+{
+	if (!c || !s || !pb || !q || !text) { set_err("b200_view_text: null argument"); return -1; }
+	if (s->ctx != c || pb->ctx != c || q->ctx != c) { set_err("b200_view_text: handles belong to another context"); return -1; }
+	cudaSetDevice(c->dev);
+	const int64_t row_lo = b200_pbf_row_beg(pb), n_rows = b200_pbf_row_end(pb) - row_lo;
+	if (q->has_flt && q->prog.needs_host) { set_err("b200_view_text: filters using ** are evaluated with the host libm; use b200_scan"); return -1; }
+	if (q->has_flt) with_counts = 1;                                 // bgt.c:850: a filter implies AC/AN in the output
+	if (q->G > 1) with_counts = 1;
+	if (contig_names && n_contigs > 0) { // the output header's contig dictionary (bgt.c:626-662) instead of the file's own
+		std::string names; std::vector<int> coff(1, 0);
+		for (int i = 0; i < n_contigs; ++i) { names += contig_names[i]; coff.push_back((int)names.size()); }
+		cudaStreamSynchronize(c->st);
+		if (s->d_ctg) cudaFree(s->d_ctg);
+		if (s->d_ctg_off) cudaFree(s->d_ctg_off);
+		s->d_ctg = nullptr; s->d_ctg_off = nullptr;
+		if (!CU_OK(cudaMalloc(&s->d_ctg, names.size() + 16)) || !CU_OK(cudaMalloc(&s->d_ctg_off, coff.size() * sizeof(int))) ||
+		    !CU_OK(cudaMemcpy(s->d_ctg, names.data(), names.size(), cudaMemcpyHostToDevice)) ||
+		    !CU_OK(cudaMemcpy(s->d_ctg_off, coff.data(), coff.size() * sizeof(int), cudaMemcpyHostToDevice))) return -1;
+		s->contigs.assign(contig_names, contig_names + n_contigs);
+	}
+	// ---- the scan: per-row counts and verdicts stay on the device
+	const int stride = 3 + 3 * q->G;
+	if (!c->counts.reserve((size_t)n_rows * stride * sizeof(int32_t) + 16) || !c->pass.reserve((size_t)n_rows + 16)) return -1;
+	b200_scan_out_t so;
+	memset(&so, 0, sizeof(so));
+	so.counts = (int32_t*)c->counts.p; so.pass = (uint8_t*)c->pass.p;
+	if (n_rows > 0 && b200_scan(c, pb, q, row_lo, n_rows, B200_SCAN_COUNTS | B200_SCAN_DEVICE_OUT, &so) != n_rows) return -1;
+	// ---- lines
+	const size_t tb = view_scan_temp_bytes(s->n);
+	if (!s->len.reserve(8 * (size_t)(s->n + 2)) || !s->off.reserve(8 * (size_t)(s->n + 2)) || !s->temp.reserve(tb + 16)) return -1;
+	ViewParams P;
+	memset(&P, 0, sizeof(P));
+	P.sites = s->d_sites; P.n_rec = s->n; P.bcf = s->d_bcf; P.ctg_names = s->d_ctg; P.ctg_off = s->d_ctg_off; P.n_ctg = (int)(s->contigs.empty() ? 1 : s->contigs.size());
+	P.counts = (const int32_t*)c->counts.p; P.pass = q->has_flt ? (const uint8_t*)c->pass.p : nullptr; P.stride = stride; P.G = q->G; P.with_counts = with_counts ? 1 : 0;
+	P.row_lo = row_lo; P.n_rows = n_rows; P.err = c->d_err;
+	unsigned long long total = 0, lines = 0;
+	bool ok = CU_OK(cudaMemsetAsync(s->len.p, 0, 8 * (size_t)(s->n + 2), c->st)) && CU_OK(cudaMemsetAsync(s->d_nlines, 0, 8, c->st)) &&
+	          CU_OK(launch_view_text(P, (unsigned long long*)s->len.p, (unsigned long long*)s->off.p, s->temp.p, tb, nullptr, nullptr, 0, c->st)) &&
+	          CU_OK(cudaMemcpyAsync(&total, (unsigned long long*)s->off.p + s->n, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+	c->launches += 2;
+	if (!ok) return -1;
+	if (s->n == 0) total = 0;
+	if (!s->text.reserve((size_t)total + 64)) return -1;
+	if ((size_t)total + 1 > s->h_text_cap) {
+		if (s->h_text) cudaFreeHost(s->h_text);
+		s->h_text = nullptr; s->h_text_cap = 0;
+		if (!CU_OK(cudaMallocHost((void**)&s->h_text, (size_t)total + 64))) return -1;
+		s->h_text_cap = (size_t)total + 64;
+	}
+	int err = 0;
+	ok = CU_OK(launch_view_text(P, (unsigned long long*)s->len.p, (unsigned long long*)s->off.p, nullptr, 0, (char*)s->text.p, s->d_nlines, 1, c->st)) &&
+	     (total == 0 || CU_OK(cudaMemcpyAsync(s->h_text, s->text.p, (size_t)total, cudaMemcpyDeviceToHost, c->st))) &&
+	     CU_OK(cudaMemcpyAsync(&lines, s->d_nlines, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->st)) &&
+	     CU_OK(cudaStreamSynchronize(c->st));
+	++c->launches;
+	if (!ok) return -1;
+	if (err & 2048) { set_err("a site record points at a row outside the resident PBF rows"); return -1; }
+	if (err) { set_err("device error flags 0x%x while formatting", err); return -1; }
+	s->h_text[total] = 0;
+	*text = s->h_text;
+	if (n_lines) *n_lines = (int64_t)lines;
+	read_scan_timings(c);
+	return (int64_t)total;
 }

@@ -198,6 +198,30 @@ struct InflateParams {
 };
 cudaError_t launch_bgzf_inflate(const InflateParams &P, int n_blk, cudaStream_t st);
 
+// site side of `bgt view` (sites.cu)
+struct SiteRec {
+	int32_t rid, pos, rlen, n_allele;
+	int32_t ref_len, alt_len;
+	unsigned long long ref_off, alt_off;   // where REF and the first ALT lie in the inflated BCF stream
+	long long row;                         // INFO/_row (bgt.c:279-286); -1 = the record did not parse
+};
+struct ViewParams {
+	const SiteRec *sites; long long n_rec;
+	const uint8_t *bcf;
+	const char *ctg_names; const int *ctg_off; int n_ctg;   // contig names back to back, ctg_off[n_ctg+1]
+	const int32_t *counts; const uint8_t *pass;              // the scan's per-row results (rows row_lo .. row_lo+n_rows)
+	int stride, G, with_counts;
+	long long row_lo, n_rows;
+	int *err;
+};
+cudaError_t launch_bcf_chase(const uint8_t *bcf, unsigned long long bcf_len, const unsigned long long *seg_pos, int n_seg, int seg_len, long long n_rec,
+                             unsigned long long *rec_off, unsigned long long *counted, int *err, cudaStream_t st);
+cudaError_t launch_bcf_parse(const uint8_t *bcf, unsigned long long bcf_len, const unsigned long long *rec_off, long long n_rec, int row_key, SiteRec *sites,
+                             int *err, cudaStream_t st);
+size_t view_scan_temp_bytes(long long n);
+cudaError_t launch_view_text(const ViewParams &P, unsigned long long *len, unsigned long long *off, void *temp, size_t temp_bytes, char *text,
+                             unsigned long long *n_lines, int phase, cudaStream_t st);
+
 // synthetic cohort generator (synth.cu)
 struct SynthCfg { uint32_t m; long long n_rows; int shift; uint64_t seed; int r_max; int p1_one_in; };
 cudaError_t launch_synth_lengths(const SynthCfg &c, uint32_t *len2 /*[n_rows][2]*/, cudaStream_t st);

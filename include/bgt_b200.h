@@ -157,6 +157,27 @@ void        b200_enc_destroy(b200_enc_t *e);
  * (block headers only).  Returns the number of bytes written, <0 on a malformed file. */
 int64_t     b200_bgzf_inflate(b200_ctx_t *ctx, const uint8_t *bytes, size_t n_bytes, uint8_t *out, size_t out_cap);
 
+/* ---------------------------------------------------------------- sites + the text of `bgt view -G` (output assembly and BCF parse off the host thread) */
+/* The site side of a BGT database on the device: <prefix>.bgt.bcf (site-only BCF2, bgzf) and <prefix>.bgt.bcf.csi.  Both are
+ * inflated by the kernel above; the record-number index of the .csi (RNI, hts.c:536-542: one virtual offset per 1024
+ * records) gives independent starting points for the record-length chase (vcf.c:316-336 bcf_read1_core); every record is
+ * parsed by one thread (vcf.c:338-360 bcf_unpack; INFO/_row, bgt.c:279-286).  csi may be NULL (one sequential chase).
+ * row_key: header-dictionary id of INFO/_row (bcf_id2int(h, BCF_DT_ID, "_row")), or -1 = take it from the header text. */
+typedef struct b200_sites_s b200_sites_t;
+b200_sites_t *b200_sites_load(b200_ctx_t *ctx, const uint8_t *bcf, size_t n_bcf, const uint8_t *csi, size_t n_csi, int row_key);
+int64_t     b200_sites_n(const b200_sites_t *s);                        /* records */
+const char *b200_sites_header(const b200_sites_t *s, int64_t *len);      /* BCF header text (vcf.c:263-288) */
+int         b200_sites_rows(const b200_sites_t *s, int64_t *rows, int32_t *pos);  /* per record: INFO/_row and 0-based POS */
+void        b200_sites_destroy(b200_sites_t *s);
+/* `bgt view -G [-C] [-f EXPR] [-s ...]` over the whole resident PBF: the scan (b200_scan) with its results kept on the
+ * device, then one VCF line per site that passes, assembled on the device in file order -- byte for byte what
+ * vcf_format1 (vcf.c:895-969) prints for the record that bgtm_read_core builds (bcfcpy_min vcf.c:1166-1182, END bgt.c:824-827,
+ * bgtm_fill_info bgt.c:721-733).  with_counts = the -C flag (forced on by a filter or several groups, bgt.c:850).
+ * contig_names: the output header's contig dictionary, or NULL = the .bcf's own.  *text = pinned host buffer owned by
+ * `s`, valid until the next call; returns its length, *n_lines = records printed.  The header lines are the caller's. */
+int64_t     b200_view_text(b200_ctx_t *ctx, b200_sites_t *s, const b200_pbf_t *pb, const b200_query_t *q, int with_counts,
+                           const char *const *contig_names, int n_contigs, const char **text, int64_t *n_lines);
+
 #ifdef __cplusplus
 }
 #endif
