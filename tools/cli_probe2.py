@@ -15,7 +15,7 @@ try:
     subprocess.run([orc.MKSITES, prefix], check=True, stderr=subprocess.DEVNULL)
     exe = os.path.join(ROOT, "integration", "_build", "bgt")
     env = dict(os.environ, BGT_B200_TRACE="1")
-    for args in (["-G", "-C"], ["-f", "AC>0", "-G"]):
+    for args in (["-f", "AC>0", "-G"], ["-f", "AC>0", "-G"]):
         t = time.perf_counter()
         r = subprocess.run([exe, "view"] + args + [prefix], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
         print(args, "%.2f s" % (time.perf_counter() - t)); print(r.stderr.decode()[-3000:])
