@@ -129,6 +129,8 @@ struct b200_pbf_s {
 	mutable uint32_t *d_comp_start = nullptr;
 	mutable int32_t *d_comp_delta = nullptr;
 	mutable int *d_comp_n = nullptr;
+	mutable uint16_t *d_comp_dir = nullptr;   // bucket directories of the forward composites
+	int dir_shift = 0, dir_n = 0;
 	mutable uint32_t *d_vcomp_start = nullptr;   // inverse composites of the plane-1 view rows (plane1_select_kernel)
 	mutable int32_t *d_vcomp_delta = nullptr;
 	mutable int *d_vcomp_n = nullptr;
@@ -316,6 +318,7 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_comp_start);
 	pool_free(pb->ctx, pb->d_comp_delta);
 	pool_free(pb->ctx, pb->d_comp_n);
+	pool_free(pb->ctx, pb->d_comp_dir);
 	pool_free(pb->ctx, pb->d_vcomp_start);
 	pool_free(pb->ctx, pb->d_vcomp_delta);
 	pool_free(pb->ctx, pb->d_vcomp_n);
@@ -372,6 +375,7 @@ static bool compose_alloc(const b200_pbf_t *pb)
 	bool ok = pool_malloc(c, (void**)&pb->d_comp_start, slots * COMP_CAP * sizeof(uint32_t)) &&
 	          pool_malloc(c, (void**)&pb->d_comp_delta, slots * COMP_CAP * sizeof(int32_t)) &&
 	          pool_malloc(c, (void**)&pb->d_comp_n, slots * sizeof(int) + 16) &&
+	          pool_malloc(c, (void**)&pb->d_comp_dir, slots * COMP_DIR_STRIDE * sizeof(uint16_t) + 16) &&
 	          pool_malloc(c, (void**)&pb->d_vcomp_start, vslots * SELECT_COMP_CAP * sizeof(uint32_t)) &&
 	          pool_malloc(c, (void**)&pb->d_vcomp_delta, vslots * SELECT_COMP_CAP * sizeof(int32_t)) &&
 	          pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16);
@@ -389,7 +393,9 @@ static bool compose_queue(const b200_pbf_t *pb, int b0, int b1)
 	K.blk_ok = pb->d_blk_sparse;
 	K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
 	K.n_grp = (pb->BS + COMP_K - 1) / COMP_K; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0; K.row_base = nullptr; K.n1_step = 2;
+	K.comp_dir = pb->d_comp_dir; K.dir_shift = pb->dir_shift; K.dir_n = pb->dir_n;
 	ComposeParams V = K;   // inverse composites of the plane-1 view rows
+	V.comp_dir = nullptr;
 	V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
 	V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
 	V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
@@ -413,6 +419,10 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	const int BS = pb->BS, nb = pb->n_blk;
 	const int n_grp = (BS + COMP_K - 1) / COMP_K;
 	pb->p1_cap = (((pb->m / 4 > 4096 ? pb->m / 4 : 4096) + 2047) / 2048) * 2048;
+	// bucket directory of the composite maps: the smallest bucket width whose directory (+ sentinel) fits COMP_DIR entries
+	pb->dir_shift = 0;
+	while ((((uint32_t)pb->m - 1) >> pb->dir_shift) + 2 > (uint32_t)COMP_DIR) ++pb->dir_shift;
+	pb->dir_n = (int)(((((uint32_t)pb->m - 1) >> pb->dir_shift) + 2 + 7) & ~7u);
 	bool ok = pool_malloc(c, (void**)&pb->d_rowoff, sizeof(uint64_t) * (size_t)nb * (BS + 1) + 8) &&
 	          pool_malloc(c, (void**)&pb->d_blkoff, sizeof(uint64_t) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_blkend, sizeof(uint64_t) * (nb + 1)) &&
@@ -1008,6 +1018,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		WalkParams B = P;
 		if (pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) {
 			B.comp_start = pb->d_comp_start; B.comp_delta = pb->d_comp_delta; B.comp_n = pb->d_comp_n; B.grp_tile_beg = pb->d_grp_tile_beg;
+			B.comp_dir = getenv("BGT_B200_NO_DIR") ? nullptr : pb->d_comp_dir; B.dir_shift = pb->dir_shift; B.dir_n = pb->dir_n;
 		}
 		B.track = (const int32_t*)c->qcol.p; B.qrow = (const uint16_t*)c->qrow.p; B.track_stride = cap;
 		B.n_track_blk = (const int*)c->qcount.p; B.n_track = cap; B.blk_list = d_split_list;

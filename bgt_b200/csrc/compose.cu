@@ -233,6 +233,19 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 		os[p] = p < n ? Sa[p] : 0xffffffffu;
 		od[p] = p < n ? Da[p] : 0;
 	}
+	// bucket directory for the walk's look-up: dir[b] = last piece that starts at or below rank b << dir_shift, so the piece
+	// of a rank r lies in [dir[r >> s], dir[(r >> s) + 1]] -- a window of a few entries instead of a search over all n
+	if (P.comp_dir) {
+		uint16_t *dir = P.comp_dir + slot * COMP_DIR_STRIDE;
+		const int sh = P.dir_shift;
+		const uint32_t nb = ((m - 1) >> sh) + 1;                         // buckets that hold a rank
+		for (int p = tid; p < n; p += CP_NT) {
+			const uint32_t s0 = Sa[p], s1 = p + 1 < n ? Sa[p + 1] : m;
+			const uint32_t b0 = (s0 + (1u << sh) - 1u) >> sh, b1 = (s1 + (1u << sh) - 1u) >> sh;   // buckets whose base lies in [s0, s1)
+			for (uint32_t b = b0; b < b1 && b < nb; ++b) dir[b] = (uint16_t)p;
+		}
+		for (int b = (int)nb + tid; b < P.dir_n; b += CP_NT) dir[b] = (uint16_t)(n - 1);    // sentinel (+ padding)
+	}
 	if (tid == 0) P.comp_n[slot] = npad;
 }
 

@@ -223,6 +223,47 @@ __device__ __forceinline__ void lookup_runs(uint32_t (&r)[C], uint32_t ts_saddr,
 	bits = b;
 }
 
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
+{
+	uint16_t v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+	return v;
+}
+
+// Look-up in a composite map through its bucket directory (compose.cu): the piece of rank r lies between dir[r >> s] and
+// dir[(r >> s) + 1], so the binary search runs over a window of a few entries (the widest window of the warp sets the
+// trip count).  Only the slots in `act` advance.
+template<int C>
+__device__ __forceinline__ void lookup_comp(uint32_t (&r)[C], uint32_t tab_saddr, uint32_t dir_saddr, int sh, uint32_t act)
+{
+	if (!__any_sync(FULL_MASK, act != 0)) return;
+	uint32_t a[C], hi[C], w = 1;
+	#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		const uint32_t d = dir_saddr + ((r[c] >> sh) << 1);
+		const uint32_t lo = lds_u16(d), h = lds_u16(d + 2);
+		a[c] = tab_saddr + (lo << 2); hi[c] = tab_saddr + (h << 2);
+		const uint32_t wc = h - lo + 1u;
+		w = wc > w ? wc : w;
+	}
+	w = __reduce_max_sync(FULL_MASK, w);
+	for (uint32_t len = w; len > 1;) {
+		const uint32_t half = len >> 1, h4 = half << 2;
+		#pragma unroll
+		for (int c = 0; c < C; ++c) {
+			const uint32_t t = a[c] + h4;
+			const uint32_t v = t <= hi[c] ? lds_u32(t) : 0xffffffffu;
+			a[c] = v <= r[c] ? t : a[c];
+		}
+		len -= half;
+	}
+	#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		const uint32_t d = lds_u32(a[c] + TD_MINUS_TS);
+		if ((act >> c) & 1u) r[c] += d;
+	}
+}
+
 // QUERY mode: only the slots in `act` advance (bit c = slot c); a warp in which no lane has slot c active skips its search
 template<int C>
 __device__ __forceinline__ void lookup_runs_masked(uint32_t (&r)[C], uint32_t ts_saddr, uint32_t n, uint32_t zeros_total, uint32_t act, uint32_t &bits)
@@ -461,21 +502,30 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 			const int g_last = (q_stop - 1) / COMP_K;            // group of the CTA's last target row
 			// two composites fit the run-table buffers side by side: while group g is searched in one half, thread 0 has the
 			// copy of group g+1 in flight into the other half (its own mbarrier)
+			// piece counts of the block's groups: read once (a global load per group would sit on the loop's critical path)
+			__shared__ int s_compn[1024];
+			const bool compn_sm = g_last <= 1024;
+			if (compn_sm) {
+				for (int i = tid; i < g_last; i += WALK_NT) s_compn[i] = P.comp_n[(size_t)blk * n_grp + i];
+				__syncthreads();
+			}
+			auto comp_n_of = [&](int gg) -> int { return compn_sm ? s_compn[gg] : P.comp_n[(size_t)blk * n_grp + gg]; };
 			auto fetch_comp = [&](int gg) {
 				const size_t slot = (size_t)blk * n_grp + gg;
-				const uint32_t np = (uint32_t)P.comp_n[slot];
+				const uint32_t np = (uint32_t)comp_n_of(gg);
 				if (np == 0) return;
 				uint64_t *bar = S.mbar + (gg & 1);
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-				mbar_expect_tx(bar, np * 8u);
+				mbar_expect_tx(bar, np * 8u + (P.comp_dir ? (uint32_t)P.dir_n * 2u : 0u));
 				tma_bulk_g2s(S.ts + (gg & 1) * COMP_CAP, P.comp_start + slot * COMP_CAP, np * 4u, bar);
 				tma_bulk_g2s(S.td + (gg & 1) * COMP_CAP, P.comp_delta + slot * COMP_CAP, np * 4u, bar);
+				if (P.comp_dir) tma_bulk_g2s(S.raw + (gg & 1) * (RAW_CAP / 2), P.comp_dir + slot * COMP_DIR_STRIDE, (uint32_t)P.dir_n * 2u, bar);
 			};
 			uint32_t parity1 = 0;
 			int g = 0;
 			if (tid == 0 && g_last > 0) fetch_comp(0);
 			for (; g < g_last; ++g) {
-				const int np = P.comp_n[(size_t)blk * n_grp + g];
+				const int np = comp_n_of(g);
 				if (np == 0) break;                                 // not available: row by row from here on (nothing is in flight)
 				if (tid == 0 && g + 1 < g_last) fetch_comp(g + 1);  // the other half was released by the barrier below
 				{
@@ -488,7 +538,8 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 				#pragma unroll
 				for (int c = 0; c < C; ++c) act |= (tgt[c] != 0xffffffffu && (int)(tgt[c] / COMP_K) > g ? 1u : 0u) << c;
 				const uint32_t tab = ts_saddr + (uint32_t)(g & 1) * (COMP_CAP * 4u);
-				if (g < g_mixed) lookup_runs<C>(r0, tab, (uint32_t)np, 0u, unused);
+				if (P.comp_dir) lookup_comp<C>(r0, tab, smem_u32(S.raw) + (uint32_t)(g & 1) * (RAW_CAP / 2), P.dir_shift, act);
+				else if (g < g_mixed) lookup_runs<C>(r0, tab, (uint32_t)np, 0u, unused);
 				else lookup_runs_masked<C>(r0, tab, (uint32_t)np, 0u, act, unused);
 				__syncthreads();
 			}

@@ -22,6 +22,8 @@ constexpr int RAW_BYTES = RAW_CAP + 32; // + 16-byte alignment slack at both end
 constexpr int T_MAX     = 64;           // rows per tile
 constexpr int COMP_K    = 32;           // rows per composite map (compose.cu); tiles never cross a multiple of it
 constexpr int COMP_CAP  = 4096;         // pieces per composite map (<= RAW_BYTES: staged in the run-table buffers)
+constexpr int COMP_DIR  = 2048;         // rank buckets of a composite map's directory (uint16 piece index per bucket + sentinel)
+constexpr int COMP_DIR_STRIDE = COMP_DIR + 8;
 constexpr int B200_MAX_GROUPS_K = 32;   // BGT_MAX_GROUPS, bgt.h:13
 
 struct RowMeta { uint32_t off[2], len[2], n1[2]; };
@@ -42,6 +44,8 @@ struct WalkParams {
 	const uint32_t *comp_start; // QUERY only: composite maps (compose.cu) [blocks][groups][COMP_CAP], or nullptr
 	const int32_t  *comp_delta;
 	const int      *comp_n;     // [blocks][groups] pieces (padded to 4), 0 = not available
+	const uint16_t *comp_dir;   // [blocks][groups][COMP_DIR_STRIDE]: last piece starting at or below rank (b << dir_shift), or nullptr
+	int dir_shift, dir_n;       // bucket width 2^dir_shift; dir_n = directory entries incl. sentinel, padded to 8
 	const int      *grp_tile_beg; // [blocks][groups+1] first tile of every row group
 	const int      *blk_list;  // resident-block indices handled by this launch (nullptr: blk_first + blockIdx.y)
 	const int      *n_track_blk; // per-block number of tracked columns (nullptr: n_track)
@@ -78,6 +82,8 @@ struct ComposeParams {
 	int rle_off;      // offset of the plane's RLE inside a row record: 5 = plane 0 of a .pbf row, 9 = plane 1 of a plane-1 view row
 	int n1_plane;     // which entry of n1[row][2] belongs to that plane
 	int inverse;      // 1: inverse composite (coordinates behind the group -> in front of it)
+	uint16_t *comp_dir; // forward maps only: bucket directory per slot (COMP_DIR_STRIDE entries), or nullptr
+	int dir_shift, dir_n;
 	uint32_t *comp_start;
 	int32_t  *comp_delta;
 	int      *comp_n;
