@@ -324,7 +324,7 @@ def run_b200(args, rank, world, local_rank):
                 t.join()
         if errs:
             raise errs[0]
-        e2e_bytes["h2d"] = img_bytes + (n + nblk + 1) * 8
+        e2e_bytes["h2d"] = img_bytes + nblk * 20      # the image + the block table (offsets, ends, rows per block); the row index is built on the device
         e2e_bytes["d2h"] = h_counts.nbytes + n
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))

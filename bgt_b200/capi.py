@@ -82,6 +82,7 @@ SIGNATURES = {
     "b200_sites_rows": (_int, [_vp, _vp, _vp]),
     "b200_sites_destroy": (None, [_vp]),
     "b200_view_text": (_i64, [_vp, _vp, _vp, _vp, _int, _vp, _int, C.POINTER(_vp), C.POINTER(_i64)]),
+    "b200_view_text_ex": (_i64, [_vp, _vp, _vp, _vp, C.c_uint, _i64, _i64, _vp, _int, C.POINTER(_vp), C.POINTER(_i64)]),
 }
 
 
@@ -255,10 +256,11 @@ class Sites:
             raise B200Error(_err())
         return rows, pos
 
-    def view_text(self, pbf, query, with_counts=False):
-        """The record lines of `bgt view -G [-C] [-f ..] [-s ..]` (b200_view_text); returns (bytes, n_lines)."""
+    def view_text(self, pbf, query, with_counts=False, genotypes=False, rec_beg=0, rec_end=-1):
+        """The record lines of `bgt view [-G] [-C] [-f ..] [-s ..]` (b200_view_text_ex); returns (bytes, n_lines)."""
         p, nl = C.c_void_p(), C.c_int64(0)
-        n = lib().b200_view_text(self.ctx.h, self.h, pbf.h, query.h, int(with_counts), None, 0, C.byref(p), C.byref(nl))
+        n = lib().b200_view_text_ex(self.ctx.h, self.h, pbf.h, query.h, (1 if with_counts else 0) | (2 if genotypes else 0), rec_beg, rec_end,
+                                    None, 0, C.byref(p), C.byref(nl))
         if n < 0:
             raise B200Error(_err())
         return C.string_at(p, n), nl.value

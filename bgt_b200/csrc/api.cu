@@ -1453,6 +1453,8 @@ struct b200_sites_s {
 	std::vector<std::string> contigs;   // BCF_DT_CTG in id order (vcf.c:121-133)
 	char *d_ctg = nullptr; int *d_ctg_off = nullptr;
 	int row_key = -1;
+	std::vector<int64_t> h_rows;        // INFO/_row of every record (host copy), and whether they ascend (records in row order)
+	bool rows_sorted = true;
 	DevBuf len, off, temp, text;
 	char *h_text = nullptr; size_t h_text_cap = 0;
 	unsigned long long *d_nlines = nullptr;
@@ -1616,6 +1618,12 @@ extern "C" b200_sites_t *b200_sites_load(b200_ctx_t *c, const uint8_t *bcf, size
 	if (d_cnt) cudaFree(d_cnt);
 	if (ok && (err & 512)) { set_err("corrupt BCF: record lengths do not chain to the end of the stream"); ok = false; }
 	if (ok && (err & 1024)) { set_err("BCF record without INFO/_row or with fewer than two alleles (not the site side of a BGT database)"); ok = false; }
+	if (ok) { // rows to the host: record windows of b200_view_text_ex are mapped to row ranges
+		std::vector<SiteRec> h((size_t)s->n + 1);
+		ok = s->n == 0 || CU_OK(cudaMemcpy(h.data(), s->d_sites, sizeof(SiteRec) * (size_t)s->n, cudaMemcpyDeviceToHost));
+		s->h_rows.resize((size_t)s->n);
+		for (int64_t i = 0; ok && i < s->n; ++i) { s->h_rows[(size_t)i] = h[(size_t)i].row; if (i && h[(size_t)i].row < h[(size_t)i - 1].row) s->rows_sorted = false; }
+	}
 	if (!ok) { b200_sites_destroy(s); return nullptr; }
 	return s;
 }
@@ -1634,50 +1642,73 @@ extern "C" int b200_sites_rows(const b200_sites_t *s, int64_t *rows, int32_t *po
 	return 0;
 }
 
-extern "C" int64_t b200_view_text(b200_ctx_t *c, b200_sites_t *s, const b200_pbf_t *pb, const b200_query_t *q, int with_counts,
-                                  const char *const *contig_names, int n_contigs, const char **text, int64_t *n_lines)
+extern "C" int64_t b200_view_text_ex(b200_ctx_t *c, b200_sites_t *s, const b200_pbf_t *pb, const b200_query_t *q, unsigned flags,
+                                     int64_t rec_beg, int64_t rec_end, const char *const *contig_names, int n_contigs, const char **text, int64_t *n_lines)
 {
 	if (!c || !s || !pb || !q || !text) { set_err("b200_view_text: null argument"); return -1; }
 	if (s->ctx != c || pb->ctx != c || q->ctx != c) { set_err("b200_view_text: handles belong to another context"); return -1; }
 	cudaSetDevice(c->dev);
-	const int64_t row_lo = b200_pbf_row_beg(pb), n_rows = b200_pbf_row_end(pb) - row_lo;
+	if (rec_end < 0 || rec_end > s->n) rec_end = s->n;
+	if (rec_beg < 0) rec_beg = 0;
+	if (rec_beg > rec_end) rec_beg = rec_end;
+	const int64_t n_rec = rec_end - rec_beg;
 	if (q->has_flt && q->prog.needs_host) { set_err("b200_view_text: filters using ** are evaluated with the host libm; use b200_scan"); return -1; }
-	if (q->has_flt) with_counts = 1;                                 // bgt.c:850: a filter implies AC/AN in the output
-	if (q->G > 1) with_counts = 1;
+	bool with_counts = (flags & B200_VIEW_COUNTS) != 0;
+	const bool with_gt = (flags & B200_VIEW_GENOTYPES) != 0;
+	if (q->has_flt || q->G > 1) with_counts = true;                  // bgt.c:850: a filter or several groups imply AC/AN in the output
+	// rows behind the records of this window
+	int64_t row_lo = b200_pbf_row_beg(pb), row_hi = b200_pbf_row_end(pb);
+	if (s->rows_sorted && n_rec > 0) { row_lo = s->h_rows[(size_t)rec_beg]; row_hi = s->h_rows[(size_t)rec_end - 1] + 1; }
+	else if (!s->rows_sorted && (rec_beg != 0 || rec_end != s->n)) { set_err("b200_view_text: the records are not in row order; only the whole file can be formatted at once"); return -1; }
+	if (row_lo < b200_pbf_row_beg(pb) || row_hi > b200_pbf_row_end(pb)) { set_err("b200_view_text: rows [%lld,%lld) of the records are not resident", (long long)row_lo, (long long)row_hi); return -1; }
+	const int64_t n_rows = row_hi - row_lo;
 	if (contig_names && n_contigs > 0) { // the output header's contig dictionary (bgt.c:626-662) instead of the file's own
-		std::string names; std::vector<int> coff(1, 0);
-		for (int i = 0; i < n_contigs; ++i) { names += contig_names[i]; coff.push_back((int)names.size()); }
-		cudaStreamSynchronize(c->st);
-		if (s->d_ctg) cudaFree(s->d_ctg);
-		if (s->d_ctg_off) cudaFree(s->d_ctg_off);
-		s->d_ctg = nullptr; s->d_ctg_off = nullptr;
-		if (!CU_OK(cudaMalloc(&s->d_ctg, names.size() + 16)) || !CU_OK(cudaMalloc(&s->d_ctg_off, coff.size() * sizeof(int))) ||
-		    !CU_OK(cudaMemcpy(s->d_ctg, names.data(), names.size(), cudaMemcpyHostToDevice)) ||
-		    !CU_OK(cudaMemcpy(s->d_ctg_off, coff.data(), coff.size() * sizeof(int), cudaMemcpyHostToDevice))) return -1;
-		s->contigs.assign(contig_names, contig_names + n_contigs);
+		bool same = (size_t)n_contigs == s->contigs.size();
+		for (int i = 0; same && i < n_contigs; ++i) same = s->contigs[(size_t)i] == contig_names[i];
+		if (!same) {
+			std::string names; std::vector<int> coff(1, 0);
+			for (int i = 0; i < n_contigs; ++i) { names += contig_names[i]; coff.push_back((int)names.size()); }
+			cudaStreamSynchronize(c->st);
+			if (s->d_ctg) cudaFree(s->d_ctg);
+			if (s->d_ctg_off) cudaFree(s->d_ctg_off);
+			s->d_ctg = nullptr; s->d_ctg_off = nullptr;
+			if (!CU_OK(cudaMalloc(&s->d_ctg, names.size() + 16)) || !CU_OK(cudaMalloc(&s->d_ctg_off, coff.size() * sizeof(int))) ||
+			    !CU_OK(cudaMemcpy(s->d_ctg, names.data(), names.size(), cudaMemcpyHostToDevice)) ||
+			    !CU_OK(cudaMemcpy(s->d_ctg_off, coff.data(), coff.size() * sizeof(int), cudaMemcpyHostToDevice))) return -1;
+			s->contigs.assign(contig_names, contig_names + n_contigs);
+		}
 	}
-	// ---- the scan: per-row counts and verdicts stay on the device
+	// ---- the scan: per-row counts, verdicts and (for genotype columns) bit planes stay on the device
 	const int stride = 3 + 3 * q->G;
-	if (!c->counts.reserve((size_t)n_rows * stride * sizeof(int32_t) + 16) || !c->pass.reserve((size_t)n_rows + 16)) return -1;
 	b200_scan_out_t so;
 	memset(&so, 0, sizeof(so));
-	so.counts = (int32_t*)c->counts.p; so.pass = (uint8_t*)c->pass.p;
-	if (n_rows > 0 && b200_scan(c, pb, q, row_lo, n_rows, B200_SCAN_COUNTS | B200_SCAN_DEVICE_OUT, &so) != n_rows) return -1;
+	unsigned sflags = B200_SCAN_DEVICE_OUT;
+	if (with_counts && n_rows > 0) {
+		if (!c->counts.reserve((size_t)n_rows * stride * sizeof(int32_t) + 16) || !c->pass.reserve((size_t)n_rows + 16)) return -1;
+		so.counts = (int32_t*)c->counts.p; so.pass = (uint8_t*)c->pass.p; sflags |= B200_SCAN_COUNTS;
+	}
+	if (with_gt && n_rows > 0) {
+		for (int p = 0; p < 2; ++p) { if (!c->hapbits[p].reserve((size_t)n_rows * q->words * sizeof(uint32_t) + 16)) return -1; so.hap_bits[p] = (uint32_t*)c->hapbits[p].p; }
+		sflags |= B200_SCAN_HAP_BITS;
+	}
+	if ((sflags & (B200_SCAN_COUNTS | B200_SCAN_HAP_BITS)) && b200_scan(c, pb, q, row_lo, n_rows, sflags, &so) != n_rows) return -1;
 	// ---- lines
-	const size_t tb = view_scan_temp_bytes(s->n);
-	if (!s->len.reserve(8 * (size_t)(s->n + 2)) || !s->off.reserve(8 * (size_t)(s->n + 2)) || !s->temp.reserve(tb + 16)) return -1;
+	const size_t tb = view_scan_temp_bytes(n_rec);
+	if (!s->len.reserve(8 * (size_t)(n_rec + 2)) || !s->off.reserve(8 * (size_t)(n_rec + 2)) || !s->temp.reserve(tb + 16)) return -1;
 	ViewParams P;
 	memset(&P, 0, sizeof(P));
-	P.sites = s->d_sites; P.n_rec = s->n; P.bcf = s->d_bcf; P.ctg_names = s->d_ctg; P.ctg_off = s->d_ctg_off; P.n_ctg = (int)(s->contigs.empty() ? 1 : s->contigs.size());
-	P.counts = (const int32_t*)c->counts.p; P.pass = q->has_flt ? (const uint8_t*)c->pass.p : nullptr; P.stride = stride; P.G = q->G; P.with_counts = with_counts ? 1 : 0;
+	P.sites = s->d_sites + rec_beg; P.n_rec = n_rec; P.bcf = s->d_bcf; P.ctg_names = s->d_ctg; P.ctg_off = s->d_ctg_off; P.n_ctg = (int)(s->contigs.empty() ? 1 : s->contigs.size());
+	P.counts = with_counts ? (const int32_t*)c->counts.p : nullptr; P.pass = q->has_flt ? (const uint8_t*)c->pass.p : nullptr; P.stride = stride; P.G = q->G; P.with_counts = with_counts ? 1 : 0;
+	P.with_gt = with_gt ? 1 : 0; P.n_out = q->n_out; P.words = q->words; P.hap[0] = (const uint32_t*)c->hapbits[0].p; P.hap[1] = (const uint32_t*)c->hapbits[1].p;
 	P.row_lo = row_lo; P.n_rows = n_rows; P.err = c->d_err;
 	unsigned long long total = 0, lines = 0;
-	bool ok = CU_OK(cudaMemsetAsync(s->len.p, 0, 8 * (size_t)(s->n + 2), c->st)) && CU_OK(cudaMemsetAsync(s->d_nlines, 0, 8, c->st)) &&
-	          CU_OK(launch_view_text(P, (unsigned long long*)s->len.p, (unsigned long long*)s->off.p, s->temp.p, tb, nullptr, nullptr, 0, c->st)) &&
-	          CU_OK(cudaMemcpyAsync(&total, (unsigned long long*)s->off.p + s->n, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
-	c->launches += 2;
-	if (!ok) return -1;
-	if (s->n == 0) total = 0;
+	if (n_rec > 0) {
+		bool ok = CU_OK(cudaMemsetAsync(s->len.p, 0, 8 * (size_t)(n_rec + 2), c->st)) && CU_OK(cudaMemsetAsync(s->d_nlines, 0, 8, c->st)) &&
+		          CU_OK(launch_view_text(P, (unsigned long long*)s->len.p, (unsigned long long*)s->off.p, s->temp.p, tb, nullptr, nullptr, 0, c->st)) &&
+		          CU_OK(cudaMemcpyAsync(&total, (unsigned long long*)s->off.p + n_rec, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+		c->launches += 2;
+		if (!ok) return -1;
+	}
 	if (!s->text.reserve((size_t)total + 64)) return -1;
 	if ((size_t)total + 1 > s->h_text_cap) {
 		if (s->h_text) cudaFreeHost(s->h_text);
@@ -1686,17 +1717,23 @@ extern "C" int64_t b200_view_text(b200_ctx_t *c, b200_sites_t *s, const b200_pbf
 		s->h_text_cap = (size_t)total + 64;
 	}
 	int err = 0;
-	ok = CU_OK(launch_view_text(P, (unsigned long long*)s->len.p, (unsigned long long*)s->off.p, nullptr, 0, (char*)s->text.p, s->d_nlines, 1, c->st)) &&
-	     (total == 0 || CU_OK(cudaMemcpyAsync(s->h_text, s->text.p, (size_t)total, cudaMemcpyDeviceToHost, c->st))) &&
-	     CU_OK(cudaMemcpyAsync(&lines, s->d_nlines, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->st)) &&
-	     CU_OK(cudaStreamSynchronize(c->st));
+	bool ok = (n_rec == 0 || CU_OK(launch_view_text(P, (unsigned long long*)s->len.p, (unsigned long long*)s->off.p, nullptr, 0, (char*)s->text.p, s->d_nlines, 1, c->st))) &&
+	          (total == 0 || CU_OK(cudaMemcpyAsync(s->h_text, s->text.p, (size_t)total, cudaMemcpyDeviceToHost, c->st))) &&
+	          CU_OK(cudaMemcpyAsync(&lines, s->d_nlines, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->st)) &&
+	          CU_OK(cudaStreamSynchronize(c->st));
 	++c->launches;
 	if (!ok) return -1;
-	if (err & 2048) { set_err("a site record points at a row outside the resident PBF rows"); return -1; }
+	if (err & 2048) { set_err("a site record points at a row outside the scanned rows"); return -1; }
 	if (err) { set_err("device error flags 0x%x while formatting", err); return -1; }
 	s->h_text[total] = 0;
 	*text = s->h_text;
 	if (n_lines) *n_lines = (int64_t)lines;
 	read_scan_timings(c);
 	return (int64_t)total;
+}
+
+extern "C" int64_t b200_view_text(b200_ctx_t *c, b200_sites_t *s, const b200_pbf_t *pb, const b200_query_t *q, int with_counts,
+                                  const char *const *contig_names, int n_contigs, const char **text, int64_t *n_lines)
+{
+	return b200_view_text_ex(c, s, pb, q, with_counts ? B200_VIEW_COUNTS : 0u, 0, -1, contig_names, n_contigs, text, n_lines);
 }

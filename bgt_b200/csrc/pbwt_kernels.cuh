@@ -217,6 +217,8 @@ struct ViewParams {
 	const char *ctg_names; const int *ctg_off; int n_ctg;   // contig names back to back, ctg_off[n_ctg+1]
 	const int32_t *counts; const uint8_t *pass;              // the scan's per-row results (rows row_lo .. row_lo+n_rows)
 	int stride, G, with_counts;
+	int with_gt, n_out, words;                               // genotype columns: samples, words per plane row of hap[]
+	const uint32_t *hap[2];                                  // the scan's bit planes [n_rows][words]
 	long long row_lo, n_rows;
 	int *err;
 };

@@ -166,7 +166,7 @@ __device__ __forceinline__ char *put_str(char *q, const char *s, int n) { for (i
 //   CHROM \t POS \t . \t REF \t ALT[,<M>] \t 0 \t . \t [END=e;]AN=..;AC=..[,..][;AN1=..;AC1=..[,..] ...] \n
 // (bcfcpy_min: empty ID, first ALT, <M> iff the stored record has more than two alleles, QUAL 0, no FILTER;
 //  bgt.c:824-827 END; bgtm_fill_info: AC has n_allele-1 values, group keys only with several groups.)
-__device__ long long site_line(const ViewParams &P, const SiteRec &s, const int32_t *c, char *out)
+__device__ long long site_line(const ViewParams &P, const SiteRec &s, const int32_t *c, char *out, bool nl)
 {
 	const bool multi = s.n_allele > 2;
 	const bool has_end = s.ref_len != s.rlen;
@@ -183,7 +183,7 @@ __device__ long long site_line(const ViewParams &P, const SiteRec &s, const int3
 					n += 1 + kl + 1 + dec_len(c[3 + 3 * g]) + 1 + kl + 1 + dec_len(c[4 + 3 * g]) + (multi ? 1 + dec_len(c[5 + 3 * g]) : 0);
 				}
 		} else if (!has_end) n += 1;   // "."
-		return n + 1;
+		return n + (nl ? 1 : 0);
 	}
 	char *q = out;
 	q = put_str(q, P.ctg_names + P.ctg_off[rid], ctg_len);
@@ -210,7 +210,7 @@ __device__ long long site_line(const ViewParams &P, const SiteRec &s, const int3
 				}
 			}
 	} else if (!has_end) *q++ = '.';
-	*q++ = '\n';
+	if (nl) *q++ = '\n';
 	return (long long)(q - out);
 }
 
@@ -222,7 +222,10 @@ __global__ void __launch_bounds__(256) view_len_kernel(const ViewParams P, unsig
 	const long long r = s.row - P.row_lo;
 	unsigned long long n = 0;
 	if (s.row >= 0 && r >= 0 && r < P.n_rows) {
-		if (!P.pass || P.pass[r]) n = (unsigned long long)site_line(P, s, P.counts ? P.counts + (size_t)r * P.stride : nullptr, nullptr);
+		if (!P.pass || P.pass[r]) {
+			n = (unsigned long long)site_line(P, s, P.counts ? P.counts + (size_t)r * P.stride : nullptr, nullptr, true);
+			if (P.with_gt) n += 3ull + 4ull * (unsigned long long)P.n_out;   // "\tGT" + "\ta/b" per sample (bgt_gen_gt bgt.c:290-313, vcf.c:940-966)
+		}
 	} else if (s.row >= 0) atomicOr(P.err, 2048);   // a site points at a row that was not scanned
 	len[i] = n;
 }
@@ -235,11 +238,41 @@ __global__ void __launch_bounds__(256) view_write_kernel(const ViewParams P, con
 	if (i < P.n_rec && len[i]) {
 		const SiteRec s = P.sites[i];
 		const long long r = s.row - P.row_lo;
-		site_line(P, s, P.counts ? P.counts + (size_t)r * P.stride : nullptr, text + off[i]);
+		site_line(P, s, P.counts ? P.counts + (size_t)r * P.stride : nullptr, text + off[i], true);
 		wrote = 1;
 	}
 	wrote = __reduce_add_sync(0xffffffffu, (unsigned)wrote);
 	if ((threadIdx.x & 31) == 0 && wrote) atomicAdd(n_lines, wrote);
+}
+
+// With genotype columns: one CTA per record.  Thread 0 writes the fixed columns and "\tGT"; all threads write the samples'
+// "\ta/b" from the scan's bit planes: code a1<<1|a0 -> bgt_bits2gt = {0, 1, ., 2} (bgt.c:250), always unphased.
+__global__ void __launch_bounds__(128) view_write_gt_kernel(const ViewParams P, const unsigned long long *__restrict__ len, const unsigned long long *__restrict__ off,
+                                                            char *__restrict__ text, unsigned long long *__restrict__ n_lines)
+{
+	const long long i = blockIdx.x;
+	const unsigned long long L = len[i];
+	if (L == 0) return;
+	const SiteRec s = P.sites[i];
+	const long long r = s.row - P.row_lo;
+	char *line = text + off[i];
+	const unsigned long long gt_bytes = 3ull + 4ull * (unsigned long long)P.n_out;
+	char *g = line + (L - 1 - gt_bytes);
+	if (threadIdx.x == 0) {
+		site_line(P, s, P.counts ? P.counts + (size_t)r * P.stride : nullptr, line, false);
+		g[0] = '\t'; g[1] = 'G'; g[2] = 'T';
+		line[L - 1] = '\n';
+		atomicAdd(n_lines, 1ull);
+	}
+	const uint32_t *h0 = P.hap[0] + (size_t)r * P.words, *h1 = P.hap[1] + (size_t)r * P.words;
+	g += 3;
+	for (int smp = threadIdx.x; smp < P.n_out; smp += 128) {
+		const int c0 = 2 * smp, w = c0 >> 5, b = c0 & 31;          // the sample's two haplotypes share a word (c0 is even)
+		const uint32_t v0 = h0[w] >> b, v1 = h1[w] >> b;
+		const uint32_t ca = (v0 & 1u) | (v1 & 1u) << 1, cb = ((v0 >> 1) & 1u) | ((v1 >> 1) & 1u) << 1;
+		char *q = g + 4 * (size_t)smp;
+		q[0] = '\t'; q[1] = "01.2"[ca]; q[2] = '/'; q[3] = "01.2"[cb];
+	}
 }
 
 size_t view_scan_temp_bytes(long long n)
@@ -260,7 +293,8 @@ cudaError_t launch_view_text(const ViewParams &P, unsigned long long *len, unsig
 		if (e != cudaSuccess) return e;
 		return cub::DeviceScan::ExclusiveSum(temp, temp_bytes, len, off, (int)(P.n_rec + 1), st);
 	}
-	view_write_kernel<<<grid, 256, 0, st>>>(P, len, off, text, n_lines);
+	if (P.with_gt) view_write_gt_kernel<<<(unsigned)P.n_rec, 128, 0, st>>>(P, len, off, text, n_lines);
+	else view_write_kernel<<<grid, 256, 0, st>>>(P, len, off, text, n_lines);
 	return cudaGetLastError();
 }
 

@@ -177,6 +177,15 @@ void        b200_sites_destroy(b200_sites_t *s);
  * `s`, valid until the next call; returns its length, *n_lines = records printed.  The header lines are the caller's. */
 int64_t     b200_view_text(b200_ctx_t *ctx, b200_sites_t *s, const b200_pbf_t *pb, const b200_query_t *q, int with_counts,
                            const char *const *contig_names, int n_contigs, const char **text, int64_t *n_lines);
+/* The same for records [rec_beg, rec_end) only (rec_end < 0: to the last), optionally WITH the genotype columns
+ * (`bgt view` without -G, e.g. a 200-sample subset: FORMAT GT and one unphased `a/b` per selected sample from the
+ * scan's bit planes, bgt_gen_gt bgt.c:290-313 + vcf.c:940-966).  Only the rows behind the window are scanned, so a
+ * caller bounds the text per call by the window (records must be in row order for windows smaller than the file). */
+#define B200_VIEW_COUNTS    0x1   /* -C */
+#define B200_VIEW_GENOTYPES 0x2   /* no -G */
+int64_t     b200_view_text_ex(b200_ctx_t *ctx, b200_sites_t *s, const b200_pbf_t *pb, const b200_query_t *q, unsigned flags,
+                              int64_t rec_beg, int64_t rec_end, const char *const *contig_names, int n_contigs,
+                              const char **text, int64_t *n_lines);
 
 #ifdef __cplusplus
 }

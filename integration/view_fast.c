@@ -2,13 +2,14 @@
  * view_fast.c -- `bgt view -G` with the whole per-site pipeline on the device.
  *
  * The reference's view.c is compiled unchanged with -Dmain_view=ref_main_view; this main_view looks at the options
- * first.  For the count-only VCF scan of one BGT -- `view -G [-C] [-f EXPR] [-s EXPR ...] prefix`, BASELINE configs
- * 2, 3, 5 -- set-up and the header are the reference's own calls (bgt_open, bgtm_reader_init, bgtm_set_flag,
+ * first.  For the VCF scan of one BGT -- `view [-G] [-C] [-f EXPR] [-s EXPR ...] prefix`, BASELINE configs 2-5 -- set-up
+ * and the header are the reference's own calls (bgt_open, bgtm_reader_init, bgtm_set_flag,
  * bgtm_set_flt_site, bgtm_add_group, bgtm_prepare, vcf_hdr_write: view.c:99-147), and the record loop of
  * view.c:150-155 (bgtm_read + vcf_write1 per site on the host thread) is replaced by ONE call: the .bcf/.csi are
  * inflated, indexed and parsed on the GPU (b200_sites_load), the .pbf is scanned (b200_view_text -> b200_scan) and the
- * VCF lines of the passing sites come back as text.  Anything else (-r/-B/-i/-n/-a/-t/-b/-u, genotype output, several
- * files, filters the device compiler rejects) goes to ref_main_view, i.e. seam B.
+ * VCF lines of the passing sites come back as text, window by window when genotype columns are printed.  Anything else
+ * (-r/-B/-i/-n/-a/-t/-b/-u, several files, _mgs-masked genotypes, filters the device compiler rejects) goes to
+ * ref_main_view, i.e. seam B.
  */
 #include <fcntl.h>
 #include <getopt.h>
@@ -69,7 +70,7 @@ int main_view(int argc, char *argv[])
 		else other = 1;
 	}
 	i = argc - optind;
-	if (other || i != 1 || !(multi_flag & BGT_F_NO_GT) || (off && *off == '1') || (nofast && *nofast == '1')) { free(av); return run_reference(argc, argv); }
+	if (other || i != 1 || (off && *off == '1') || (nofast && *nofast == '1')) { free(av); return run_reference(argc, argv); }
 	{
 		const char *prefix = av[optind];
 		bgt_file_t *file;
@@ -114,6 +115,8 @@ int main_view(int argc, char *argv[])
 		bcf = map_file(prefix, ".bcf", &n_bcf);
 		csi = map_file(prefix, ".bcf.csi", &n_csi);
 		if (bm->bgt[0]->n_out <= 0 || pbf == 0 || bcf == 0) fallback = 1;
+		if (!(multi_flag & BGT_F_NO_GT) && bm->mgs)                /* minimal-group-size masking of genotypes (bgt.c:294-307) stays the reference's */
+			for (i = 0; i < bm->n_out; ++i) if (bm->mgs[i] > 1) fallback = 1;
 		if (!fallback) {
 			pb = b200_pbf_load_ex(ctx, pbf, n_pbf, 0, -1, B200_LOAD_PREPARE_COUNT_SCAN);
 			if (pb == 0) { fprintf(stderr, "[E::bgt_b200] %s\n", b200_strerror()); exit(1); }
@@ -127,19 +130,31 @@ int main_view(int argc, char *argv[])
 			TRACE("sites: inflate, index, parse");
 			ctg = (const char**)malloc((bm->h_out->n[BCF_DT_CTG] + 1) * sizeof(char*));
 			for (i = 0; i < bm->h_out->n[BCF_DT_CTG]; ++i) ctg[i] = bm->h_out->id[BCF_DT_CTG][i].key;
-			len = b200_view_text(ctx, sites, pb, q, (multi_flag & BGT_F_SET_AC) != 0, ctg, bm->h_out->n[BCF_DT_CTG], &text, &n_lines);
-			TRACE("scan + text");
-			if (len < 0) {
-				if (strstr(b200_strerror(), "host libm")) fallback = 1;   /* `**` filters: verdicts on the host (seam B) */
-				else { fprintf(stderr, "[E::bgt_b200] %s\n", b200_strerror()); exit(1); }
-			}
-			if (!fallback) {
-				out = hts_open("-", "w-1", 0);                   /* view.c:142-147 */
-				vcf_hdr_write(out, bm->h_out);
-				if (len > 0 && fwrite(text, 1, (size_t)len, (FILE*)out->fp) != (size_t)len) { fprintf(stderr, "[E::%s] write failed\n", __func__); exit(1); }
-				hts_close(out);
-				TRACE("write");
-				ret = 0;
+			{
+				/* records in windows that bound the text per call: 4 bytes per sample and record when genotypes are printed */
+				const int want_gt = !(multi_flag & BGT_F_NO_GT);
+				const unsigned vflags = ((multi_flag & BGT_F_SET_AC) ? B200_VIEW_COUNTS : 0) | (want_gt ? B200_VIEW_GENOTYPES : 0);
+				const int64_t n_rec = b200_sites_n(sites);
+				int64_t per = n_rec, beg;
+				if (want_gt) { per = (256LL << 20) / (4LL * bm->bgt[0]->n_out + 96); if (per < 1) per = 1; }
+				out = 0;
+				for (beg = 0; beg < n_rec || beg == 0; beg += per) {
+					const int64_t end = beg + per < n_rec ? beg + per : n_rec;
+					len = b200_view_text_ex(ctx, sites, pb, q, vflags, beg, end, ctg, bm->h_out->n[BCF_DT_CTG], &text, &n_lines);
+					if (len < 0) {
+						if (beg == 0 && (strstr(b200_strerror(), "host libm") || strstr(b200_strerror(), "row order"))) { fallback = 1; break; }   /* `**` filters, unordered records: seam B */
+						fprintf(stderr, "[E::bgt_b200] %s\n", b200_strerror());
+						exit(1);
+					}
+					if (out == 0) {
+						TRACE("first window: scan + text");
+						out = hts_open("-", "w-1", 0);               /* view.c:142-147 */
+						vcf_hdr_write(out, bm->h_out);
+					}
+					if (len > 0 && fwrite(text, 1, (size_t)len, (FILE*)out->fp) != (size_t)len) { fprintf(stderr, "[E::%s] write failed\n", __func__); exit(1); }
+					if (n_rec == 0) break;
+				}
+				if (out) { hts_close(out); TRACE("remaining windows + write"); ret = 0; }
 			}
 		}
 		free(ctg);

@@ -127,3 +127,29 @@ def test_wide_cohort_and_random_codes(b200, ctx, ref, tmp_path):
     got, _ = sites.view_text(pb, q)
     assert got == ref_lines(ref, ["-f", "AC*3>AN", "-G"], prefix)
     q.close(); sites.close(); pb.close()
+
+
+def test_view_text_with_genotype_columns(b200, ctx, ref, tmp_path):
+    """`bgt view` WITHOUT -G (config 4: sample-subset extraction to VCF): FORMAT GT + one unphased a/b per selected sample
+    from the device-decoded bit planes (bgt_gen_gt bgt.c:290-313), in record windows."""
+    mat = haplo_matrix(9000, 400, 78, switch=0.01)
+    prefix = make_bgt(ref, tmp_path, "g", mat)
+    sites, pb = open_db(b200, ctx, prefix)
+    ns = mat.shape[1] // 2
+    sel = np.array([0, 3, 17, 18, 50, 99, 100, 101, 150, 198, 199], np.int32)
+    names = "," + ",".join("S%07d" % s for s in sel)
+    grp = (np.arange(ns) % 2 + 1).astype(np.uint32)
+    cases = [(["-s", names], dict(out_samples=sel), False), (["-s", names, "-f", "AC>0"], dict(out_samples=sel, flt="AC>0"), False),
+             (["-C"], dict(), True), ([], dict(), False), (["-s", ",S0000017", "-C"], dict(out_samples=np.array([17], np.int32)), True),
+             (["-s", 'grp=="A"', "-s", 'grp=="B"', "-f", "AC1/AN1>=0.1&&AC2==0"], dict(group=grp, n_groups=2, flt="AC1/AN1>=0.1&&AC2==0"), False)]
+    for args, qa, wc in cases:
+        q = b200.Query(ctx, pb, **qa)
+        want = ref_lines(ref, args, prefix)
+        got, n_lines = sites.view_text(pb, q, with_counts=wc, genotypes=True)
+        assert got == want, args
+        assert n_lines == want.count(b"\n")
+        # the same in three record windows (one of them crossing the checkpoint at row 8192)
+        parts = [sites.view_text(pb, q, with_counts=wc, genotypes=True, rec_beg=a, rec_end=b)[0] for a, b in ((0, 1000), (1000, 8500), (8500, 9000))]
+        assert b"".join(parts) == want, args
+        q.close()
+    sites.close(); pb.close()
