@@ -149,9 +149,17 @@ def cpu_baseline_sample(ctx, samples, seed, sample_rows, gpu_counts, gpu_pass):
             else:
                 ok = ok and pos not in got
         ok = ok and n_pass == len(got)
-        return {"value": sample_rows / best, "unit": "sites/s", "cores": 1, "kind": "reference",
-                "sample": "first %d sites of the same cohort, `bgt view -f'%s' -G`, 1 thread, best of 2, %.1f s" % (sample_rows, FILTER, best),
-                "gpu_matches_reference_vcf": bool(ok)}
+        res = {"value": sample_rows / best, "unit": "sites/s", "cores": 1, "kind": "reference",
+               "sample": "first %d sites of the same cohort, `bgt view -f'%s' -G`, 1 thread, best of 2, %.1f s" % (sample_rows, FILTER, best),
+               "gpu_matches_reference_vcf": bool(ok)}
+        # the same query through the drop-in CLI (reference host application linked against the B200 seams): whole VCF, byte for byte
+        dropin = os.path.join(ROOT, "integration", "_build", "bgt")
+        if os.path.exists(dropin):
+            t0 = time.perf_counter()
+            mine = subprocess.run([dropin] + ref_view_cmd(prefix)[1:], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            res["dropin_cli"] = {"vcf_identical_to_reference": bool(mine.returncode == 0 and mine.stdout == out), "seconds": round(time.perf_counter() - t0, 3),
+                                 "note": "process start + CUDA context creation included"}
+        return res
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

@@ -122,24 +122,35 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 			if (n1 == 0) { /* nothing moves, no ones */ }
 			else if (n1 == m) { if (tid == 0) r_cnt[r] = group_cols; }
 			else if (!big) {
+				// every thread owns a contiguous stretch of words: ONE search for the run under its first word, then the run cursor
+				// only moves forward; a word is cleared as it is consumed, so the old vector is the next row's zeroed target
 				const uint32_t zt = m - n1;
-				for (int w = tid; w < words; w += MG_NT) {
-					const uint32_t bits = Vold[w];
-					if (bits == 0) continue;                 // Vnew is pre-zeroed: only 1 bits have to be moved
-					const uint32_t pos = (uint32_t)w * 32;
-					uint32_t lo = 0;
-					for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; lo += rts[lo + half] <= pos ? half : 0u; len -= half; }
-					for (uint32_t j = lo; j < n; ++j) {
-						const uint32_t s = rts[j], e = j + 1 < n ? rts[j + 1] : m;
-						if (s >= pos + 32) break;
-						const uint32_t a = s > pos ? s : pos, b = e < pos + 32 ? e : pos + 32;
-						if (b <= a) continue;
-						const uint32_t piece = (bits >> (a - pos)) & (b - a == 32 ? 0xffffffffu : ((1u << (b - a)) - 1u));
-						if (piece == 0) continue;
-						const uint32_t dst = a + (uint32_t)rtd[j], dw = dst >> 5, db = dst & 31;
-						atomicOr(&Vnew[dw], piece << db);
-						if (db && (piece >> (32 - db))) atomicOr(&Vnew[dw + 1], piece >> (32 - db));
-						if (dst >= zt) cnt += __popc(piece);
+				const int per = (words + MG_NT - 1) / MG_NT;
+				const int w_lo = tid * per, w_hi = w_lo + per < words ? w_lo + per : words;
+				if (w_lo < w_hi) {
+					uint32_t j = 0;
+					{
+						const uint32_t pos0 = (uint32_t)w_lo * 32;
+						for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; j += rts[j + half] <= pos0 ? half : 0u; len -= half; }
+					}
+					for (int w = w_lo; w < w_hi; ++w) {
+						const uint32_t bits = Vold[w];
+						if (bits == 0) continue;                 // Vnew is zero: only 1 bits have to be moved
+						Vold[w] = 0;
+						const uint32_t pos = (uint32_t)w * 32;
+						while (j + 1 < n && rts[j + 1] <= pos) ++j;
+						for (uint32_t jj = j; jj < n; ++jj) {
+							const uint32_t s = rts[jj], e = jj + 1 < n ? rts[jj + 1] : m;
+							if (s >= pos + 32) break;
+							const uint32_t a = s > pos ? s : pos, b = e < pos + 32 ? e : pos + 32;
+							if (b <= a) continue;
+							const uint32_t piece = (bits >> (a - pos)) & (b - a == 32 ? 0xffffffffu : ((1u << (b - a)) - 1u));
+							if (piece == 0) continue;
+							const uint32_t dst = a + (uint32_t)rtd[jj], dw = dst >> 5, db = dst & 31;
+							atomicOr(&Vnew[dw], piece << db);
+							if (db && (piece >> (32 - db))) atomicOr(&Vnew[dw + 1], piece >> (32 - db));
+							if (dst >= zt) cnt += __popc(piece);
+						}
 					}
 				}
 			} else {
@@ -207,8 +218,10 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 				if (lane == 0 && cnt) atomicAdd(&r_cnt[r], cnt);
 				__syncthreads();                             // all bits have landed in Vnew
 				uint32_t *t = Vold; Vold = Vnew; Vnew = t;
-				for (int w = tid; w < wpad; w += MG_NT) Vnew[w] = 0;
-				__syncthreads();
+				if (big) {                                   // (the tile path clears the old vector while reading it)
+					for (int w = tid; w < wpad; w += MG_NT) Vnew[w] = 0;
+					__syncthreads();
+				}
 			}
 		}
 		__syncthreads();
