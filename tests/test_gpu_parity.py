@@ -240,6 +240,36 @@ def test_error_behaviour(b200, ctx, oracle):
         b200.Pbf.from_bytes(ctx, pbf[:-9])
 
 
+def test_device_index_reports_corruption(b200, ctx, oracle):
+    """The row index is built on the device (index.cu); damaged tags / lengths / snapshots inside a block must fail the load
+    (pbf_read would run off the rails: pbwt.c:318-328 has no checks), a row whose run lengths do not sum to m is counted."""
+    mat = haplo_matrix(300, 96, 4)
+    good = oracle.encode_pbf(mat, shift=5)
+    ref_pb = oracle.Pbf(good)
+    pb = b200.Pbf.from_bytes(ctx, good)
+    assert pb.bad_rows == 0 and pb.row_bytes(0, 300) == ref_pb.row_bytes(0, 300) and pb.row_bytes(37, 201, False) == ref_pb.row_bytes(37, 201, False)
+    pb.close()
+    first_rec = 16 + 1 + 8 * 96                               # header, 'S', two snapshots: the first 'B' record
+    assert good[first_rec:first_rec + 1] == b"B"
+    for off, val in ((first_rec, ord("X")),                    # record tag
+                     (first_rec + 3, 0x7f),                    # plane-0 length far beyond the block
+                     (first_rec + 4, 0x80)):                   # negative length
+        bad = bytearray(good); bad[off] = val
+        with pytest.raises(b200.B200Error):
+            b200.Pbf.from_bytes(ctx, bytes(bad))
+    bad = bytearray(good); bad[17:21] = (96).to_bytes(4, "little")    # snapshot names column m
+    with pytest.raises(b200.B200Error):
+        b200.Pbf.from_bytes(ctx, bytes(bad))
+    # lengths that parse but do not sum to m: the row decodes as all-REF and is counted (the reference has undefined behaviour)
+    bad = bytearray(good)
+    l0 = int.from_bytes(good[first_rec + 1:first_rec + 5], "little")
+    assert l0 >= 1
+    bad[first_rec + 5] ^= 0x02                                 # change the first run's length digit
+    pb = b200.Pbf.from_bytes(ctx, bytes(bad))
+    assert pb.bad_rows >= 1
+    pb.close()
+
+
 def test_synth_generator_is_truthful_and_canonical(b200, ctx, oracle):
     # the device generator must produce exactly the file the reference encoder writes for the decoded matrix
     for n_samples, n_rows, shift, seed in [(40, 300, 5, 1), (333, 200, 6, 2), (1500, 70, 4, 3)]:
