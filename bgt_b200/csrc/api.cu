@@ -107,7 +107,7 @@ struct b200_pbf_s {
 	std::vector<uint64_t> h_blkend;   // [n_blk] end of the block's records (next 'S' record or the 'I' record)
 	uint8_t *d_img = nullptr; size_t img_bytes = 0; uint64_t file_off0 = 0;
 	size_t file_size = 0;             // size of the complete file image (0 unless fully resident)
-	uint64_t *d_rowoff = nullptr, *d_blkoff = nullptr, *d_blkend = nullptr;
+	uint64_t *d_rowoff = nullptr, *d_blkoff = nullptr, *d_blkend = nullptr, *d_ix_scratch = nullptr;
 	int *d_rows_in_blk = nullptr, *d_blk_tile_beg = nullptr, *d_blk_tile_end = nullptr;
 	uint8_t *d_blk_sparse = nullptr;
 	int2 *d_tiles = nullptr;
@@ -306,6 +306,7 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_blk_tile_beg);
 	pool_free(pb->ctx, pb->d_blk_tile_end);
 	pool_free(pb->ctx, pb->d_blkend);
+	pool_free(pb->ctx, pb->d_ix_scratch);
 	pool_free(pb->ctx, pb->d_blk_sparse);
 	pool_free(pb->ctx, pb->d_tiles);
 	pool_free(pb->ctx, pb->d_n1);
@@ -426,6 +427,7 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	bool ok = pool_malloc(c, (void**)&pb->d_rowoff, sizeof(uint64_t) * (size_t)nb * (BS + 1) + 8) &&
 	          pool_malloc(c, (void**)&pb->d_blkoff, sizeof(uint64_t) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_blkend, sizeof(uint64_t) * (nb + 1)) &&
+	          pool_malloc(c, (void**)&pb->d_ix_scratch, sizeof(uint64_t) * (size_t)nb * IX_SCRATCH_LANES * (BS + 1) + 8) &&
 	          pool_malloc(c, (void**)&pb->d_rows_in_blk, sizeof(int) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_blk_tile_beg, sizeof(int) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_blk_tile_end, sizeof(int) * (nb + 1)) &&
@@ -441,7 +443,7 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	          pool_malloc(c, (void**)&pb->d_p1_vbase, sizeof(long long) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_blk_sparse, (size_t)nb + 16);
 	if (!ok) return false;
-	return CU_OK(cudaMemsetAsync(c->d_acc + 4, 0, sizeof(unsigned long long), up)) &&
+	return CU_OK(cudaMemsetAsync(c->d_acc + 4, 0, 2 * sizeof(unsigned long long), up)) &&
 	       CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), up)) &&
 	       CU_OK(cudaMemcpyAsync(pb->d_blkoff, pb->h_blkoff.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, up)) &&
 	       CU_OK(cudaMemcpyAsync(pb->d_blkend, pb->h_blkend.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, up)) &&
@@ -455,8 +457,8 @@ static IndexParams index_params(const b200_pbf_t *pb, int b0)
 	IndexParams X;
 	memset(&X, 0, sizeof(X));
 	X.img = pb->d_img; X.blkoff = pb->d_blkoff; X.blkend = pb->d_blkend; X.rows_in_blk = pb->d_rows_in_blk;
-	X.m = pb->m; X.shift = pb->shift; X.blk_first = b0; X.rowoff = pb->d_rowoff; X.tiles = pb->d_tiles;
-	X.blk_tile_beg = pb->d_blk_tile_beg; X.blk_tile_end = pb->d_blk_tile_end; X.grp_tile_beg = pb->d_grp_tile_beg; X.err = pb->ctx->d_err;
+	X.m = pb->m; X.shift = pb->shift; X.blk_first = b0; X.rowoff = pb->d_rowoff; X.scratch = pb->d_ix_scratch; X.tiles = pb->d_tiles;
+	X.blk_tile_beg = pb->d_blk_tile_beg; X.blk_tile_end = pb->d_blk_tile_end; X.grp_tile_beg = pb->d_grp_tile_beg; X.err = pb->ctx->d_err; X.fallbacks = (int*)(pb->ctx->d_acc + 5);
 	return X;
 }
 
@@ -499,6 +501,11 @@ static bool pbf_finish_load(b200_pbf_t *pb)
 	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
 	if (!ok) return false;
 	pb->bad_rows = (int64_t)bad;
+	if (getenv("BGT_B200_TRACE")) {
+		unsigned long long fb = 0;
+		cudaMemcpy(&fb, c->d_acc + 5, sizeof(fb), cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[b200 trace]   row index: %llu block(s) re-chased by a single lane\n", fb & 0xffffffffull);
+	}
 	if (err & 128) { set_err("the records of one checkpoint block exceed 4 GiB; not supported"); return false; }
 	if (err & 2) { set_err("corrupt PBF: record tags/lengths inside a checkpoint block do not parse"); return false; }
 	if (err & 1) { set_err("corrupt PBF: an 'S' snapshot holds a column index >= m"); return false; }

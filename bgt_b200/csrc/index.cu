@@ -4,8 +4,9 @@
 // block are length-prefixed records ('B', then per plane int32 l + l bytes, pbwt.c:302-308) that pbf_read
 // (pbwt.c:313-337) steps through one fread at a time.  Everything per-row that the scan kernels need is derived here
 // from the image bytes as they arrive in HBM, so the host only queues the copy:
-//   pbf_index_kernel   one CTA (a single running thread) per block chases the length prefixes through a shared-memory
-//                      ring that is kept full by TMA bulk copies -> rowoff[blk][0..rows]; validates tags and lengths.
+//   pbf_index_kernel   one warp per block chases the length prefixes through shared-memory rings that are kept full by TMA
+//                      bulk copies -> rowoff[blk][0..rows]; validates tags and lengths.  Six lanes share the chain, each
+//                      starting at a verified record start of its stretch; lane 0 alone if the pieces do not join up.
 //   plan_tiles_kernel  groups rows into the walk kernel's tiles (<= RAW_CAP bytes, never across a COMP_K boundary).
 //   p1view_kernel      compacts the rows whose second bit plane is not empty into the "plane-1 view" (a miniature
 //                      PBF image per block in fixed-size slots) and decides whether the block qualifies for the split
@@ -18,9 +19,10 @@ namespace b200 {
 
 // ------------------------------------------------------------------------------------------------ row offsets
 
-constexpr int IX_STAGE = 2048, IX_SLOTS = 8, IX_RING = IX_STAGE * IX_SLOTS;   // small on purpose: a chase CTA (16 KB) must fit
-                                                                            // beside the resident CTAs of the kernels it overlaps
-constexpr int IX_LANES = 1;   // checkpoint blocks chased per CTA, one lane each (see pbf_index_kernel)
+constexpr int IX_K = 6;         // lanes that chase one block together, each from its own (verified) record start
+constexpr int IX_STAGE = 1024, IX_SLOTS = 4, IX_RING = IX_STAGE * IX_SLOTS;   // per-lane ring; small on purpose: a chase CTA
+                                                                            // (24 KB) must fit beside the resident CTAs it overlaps
+constexpr uint32_t IX_BAD = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t ix_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -87,45 +89,16 @@ __device__ __forceinline__ uint32_t ix_read4(uint32_t ring_saddr, uint32_t o)
 	return __funnelshift_r(w0, w1, (o & 3u) * 8u);
 }
 
-// One LANE per checkpoint block, IX_LANES blocks per CTA, each with its own ring.  The chain of a block is
-// rows x 2 dependent hops ('B', l0 | plane-0 bytes | l1 | plane-1 bytes), so the loop is written for latency: offsets are
-// 32-bit and relative to the ring base, both length words are read speculatively from the ring (always safe: it is
-// shared memory) and ONE combined test per row decides whether they were resident and valid; only rows at the edge of
-// the two-stage window take the careful path.
-__global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
-{
-	extern __shared__ __align__(128) uint8_t ix_sm_all[];
-	const int lane = threadIdx.x;
-	if (lane >= P.lanes || (int)blockIdx.x * P.lanes + lane >= P.blk_count) return;   // P.lanes == IX_LANES, but a run-time value:
-	// with a compile-time single lane the whole chase lands on the uniform datapath (R2UR after every shared-memory load)
-	uint8_t *ix_sm = ix_sm_all + (size_t)lane * (IX_RING + 64);
-	const int blk = P.blk_first + (int)blockIdx.x * P.lanes + lane;
-	const int BS = 1 << P.shift;
-	uint64_t *ro = P.rowoff + (size_t)blk * (BS + 1);
-	const int rows = P.rows_in_blk[blk];
-	const uint64_t first = P.blkoff[blk] + 1 + 8ull * (uint64_t)P.m;  // behind the 'S' record (pbwt.c:298-300)
-	const uint64_t base = first & ~15ull;
-
-	IxRing R;   // ring bookkeeping (local memory, touched only on the careful path)
-	R.ring = ix_sm; R.bar = (uint64_t*)(ix_sm + IX_RING); R.img = P.img; R.err = P.err;
-	R.base = base; R.end16 = (P.blkend[blk] + 15) & ~15ull;
-	#pragma unroll
-	for (int s = 0; s < IX_SLOTS; ++s) {
-		R.stage[s] = -1; R.parity[s] = 0; R.inflight[s] = false;
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ix_smem_u32(R.bar + s)), "r"(1));
-	}
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-
-	const uint64_t end64 = P.blkend[blk] - base;
-	const uint32_t ring_saddr = ix_smem_u32(ix_sm);
-	bool bad = P.img[P.blkoff[blk]] != 'S' || first > P.blkend[blk];
-	if (end64 > 0xfff00000ull) { atomicOr(P.err, 128); bad = true; }   // the records of one block must fit 32-bit offsets
-	const uint32_t end = (uint32_t)end64;
-	uint32_t o = (uint32_t)(first - base);
-	uint32_t wlo = 1, whi = 0;              // complete stages hold [wlo, whi)
-	int r = 0;
-	while (r < rows && !bad) {
-		// speculative: 'B' + l0 at o, l1 behind the plane-0 bytes
+// One record at ring-relative offset o: the offset of the next record, or IX_BAD.  Written for latency: offsets are 32-bit
+// and relative to the ring base, both length words are read speculatively from the ring (always safe: it is shared
+// memory) and ONE combined test decides whether they were resident and valid; only records at the edge of the two-stage
+// window take the careful path.
+struct IxCursor {
+	IxRing R;
+	uint32_t ring_saddr, wlo, whi, end;
+	uint64_t end64;
+	__device__ __forceinline__ uint32_t step(uint32_t o)
+	{
 		const uint32_t w0 = ix_read4(ring_saddr, o), w1 = ix_read4(ring_saddr, o + 4);
 		const uint32_t l0 = __funnelshift_r(w0, w1, 8);
 		const uint32_t p1 = o + 5u + l0;
@@ -133,47 +106,176 @@ __global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
 		const uint32_t nxt = p1 + 4u + l1;
 		const bool resident = o >= wlo && o + 8u <= whi && p1 >= wlo && p1 + 8u <= whi;
 		const bool valid = (w0 & 0xffu) == 'B' && (l0 | l1) < 0x80000000u && nxt >= p1 && nxt <= end;   // (resident => p1 did not wrap)
-		if (resident && valid) { ro[r++] = base + o; o = nxt; continue; }
-		// careful path for this one row
-		if ((uint64_t)o + 9 > end64) { bad = true; break; }
+		if (resident && valid) return nxt;
+		// careful path
+		if ((uint64_t)o + 9 > end64) return IX_BAD;
 		R.window((long long)(o / IX_STAGE));
 		wlo = (o / IX_STAGE) * IX_STAGE; whi = wlo + 2 * IX_STAGE;
 		const uint32_t c0 = ix_read4(ring_saddr, o), c1 = ix_read4(ring_saddr, o + 4);
 		const uint32_t cl0 = __funnelshift_r(c0, c1, 8);
 		const uint64_t cp1 = (uint64_t)o + 5 + cl0;
-		if ((c0 & 0xffu) != 'B' || cl0 >= 0x80000000u || cp1 + 4 > end64) { bad = true; break; }
+		if ((c0 & 0xffu) != 'B' || cl0 >= 0x80000000u || cp1 + 4 > end64) return IX_BAD;
 		if (!((uint32_t)cp1 >= wlo && (uint32_t)cp1 + 8u <= whi)) {
 			R.window((long long)(cp1 / IX_STAGE));
 			wlo = (uint32_t)(cp1 / IX_STAGE) * IX_STAGE; whi = wlo + 2 * IX_STAGE;
 		}
 		const uint32_t cl1 = ix_read4(ring_saddr, (uint32_t)cp1);
 		const uint64_t cn = cp1 + 4 + cl1;
-		if (cl1 >= 0x80000000u || cn > end64) { bad = true; break; }
-		ro[r++] = base + o;
-		o = (uint32_t)cn;
+		if (cl1 >= 0x80000000u || cn > end64) return IX_BAD;
+		return (uint32_t)cn;
 	}
-	#pragma unroll 1
-	for (int s = 0; s < IX_SLOTS; ++s) if (R.inflight[s]) R.wait(s);   // no copy may be in flight when the CTA exits
+};
+
+__device__ __forceinline__ uint32_t ix_gld_u32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+
+// does a chain of `need` well-formed records start at image offset p (or reach the block end earlier), and do the run
+// lengths of both planes of the first one add up to m?  Global loads.  (The length chain alone is not enough: a 'B'
+// byte in front of a real length field can fake one record whose end falls on a real boundary -- seen once per ~600
+// starts; run lengths of arbitrary bytes do not sum to m.)
+__device__ bool ix_verify_start(const uint8_t *img, uint64_t p, uint64_t end, int need, uint32_t m)
+{
+	{
+		if (p + 9 > end || img[p] != 'B') return false;
+		const uint32_t l0 = ix_gld_u32(img + p + 1);
+		if (l0 >= 0x80000000u || p + 9 + l0 > end) return false;
+		const uint32_t l1 = ix_gld_u32(img + p + 5 + l0);
+		if (l1 >= 0x80000000u || p + 9 + l0 + (uint64_t)l1 > end) return false;
+		unsigned long long t0 = 0, t1 = 0;
+		const uint8_t *r0 = img + p + 5, *r1 = img + p + 9 + l0;
+		// (a faked record can claim a megabyte of "runs": stop as soon as the sum passes m)
+		for (uint32_t i = 0; i < l0 && t0 <= m; ++i) { const uint32_t v = r0[i] >> 1; t0 += (v & 15u) << ((v >> 4) << 2); }
+		if (t0 != m) return false;
+		for (uint32_t i = 0; i < l1 && t1 <= m; ++i) { const uint32_t v = r1[i] >> 1; t1 += (v & 15u) << ((v >> 4) << 2); }
+		if (t1 != m) return false;
+	}
+	for (int v = 0; v < need; ++v) {
+		if (p == end) return v > 0;
+		if (p + 9 > end || img[p] != 'B') return false;
+		const uint32_t l0 = ix_gld_u32(img + p + 1);
+		if (l0 >= 0x80000000u || p + 9 + l0 > end) return false;
+		const uint32_t l1 = ix_gld_u32(img + p + 5 + l0);
+		if (l1 >= 0x80000000u || p + 9 + l0 + (uint64_t)l1 > end) return false;
+		p += 9ull + l0 + l1;
+	}
+	return true;
+}
+
+// One warp per checkpoint block.  The chain of a block is rows x 2 dependent hops ('B', l0 | plane-0 bytes | l1 | plane-1
+// bytes) -- pure latency -- so IX_K lanes chase it together: lane 0 from the block's first record, lane l from the first
+// position in its stretch of the byte range at which a chain of four well-formed records starts whose first one carries
+// run lengths that add up to m in both planes.  A lane stops where the next lane began;
+// if every lane lands EXACTLY on its successor's start and the counts add up to the block's rows, the pieces are the
+// chain and are copied to their places.  Otherwise (damaged or unusual blocks) lane 0 walks the whole block alone.
+__global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
+{
+	extern __shared__ __align__(128) uint8_t ix_sm_all[];
+	const int lane = threadIdx.x;
+	const int blk = P.blk_first + (int)blockIdx.x;
+	const int BS = 1 << P.shift;
+	uint64_t *ro = P.rowoff + (size_t)blk * (BS + 1);
+	const int rows = P.rows_in_blk[blk];
+	const uint64_t first = P.blkoff[blk] + 1 + 8ull * (uint64_t)P.m;  // behind the 'S' record (pbwt.c:298-300)
+	const uint64_t base = first & ~15ull;
+	const uint64_t blkend = P.blkend[blk];
+	const uint64_t end64 = blkend - base;
+	bool bad = P.img[P.blkoff[blk]] != 'S' || first > blkend;
+	if (end64 > 0xfff00000ull) { if (lane == 0) atomicOr(P.err, 128); bad = true; }   // the records of one block must fit 32-bit offsets
 	if (bad) {
+		if (lane == 0) { atomicOr(P.err, 2); P.rows_in_blk[blk] = 0; ro[0] = P.blkoff[blk]; }
+		return;
+	}
+	IxCursor C;
+	if (lane < IX_K) {
+		uint8_t *ix_sm = ix_sm_all + (size_t)lane * (IX_RING + 64);
+		C.R.ring = ix_sm; C.R.bar = (uint64_t*)(ix_sm + IX_RING); C.R.img = P.img; C.R.err = P.err;
+		C.R.base = base; C.R.end16 = (blkend + 15) & ~15ull;
+		#pragma unroll
+		for (int s = 0; s < IX_SLOTS; ++s) {
+			C.R.stage[s] = -1; C.R.parity[s] = 0; C.R.inflight[s] = false;
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ix_smem_u32(C.R.bar + s)), "r"(1));
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		C.ring_saddr = ix_smem_u32(ix_sm); C.wlo = 1; C.whi = 0; C.end64 = end64; C.end = (uint32_t)end64;
+	}
+	const uint32_t first_rel = (uint32_t)(first - base), end_rel = (uint32_t)end64;
+	const bool team = rows >= 64 * IX_K && P.scratch != nullptr;
+	bool done = false;
+	if (team) {
+		// ---- starts
+		uint32_t s = IX_BAD;
+		if (lane == 0) s = first_rel;
+		else if (lane < IX_K) {
+			const uint64_t span = blkend - first;
+			uint64_t p = first + span * (uint64_t)lane / IX_K;
+			const uint64_t lim = first + span * (uint64_t)(lane + 1) / IX_K;
+			for (; p < lim; ++p)
+				if (P.img[p] == 'B' && ix_verify_start(P.img, p, blkend, 4, (uint32_t)P.m)) { s = (uint32_t)(p - base); break; }
+		}
+		uint32_t stop = end_rel;                       // where my stretch ends: the first valid start behind me
+		for (int d = IX_K - 1; d >= 1; --d) {
+			const uint32_t t = __shfl_down_sync(0xffffffffu, s, d);
+			if (lane + d < IX_K && t != IX_BAD) stop = t;
+		}
+		// ---- chase my stretch into my scratch column
+		uint64_t *mine = P.scratch + ((size_t)blk * IX_K + (lane < IX_K ? lane : 0)) * (size_t)(BS + 1);
+		uint32_t cnt = 0, o = s;
+		bool ok = true;
+		if (lane < IX_K && s != IX_BAD) {
+			while (o < stop) {
+				const uint32_t n = C.step(o);
+				if (n == IX_BAD || cnt >= (uint32_t)rows) { ok = false; break; }
+				mine[cnt++] = base + o;
+				o = n;
+			}
+			if (o != stop) ok = false;                  // ran past the successor's start: one of the two is not on the chain
+		}
+		const bool all_ok = __all_sync(0xffffffffu, ok);
+		uint32_t x = (lane < IX_K && s != IX_BAD) ? cnt : 0u, incl = x;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		if (all_ok && total == (uint32_t)rows) {
+			// ---- the pieces are the chain: copy them to their places (coalesced, all lanes)
+			for (int l = 0; l < IX_K; ++l) {
+				const uint32_t c = __shfl_sync(0xffffffffu, x, l), b0 = __shfl_sync(0xffffffffu, incl - x, l);
+				const uint64_t *src = P.scratch + ((size_t)blk * IX_K + l) * (size_t)(BS + 1);
+				for (uint32_t i = lane; i < c; i += 32) ro[b0 + i] = src[i];
+			}
+			if (lane == 0) ro[rows] = blkend;
+			done = true;
+		}
+	}
+	if (!done && lane == 0) { // ---- the whole block, alone
+		if (team) atomicAdd(P.fallbacks, 1);
+		uint32_t o = first_rel;
+		int r = 0;
+		for (; r < rows; ++r) {
+			const uint32_t n = C.step(o);
+			if (n == IX_BAD) { bad = true; break; }
+			ro[r] = base + o;
+			o = n;
+		}
+		if (!bad) ro[rows] = base + o;
+	}
+	if (lane < IX_K) {
+		#pragma unroll 1
+		for (int s = 0; s < IX_SLOTS; ++s) if (C.R.inflight[s]) C.R.wait(s);   // no copy may be in flight when the CTA exits
+	}
+	if (bad && lane == 0) {
 		// the records of this block do not parse: it decodes as an empty block and the load reports the corruption
 		atomicOr(P.err, 2);
 		P.rows_in_blk[blk] = 0;
 		ro[0] = P.blkoff[blk];
-		return;
 	}
-	ro[rows] = base + o;
 }
 
 cudaError_t launch_index(const IndexParams &P, int n_blk, cudaStream_t st)
 {
 	if (n_blk <= 0) return cudaSuccess;
-	const size_t smem = (size_t)IX_LANES * (IX_RING + 64);
+	const size_t smem = (size_t)IX_K * (IX_RING + 64);
 	cudaError_t e = cudaFuncSetAttribute(pbf_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
-	IndexParams Q = P;
-	Q.blk_count = n_blk;
-	Q.lanes = IX_LANES;
-	pbf_index_kernel<<<(n_blk + IX_LANES - 1) / IX_LANES, 32, smem, st>>>(Q);
+	pbf_index_kernel<<<n_blk, 32, smem, st>>>(P);
 	return cudaGetLastError();
 }
 

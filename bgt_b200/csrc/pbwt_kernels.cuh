@@ -122,12 +122,15 @@ struct IndexParams {
 	const uint64_t *blkoff;       // [blocks] offset of the 'S' record of every resident block, relative to img
 	const uint64_t *blkend;       // [blocks] end of the block's records (next 'S' record or the 'I' record)
 	int            *rows_in_blk;  // [blocks] rows per block; set to 0 by the index kernel if the block's records do not parse
-	int m, shift, blk_first, blk_count, lanes;
+	int m, shift, blk_first;
 	uint64_t *rowoff;             // out [blocks][BS+1]
+	uint64_t *scratch;            // [blocks][IX_SCRATCH_LANES][BS+1] per-lane pieces of the chain, or nullptr (single-lane chase)
 	int2     *tiles;              // out [blocks][BS]
 	int      *blk_tile_beg, *blk_tile_end, *grp_tile_beg;  // out [blocks], [blocks], [blocks][groups+1]
 	int      *err;
+	int      *fallbacks;          // diagnostics: blocks whose pieces did not join up (chased again by one lane)
 };
+constexpr int IX_SCRATCH_LANES = 6;
 cudaError_t launch_index(const IndexParams &P, int n_blk, cudaStream_t st);
 cudaError_t launch_plan_tiles(const IndexParams &P, int n_blk, cudaStream_t st);
 
