@@ -22,7 +22,8 @@
 namespace b200 {
 
 constexpr int CP_NT = 256, CP_NW = CP_NT / 32;
-constexpr int CP_RUNS = 4096;      // merged runs of all rows of a group held in shared memory
+constexpr int CP_RUNS_BIG = 4096, CP_RUNS_SMALL = 3040;   // merged runs of all rows of a group held in shared memory: the small
+// variant (49 KB, 4 CTAs per SM) takes every group first, the big one (66 KB, 3 per SM) re-does the few that did not fit
 constexpr int CP_CACHE = 10;       // look-ups per thread kept in registers between the two passes of a level (total/2/CP_NT ~ 8)
 
 __device__ __forceinline__ uint32_t cp_rle_len(uint32_t c) { const uint32_t v = c >> 1; return (v & 15u) << ((v >> 4) << 2); }
@@ -38,6 +39,7 @@ __device__ __forceinline__ uint32_t cp_ld_u32_unaligned(const uint8_t *p)
 
 // Pieces of the maps of one level live back to back in (S, D): S = start of the piece in the map's input coordinates,
 // D = translation.  off[i] .. off[i+1] are the pieces of map i.
+template<int CP_RUNS>
 __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams P)
 {
 	extern __shared__ __align__(16) uint8_t sm[];
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	const int nrow = P.rows_in_blk[blk] - r_lo;
 	const size_t slot = ((size_t)blk * n_grp + g);
 	const int cap = P.cap;
+	if (CP_RUNS == CP_RUNS_BIG && P.retry && P.comp_n[slot] != 0) return;   // second launch: only the groups the small variant gave up on
 	if (nrow < COMP_K || (P.blk_ok && !P.blk_ok[blk])) { if (tid == 0) P.comp_n[slot] = 0; return; }   // partial last group: never crossed as a whole
 	if (tid == 0) { s_fail = 0; s_n = 0; }
 	__syncthreads();
@@ -249,16 +252,22 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	if (tid == 0) P.comp_n[slot] = npad;
 }
 
-size_t compose_smem_bytes() { return sizeof(uint32_t) * 4 * (CP_RUNS + COMP_K + 8) + 64; }
+size_t compose_smem_bytes() { return sizeof(uint32_t) * 4 * (CP_RUNS_BIG + COMP_K + 8) + 64; }
+static size_t compose_smem_of(int runs) { return sizeof(uint32_t) * 4 * (size_t)(runs + COMP_K + 8) + 64; }
 
 cudaError_t launch_compose(const ComposeParams &P, int n_blk, cudaStream_t st)
 {
 	if (n_blk <= 0) return cudaSuccess;
 	const int n_grp = P.n_grp;
-	const size_t smem = compose_smem_bytes();
-	cudaError_t e = cudaFuncSetAttribute(pbwt_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	const unsigned grid = (unsigned)((long long)n_blk * n_grp);
+	cudaError_t e = cudaFuncSetAttribute(pbwt_compose_kernel<CP_RUNS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compose_smem_of(CP_RUNS_SMALL));
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(pbwt_compose_kernel<CP_RUNS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compose_smem_of(CP_RUNS_BIG));
 	if (e != cudaSuccess) return e;
-	pbwt_compose_kernel<<<(unsigned)((long long)n_blk * n_grp), CP_NT, smem, st>>>(P);
+	ComposeParams Q = P;
+	Q.retry = 0;
+	pbwt_compose_kernel<CP_RUNS_SMALL><<<grid, CP_NT, compose_smem_of(CP_RUNS_SMALL), st>>>(Q);
+	Q.retry = 1;
+	pbwt_compose_kernel<CP_RUNS_BIG><<<grid, CP_NT, compose_smem_of(CP_RUNS_BIG), st>>>(Q);
 	return cudaGetLastError();
 }
 

@@ -82,6 +82,7 @@ struct ComposeParams {
 	int rle_off;      // offset of the plane's RLE inside a row record: 5 = plane 0 of a .pbf row, 9 = plane 1 of a plane-1 view row
 	int n1_plane;     // which entry of n1[row][2] belongs to that plane
 	int inverse;      // 1: inverse composite (coordinates behind the group -> in front of it)
+	int retry;        // set by launch_compose: second launch, only the groups whose first attempt ran out of room
 	uint16_t *comp_dir; // forward maps only: bucket directory per slot (COMP_DIR_STRIDE entries), or nullptr
 	int dir_shift, dir_n;
 	uint32_t *comp_start;
