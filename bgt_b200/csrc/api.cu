@@ -1025,7 +1025,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		WalkParams B = P;
 		if (pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) {
 			B.comp_start = pb->d_comp_start; B.comp_delta = pb->d_comp_delta; B.comp_n = pb->d_comp_n; B.grp_tile_beg = pb->d_grp_tile_beg;
-			B.comp_dir = getenv("BGT_B200_NO_DIR") ? nullptr : pb->d_comp_dir; B.dir_shift = pb->dir_shift; B.dir_n = pb->dir_n;
+			B.comp_dir = pb->d_comp_dir; B.dir_shift = pb->dir_shift; B.dir_n = pb->dir_n;
 		}
 		B.track = (const int32_t*)c->qcol.p; B.qrow = (const uint16_t*)c->qrow.p; B.track_stride = cap;
 		B.n_track_blk = (const int*)c->qcount.p; B.n_track = cap; B.blk_list = d_split_list;
@@ -1434,12 +1434,13 @@ static bool bgzf_inflate_device(b200_ctx_t *c, const uint8_t *f, size_t n, uint8
 
 extern "C" int64_t b200_bgzf_inflate(b200_ctx_t *c, const uint8_t *bytes, size_t n_bytes, uint8_t *out, size_t out_cap)
 {
-	if (!c || !bytes) { set_err("b200_bgzf_inflate: null argument"); return -1; }
-	cudaSetDevice(c->dev);
-	if (!out) { // size query: headers only
+	if (!bytes) { set_err("b200_bgzf_inflate: null argument"); return -1; }
+	if (!out) { // size query: block headers only, host logic (no device needed)
 		BgzfIndex ix;
 		return bgzf_index(bytes, n_bytes, ix) ? (int64_t)ix.total : -1;
 	}
+	if (!c) { set_err("b200_bgzf_inflate: null context"); return -1; }
+	cudaSetDevice(c->dev);
 	uint8_t *d = nullptr; uint64_t len = 0;
 	if (!bgzf_inflate_device(c, bytes, n_bytes, &d, &len)) return -1;
 	bool ok = true;

@@ -234,7 +234,7 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
 // dir[(r >> s) + 1], so the binary search runs over a window of a few entries (the widest window of the warp sets the
 // trip count).  Only the slots in `act` advance.
 template<int C>
-__device__ __forceinline__ void lookup_comp(uint32_t (&r)[C], uint32_t tab_saddr, uint32_t dir_saddr, int sh, uint32_t act)
+__device__ __forceinline__ void lookup_comp(uint32_t (&r)[C], uint32_t tab_saddr, uint32_t td_off, uint32_t dir_saddr, int sh, uint32_t act)
 {
 	if (!__any_sync(FULL_MASK, act != 0)) return;
 	uint32_t a[C], hi[C], w = 1;
@@ -259,7 +259,7 @@ __device__ __forceinline__ void lookup_comp(uint32_t (&r)[C], uint32_t tab_saddr
 	}
 	#pragma unroll
 	for (int c = 0; c < C; ++c) {
-		const uint32_t d = lds_u32(a[c] + TD_MINUS_TS);
+		const uint32_t d = lds_u32(a[c] + td_off);
 		if ((act >> c) & 1u) r[c] += d;
 	}
 }
@@ -318,13 +318,19 @@ struct WalkSmem {
 	uint32_t *scratch;  // [8]
 };
 
-__host__ __device__ inline size_t walk_smem_layout(int C, int G, size_t off[8])
+// composite stages of the QUERY walk (three, so that two TMA copies are in flight while one map is searched): piece starts,
+// translations, bucket directory -- overlaid on the raw / run-table buffers, which the composite phase does not use
+constexpr uint32_t CSTG_TD = COMP_CAP * 4u, CSTG_DIR = COMP_CAP * 8u, CSTG_BYTES = COMP_CAP * 8u + COMP_DIR * 2u;
+constexpr int CSTG_N = 3;
+
+__host__ __device__ inline size_t walk_smem_layout(int C, int G, size_t off[8], bool query = false)
 {
 	size_t o = 0;
-	off[0] = o; o += 16;                                  // mbarrier
+	off[0] = o; o += 32;                                  // mbarriers (tile copy / composite stage 0, stages 1 and 2)
 	off[1] = o; o += RAW_BYTES;                           // raw
 	off[2] = o; o += sizeof(uint32_t) * RAW_BYTES;        // ts
 	off[3] = o; o += sizeof(int32_t) * RAW_BYTES;         // td (must directly follow ts: TD_MINUS_TS)
+	if (query && o - off[1] < (size_t)CSTG_N * CSTG_BYTES) o = off[1] + (size_t)CSTG_N * CSTG_BYTES;
 	off[4] = o; o += sizeof(RowMeta) * T_MAX;             // meta
 	off[5] = o; o += sizeof(int32_t) * T_MAX * G * 3;     // rowcnt
 	off[6] = o; o += (G > 2 ? (size_t)G * WALK_NT : 16);  // gmask
@@ -334,7 +340,7 @@ __host__ __device__ inline size_t walk_smem_layout(int C, int G, size_t off[8])
 	return (o + 15) & ~(size_t)15;
 }
 
-size_t walk_smem_bytes(int C, int G) { size_t off[8]; return walk_smem_layout(C, G, off); }
+size_t walk_smem_bytes(int C, int G, bool query) { size_t off[8]; return walk_smem_layout(C, G, off, query); }
 
 // Per-row reduction (bgt.c:743-756).  bits0/bits1: bit c = plane-0/1 bit of this thread's column slot c (already
 // masked to valid slots).  Every thread popcounts its own C codes per group, one REDUX.SUM per counter folds the
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 	WalkSmem S;
 	{
 		size_t off[8];
-		walk_smem_layout(C, P.G, off);
+		walk_smem_layout(C, P.G, off, QUERY);
 		S.mbar = (uint64_t*)(smem + off[0]); S.raw = smem + off[1]; S.ts = (uint32_t*)(smem + off[2]); S.td = (int32_t*)(smem + off[3]);
 		S.meta = (RowMeta*)(smem + off[4]); S.rowcnt = (int32_t*)(smem + off[5]); S.gmask = smem + off[6];
 		S.scratch = (uint32_t*)(smem + off[7]);
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 		r0[c] = r1[c] = CHAIN ? (uint32_t)col[c] : 0u; // generator: identity before row 0 (pbwt.c:103)
 	}
 	for (int i = tid; i < T_MAX * P.G * 3; i += WALK_NT) S.rowcnt[i] = 0;
-	if (tid == 0) { mbar_init(S.mbar, 1); mbar_init(S.mbar + 1, 1); }
+	if (tid == 0) { mbar_init(S.mbar, 1); mbar_init(S.mbar + 1, 1); mbar_init(S.mbar + 2, 1); }
 	__syncthreads();
 
 	uint32_t parity = 0;
@@ -500,49 +506,46 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 			const int n_grp = (BS + COMP_K - 1) / COMP_K;
 			const int g_mixed = (int)P.qrow[(size_t)blk_own * P.track_stride + slice_base] / COMP_K;
 			const int g_last = (q_stop - 1) / COMP_K;            // group of the CTA's last target row
-			// two composites fit the run-table buffers side by side: while group g is searched in one half, thread 0 has the
-			// copy of group g+1 in flight into the other half (its own mbarrier)
-			// piece counts of the block's groups: read once (a global load per group would sit on the loop's critical path)
-			__shared__ int s_compn[1024];
-			const bool compn_sm = g_last <= 1024;
-			if (compn_sm) {
-				for (int i = tid; i < g_last; i += WALK_NT) s_compn[i] = P.comp_n[(size_t)blk * n_grp + i];
-				__syncthreads();
-			}
-			auto comp_n_of = [&](int gg) -> int { return compn_sm ? s_compn[gg] : P.comp_n[(size_t)blk * n_grp + gg]; };
+			// g_avail: the groups in front of the first one without a usable composite (all of them, as a rule)
+			__shared__ int s_avail;
+			if (tid == 0) s_avail = g_last;
+			__syncthreads();
+			for (int i = tid; i < g_last; i += WALK_NT) if (P.comp_n[(size_t)blk * n_grp + i] == 0) atomicMin(&s_avail, i);
+			__syncthreads();
+			const int g_avail = s_avail;
+			// three stages: while group g is searched, the copies of g+1 and g+2 are in flight (a TMA round trip is longer
+			// than one search); stage s has its own mbarrier and is re-filled after the CTA barrier that ends its last use
+			uint8_t *stg0 = S.raw;
+			const uint32_t stg0_saddr = smem_u32(stg0);
 			auto fetch_comp = [&](int gg) {
 				const size_t slot = (size_t)blk * n_grp + gg;
-				const uint32_t np = (uint32_t)comp_n_of(gg);
-				if (np == 0) return;
-				uint64_t *bar = S.mbar + (gg & 1);
+				const uint32_t np = (uint32_t)P.comp_n[slot];
+				uint64_t *bar = S.mbar + gg % CSTG_N;
+				uint8_t *dst = stg0 + (size_t)(gg % CSTG_N) * CSTG_BYTES;
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-				mbar_expect_tx(bar, np * 8u + (P.comp_dir ? (uint32_t)P.dir_n * 2u : 0u));
-				tma_bulk_g2s(S.ts + (gg & 1) * COMP_CAP, P.comp_start + slot * COMP_CAP, np * 4u, bar);
-				tma_bulk_g2s(S.td + (gg & 1) * COMP_CAP, P.comp_delta + slot * COMP_CAP, np * 4u, bar);
-				if (P.comp_dir) tma_bulk_g2s(S.raw + (gg & 1) * (RAW_CAP / 2), P.comp_dir + slot * COMP_DIR_STRIDE, (uint32_t)P.dir_n * 2u, bar);
+				mbar_expect_tx(bar, np * 8u + (uint32_t)P.dir_n * 2u);
+				tma_bulk_g2s(dst, P.comp_start + slot * COMP_CAP, np * 4u, bar);
+				tma_bulk_g2s(dst + CSTG_TD, P.comp_delta + slot * COMP_CAP, np * 4u, bar);
+				tma_bulk_g2s(dst + CSTG_DIR, P.comp_dir + slot * COMP_DIR_STRIDE, (uint32_t)P.dir_n * 2u, bar);
 			};
-			uint32_t parity1 = 0;
 			int g = 0;
-			if (tid == 0 && g_last > 0) fetch_comp(0);
-			for (; g < g_last; ++g) {
-				const int np = comp_n_of(g);
-				if (np == 0) break;                                 // not available: row by row from here on (nothing is in flight)
-				if (tid == 0 && g + 1 < g_last) fetch_comp(g + 1);  // the other half was released by the barrier below
+			if (tid == 0) for (int k = 0; k < CSTG_N - 1 && k < g_avail; ++k) fetch_comp(k);
+			for (; g < g_avail; ++g) {
+				if (tid == 0 && g + CSTG_N - 1 < g_avail) fetch_comp(g + CSTG_N - 1);   // its stage was released by the barrier below
 				{
 					uint32_t spins = 0;
-					while (!mbar_try_wait(S.mbar + (g & 1), (g & 1) ? parity1 : parity))
+					const uint32_t par = (uint32_t)(g / CSTG_N) & 1u;
+					while (!mbar_try_wait(S.mbar + g % CSTG_N, par))
 						if (++spins > (1u << 26)) { atomicOr(P.err, 8); __trap(); }
-					if (g & 1) parity1 ^= 1; else parity ^= 1;
 				}
-				uint32_t act = 0, unused;
+				uint32_t act = 0;
 				#pragma unroll
 				for (int c = 0; c < C; ++c) act |= (tgt[c] != 0xffffffffu && (int)(tgt[c] / COMP_K) > g ? 1u : 0u) << c;
-				const uint32_t tab = ts_saddr + (uint32_t)(g & 1) * (COMP_CAP * 4u);
-				if (P.comp_dir) lookup_comp<C>(r0, tab, smem_u32(S.raw) + (uint32_t)(g & 1) * (RAW_CAP / 2), P.dir_shift, act);
-				else if (g < g_mixed) lookup_runs<C>(r0, tab, (uint32_t)np, 0u, unused);
-				else lookup_runs_masked<C>(r0, tab, (uint32_t)np, 0u, act, unused);
+				const uint32_t tab = stg0_saddr + (uint32_t)(g % CSTG_N) * CSTG_BYTES;
+				lookup_comp<C>(r0, tab, CSTG_TD, tab + CSTG_DIR, P.dir_shift, act);
 				__syncthreads();
 			}
+			parity = (uint32_t)((g_avail + CSTG_N - 1) / CSTG_N) & 1u;   // phases completed on barrier 0, which the tile loop uses next
 			// g = first group without a usable composite (or the last group): entries with a later target walk from there
 			#pragma unroll
 			for (int c = 0; c < C; ++c) {
@@ -729,7 +732,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 template<int C, int MODE>
 static cudaError_t launch_walk_t(const WalkParams &P, int slices, int n_blk, cudaStream_t st)
 {
-	const size_t smem = walk_smem_bytes(C, P.G);
+	const size_t smem = walk_smem_bytes(C, P.G, MODE == WALK_QUERY);
 	cudaError_t e = cudaFuncSetAttribute(pbwt_walk_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	for (int b0 = 0; b0 < n_blk; b0 += 32768) {

@@ -60,7 +60,7 @@ struct WalkParams {
 	int *err;
 };
 
-size_t walk_smem_bytes(int C, int G);
+size_t walk_smem_bytes(int C, int G, bool query = false);
 // C = tracked columns per thread (1,2,4,8); mode = WALK_COUNT / WALK_EMIT / WALK_CHAIN / WALK_QUERY (pbwt_kernels.cu)
 enum { WALK_MODE_COUNT = 0, WALK_MODE_EMIT = 1, WALK_MODE_CHAIN = 2, WALK_MODE_QUERY = 3 };
 cudaError_t launch_walk(const WalkParams &P, int C, int mode, int slices, int n_blk, cudaStream_t st);

@@ -202,3 +202,29 @@ def test_two_rank_sharding_over_gloo(oracle, tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0 and b"rank ok" in out, out.decode()[-800:]
+
+
+def test_bgzf_block_walk_without_a_device():
+    """b200_bgzf_inflate(out=NULL) only walks the BGZF block headers (bgzf.c:259-281, 318-351) and sums ISIZE: host logic."""
+    import ctypes as C
+    import struct
+    import zlib
+    import bgt_b200
+    L = bgt_b200.load_library()
+
+    def block(data, extra=b""):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        raw = c.compress(data) + c.flush()
+        xlen = 6 + len(extra)
+        total = 12 + xlen + len(raw) + 8
+        return (b"\x1f\x8b\x08\x04\0\0\0\0\x00\xff" + struct.pack("<H", xlen) + extra + b"BC" + struct.pack("<HH", 2, total - 1) + raw +
+                struct.pack("<II", zlib.crc32(data), len(data)))
+
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    f = block(b"a" * 1000) + block(b"hello", extra=b"XY\x01\x00z") + block(b"") + block(bytes(65536)) + eof
+    buf = (C.c_uint8 * len(f)).from_buffer_copy(f)
+    assert L.b200_bgzf_inflate(None, buf, len(f), None, 0) == 1000 + 5 + 65536
+    for bad in (f[:50], b"\x1f\x8b\x08\x00" + f[4:], f[:-10]):
+        b2 = (C.c_uint8 * len(bad)).from_buffer_copy(bad)
+        assert L.b200_bgzf_inflate(None, b2, len(bad), None, 0) < 0
+        assert L.b200_strerror()
