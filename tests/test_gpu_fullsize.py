@@ -131,3 +131,39 @@ def test_config5_width_one_million_haplotypes(b200, ctx, oracle):
     assert (np.concatenate(parts) == res["counts"]).all()
     q.close()
     pb.close()
+
+
+def test_encoder_reproduces_the_generated_image_at_full_width(b200, ctx, cohort):
+    """decode the first 12 000 rows of the 100 k-sample cohort on the device (crossing the checkpoint at row 8192), encode
+    them on the device: the generator's image is canonical and truthful, so the file must come out byte for byte -- 'S'
+    snapshots, run-length bytes, index."""
+    n = 12000
+    small = b200.synth_cohort(ctx, SAMPLES, n, seed=SEED)          # rows are seeded per row: the same first rows
+    want = small.image().tobytes()
+    q = b200.Query.columns(ctx, small)
+    enc = b200.Encoder(ctx, 2 * SAMPLES, 13)
+    for beg in range(0, n, 3000):
+        r = b200.scan(ctx, small, q, beg, 3000, counts=False, hap_bits=True)
+        enc.write_bits(np.ascontiguousarray(np.stack([r["hap_bits"][0], r["hap_bits"][1]], axis=1)))
+    assert enc.finish() == want
+    enc.close(); q.close(); small.close()
+
+
+def test_view_text_at_full_width_against_the_reference(b200, ctx, ref, tmp_path):
+    """the whole device pipeline of `view -f'AC>0' -G` (inflate, BCF parse, scan, text) on 100 k samples x 16 384 sites against
+    the unmodified reference's record lines (the reference needs ~8 s for them)."""
+    import os
+    import subprocess
+    n = 16384
+    small = b200.synth_cohort(ctx, SAMPLES, n, seed=SEED)
+    prefix = os.path.join(str(tmp_path), "f.bgt")
+    with open(prefix + ".pbf", "wb") as f:
+        f.write(memoryview(small.image()))
+    subprocess.run([ref.MKSITES, prefix], check=True, stderr=subprocess.DEVNULL)
+    sites = b200.Sites(ctx, open(prefix + ".bcf", "rb").read(), open(prefix + ".bcf.csi", "rb").read())
+    q = b200.Query(ctx, small, flt="AC>0")
+    got, n_lines = sites.view_text(small, q)
+    out = subprocess.run([ref.REF_BGT, "view", "-f", "AC>0", "-G", prefix], stdout=subprocess.PIPE, check=True).stdout
+    want = b"".join(ln + b"\n" for ln in out.split(b"\n") if ln and not ln.startswith(b"#"))
+    assert got == want and n_lines == want.count(b"\n")
+    q.close(); sites.close(); small.close()
