@@ -380,6 +380,7 @@ def run_b200(args, rank, world, local_rank):
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": k_ms,
                          "equivalent_rank_updates_per_s": 2.0 * 2 * samples * n / (dev_ms / args.steps * 1e-3),
                          "other_kernels_ms": {"plane1_select_kernel": sum(sel_ms) / len(sel_ms)},
+                         "other_kernels_note": "plane1_select_kernel does not depend on the query: it runs once per resident PBF (inside the load; about 1.0 ms for the whole file) and is 0 in resident steps",
                          "note": "dominant kernel = pbwt_walk_kernel (QUERY mode of the split scan); it is bound by shared-memory run look-ups / issue slots, not HBM (SURVEY 8d); the HBM fraction is reported as asked"},
             "clocks": clocks,
         }

@@ -78,7 +78,7 @@ struct b200_ctx_s {
 	cudaStream_t st_copy = nullptr;   // H2D of PBF images, so that per-chunk kernels on `st` overlap the rest of the copy
 	cudaStream_t st_idx[N_IDX_STREAMS] = {};      // the row-index chase of a chunk is one long dependent chain per block (latency bound, a few
 	                                  // lanes): the chases of consecutive chunks overlap each other and the kernels of earlier chunks
-	cudaEvent_t ev_chunk[LOAD_CHUNKS] = {}, ev_idx[LOAD_CHUNKS] = {};
+	cudaEvent_t ev_chunk[LOAD_CHUNKS] = {}, ev_idx[LOAD_CHUNKS] = {}, ev_sel[LOAD_CHUNKS] = {};
 	cudaEvent_t ev[12] = {};  // 0/1 walk phase(s), 2/3 scan, 4/5 h2d, 6/7 d2h, 8/9 plane1 select, 10/11 marginals
 	cudaEvent_t mark[4] = {};
 	cudaEvent_t ev_zero = nullptr;
@@ -130,6 +130,10 @@ struct b200_pbf_s {
 	mutable int32_t *d_comp_delta = nullptr;
 	mutable int *d_comp_n = nullptr;
 	mutable uint16_t *d_comp_dir = nullptr;   // bucket directories of the forward composites
+	// the (column, row) pairs that carry a plane-1 bit, per sparse block (plane1_select_kernel): query independent, so they
+	// are found once per resident PBF together with the composites
+	mutable int32_t *d_qcol = nullptr; mutable uint16_t *d_qrow = nullptr; mutable int *d_qcount = nullptr;
+	mutable bool sel_ready = false;
 	int dir_shift = 0, dir_n = 0;
 	mutable uint32_t *d_vcomp_start = nullptr;   // inverse composites of the plane-1 view rows (plane1_select_kernel)
 	mutable int32_t *d_vcomp_delta = nullptr;
@@ -226,7 +230,8 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 		cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
 		for (int i = 0; ok && i < N_IDX_STREAMS; ++i) ok = CU_OK(cudaStreamCreateWithPriority(&c->st_idx[i], cudaStreamNonBlocking, prio_hi));
 	}
-	for (int i = 0; ok && i < LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming)) && CU_OK(cudaEventCreateWithFlags(&c->ev_idx[i], cudaEventDisableTiming));
+	for (int i = 0; ok && i < LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming)) && CU_OK(cudaEventCreateWithFlags(&c->ev_idx[i], cudaEventDisableTiming)) &&
+	                                              CU_OK(cudaEventCreateWithFlags(&c->ev_sel[i], cudaEventDisableTiming));
 	for (int i = 0; ok && i < 12; ++i) ok = CU_OK(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; ok && i < 4; ++i) ok = CU_OK(cudaEventCreate(&c->mark[i]));
 	ok = ok && CU_OK(cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming));
@@ -253,7 +258,7 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	for (auto &b : c->pool_live) cudaFree(b.p);
 	if (c->d_err) cudaFree(c->d_err);
 	if (c->d_acc) cudaFree(c->d_acc);
-	for (int i = 0; i < LOAD_CHUNKS; ++i) { if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]); if (c->ev_idx[i]) cudaEventDestroy(c->ev_idx[i]); }
+	for (int i = 0; i < LOAD_CHUNKS; ++i) { if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]); if (c->ev_idx[i]) cudaEventDestroy(c->ev_idx[i]); if (c->ev_sel[i]) cudaEventDestroy(c->ev_sel[i]); }
 	if (c->st_copy) cudaStreamDestroy(c->st_copy);
 	for (int i = 0; i < N_IDX_STREAMS; ++i) if (c->st_idx[i]) cudaStreamDestroy(c->st_idx[i]);
 	if (c->st) cudaStreamDestroy(c->st);
@@ -320,6 +325,7 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_comp_delta);
 	pool_free(pb->ctx, pb->d_comp_n);
 	pool_free(pb->ctx, pb->d_comp_dir);
+	pool_free(pb->ctx, pb->d_qcol); pool_free(pb->ctx, pb->d_qrow); pool_free(pb->ctx, pb->d_qcount);
 	pool_free(pb->ctx, pb->d_vcomp_start);
 	pool_free(pb->ctx, pb->d_vcomp_delta);
 	pool_free(pb->ctx, pb->d_vcomp_n);
@@ -379,15 +385,15 @@ static bool compose_alloc(const b200_pbf_t *pb)
 	          pool_malloc(c, (void**)&pb->d_comp_dir, slots * COMP_DIR_STRIDE * sizeof(uint16_t) + 16) &&
 	          pool_malloc(c, (void**)&pb->d_vcomp_start, vslots * SELECT_COMP_CAP * sizeof(uint32_t)) &&
 	          pool_malloc(c, (void**)&pb->d_vcomp_delta, vslots * SELECT_COMP_CAP * sizeof(int32_t)) &&
-	          pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16);
+	          pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16) &&
+	          pool_malloc(c, (void**)&pb->d_qcol, (size_t)pb->n_blk * pb->p1_cap * sizeof(int32_t) + 16) &&
+	          pool_malloc(c, (void**)&pb->d_qrow, (size_t)pb->n_blk * pb->p1_cap * sizeof(uint16_t) + 16) &&
+	          pool_malloc(c, (void**)&pb->d_qcount, (size_t)pb->n_blk * sizeof(int) + 16);
 	return ok && CU_OK(cudaMemsetAsync(pb->d_comp_n, 0, slots * sizeof(int), c->st)) && CU_OK(cudaMemsetAsync(pb->d_vcomp_n, 0, vslots * sizeof(int), c->st));
 }
 
-// composites of resident blocks [b0,b1): their image bytes, row index, n1 and plane-1 view must be queued before on st
-static bool compose_queue(const b200_pbf_t *pb, int b0, int b1)
+static ComposeParams compose_params(const b200_pbf_t *pb, int b0)
 {
-	if (b1 <= b0) return true;
-	b200_ctx_t *c = pb->ctx;
 	ComposeParams K;
 	memset(&K, 0, sizeof(K));
 	K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rows_in_blk = pb->d_rows_in_blk; K.blk_list = nullptr; K.blk_first = b0;
@@ -395,20 +401,44 @@ static bool compose_queue(const b200_pbf_t *pb, int b0, int b1)
 	K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
 	K.n_grp = (pb->BS + COMP_K - 1) / COMP_K; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0; K.row_base = nullptr; K.n1_step = 2;
 	K.comp_dir = pb->d_comp_dir; K.dir_shift = pb->dir_shift; K.dir_n = pb->dir_n;
-	ComposeParams V = K;   // inverse composites of the plane-1 view rows
+	return K;
+}
+
+// forward composites (plane 0) of resident blocks [b0,b1): their image bytes, row index, n1 and sparse flags must be queued before
+static bool compose_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
+{
+	if (b1 <= b0) return true;
+	const bool ok = CU_OK(launch_compose(compose_params(pb, b0), b1 - b0, st));
+	pb->ctx->launches += 2;
+	return ok;
+}
+
+// inverse composites of the plane-1 view rows of blocks [b0,b1), then the plane-1 select over them (needs the view)
+static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
+{
+	if (b1 <= b0) return true;
+	b200_ctx_t *c = pb->ctx;
+	ComposeParams V = compose_params(pb, b0);
 	V.comp_dir = nullptr;
 	V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
 	V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
 	V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
-	const bool ok = CU_OK(launch_compose(K, b1 - b0, c->st)) && CU_OK(launch_compose(V, b1 - b0, c->st));
-	c->launches += 2;
+	SelectParams A;
+	memset(&A, 0, sizeof(A));
+	A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
+	A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = nullptr; A.blk_first = b0; A.blk_ok = pb->d_blk_sparse;
+	A.m = pb->m; A.shift = pb->shift; A.cap = pb->p1_cap;
+	A.vcomp_start = pb->d_vcomp_start; A.vcomp_delta = pb->d_vcomp_delta; A.vcomp_n = pb->d_vcomp_n;
+	A.qcol = pb->d_qcol; A.qrow = pb->d_qrow; A.qcount = pb->d_qcount; A.err = c->d_err;
+	const bool ok = CU_OK(launch_compose(V, b1 - b0, st)) && CU_OK(launch_plane1_select(A, b1 - b0, st));
+	c->launches += 3;
 	return ok;
 }
 
 static bool build_composites(const b200_pbf_t *pb)
 {
-	if (!compose_alloc(pb) || !compose_queue(pb, 0, pb->n_blk)) return false;
-	pb->comp_ready = true;
+	if (!compose_alloc(pb) || !compose_queue(pb, 0, pb->n_blk, pb->ctx->st) || !select_queue(pb, 0, pb->n_blk, pb->ctx->st)) return false;
+	pb->comp_ready = true; pb->sel_ready = true;
 	return true;
 }
 
@@ -689,16 +719,20 @@ extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t 
 		++c->launches;
 		ok = ok && queue_tiles_rowmeta(pb, b0, b1, sx) && queue_ranks_view(pb, b0, b1, sx);
 		ok = ok && CU_OK(cudaEventRecord(c->ev_idx[k], sx)) && CU_OK(cudaStreamWaitEvent(c->st, c->ev_idx[k], 0));
-		if (eager) ok = ok && compose_queue(pb, b0, b1);
+		if (eager) { // forward composites on the main stream; the plane-1 side (inverse composites + select: small grids) stays on the index stream
+			ok = ok && compose_queue(pb, b0, b1, c->st) && select_queue(pb, b0, b1, sx) &&
+			     CU_OK(cudaEventRecord(c->ev_sel[k], sx));
+		}
 		if (trace) {
 			for (int j = 0; j < 3; ++j) cudaEventCreate(&tev[k][j]);
 			cudaEventRecord(tev[k][1], sx); cudaEventRecord(tev[k][2], c->st);
 		}
 	}
 	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st_copy));
+	if (eager && !copy_only) for (int k = 0; ok && k < n_chunks; ++k) ok = CU_OK(cudaStreamWaitEvent(c->st, c->ev_sel[k], 0));
 	const double t1 = now_ms();
 	ok = ok && pbf_finish_load(pb);
-	if (ok && eager) pb->comp_ready = true;
+	if (ok && eager) { pb->comp_ready = true; pb->sel_ready = true; }
 	if (trace) {
 		fprintf(stderr, "[b200 trace] load: queued in %.2f ms, device done after %.2f ms\n", t1 - t0, now_ms() - t0);
 		for (int k = 0; k < n_chunks && !copy_only; ++k) {
@@ -1012,26 +1046,33 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		if (!pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) { // composite maps of the row groups: once per resident PBF
 			if (!build_composites(pb)) return -1;
 		}
-		// phase 1 (plane1.cu): the (column, row) pairs that carry a plane-1 bit, per block, in row order
-		SelectParams A;
-		A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
-		A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
-		A.m = pb->m; A.shift = pb->shift; A.cap = cap;
-		const bool use_comp = pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE);
-		A.vcomp_start = use_comp ? pb->d_vcomp_start : nullptr; A.vcomp_delta = use_comp ? pb->d_vcomp_delta : nullptr; A.vcomp_n = use_comp ? pb->d_vcomp_n : nullptr;
-		A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err;
-		ok = CU_OK(cudaEventRecord(c->ev[8], c->st)) && CU_OK(launch_plane1_select(A, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[9], c->st));
+		// phase 1 (plane1.cu): the (column, row) pairs that carry a plane-1 bit, per block, in row order.  They do not depend
+		// on the query: found once per resident PBF next to the composite maps (select_queue); only the testing path without
+		// composites runs the select per scan.
+		const bool use_comp = pb->comp_ready && pb->sel_ready && !(flags & B200_SCAN_NO_COMPOSE);
+		const int32_t *qcol = pb->d_qcol; const uint16_t *qrow = pb->d_qrow; const int *qcount = pb->d_qcount;
+		if (!use_comp) {
+			SelectParams A;
+			memset(&A, 0, sizeof(A));
+			A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
+			A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
+			A.m = pb->m; A.shift = pb->shift; A.cap = cap;
+			A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err;
+			ok = CU_OK(cudaEventRecord(c->ev[8], c->st)) && CU_OK(launch_plane1_select(A, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[9], c->st));
+			++c->launches;
+			qcol = (const int32_t*)c->qcol.p; qrow = (const uint16_t*)c->qrow.p; qcount = (const int*)c->qcount.p;
+		} else c->split_used = false;   // (no select time in this scan)
 		// phase 2: walk those haplotypes through plane 0 up to their row and add code 3 (other-ALT) or 2 (missing) there
 		WalkParams B = P;
-		if (pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) {
+		if (use_comp) {
 			B.comp_start = pb->d_comp_start; B.comp_delta = pb->d_comp_delta; B.comp_n = pb->d_comp_n; B.grp_tile_beg = pb->d_grp_tile_beg;
 			B.comp_dir = pb->d_comp_dir; B.dir_shift = pb->dir_shift; B.dir_n = pb->dir_n;
 		}
-		B.track = (const int32_t*)c->qcol.p; B.qrow = (const uint16_t*)c->qrow.p; B.track_stride = cap;
-		B.n_track_blk = (const int*)c->qcount.p; B.n_track = cap; B.blk_list = d_split_list;
+		B.track = qcol; B.qrow = qrow; B.track_stride = cap;
+		B.n_track_blk = qcount; B.n_track = cap; B.blk_list = d_split_list;
 		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : (use_comp ? 2 : 8);
 		ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_QUERY, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
-		c->launches += 2;
+		++c->launches;
 		if (G > 1) { // per-group plane-0 marginals for the first G-1 groups (the last one is the remainder)
 			if (!c->n0g.reserve(nr * (size_t)(G - 1) * sizeof(int32_t))) return -1;
 			MarginalParams M;

@@ -102,7 +102,9 @@ struct SelectParams {
 	const int      *p1_rows_in_blk;
 	const uint8_t  *img;          // the real image (for the block's plane-1 snapshot)
 	const uint64_t *blkoff;
-	const int      *blk_list;
+	const int      *blk_list;     // blocks handled by this launch; nullptr: blk_first + index
+	const uint8_t  *blk_ok;       // nullptr, or per block 1 = sparse (select it)
+	int blk_first;
 	int m, shift, cap;
 	const uint32_t *vcomp_start;  // inverse composites of the view rows (compose.cu, inverse = 1) [blocks][SELECT_GROUPS][SELECT_COMP_CAP], or nullptr
 	const int32_t  *vcomp_delta;

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(1024) plane1_select_kernel(const SelectParams 
 	__shared__ uint32_t warp_tot[32];
 	__shared__ int cg_off[SELECT_GROUPS + 1];                       // first piece of group g in cs/cd; cg_off[g+1]-cg_off[g] = 0: not available
 
-	const int blk = P.blk_list[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int blk = P.blk_list ? P.blk_list[blockIdx.x] : P.blk_first + (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (P.blk_ok && !P.blk_ok[blk]) { if (tid == 0) P.qcount[blk] = 0; return; }   // not a sparse block: the general walk takes it
 	const int nv = P.p1_rows_in_blk[blk];
 	const long long vb = P.p1_vbase[blk];
 	const uint64_t *ro = P.p1_rowoff + vb + blk;
@@ -115,7 +116,9 @@ __global__ void __launch_bounds__(1024) plane1_select_kernel(const SelectParams 
 	if (Q > (uint32_t)P.cap) { if (tid == 0) { atomicOr(P.err, 32); P.qcount[blk] = 0; } return; }
 	const uint8_t *S1 = P.img + P.blkoff[blk] + 1 + 4 * (size_t)P.m;   // plane-1 snapshot of the block (pbwt.c:298-300)
 	const uint32_t m = (uint32_t)P.m;
-	for (uint32_t q = tid; q < Q; q += 1024) {
+	// the block's pairs are dealt out over gridDim.y CTAs (each stages the view itself): a launch over few blocks -- one chunk
+	// of the load pipeline -- is latency bound, and this is its latency
+	for (uint32_t q = blockIdx.y * 1024u + tid; q < Q; q += 1024u * gridDim.y) {
 		int lo = 0;                                           // view row of the q-th plane-1 bit: last v with prefix[v] <= q
 		for (int len = nv; len > 1;) { const int half = len >> 1; lo += prefix[lo + half] <= q ? half : 0; len -= half; }
 		const int v = lo;
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(1024) plane1_select_kernel(const SelectParams 
 		P.qcol[(size_t)blk * P.cap + q] = (int32_t)col;
 		P.qrow[(size_t)blk * P.cap + q] = P.p1_realrow[vb + v];
 	}
-	if (tid == 0) P.qcount[blk] = (int)Q;
+	if (tid == 0 && blockIdx.y == 0) P.qcount[blk] = (int)Q;
 }
 
 cudaError_t launch_plane1_select(const SelectParams &P, int n_blk, cudaStream_t st)
@@ -148,7 +151,7 @@ cudaError_t launch_plane1_select(const SelectParams &P, int n_blk, cudaStream_t 
 	const size_t smem = sizeof(uint32_t) * (3 * SELECT_MAX_ROWS + 2) + SELECT_MAX_BYTES + 8 * SELECT_COMP_SMEM;
 	cudaError_t e = cudaFuncSetAttribute(plane1_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
-	plane1_select_kernel<<<n_blk, 1024, smem, st>>>(P);
+	plane1_select_kernel<<<dim3(n_blk, n_blk <= 32 ? 4 : 1), 1024, smem, st>>>(P);
 	return cudaGetLastError();
 }
 
