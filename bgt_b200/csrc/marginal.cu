@@ -8,7 +8,8 @@
 // behind them, both in order.  The popcount of the part that moved behind is the group's number of ones.
 // m/32 words per row instead of m rank updates.
 //
-// grid = (blocks, groups-1); one CTA of 1024 threads owns one bit vector (two buffers in shared memory).  Rows are
+// grid = (blocks, groups-1); one CTA of 1024 threads owns one bit vector (two buffers in shared memory); the next vector
+// is GATHERED through the row's inverse run table (sorted by landing position).  Rows are
 // staged in tiles like in the walk kernel (plain cooperative loads here: this kernel is a few percent of the scan).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,7 +34,7 @@ __device__ __forceinline__ uint32_t mg_ld_u32_unaligned(const uint8_t *p)
 __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalParams P)
 {
 	extern __shared__ __align__(16) uint8_t sm[];
-	const int words = (P.m + 31) / 32, wpad = (words + 3) & ~3;
+	const int words = (P.m + 31) / 32, wpad = (words + 4 + 3) & ~3;   // (+ the word a funnel shift reads past the end)
 	uint32_t *V0 = (uint32_t*)sm, *V1 = V0 + wpad;
 	uint32_t *ts = V1 + wpad;                       // [MG_RAW] run starts (per RLE byte)
 	int32_t *td = (int32_t*)(ts + MG_RAW);          // [MG_RAW] rank shift of the run
@@ -91,10 +92,19 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 				r_n1[tid] = P.n1[((size_t)blk * BS + r0 + tid) * 2];
 			}
 			__syncthreads();
-			for (int r = warp; r < nr; r += MG_NW) {     // per-byte run table of plane 0 (same arithmetic as parse_runs)
+			// per row the INVERSE run table of plane 0, one entry per RLE byte: where the entry's bits LAND (0-entries in
+			// front in order, 1-entries behind the zt zeros in order, pbwt.c:79-88) and how far back their source lies --
+			// sorted by landing position, so the next vector can be gathered word by word
+			for (int r = warp; r < nr; r += MG_NW) {
 				const uint32_t n1 = r_n1[r], len = r_len[r], off = r_off[r];
 				if (n1 == 0 || n1 == m) continue;
-				uint32_t tot = 0, ones = 0;
+				const uint32_t zt = m - n1;
+				uint32_t nz = 0;                                  // entries with bit 0
+				for (uint32_t base = 0; base < len; base += 32) {
+					const uint32_t i = base + lane;
+					nz += __popc(__ballot_sync(0xffffffffu, i < len && !(raw[off + (i < len ? i : 0)] & 1u)));
+				}
+				uint32_t tot = 0, ones = 0, kz = 0, ko = 0;
 				for (uint32_t base = 0; base < len; base += 32) {
 					const uint32_t i = base + lane;
 					const uint32_t c = i < len ? raw[off + i] : 0u;
@@ -106,7 +116,14 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 						if (lane >= d) { x += tx; y += ty; }
 					}
 					const uint32_t start = tot + x - L, ones_before = ones + y - L1;
-					if (i < len) { ts[off + i] = start; td[off + i] = b ? (int32_t)((m - n1) - (start - ones_before)) : -(int32_t)ones_before; }
+					const uint32_t zmask = __ballot_sync(0xffffffffu, i < len && !b), omask = __ballot_sync(0xffffffffu, i < len && b);
+					const uint32_t lt = (1u << lane) - 1u;
+					if (i < len) {
+						const uint32_t dst = b ? zt + ones_before : start - ones_before;
+						const uint32_t k = b ? nz + ko + __popc(omask & lt) : kz + __popc(zmask & lt);
+						ts[off + k] = dst; td[off + k] = (int32_t)(start - dst);
+					}
+					kz += __popc(zmask); ko += __popc(omask);
 					tot += __shfl_sync(0xffffffffu, x, 31);
 					ones += __shfl_sync(0xffffffffu, y, 31);
 				}
@@ -122,39 +139,89 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 			if (n1 == 0) { /* nothing moves, no ones */ }
 			else if (n1 == m) { if (tid == 0) r_cnt[r] = group_cols; }
 			else if (!big) {
-				// every thread owns a contiguous stretch of words: ONE search for the run under its first word, then the run cursor
-				// only moves forward; a word is cleared as it is consumed, so the old vector is the next row's zeroed target
+				// gather, in two passes.  (1) every thread builds a contiguous stretch of words of the NEXT vector: one search for
+				// the entry under its first bit, then the entry cursor only moves forward; a word that lies inside ONE entry --
+				// nearly all of them -- is a single funnel shift of two source words.  (2) the words that contain an entry
+				// boundary (one thread per boundary) are assembled piece by piece.  Every word is written, none needs clearing.
 				const uint32_t zt = m - n1;
+				auto word_of = [&](uint32_t w, uint32_t k) -> uint32_t {   // general case; k = last entry starting at or below 32w
+					const uint32_t pos = w * 32, lim = pos + 32 < m ? pos + 32 : m;
+					uint32_t word = 0, cur = pos;
+					while (cur < lim) {
+						const uint32_t next = k + 1 < n ? rts[k + 1] : m;
+						const uint32_t stop = next < lim ? next : lim;
+						if (stop > cur) {
+							const uint32_t src = cur + (uint32_t)rtd[k], sw = src >> 5, take = stop - cur;
+							const uint32_t v = __funnelshift_r(Vold[sw], Vold[sw + 1], src & 31u) & (take == 32 ? 0xffffffffu : ((1u << take) - 1u));
+							word |= v << (cur - pos);
+							cur = stop;
+						}
+						if (cur >= next) ++k;
+					}
+					return word;
+				};
 				const int per = (words + MG_NT - 1) / MG_NT;
 				const int w_lo = tid * per, w_hi = w_lo + per < words ? w_lo + per : words;
 				if (w_lo < w_hi) {
-					uint32_t j = 0;
+					uint32_t k = 0;
 					{
 						const uint32_t pos0 = (uint32_t)w_lo * 32;
-						for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; j += rts[j + half] <= pos0 ? half : 0u; len -= half; }
+						for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; k += rts[k + half] <= pos0 ? half : 0u; len -= half; }
 					}
-					for (int w = w_lo; w < w_hi; ++w) {
-						const uint32_t bits = Vold[w];
-						if (bits == 0) continue;                 // Vnew is zero: only 1 bits have to be moved
-						Vold[w] = 0;
-						const uint32_t pos = (uint32_t)w * 32;
-						while (j + 1 < n && rts[j + 1] <= pos) ++j;
-						for (uint32_t jj = j; jj < n; ++jj) {
-							const uint32_t s = rts[jj], e = jj + 1 < n ? rts[jj + 1] : m;
-							if (s >= pos + 32) break;
-							const uint32_t a = s > pos ? s : pos, b = e < pos + 32 ? e : pos + 32;
-							if (b <= a) continue;
-							const uint32_t piece = (bits >> (a - pos)) & (b - a == 32 ? 0xffffffffu : ((1u << (b - a)) - 1u));
-							if (piece == 0) continue;
-							const uint32_t dst = a + (uint32_t)rtd[jj], dw = dst >> 5, db = dst & 31;
-							atomicOr(&Vnew[dw], piece << db);
-							if (db && (piece >> (32 - db))) atomicOr(&Vnew[dw + 1], piece >> (32 - db));
-							if (dst >= zt) cnt += __popc(piece);
+					int w = w_lo;
+					while (w < w_hi) {
+						// words [w, we) lie entirely inside entry k: consecutive source words, one funnel shift each
+						const uint32_t next = k + 1 < n ? rts[k + 1] : m;
+						const int we = (int)(next >> 5) < w_hi ? (int)(next >> 5) : w_hi;
+						if (w < we) {
+							const uint32_t src = (uint32_t)w * 32 + (uint32_t)rtd[k], sh = src & 31u;
+							uint32_t sw = src >> 5, prev = Vold[sw];
+							for (; w < we; ++w) {
+								const uint32_t cur = Vold[++sw], word = __funnelshift_r(prev, cur, sh);
+								Vnew[w] = word;
+								if ((uint32_t)w * 32 >= zt) cnt += __popc(word);
+								prev = cur;
+							}
 						}
+						if (w < w_hi) {
+							// entry k ends in word w.  Strictly inside it (or at the ragged end of the vector): the word is left to the
+							// second pass; exactly at its start: the word belongs to the entries that follow
+							if (next & 31u) ++w;
+							while (k + 1 < n && rts[k + 1] <= (uint32_t)w * 32) ++k;
+						}
+					}
+				}
+				__syncthreads();
+				// second pass: exactly one thread per word that holds an entry boundary -- the one whose boundary is the first in it
+				for (uint32_t i = tid; i + 1 < n; i += MG_NT) {
+					const uint32_t p = rts[i + 1];
+					if (p >= m || (p & 31u) == 0) continue;           // (a boundary at a word start leaves both words whole)
+					const uint32_t w = p >> 5, pos = w * 32;
+					if (rts[i] > pos) continue;                       // an earlier boundary lies in the same word
+					uint32_t k = 0;
+					for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; k += rts[k + half] <= pos ? half : 0u; len -= half; }
+					const uint32_t word = word_of(w, k);
+					Vnew[w] = word;
+					if (pos >= zt) cnt += __popc(word);
+					else if (pos + 32 > zt) cnt += __popc(word >> (zt - pos));
+				}
+				if (tid == 0 && (m & 31u)) {                          // the ragged last word, if no boundary lies inside it
+					const uint32_t w = (uint32_t)words - 1, pos = w * 32;
+					uint32_t k = 0;
+					for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; k += rts[k + half] <= pos ? half : 0u; len -= half; }
+					bool inside = false;
+					for (uint32_t j = k + 1; j < n && rts[j] < m; ++j) if (rts[j] > pos) { inside = true; break; }
+					if (!inside) {
+						const uint32_t word = word_of(w, k);
+						Vnew[w] = word;
+						if (pos >= zt) cnt += __popc(word);
+						else if (pos + 32 > zt) cnt += __popc(word >> (zt - pos));
 					}
 				}
 			} else {
 				// a row larger than the staging buffer: stream its plane-0 RLE in pieces; every piece covers a rank range
+				for (int w = tid; w < wpad; w += MG_NT) Vnew[w] = 0;   // (this path scatters with atomicOr)
+				__syncthreads();
 				const uint8_t *rec = P.img + roff[r0];
 				const uint32_t l = mg_ld_u32_unaligned(rec + 1), zt = m - n1;
 				const uint8_t *rle = rec + 5;
@@ -218,10 +285,6 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 				if (lane == 0 && cnt) atomicAdd(&r_cnt[r], cnt);
 				__syncthreads();                             // all bits have landed in Vnew
 				uint32_t *t = Vold; Vold = Vnew; Vnew = t;
-				if (big) {                                   // (the tile path clears the old vector while reading it)
-					for (int w = tid; w < wpad; w += MG_NT) Vnew[w] = 0;
-					__syncthreads();
-				}
 			}
 		}
 		__syncthreads();
@@ -237,7 +300,7 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 
 size_t marginal_smem_bytes(int m)
 {
-	const int words = (m + 31) / 32, wpad = (words + 3) & ~3;
+	const int words = (m + 31) / 32, wpad = (words + 4 + 3) & ~3;
 	return (size_t)wpad * 8 + MG_RAW * 8 + MG_RAW + 16 + MG_TMAX * 16 + 64;
 }
 
