@@ -999,7 +999,6 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	// ---- launch
 	const int b_first = (int)(row_beg >> pb->shift) - pb->blk0;
 	const int b_last = (int)((row_beg + n_rows - 1) >> pb->shift) - pb->blk0;
-	const int n_blk = b_last - b_first + 1;
 	WalkParams P;
 	memset(&P, 0, sizeof(P));
 	P.img = pb->d_img; P.rowoff = pb->d_rowoff; P.n1 = pb->d_n1; P.tiles = pb->d_tiles; P.blk_tile_beg = pb->d_blk_tile_beg; P.blk_tile_end = pb->d_blk_tile_end;
