@@ -209,6 +209,22 @@ def test_row_shards_resident(b200, ctx, oracle):
         pb.close()
 
 
+def test_open_from_a_file_path(b200, ctx, oracle, tmp_path):
+    """b200_pbf_open (pbf_open_r's file-name form, pbwt.c:221-262): whole file and a row range; a missing file fails."""
+    mat = haplo_matrix(500, 64, 9)
+    fn = tmp_path / "x.pbf"
+    fn.write_bytes(oracle.encode_pbf(mat, shift=6))
+    for beg, end in ((0, -1), (130, 400)):
+        pb = b200.Pbf.open(ctx, str(fn), beg, end)
+        q = b200.Query.columns(ctx, pb)
+        lo, hi = (0, 500) if end < 0 else (beg, end)
+        got = b200.scan(ctx, pb, q, lo, hi - lo, hap_bytes=True)
+        assert ((got["hap_bytes"][0] | got["hap_bytes"][1] << 1) == mat[lo:hi]).all()
+        q.close(); pb.close()
+    with pytest.raises(b200.B200Error):
+        b200.Pbf.open(ctx, str(tmp_path / "missing.pbf"))
+
+
 def test_noncanonical_rle_streams(b200, ctx, oracle):
     m = 40
     rows = [(bytes([5 << 1, 1, 3 << 1, 12 << 1 | 1, 32, (16 + 1) << 1, 4 << 1]), bytes([(16 + 2) << 1, 8 << 1 | 1])),
