@@ -66,12 +66,23 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	if (tid == 0) { s_fail = 0; s_n = 0; }
 	__syncthreads();
 
+	// The records of the group lie back to back in the image: stage them once in the second buffer (idle until level 1)
+	// so both passes of level 0 read shared memory.
+	const uint64_t g_beg = roff[r_lo] & ~(uint64_t)3, g_end = roff[r_lo + COMP_K];
+	const bool staged = g_end - g_beg + 8 <= (uint64_t)CPX * 8;
+	if (staged) {
+		const uint32_t nw = (uint32_t)((g_end - g_beg + 3) >> 2) + 1;        // one word of slack for the funnel-shift read
+		const uint32_t *src = (const uint32_t*)(P.img + g_beg);
+		for (uint32_t i = tid; i < nw; i += CP_NT) S1[i] = src[i];           // the images end with 64 bytes of padding
+		__syncthreads();
+	}
+
 	// ---- level 0: one map per row, in the order they are applied (inverse composite: last row first).  Warps take
 	// rows round-robin; run counts first (to place the maps), then the tables.  A constant row is the identity.
 	for (int pass = 0; pass < 2; ++pass) {
 		for (int j = warp; j < COMP_K; j += CP_NW) {
 			const int k_map = P.inverse ? COMP_K - 1 - j : j;
-			const uint8_t *rec = P.img + roff[r_lo + j];
+			const uint8_t *rec = staged ? (const uint8_t*)S1 + (roff[r_lo + j] - g_beg) : P.img + roff[r_lo + j];
 			const uint32_t l = cp_ld_u32_unaligned(rec + P.rle_off - 4);
 			const uint8_t *rle = rec + P.rle_off;
 			const uint32_t n1 = P.n1[(size_t)(rbase + r_lo + j) * P.n1_step + P.n1_plane];

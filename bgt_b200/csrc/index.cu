@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
 		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
 		if (all_ok && total == (uint32_t)rows) {
 			// ---- the pieces are the chain: copy them to their places (coalesced, all lanes)
+			__syncwarp();                               // the other lanes' scratch columns are read below
 			for (int l = 0; l < IX_K; ++l) {
 				const uint32_t c = __shfl_sync(0xffffffffu, x, l), b0 = __shfl_sync(0xffffffffu, incl - x, l);
 				const uint64_t *src = P.scratch + ((size_t)blk * IX_K + l) * (size_t)(BS + 1);
