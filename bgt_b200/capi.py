@@ -330,7 +330,7 @@ class Query:
             self.h = None
 
 
-def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, hap_bytes=False, out=None, cols_per_thread=0, no_split=False, no_compose=False):
+def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, hap_bytes=False, out=None, cols_per_thread=0, no_split=False, no_compose=False, no_segments=False):
     """b200_scan with host outputs.  Returns dict(n, counts, passed, hap_bits, hap_bytes, totals)."""
     if n_rows is None:
         n_rows = pbf.row_end - row_beg
@@ -347,7 +347,7 @@ def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, h
     so = ScanOut()
     so.counts = _ptr(res["counts"]) if counts else None
     so.passed = _ptr(res["passed"])
-    flags = (SCAN_COUNTS if counts else 0) | (int(cols_per_thread) << 8) | (SCAN_NO_SPLIT if no_split else 0) | (0x40 if no_compose else 0)
+    flags = (SCAN_COUNTS if counts else 0) | (int(cols_per_thread) << 8) | (SCAN_NO_SPLIT if no_split else 0) | (0x40 if no_compose else 0) | (0x80 if no_segments else 0)
     if hap_bits:
         flags |= SCAN_HAP_BITS
         so.hap_bits[0], so.hap_bits[1] = _ptr(res["hap_bits"][0]), _ptr(res["hap_bits"][1])

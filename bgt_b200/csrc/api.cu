@@ -86,7 +86,7 @@ struct b200_ctx_s {
 	int64_t launches = 0;
 	int *d_err = nullptr;
 	unsigned long long *d_acc = nullptr; // [0..3] totals, [4] bad rows
-	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], qcol, qrow, qcount, blk_lists, blk_split, n0g;
+	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], qcol, qrow, qcount, blk_lists, blk_split, n0g, vseg, seg_ok;
 	int sm_count = 148;
 	bool split_used = false, marginal_used = false;
 };
@@ -250,7 +250,7 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	for (int i = 0; i < N_IDX_STREAMS; ++i) if (c->st_idx[i]) cudaStreamSynchronize(c->st_idx[i]);
 	c->cnt_raw.release(); c->counts.release(); c->pass.release();
 	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
-	c->n0g.release(); c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
+	c->n0g.release(); c->vseg.release(); c->seg_ok.release(); c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
 	for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
 	if (c->ev_zero) cudaEventDestroy(c->ev_zero);
@@ -1075,6 +1075,21 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		if (G > 1) { // per-group plane-0 marginals for the first G-1 groups (the last one is the remainder)
 			if (!c->n0g.reserve(nr * (size_t)(G - 1) * sizeof(int32_t))) return -1;
 			MarginalParams M;
+			memset(&M, 0, sizeof(M));
+			M.n_seg = 1;
+			if (use_comp && !(flags & B200_SCAN_NO_SEGMENTS)) { // segments of 8+ row groups, as many as 512 MB of segment vectors allow
+				const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
+				int seg_groups = 8;
+				const size_t per_seg = (size_t)n_split * (size_t)(G - 1) * marginal_seg_words(pb->m) * sizeof(uint32_t);
+				while (seg_groups < n_grp && per_seg * (size_t)((n_grp + seg_groups - 1) / seg_groups) > ((size_t)512 << 20)) seg_groups *= 2;
+				const int n_seg = (n_grp + seg_groups - 1) / seg_groups;
+				if (n_seg > 1) {
+					if (!c->vseg.reserve(per_seg * (size_t)n_seg) || !c->seg_ok.reserve((size_t)n_split * (size_t)(G - 1) + 16)) return -1;
+					M.comp_start = pb->d_comp_start; M.comp_delta = pb->d_comp_delta; M.comp_n = pb->d_comp_n;
+					M.n_grp = n_grp; M.seg_groups = seg_groups; M.n_seg = n_seg; M.vseg = (uint32_t*)c->vseg.p; M.seg_ok = (uint8_t*)c->seg_ok.p;
+					++c->launches;
+				}
+			}
 			M.img = pb->d_img; M.rowoff = pb->d_rowoff; M.n1 = pb->d_n1; M.blkoff = pb->d_blkoff; M.rows_in_blk = pb->d_rows_in_blk;
 			M.blk_list = d_split_list; M.tgrp = q->d_tgrp; M.n0g = (int32_t*)c->n0g.p; M.m = pb->m; M.shift = pb->shift; M.n_vec = G - 1;
 			M.blk_row0 = P.blk_row0; M.row_lo = row_beg; M.row_hi = row_beg + n_rows;

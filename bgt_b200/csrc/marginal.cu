@@ -17,7 +17,8 @@
 
 namespace b200 {
 
-constexpr int MG_NT = 1024, MG_NW = MG_NT / 32, MG_RAW = 4096, MG_TMAX = 32;
+constexpr int MG_NT = 1024, MG_RAW = 4096, MG_TMAX = 32;      // one CTA per block
+constexpr int MG_NT_SEG = 256, MG_RAW_SEG = 2048;              // one CTA per segment of a block
 
 __device__ __forceinline__ uint32_t mg_rle_len(uint32_t c) { const uint32_t v = c >> 1; return (v & 15u) << ((v >> 4) << 2); }
 
@@ -31,8 +32,28 @@ __device__ __forceinline__ uint32_t mg_ld_u32_unaligned(const uint8_t *p)
 	return __funnelshift_r(lo, w[1], sh);
 }
 
-__global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalParams P)
+// the block's start vector: bit i = group of the column at rank i under the plane-0 snapshot (pbwt.c:298-300)
+template<int NT>
+__device__ __forceinline__ void mg_snapshot_vector(const MarginalParams &P, int blk, int g, int wpad, uint32_t *V0, uint32_t *V1)
 {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t m = (uint32_t)P.m;
+	const uint8_t *S0 = P.img + P.blkoff[blk] + 1;
+	for (int w = warp; w < wpad; w += NT / 32) {
+		const uint32_t i = (uint32_t)w * 32 + lane;
+		bool in = false;
+		if (i < m) { const uint32_t col = mg_ld_u32_unaligned(S0 + 4 * (size_t)i); in = col < m && P.tgrp[col] == g; }
+		const uint32_t bits = __ballot_sync(0xffffffffu, in);
+		if (lane == 0) { V0[w] = bits; V1[w] = 0; }
+	}
+}
+
+// Rows [seg * seg_rows, (seg+1) * seg_rows) of one block and one group: NT threads, RAW bytes of staged records.  With
+// one segment per block the vector starts at the snapshot; otherwise at the segment vector left by the seed kernel.
+template<int NT, int RAW>
+__global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams P)
+{
+	constexpr int MG_NT = NT, MG_NW = NT / 32, MG_RAW = RAW;
 	extern __shared__ __align__(16) uint8_t sm[];
 	const int words = (P.m + 31) / 32, wpad = (words + 4 + 3) & ~3;   // (+ the word a funnel shift reads past the end)
 	uint32_t *V0 = (uint32_t*)sm, *V1 = V0 + wpad;
@@ -44,22 +65,27 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 	int32_t *r_cnt = (int32_t*)(r_n1 + MG_TMAX);    // [MG_TMAX] ones of the group per row
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int blk = P.blk_list[blockIdx.x], g = blockIdx.y;
+	const int bi = (int)blockIdx.x / P.n_seg, seg = (int)blockIdx.x % P.n_seg;
+	const int blk = P.blk_list[bi], g = blockIdx.y;
 	const int BS = 1 << P.shift;
 	const uint32_t m = (uint32_t)P.m;
 	const uint64_t *roff = P.rowoff + (size_t)blk * (BS + 1);
 	const long long blk_row = P.blk_row0 + ((long long)blk << P.shift);
 	int rows = P.rows_in_blk[blk];
 	if (blk_row + rows > P.row_hi) rows = (int)(P.row_hi - blk_row);
+	int row_a = 0;
+	if (P.n_seg > 1) {
+		const int seg_rows = P.seg_groups * COMP_K;
+		if (P.seg_ok[(size_t)bi * P.n_vec + g]) { row_a = seg * seg_rows; if (row_a + seg_rows < rows) rows = row_a + seg_rows; }
+		else if (seg > 0) return;                        // no segment vectors for this block: segment 0 takes all its rows
+		if (row_a >= rows || blk_row + rows <= P.row_lo) return;
+	}
 
-	// ---- the block's start vector: bit i = group of the column at rank i under the plane-0 snapshot (pbwt.c:298-300)
-	const uint8_t *S0 = P.img + P.blkoff[blk] + 1;
-	for (int w = warp; w < wpad; w += MG_NW) {
-		const uint32_t i = (uint32_t)w * 32 + lane;
-		bool in = false;
-		if (i < m) { const uint32_t col = mg_ld_u32_unaligned(S0 + 4 * (size_t)i); in = col < m && P.tgrp[col] == g; }
-		const uint32_t bits = __ballot_sync(0xffffffffu, in);
-		if (lane == 0) { V0[w] = bits; V1[w] = 0; }
+	// ---- the start vector
+	if (row_a == 0) mg_snapshot_vector<NT>(P, blk, g, wpad, V0, V1);
+	else {
+		const uint32_t *src = P.vseg + (((size_t)bi * P.n_vec + g) * P.n_seg + seg) * (size_t)wpad;
+		for (int w = tid; w < wpad; w += MG_NT) { V0[w] = src[w]; V1[w] = 0; }
 	}
 	__syncthreads();
 	int total = 0;                                   // columns of the group (for all-ones rows)
@@ -75,7 +101,7 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 	const int group_cols = s_total;
 
 	uint32_t *Vold = V0, *Vnew = V1;                 // Vnew is all zero here
-	for (int r0 = 0; r0 < rows;) {
+	for (int r0 = row_a; r0 < rows;) {
 		// ---- tile: as many rows as fit MG_RAW bytes (a single larger row is staged piecewise below)
 		int nr = 1;
 		while (r0 + nr < rows && nr < MG_TMAX && roff[r0 + nr + 1] - roff[r0] <= (uint64_t)MG_RAW) ++nr;
@@ -298,6 +324,101 @@ __global__ void __launch_bounds__(MG_NT) pbwt_marginal_kernel(const MarginalPara
 	}
 }
 
+// Segment vectors: the block's start vector pushed through the composite maps of its row groups (compose.cu), stored in
+// front of every segment of seg_groups groups, so that the segments of a block can be walked row by row side by side.
+// A composite is a list of pieces (start, translation) ordered by start: every thread moves a contiguous stretch of
+// source words, piece by piece, with shared-memory atomicOr (the pieces of the next group are fetched meanwhile).
+constexpr int MS_NT = 1024;
+__global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const MarginalParams P)
+{
+	extern __shared__ __align__(16) uint8_t sm[];
+	const int words = (P.m + 31) / 32, wpad = (words + 4 + 3) & ~3;
+	uint32_t *V0 = (uint32_t*)sm, *V1 = V0 + wpad;
+	uint32_t *cs = V1 + wpad;                        // [COMP_CAP] piece starts
+	int32_t *cd = (int32_t*)(cs + COMP_CAP);         // [COMP_CAP] translations
+	__shared__ int s_bad;
+	constexpr int PER = COMP_CAP / MS_NT;
+	const int tid = threadIdx.x;
+	const int bi = blockIdx.x, blk = P.blk_list[bi], g = blockIdx.y;
+	const uint32_t m = (uint32_t)P.m;
+	const long long blk_row = P.blk_row0 + ((long long)blk << P.shift);
+	int rows = P.rows_in_blk[blk];
+	if (blk_row + rows > P.row_hi) rows = (int)(P.row_hi - blk_row);
+	const int seg_rows = P.seg_groups * COMP_K;
+	const int n_seg_used = rows > 0 ? (rows + seg_rows - 1) / seg_rows : 0;
+	const int g_end = n_seg_used > 1 ? (n_seg_used - 1) * P.seg_groups : 0;   // groups in front of the last segment start
+	const size_t slot0 = (size_t)blk * P.n_grp;
+	if (tid == 0) s_bad = 0;
+	__syncthreads();
+	for (int i = tid; i < g_end; i += MS_NT) if (P.comp_n[slot0 + i] <= 0 || P.comp_n[slot0 + i] > COMP_CAP) s_bad = 1;
+	__syncthreads();
+	if (s_bad || g_end == 0) { if (tid == 0) P.seg_ok[(size_t)bi * P.n_vec + g] = s_bad ? 0 : 1; return; }
+	if (tid == 0) P.seg_ok[(size_t)bi * P.n_vec + g] = 1;
+	mg_snapshot_vector<MS_NT>(P, blk, g, wpad, V0, V1);
+	uint32_t *Vold = V0, *Vnew = V1;
+	uint32_t ps[PER]; int32_t pd[PER]; int np_next = 0;
+	auto fetch = [&](int gg) {
+		np_next = P.comp_n[slot0 + gg];
+		const uint32_t *s = P.comp_start + (slot0 + gg) * COMP_CAP; const int32_t *d = P.comp_delta + (slot0 + gg) * COMP_CAP;
+		#pragma unroll
+		for (int j = 0; j < PER; ++j) { const int i = tid + j * MS_NT; if (i < np_next) { ps[j] = s[i]; pd[j] = d[i]; } }
+	};
+	fetch(0);
+	uint32_t *out = P.vseg + ((size_t)bi * P.n_vec + g) * P.n_seg * (size_t)wpad;
+	const int per = (words + MS_NT - 1) / MS_NT;
+	const int w_lo = tid * per, w_hi = w_lo + per < words ? w_lo + per : words;
+	for (int gg = 0; gg < g_end; ++gg) {
+		const uint32_t np = (uint32_t)np_next;
+		#pragma unroll
+		for (int j = 0; j < PER; ++j) { const uint32_t i = tid + j * MS_NT; if (i < np) { cs[i] = ps[j]; cd[i] = pd[j]; } }
+		for (int w = tid; w < wpad; w += MS_NT) Vnew[w] = 0;
+		if (gg + 1 < g_end) fetch(gg + 1);
+		__syncthreads();
+		if (w_lo < w_hi) {
+			uint32_t k = 0;
+			{
+				const uint32_t pos0 = (uint32_t)w_lo * 32;
+				for (uint32_t len = np; len > 1;) { const uint32_t half = len >> 1; k += cs[k + half] <= pos0 ? half : 0u; len -= half; }
+			}
+			for (int w = w_lo; w < w_hi; ++w) {
+				const uint32_t bits = Vold[w], pos = (uint32_t)w * 32, lim = pos + 32 < m ? pos + 32 : m;
+				uint32_t cur = pos;
+				while (cur < lim) {
+					const uint32_t next = k + 1 < np ? cs[k + 1] : m;
+					const uint32_t stop = next < lim ? next : lim;
+					if (stop > cur) {
+						const uint32_t take = stop - cur;
+						const uint32_t piece = (bits >> (cur - pos)) & (take == 32 ? 0xffffffffu : ((1u << take) - 1u));
+						if (piece) {
+							const uint32_t dst = cur + (uint32_t)cd[k], dw = dst >> 5, db = dst & 31u;
+							if (dst < m) {                                  // (a well-formed map never leaves [0, m))
+								atomicOr(&Vnew[dw], piece << db);
+								if (db && (piece >> (32 - db))) atomicOr(&Vnew[dw + 1], piece >> (32 - db));
+							}
+						}
+						cur = stop;
+					}
+					if (cur >= next) ++k;
+				}
+			}
+		}
+		__syncthreads();
+		uint32_t *t = Vold; Vold = Vnew; Vnew = t;
+		if ((gg + 1) % P.seg_groups == 0) {
+			uint32_t *dst = out + (size_t)((gg + 1) / P.seg_groups) * wpad;
+			for (int w = tid; w < wpad; w += MS_NT) dst[w] = w < words ? Vold[w] : 0u;
+		}
+	}
+}
+
+static size_t marginal_smem_raw(int m, int raw)
+{
+	const int words = (m + 31) / 32, wpad = (words + 4 + 3) & ~3;
+	return (size_t)wpad * 8 + (size_t)raw * 8 + raw + 16 + MG_TMAX * 16 + 64;
+}
+
+size_t marginal_seg_words(int m) { return (size_t)(((m + 31) / 32 + 4 + 3) & ~3); }
+
 size_t marginal_smem_bytes(int m)
 {
 	const int words = (m + 31) / 32, wpad = (words + 4 + 3) & ~3;
@@ -307,11 +428,25 @@ size_t marginal_smem_bytes(int m)
 cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st)
 {
 	if (n_blk <= 0 || P.n_vec <= 0) return cudaSuccess;
+	cudaError_t e;
+	if (P.n_seg > 1) { // segment vectors first, then every segment on its own (smaller CTAs, three to an SM)
+		const int words = (P.m + 31) / 32, wpad = (words + 4 + 3) & ~3;
+		const size_t smem_a = (size_t)wpad * 8 + (size_t)COMP_CAP * 8;
+		e = cudaFuncSetAttribute(pbwt_marginal_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+		if (e != cudaSuccess) return e;
+		pbwt_marginal_seed_kernel<<<dim3(n_blk, P.n_vec, 1), MS_NT, smem_a, st>>>(P);
+		if ((e = cudaGetLastError()) != cudaSuccess) return e;
+		const size_t smem_b = marginal_smem_raw(P.m, MG_RAW_SEG);
+		e = cudaFuncSetAttribute(pbwt_marginal_kernel<MG_NT_SEG, MG_RAW_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+		if (e != cudaSuccess) return e;
+		pbwt_marginal_kernel<MG_NT_SEG, MG_RAW_SEG><<<dim3(n_blk * P.n_seg, P.n_vec, 1), MG_NT_SEG, smem_b, st>>>(P);
+		return cudaGetLastError();
+	}
 	const size_t smem = marginal_smem_bytes(P.m);
-	cudaError_t e = cudaFuncSetAttribute(pbwt_marginal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	e = cudaFuncSetAttribute(pbwt_marginal_kernel<MG_NT, MG_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	dim3 grid(n_blk, P.n_vec, 1);
-	pbwt_marginal_kernel<<<grid, MG_NT, smem, st>>>(P);
+	pbwt_marginal_kernel<MG_NT, MG_RAW><<<grid, MG_NT, smem, st>>>(P);
 	return cudaGetLastError();
 }
 

@@ -165,8 +165,15 @@ struct MarginalParams {
 	int32_t        *n0g;       // out [rows out][n_vec]
 	int m, shift, n_vec;
 	long long blk_row0, row_lo, row_hi;
+	// segmented run (n_seg > 1): the blocks' vectors are first pushed through the composite maps of the row groups and stored
+	// in front of every segment of seg_groups groups (vseg [launch block][vector][segment][marginal_seg_words(m)]); every
+	// segment is then walked by its own CTA.  seg_ok [launch block][vector] = 0: a composite was missing, one CTA takes the block
+	const uint32_t *comp_start; const int32_t *comp_delta; const int *comp_n;
+	int n_grp, seg_groups, n_seg;
+	uint32_t *vseg; uint8_t *seg_ok;
 };
 size_t marginal_smem_bytes(int m);
+size_t marginal_seg_words(int m);
 cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st);
 
 // split scan: rows of blocks flagged in blk_split take #ALT of group g from the plane-0 marginal -- n0g[row][g] for the

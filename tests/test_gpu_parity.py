@@ -307,7 +307,7 @@ def test_synth_generator_is_truthful_and_canonical(b200, ctx, oracle):
         q.close(); pb.close(); pb2.close()
 
 
-@pytest.mark.parametrize("case", ["sparse", "dense", "mixed", "allones", "wide", "noisy0", "deep"])
+@pytest.mark.parametrize("case", ["sparse", "dense", "mixed", "allones", "wide", "noisy0", "deep", "noisydeep"])
 def test_split_scan_equals_general_and_oracle(b200, ctx, oracle, case):
     """Count-only full-cohort scans take the split path (plane-0 marginal + walk of the columns that carry plane-1 codes);
     it must agree with the general walk and with the oracle whatever the density of plane 1."""
@@ -328,13 +328,20 @@ def test_split_scan_equals_general_and_oracle(b200, ctx, oracle, case):
         mat = (rng.random((400, 4400)) < 0.5).astype(np.uint8)
         for k in range(0, 400, 7):
             mat[k, rng.integers(0, 4400, size=5)] = 2 + (k & 1)
+    elif case == "noisydeep":
+        # the same with 32 row groups per checkpoint block: the segmented marginals find no composite maps and hand the
+        # block to a single CTA; the quiet stretch in the second block has them
+        mat = (rng.random((1700, 1300)) < 0.5).astype(np.uint8)
+        mat[1024:1700] = haplo_matrix(676, 1300, 13)
+        for k in range(0, 1700, 31):
+            mat[k, rng.integers(0, 1300, size=3)] = 2 + (k & 1)
     elif case == "deep":
         # long blocks (many 32-row groups per checkpoint) with plane-1 codes on most rows: exercises the composite
         # maps of both planes and the per-group fallbacks at block ends
         mat = haplo_matrix(2300, 1200, 11, p_missing_row=0.45, p_multi_row=0.45)
     else:
         mat = haplo_matrix(70, 70002, 10, p_missing_row=0.3, p_multi_row=0.3)
-    shift = 4 if case == "wide" else 11 if case == "deep" else 8 if case == "noisy0" else 6
+    shift = 4 if case == "wide" else 11 if case == "deep" else 10 if case == "noisydeep" else 8 if case == "noisy0" else 6
     pbf = oracle.encode_pbf(mat, shift=shift)
     n = mat.shape[0]
     want = oracle.Pbf(pbf).scan(0, n, flt="AC>0")
@@ -356,11 +363,13 @@ def test_split_scan_equals_general_and_oracle(b200, ctx, oracle, case):
         flt = "AC1/AN1>0.1&&AC2==0"
         wantg = oracle.Pbf(pbf).scan(0, n, group=grp, n_groups=G, flt=flt)
         qg = b200.Query(ctx, pb, group=grp, n_groups=G, flt=flt)
-        for kw in (dict(), dict(no_split=True)):
+        for kw in (dict(), dict(no_split=True), dict(no_segments=True)):
             got = b200.scan(ctx, pb, qg, 0, n, **kw)
             assert (got["counts"] == wantg["counts"]).all(), (case, G, kw)
             assert (got["passed"] == wantg["passed"]).all()
-        got = b200.scan(ctx, pb, qg, 41, min(150, n - 41))
-        assert (got["counts"] == wantg["counts"][41:41 + min(150, n - 41)]).all(), (case, G)
+        for beg, cnt in ((41, 150), (n // 2 + 3, n // 2 - 20), (n - 9, 9)):
+            cnt = min(cnt, n - beg)
+            got = b200.scan(ctx, pb, qg, beg, cnt)
+            assert (got["counts"] == wantg["counts"][beg:beg + cnt]).all(), (case, G, beg)
         qg.close()
     pb.close()
