@@ -13,6 +13,7 @@
 // staged in tiles like in the walk kernel (plain cooperative loads here: this kernel is a few percent of the scan).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "pbwt_kernels.cuh"
 
 namespace b200 {
@@ -61,8 +62,12 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 	int32_t *td = (int32_t*)(ts + MG_RAW);          // [MG_RAW] rank shift of the run
 	uint8_t *raw = (uint8_t*)(td + MG_RAW);         // [MG_RAW + 16]
 	uint32_t *r_off = (uint32_t*)(raw + MG_RAW + 16); // [MG_TMAX] offset of the plane-0 RLE of the tile's rows in raw
-	uint32_t *r_len = r_off + MG_TMAX, *r_n1 = r_len + MG_TMAX;
+	uint32_t *r_len = r_off + MG_TMAX, *r_n1 = r_len + MG_TMAX;   // entries of the row's table; ones of the row
 	int32_t *r_cnt = (int32_t*)(r_n1 + MG_TMAX);    // [MG_TMAX] ones of the group per row
+	uint32_t *r_nz = (uint32_t*)(r_cnt + MG_TMAX);  // [MG_TMAX] entries that are 0-runs (they come first)
+	uint32_t *r_nch = r_nz + MG_TMAX;               // [MG_TMAX] 32-word chunks of whole words over all entries
+	uint16_t *cst = (uint16_t*)(r_nch + MG_TMAX);   // [MG_RAW] per entry: chunks in front of it
+	__shared__ int s_nr;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int bi = (int)blockIdx.x / P.n_seg, seg = (int)blockIdx.x % P.n_seg;
@@ -103,9 +108,15 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 	uint32_t *Vold = V0, *Vnew = V1;                 // Vnew is all zero here
 	for (int r0 = row_a; r0 < rows;) {
 		// ---- tile: as many rows as fit MG_RAW bytes (a single larger row is staged piecewise below)
-		int nr = 1;
-		while (r0 + nr < rows && nr < MG_TMAX && roff[r0 + nr + 1] - roff[r0] <= (uint64_t)MG_RAW) ++nr;
 		const uint64_t t_beg = roff[r0];
+		if (warp == 0) { // (MG_TMAX == 32: one lane per candidate row)
+			const bool fits = r0 + lane < rows && roff[r0 + lane + 1] - t_beg <= (uint64_t)MG_RAW;
+			const uint32_t no = ~__ballot_sync(0xffffffffu, fits);
+			const int k = no ? __ffs(no) - 1 : 32;
+			if (lane == 0) s_nr = k > 0 ? k : 1;
+		}
+		__syncthreads();
+		const int nr = s_nr;
 		const bool big = roff[r0 + 1] - t_beg > (uint64_t)MG_RAW;
 		if (!big) {
 			const uint32_t nbytes = (uint32_t)(roff[r0 + nr] - t_beg);
@@ -118,19 +129,28 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 				r_n1[tid] = P.n1[((size_t)blk * BS + r0 + tid) * 2];
 			}
 			__syncthreads();
-			// per row the INVERSE run table of plane 0, one entry per RLE byte: where the entry's bits LAND (0-entries in
-			// front in order, 1-entries behind the zt zeros in order, pbwt.c:79-88) and how far back their source lies --
-			// sorted by landing position, so the next vector can be gathered word by word
+			// per row the INVERSE run table of plane 0, one entry per run (RLE bytes of the same symbol merged): where the run's
+			// bits LAND (0-runs in front in order, 1-runs behind the zt zeros in order, pbwt.c:79-88) and how far back their
+			// source lies -- sorted by landing position, so the next vector can be gathered word by word
 			for (int r = warp; r < nr; r += MG_NW) {
 				const uint32_t n1 = r_n1[r], len = r_len[r], off = r_off[r];
 				if (n1 == 0 || n1 == m) continue;
 				const uint32_t zt = m - n1;
-				uint32_t nz = 0;                                  // entries with bit 0
+				const uint32_t lt = (1u << lane) - 1u;
+				uint32_t nzr = 0, nrun = 0, prev_bit = 2;        // 0-runs, runs
 				for (uint32_t base = 0; base < len; base += 32) {
 					const uint32_t i = base + lane;
-					nz += __popc(__ballot_sync(0xffffffffu, i < len && !(raw[off + (i < len ? i : 0)] & 1u)));
+					const uint32_t c = i < len ? raw[off + i] : 0u;
+					const uint32_t L = mg_rle_len(c), b = c & 1u;
+					const uint32_t valid = __ballot_sync(0xffffffffu, L > 0), bitm = __ballot_sync(0xffffffffu, b != 0);
+					const uint32_t below = valid & lt;
+					const uint32_t pb = below ? (bitm >> (31 - __clz(below))) & 1u : prev_bit;
+					const uint32_t sm_ = __ballot_sync(0xffffffffu, L > 0 && pb != b);
+					nrun += __popc(sm_); nzr += __popc(sm_ & ~bitm);
+					if (valid) prev_bit = (bitm >> (31 - __clz(valid))) & 1u;
 				}
 				uint32_t tot = 0, ones = 0, kz = 0, ko = 0;
+				prev_bit = 2;
 				for (uint32_t base = 0; base < len; base += 32) {
 					const uint32_t i = base + lane;
 					const uint32_t c = i < len ? raw[off + i] : 0u;
@@ -142,17 +162,40 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 						if (lane >= d) { x += tx; y += ty; }
 					}
 					const uint32_t start = tot + x - L, ones_before = ones + y - L1;
-					const uint32_t zmask = __ballot_sync(0xffffffffu, i < len && !b), omask = __ballot_sync(0xffffffffu, i < len && b);
-					const uint32_t lt = (1u << lane) - 1u;
-					if (i < len) {
+					const uint32_t valid = __ballot_sync(0xffffffffu, L > 0), bitm = __ballot_sync(0xffffffffu, b != 0);
+					const uint32_t below = valid & lt;
+					const uint32_t pb = below ? (bitm >> (31 - __clz(below))) & 1u : prev_bit;
+					const bool is_start = L > 0 && pb != b;
+					const uint32_t sm_ = __ballot_sync(0xffffffffu, is_start);
+					const uint32_t zmask = sm_ & ~bitm, omask = sm_ & bitm;
+					if (is_start) {
 						const uint32_t dst = b ? zt + ones_before : start - ones_before;
-						const uint32_t k = b ? nz + ko + __popc(omask & lt) : kz + __popc(zmask & lt);
+						const uint32_t k = b ? nzr + ko + __popc(omask & lt) : kz + __popc(zmask & lt);
 						ts[off + k] = dst; td[off + k] = (int32_t)(start - dst);
 					}
 					kz += __popc(zmask); ko += __popc(omask);
+					if (valid) prev_bit = (bitm >> (31 - __clz(valid))) & 1u;
 					tot += __shfl_sync(0xffffffffu, x, 31);
 					ones += __shfl_sync(0xffffffffu, y, 31);
 				}
+				__syncwarp();
+				// whole words of every entry, in chunks of 32 (one warp step each), as a running count in front of the entry
+				uint32_t carry = 0;
+				for (uint32_t base = 0; base < nrun; base += 32) {
+					const uint32_t k = base + lane;
+					uint32_t ch = 0;
+					if (k < nrun) {
+						const uint32_t nxt = k + 1 < nrun ? ts[off + k + 1] : m;
+						const uint32_t wa = (ts[off + k] + 31u) >> 5, we = nxt >> 5;
+						ch = we > wa ? (we - wa + 31u) >> 5 : 0u;
+					}
+					uint32_t x = ch;
+					#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) { const uint32_t tx = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += tx; }
+					if (k < nrun) cst[off + k] = (uint16_t)(carry + x - ch);
+					carry += __shfl_sync(0xffffffffu, x, 31);
+				}
+				if (lane == 0) { r_len[r] = nrun; r_nz[r] = nzr; r_nch[r] = carry; }
 			}
 			__syncthreads();
 		}
@@ -165,10 +208,10 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 			if (n1 == 0) { /* nothing moves, no ones */ }
 			else if (n1 == m) { if (tid == 0) r_cnt[r] = group_cols; }
 			else if (!big) {
-				// gather, in two passes.  (1) every thread builds a contiguous stretch of words of the NEXT vector: one search for
-				// the entry under its first bit, then the entry cursor only moves forward; a word that lies inside ONE entry --
-				// nearly all of them -- is a single funnel shift of two source words.  (2) the words that contain an entry
-				// boundary (one thread per boundary) are assembled piece by piece.  Every word is written, none needs clearing.
+				// gather, in two passes.  (1) the words that lie inside ONE entry -- nearly all of them -- are a single funnel shift
+				// of two source words: they are dealt to the warps in chunks of 32 consecutive words of one entry (warp-uniform
+				// entry cursor, one word per lane).  (2) the words that contain an entry boundary (one thread per boundary) are
+				// assembled piece by piece.  Every word is written, none needs clearing.
 				const uint32_t zt = m - n1;
 				auto word_of = [&](uint32_t w, uint32_t k) -> uint32_t {   // general case; k = last entry starting at or below 32w
 					const uint32_t pos = w * 32, lim = pos + 32 < m ? pos + 32 : m;
@@ -186,34 +229,34 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 					}
 					return word;
 				};
-				const int per = (words + MG_NT - 1) / MG_NT;
-				const int w_lo = tid * per, w_hi = w_lo + per < words ? w_lo + per : words;
-				if (w_lo < w_hi) {
-					uint32_t k = 0;
-					{
-						const uint32_t pos0 = (uint32_t)w_lo * 32;
-						for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; k += rts[k + half] <= pos0 ? half : 0u; len -= half; }
-					}
-					int w = w_lo;
-					while (w < w_hi) {
-						// words [w, we) lie entirely inside entry k: consecutive source words, one funnel shift each
-						const uint32_t next = k + 1 < n ? rts[k + 1] : m;
-						const int we = (int)(next >> 5) < w_hi ? (int)(next >> 5) : w_hi;
-						if (w < we) {
-							const uint32_t src = (uint32_t)w * 32 + (uint32_t)rtd[k], sh = src & 31u;
-							uint32_t sw = src >> 5, prev = Vold[sw];
-							for (; w < we; ++w) {
-								const uint32_t cur = Vold[++sw], word = __funnelshift_r(prev, cur, sh);
-								Vnew[w] = word;
-								if ((uint32_t)w * 32 >= zt) cnt += __popc(word);
-								prev = cur;
+				{
+					const uint16_t *rc = cst + r_off[r];
+					const uint32_t T = r_nch[r], nz = r_nz[r];
+					uint32_t j = T * (uint32_t)warp / MG_NW;
+					const uint32_t j_hi = T * (uint32_t)(warp + 1) / MG_NW;       // this warp's share of the chunks
+					if (j < j_hi) {
+						uint32_t k = 0;                                            // entry of chunk j: the last one with rc[k] <= j
+						for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; k += rc[k + half] <= j ? half : 0u; len -= half; }
+						while (j < j_hi) {
+							const uint32_t nxt = k + 1 < n ? rts[k + 1] : m;
+							const uint32_t wa = (rts[k] + 31u) >> 5, we = nxt >> 5;
+							if (we <= wa) { ++k; continue; }                        // no whole word inside this entry
+							const uint32_t base = rc[k];
+							uint32_t c_end = (we - wa + 31u) >> 5;
+							if (base + c_end > j_hi) c_end = j_hi - base;
+							const uint32_t d = (uint32_t)rtd[k], sh = d & 31u;
+							const bool ones = k >= nz;
+							for (uint32_t c = j - base; c < c_end; ++c) {
+								const uint32_t w = wa + c * 32 + lane;
+								if (w < we) {
+									const uint32_t sw = (w * 32 + d) >> 5;
+									const uint32_t word = __funnelshift_r(Vold[sw], Vold[sw + 1], sh);
+									Vnew[w] = word;
+									if (ones) cnt += __popc(word);
+								}
 							}
-						}
-						if (w < w_hi) {
-							// entry k ends in word w.  Strictly inside it (or at the ragged end of the vector): the word is left to the
-							// second pass; exactly at its start: the word belongs to the entries that follow
-							if (next & 31u) ++w;
-							while (k + 1 < n && rts[k + 1] <= (uint32_t)w * 32) ++k;
+							j = base + c_end;
+							++k;
 						}
 					}
 				}
@@ -414,15 +457,14 @@ __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const Margina
 static size_t marginal_smem_raw(int m, int raw)
 {
 	const int words = (m + 31) / 32, wpad = (words + 4 + 3) & ~3;
-	return (size_t)wpad * 8 + (size_t)raw * 8 + raw + 16 + MG_TMAX * 16 + 64;
+	return (size_t)wpad * 8 + (size_t)raw * 8 + raw + 16 + MG_TMAX * 24 + (size_t)raw * 2 + 64;
 }
 
 size_t marginal_seg_words(int m) { return (size_t)(((m + 31) / 32 + 4 + 3) & ~3); }
 
 size_t marginal_smem_bytes(int m)
 {
-	const int words = (m + 31) / 32, wpad = (words + 4 + 3) & ~3;
-	return (size_t)wpad * 8 + MG_RAW * 8 + MG_RAW + 16 + MG_TMAX * 16 + 64;
+	return marginal_smem_raw(m, MG_RAW);
 }
 
 cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st)
@@ -436,6 +478,21 @@ cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st)
 		if (e != cudaSuccess) return e;
 		pbwt_marginal_seed_kernel<<<dim3(n_blk, P.n_vec, 1), MS_NT, smem_a, st>>>(P);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
+		if (getenv("MG_SKIP_ROWS")) return cudaSuccess;
+		if (getenv("MG_512")) {
+			const size_t smem_b = marginal_smem_raw(P.m, 4096);
+			e = cudaFuncSetAttribute(pbwt_marginal_kernel<512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+			if (e != cudaSuccess) return e;
+			pbwt_marginal_kernel<512, 4096><<<dim3(n_blk * P.n_seg, P.n_vec, 1), 512, smem_b, st>>>(P);
+			return cudaGetLastError();
+		}
+		if (getenv("MG_128")) {
+			const size_t smem_b = marginal_smem_raw(P.m, 1024);
+			e = cudaFuncSetAttribute(pbwt_marginal_kernel<128, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+			if (e != cudaSuccess) return e;
+			pbwt_marginal_kernel<128, 1024><<<dim3(n_blk * P.n_seg, P.n_vec, 1), 128, smem_b, st>>>(P);
+			return cudaGetLastError();
+		}
 		const size_t smem_b = marginal_smem_raw(P.m, MG_RAW_SEG);
 		e = cudaFuncSetAttribute(pbwt_marginal_kernel<MG_NT_SEG, MG_RAW_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
 		if (e != cudaSuccess) return e;

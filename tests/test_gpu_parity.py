@@ -232,6 +232,18 @@ def test_noncanonical_rle_streams(b200, ctx, oracle):
             (bytes([1, 7 << 1, 1, 33, 13 << 1 | 1, (16 + 1) << 1, 4 << 1 | 1]), bytes([(16 + 2) << 1, 8 << 1]))] * 5
     pbf = oracle.encode_pbf_rle(m, rows, shift=2)
     check_scan(b200, ctx, oracle, pbf, flt="AC>0")
+    # the same plane-0 streams over an empty plane 1: grouped count-only queries take the split scan, whose per-group
+    # marginals merge the bytes of a run and skip the empty ones (marginal.cu)
+    quiet = bytes([(16 + 2) << 1, 8 << 1])
+    pbf = oracle.encode_pbf_rle(m, [(r0, quiet) for r0, _ in rows], shift=3)
+    grp = (np.arange(m // 2) % 3 + 1).astype(np.uint32)
+    want = oracle.Pbf(pbf).scan(0, len(rows), group=grp, n_groups=3, flt="AC1>0")
+    pb = b200.Pbf.from_bytes(ctx, pbf)
+    q = b200.Query(ctx, pb, group=grp, n_groups=3, flt="AC1>0")
+    for kw in (dict(), dict(no_split=True)):
+        got = b200.scan(ctx, pb, q, 0, len(rows), **kw)
+        assert (got["counts"] == want["counts"]).all() and (got["passed"] == want["passed"]).all(), kw
+    q.close(); pb.close()
 
 
 def test_error_behaviour(b200, ctx, oracle):

@@ -21,6 +21,7 @@ for name, qa, sa in cases:
     q = bgt_b200.Query(ctx, cohort, **qa)
     for _ in range(2):
         t = time.perf_counter(); r = bgt_b200.scan(ctx, cohort, q, 0, n, **sa); dt = time.perf_counter() - t
+    print("marginal %.2f ms" % ctx.last_ms(5), end="  ")
     print("%-50s kernels %.1f ms  (call %.1f ms)  %.2f M sites/s  passed %d" % (name, ctx.last_ms(1), dt * 1e3, n / ctx.last_ms(1) / 1e3, r["totals"][3]))
     key = name.split()[0]
     if key in ref: assert (ref[key] == r["counts"]).all(), "counts differ between the paths of " + key
