@@ -1079,7 +1079,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			M.n_seg = 1;
 			if (use_comp && !(flags & B200_SCAN_NO_SEGMENTS)) { // segments of 8+ row groups, as many as 512 MB of segment vectors allow
 				const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
-				int seg_groups = getenv("MG_SEG_GROUPS") ? atoi(getenv("MG_SEG_GROUPS")) : 8;
+				int seg_groups = 8;
 				const size_t per_seg = (size_t)n_split * (size_t)(G - 1) * marginal_seg_words(pb->m) * sizeof(uint32_t);
 				while (seg_groups < n_grp && per_seg * (size_t)((n_grp + seg_groups - 1) / seg_groups) > ((size_t)512 << 20)) seg_groups *= 2;
 				const int n_seg = (n_grp + seg_groups - 1) / seg_groups;

@@ -13,7 +13,6 @@
 // staged in tiles like in the walk kernel (plain cooperative loads here: this kernel is a few percent of the scan).
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 #include "pbwt_kernels.cuh"
 
 namespace b200 {
@@ -478,21 +477,6 @@ cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st)
 		if (e != cudaSuccess) return e;
 		pbwt_marginal_seed_kernel<<<dim3(n_blk, P.n_vec, 1), MS_NT, smem_a, st>>>(P);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
-		if (getenv("MG_SKIP_ROWS")) return cudaSuccess;
-		if (getenv("MG_512")) {
-			const size_t smem_b = marginal_smem_raw(P.m, 4096);
-			e = cudaFuncSetAttribute(pbwt_marginal_kernel<512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-			if (e != cudaSuccess) return e;
-			pbwt_marginal_kernel<512, 4096><<<dim3(n_blk * P.n_seg, P.n_vec, 1), 512, smem_b, st>>>(P);
-			return cudaGetLastError();
-		}
-		if (getenv("MG_128")) {
-			const size_t smem_b = marginal_smem_raw(P.m, 1024);
-			e = cudaFuncSetAttribute(pbwt_marginal_kernel<128, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-			if (e != cudaSuccess) return e;
-			pbwt_marginal_kernel<128, 1024><<<dim3(n_blk * P.n_seg, P.n_vec, 1), 128, smem_b, st>>>(P);
-			return cudaGetLastError();
-		}
 		const size_t smem_b = marginal_smem_raw(P.m, MG_RAW_SEG);
 		e = cudaFuncSetAttribute(pbwt_marginal_kernel<MG_NT_SEG, MG_RAW_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
 		if (e != cudaSuccess) return e;
