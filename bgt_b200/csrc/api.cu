@@ -111,7 +111,7 @@ struct b200_pbf_s {
 	int *d_rows_in_blk = nullptr, *d_blk_tile_beg = nullptr, *d_blk_tile_end = nullptr;
 	uint8_t *d_blk_sparse = nullptr;
 	int2 *d_tiles = nullptr;
-	uint32_t *d_n1 = nullptr;
+	uint32_t *d_n1 = nullptr, *d_nrun0 = nullptr;
 	int32_t *d_rank0 = nullptr;
 	int64_t bad_rows = 0;
 	// "plane-1 view" of the resident blocks: only the rows whose second bit plane (missing / other-ALT codes) is not
@@ -315,6 +315,7 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_blk_sparse);
 	pool_free(pb->ctx, pb->d_tiles);
 	pool_free(pb->ctx, pb->d_n1);
+	pool_free(pb->ctx, pb->d_nrun0);
 	pool_free(pb->ctx, pb->d_rank0);
 	pool_free(pb->ctx, pb->d_p1img);
 	pool_free(pb->ctx, pb->d_p1_rowoff);
@@ -397,7 +398,7 @@ static ComposeParams compose_params(const b200_pbf_t *pb, int b0)
 	ComposeParams K;
 	memset(&K, 0, sizeof(K));
 	K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rows_in_blk = pb->d_rows_in_blk; K.blk_list = nullptr; K.blk_first = b0;
-	K.blk_ok = pb->d_blk_sparse;
+	K.blk_ok = pb->d_blk_sparse; K.nrun = pb->d_nrun0;
 	K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
 	K.n_grp = (pb->BS + COMP_K - 1) / COMP_K; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0; K.row_base = nullptr; K.n1_step = 2;
 	K.comp_dir = pb->d_comp_dir; K.dir_shift = pb->dir_shift; K.dir_n = pb->dir_n;
@@ -419,7 +420,7 @@ static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
 	if (b1 <= b0) return true;
 	b200_ctx_t *c = pb->ctx;
 	ComposeParams V = compose_params(pb, b0);
-	V.comp_dir = nullptr;
+	V.comp_dir = nullptr; V.nrun = nullptr;
 	V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
 	V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
 	V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
@@ -464,6 +465,7 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	          pool_malloc(c, (void**)&pb->d_grp_tile_beg, sizeof(int) * (size_t)nb * (n_grp + 1) + 16) &&
 	          pool_malloc(c, (void**)&pb->d_tiles, sizeof(int2) * ((size_t)nb * BS + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_n1, sizeof(uint32_t) * (size_t)nb * BS * 2 + 8) &&
+	          pool_malloc(c, (void**)&pb->d_nrun0, sizeof(uint32_t) * (size_t)nb * BS + 8) &&
 	          pool_malloc(c, (void**)&pb->d_rank0, sizeof(int32_t) * (size_t)nb * 2 * (size_t)pb->m + 8) &&
 	          pool_malloc(c, (void**)&pb->d_p1img, (size_t)nb * P1_SLOT_BYTES + 64) &&
 	          pool_malloc(c, (void**)&pb->d_p1_rowoff, sizeof(uint64_t) * (size_t)nb * (SELECT_MAX_ROWS + 1) + 8) &&
@@ -500,7 +502,7 @@ static bool queue_tiles_rowmeta(b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
 	c->launches += 2;
 	return CU_OK(launch_plan_tiles(index_params(pb, b0), b1 - b0, st)) &&
 	       CU_OK(launch_rowmeta(pb->d_img, pb->d_rowoff + (size_t)b0 * (BS + 1), b1 - b0, pb->shift, 0, pb->d_rows_in_blk + b0, (uint32_t)pb->m,
-	                            pb->d_n1 + (size_t)b0 * BS * 2, c->d_acc + 4, st));
+	                            pb->d_n1 + (size_t)b0 * BS * 2, pb->d_nrun0 + (size_t)b0 * BS, c->d_acc + 4, st));
 }
 
 // blocks [b0,b1) whose snapshots are in place: start ranks (pbwt.c:343) and the plane-1 view
@@ -703,8 +705,18 @@ extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t 
 	size_t done = 0;
 	cudaEvent_t tev[LOAD_CHUNKS][4];
 	if (n_chunks == 0) ok = ok && CU_OK(cudaMemsetAsync(pb->d_img, 0, 64, c->st_copy));
+	// chunk bounds: even, except that a long image starts with two short chunks (1/64 and 1/32 of the blocks) so that the
+	// first index chain -- and with it the composite maps, which everything else queues behind -- starts early
+	int cb[LOAD_CHUNKS + 1];
+	{
+		const int head = (n_chunks == LOAD_CHUNKS && nb >= 64) ? 2 : 0;
+		const int h0 = head ? nb / 64 : 0, h1 = head ? h0 + nb / 32 : 0;
+		cb[0] = 0;
+		if (head) { cb[1] = h0; cb[2] = h1; }
+		for (int k = head; k <= n_chunks; ++k) cb[k] = h1 + (int)((long long)(nb - h1) * (k - head) / (n_chunks - head > 0 ? n_chunks - head : 1));
+	}
 	for (int k = 0; ok && k < n_chunks; ++k) {
-		const int b0 = (int)((long long)nb * k / n_chunks), b1 = (int)((long long)nb * (k + 1) / n_chunks);
+		const int b0 = cb[k], b1 = cb[k + 1];
 		const size_t end = b1 < nb ? (size_t)(pb->h_idx[pb->blk0 + b1] - pb->file_off0) : pb->img_bytes;
 		ok = CU_OK(cudaMemcpyAsync(pb->d_img + done, f + pb->file_off0 + done, end - done, cudaMemcpyHostToDevice, c->st_copy));
 		if (ok && k == n_chunks - 1) ok = CU_OK(cudaMemsetAsync(pb->d_img + pb->img_bytes, 0, 64, c->st_copy));

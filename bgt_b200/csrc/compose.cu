@@ -79,7 +79,27 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 
 	// ---- level 0: one map per row, in the order they are applied (inverse composite: last row first).  Warps take
 	// rows round-robin; run counts first (to place the maps), then the tables.  A constant row is the identity.
-	for (int pass = 0; pass < 2; ++pass) {
+	auto place_maps = [&]() { // run counts in offA[1..] -> offsets; too many for the buffers: give up (the caller retries / walks rows)
+		if (tid == 0) {
+			int acc = 0;
+			offA[0] = 0;
+			for (int k = 0; k < COMP_K; ++k) { const int c = offA[k + 1]; acc += c; offA[k + 1] = acc; }
+			if (acc > CP_RUNS + COMP_K) s_fail = 1;
+		}
+		__syncthreads();
+	};
+	const bool have_counts = P.nrun != nullptr && !P.inverse;   // counted while loading (rowmeta_kernel): no counting pass
+	if (have_counts) {
+		if (tid < COMP_K) {
+			const size_t ri = (size_t)(rbase + r_lo + tid);
+			const uint32_t n1 = P.n1[ri * P.n1_step + P.n1_plane], nr = P.nrun[ri];
+			offA[tid + 1] = (n1 == 0 || n1 == m) ? 1 : (int)(nr < (1u << 20) ? nr : (1u << 20));
+		}
+		__syncthreads();
+		place_maps();
+		if (s_fail) { if (tid == 0) P.comp_n[slot] = 0; return; }
+	}
+	for (int pass = have_counts ? 1 : 0; pass < 2; ++pass) {
 		for (int j = warp; j < COMP_K; j += CP_NW) {
 			const int k_map = P.inverse ? COMP_K - 1 - j : j;
 			const uint8_t *rec = staged ? (const uint8_t*)S1 + (roff[r_lo + j] - g_beg) : P.img + roff[r_lo + j];
@@ -136,13 +156,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 		}
 		__syncthreads();
 		if (!pass) {
-			if (tid == 0) {
-				int acc = 0;
-				offA[0] = 0;
-				for (int k = 0; k < COMP_K; ++k) { const int c = offA[k + 1]; acc += c; offA[k + 1] = acc; }
-				if (acc > CP_RUNS + COMP_K) s_fail = 1;
-			}
-			__syncthreads();
+			place_maps();
 			if (s_fail) { if (tid == 0) P.comp_n[slot] = 0; return; }
 		}
 	}

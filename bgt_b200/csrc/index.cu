@@ -19,7 +19,7 @@ namespace b200 {
 
 // ------------------------------------------------------------------------------------------------ row offsets
 
-constexpr int IX_K = 6;         // lanes that chase one block together, each from its own (verified) record start
+constexpr int IX_K = IX_SCRATCH_LANES;         // lanes that chase one block together, each from its own (verified) record start
 constexpr int IX_STAGE = 1024, IX_SLOTS = 4, IX_RING = IX_STAGE * IX_SLOTS;   // per-lane ring; small on purpose: a chase CTA
                                                                             // (24 KB) must fit beside the resident CTAs it overlaps
 constexpr uint32_t IX_BAD = 0xffffffffu;
@@ -160,16 +160,20 @@ __device__ bool ix_verify_start(const uint8_t *img, uint64_t p, uint64_t end, in
 	return true;
 }
 
-// One warp per checkpoint block.  The chain of a block is rows x 2 dependent hops ('B', l0 | plane-0 bytes | l1 | plane-1
-// bytes) -- pure latency -- so IX_K lanes chase it together: lane 0 from the block's first record, lane l from the first
+// One CTA per checkpoint block.  The chain of a block is rows x 2 dependent hops ('B', l0 | plane-0 bytes | l1 | plane-1
+// bytes) -- pure latency -- so IX_K chasers share it: chaser 0 starts at the block's first record, chaser l at the first
 // position in its stretch of the byte range at which a chain of four well-formed records starts whose first one carries
-// run lengths that add up to m in both planes.  A lane stops where the next lane began;
-// if every lane lands EXACTLY on its successor's start and the counts add up to the block's rows, the pieces are the
-// chain and are copied to their places.  Otherwise (damaged or unusual blocks) lane 0 walks the whole block alone.
-__global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
+// run lengths that add up to m in both planes.  A chaser stops where the next one began; if every chaser lands EXACTLY on
+// its successor's start and the counts add up to the block's rows, the pieces are the chain and are copied to their
+// places.  Otherwise (damaged or unusual blocks) chaser 0 walks the whole block alone.  Every chaser is lane 0 of its own
+// warp: in one warp their ring refills (a TMA round trip each kilobyte) would serialise.
+__global__ void __launch_bounds__(32 * IX_K) pbf_index_kernel(const IndexParams P)
 {
 	extern __shared__ __align__(128) uint8_t ix_sm_all[];
-	const int lane = threadIdx.x;
+	__shared__ uint32_t s_start[IX_K], s_cnt[IX_K];
+	__shared__ int s_ok[IX_K];
+	const int tid = threadIdx.x, lane = tid >> 5;     // lane = chaser index
+	const bool chaser = (tid & 31) == 0;
 	const int blk = P.blk_first + (int)blockIdx.x;
 	const int BS = 1 << P.shift;
 	uint64_t *ro = P.rowoff + (size_t)blk * (BS + 1);
@@ -179,13 +183,13 @@ __global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
 	const uint64_t blkend = P.blkend[blk];
 	const uint64_t end64 = blkend - base;
 	bool bad = P.img[P.blkoff[blk]] != 'S' || first > blkend;
-	if (end64 > 0xfff00000ull) { if (lane == 0) atomicOr(P.err, 128); bad = true; }   // the records of one block must fit 32-bit offsets
+	if (end64 > 0xfff00000ull) { if (tid == 0) atomicOr(P.err, 128); bad = true; }   // the records of one block must fit 32-bit offsets
 	if (bad) {
-		if (lane == 0) { atomicOr(P.err, 2); P.rows_in_blk[blk] = 0; ro[0] = P.blkoff[blk]; }
+		if (tid == 0) { atomicOr(P.err, 2); P.rows_in_blk[blk] = 0; ro[0] = P.blkoff[blk]; }
 		return;
 	}
 	IxCursor C;
-	if (lane < IX_K) {
+	if (chaser) {
 		uint8_t *ix_sm = ix_sm_all + (size_t)lane * (IX_RING + 64);
 		C.R.ring = ix_sm; C.R.bar = (uint64_t*)(ix_sm + IX_RING); C.R.img = P.img; C.R.err = P.err;
 		C.R.base = base; C.R.end16 = (blkend + 15) & ~15ull;
@@ -198,55 +202,60 @@ __global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
 		C.ring_saddr = ix_smem_u32(ix_sm); C.wlo = 1; C.whi = 0; C.end64 = end64; C.end = (uint32_t)end64;
 	}
 	const uint32_t first_rel = (uint32_t)(first - base), end_rel = (uint32_t)end64;
-	const bool team = rows >= 64 * IX_K && P.scratch != nullptr;
+	const bool team = rows >= 64 * IX_K && P.scratch != nullptr;      // (uniform over the CTA)
 	bool done = false;
 	if (team) {
 		// ---- starts
-		uint32_t s = IX_BAD;
-		if (lane == 0) s = first_rel;
-		else if (lane < IX_K) {
-			const uint64_t span = blkend - first;
-			uint64_t p = first + span * (uint64_t)lane / IX_K;
-			const uint64_t lim = first + span * (uint64_t)(lane + 1) / IX_K;
-			for (; p < lim; ++p)
-				if (P.img[p] == 'B' && ix_verify_start(P.img, p, blkend, 4, (uint32_t)P.m)) { s = (uint32_t)(p - base); break; }
-		}
-		uint32_t stop = end_rel;                       // where my stretch ends: the first valid start behind me
-		for (int d = IX_K - 1; d >= 1; --d) {
-			const uint32_t t = __shfl_down_sync(0xffffffffu, s, d);
-			if (lane + d < IX_K && t != IX_BAD) stop = t;
-		}
-		// ---- chase my stretch into my scratch column
-		uint64_t *mine = P.scratch + ((size_t)blk * IX_K + (lane < IX_K ? lane : 0)) * (size_t)(BS + 1);
-		uint32_t cnt = 0, o = s;
-		bool ok = true;
-		if (lane < IX_K && s != IX_BAD) {
-			while (o < stop) {
-				const uint32_t n = C.step(o);
-				if (n == IX_BAD || cnt >= (uint32_t)rows) { ok = false; break; }
-				mine[cnt++] = base + o;
-				o = n;
+		if (chaser) {
+			uint32_t s = IX_BAD;
+			if (lane == 0) s = first_rel;
+			else {
+				const uint64_t span = blkend - first;
+				uint64_t p = first + span * (uint64_t)lane / IX_K;
+				const uint64_t lim = first + span * (uint64_t)(lane + 1) / IX_K;
+				for (; p < lim; ++p)
+					if (P.img[p] == 'B' && ix_verify_start(P.img, p, blkend, 4, (uint32_t)P.m)) { s = (uint32_t)(p - base); break; }
 			}
-			if (o != stop) ok = false;                  // ran past the successor's start: one of the two is not on the chain
+			s_start[lane] = s;
 		}
-		const bool all_ok = __all_sync(0xffffffffu, ok);
-		uint32_t x = (lane < IX_K && s != IX_BAD) ? cnt : 0u, incl = x;
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		__syncthreads();
+		// ---- chase my stretch into my scratch column; it ends at the first valid start behind me
+		if (chaser) {
+			const uint32_t s = s_start[lane];
+			uint32_t stop = end_rel;
+			for (int l = IX_K - 1; l > lane; --l) if (s_start[l] != IX_BAD) stop = s_start[l];
+			uint64_t *mine = P.scratch + ((size_t)blk * IX_K + lane) * (size_t)(BS + 1);
+			uint32_t cnt = 0, o = s;
+			bool ok = true;
+			if (s != IX_BAD) {
+				while (o < stop) {
+					const uint32_t n = C.step(o);
+					if (n == IX_BAD || cnt >= (uint32_t)rows) { ok = false; break; }
+					mine[cnt++] = base + o;
+					o = n;
+				}
+				if (o != stop) ok = false;              // ran past the successor's start: one of the two is not on the chain
+			}
+			s_cnt[lane] = cnt; s_ok[lane] = ok ? 1 : 0;
+		}
+		__syncthreads();                                // (also makes the scratch columns visible to the whole CTA)
+		bool all_ok = true;
+		uint32_t total = 0;
+		for (int l = 0; l < IX_K; ++l) { all_ok = all_ok && s_ok[l]; total += s_cnt[l]; }
 		if (all_ok && total == (uint32_t)rows) {
-			// ---- the pieces are the chain: copy them to their places (coalesced, all lanes)
-			__syncwarp();                               // the other lanes' scratch columns are read below
+			// ---- the pieces are the chain: copy them to their places (coalesced, all threads)
+			uint32_t b0 = 0;
 			for (int l = 0; l < IX_K; ++l) {
-				const uint32_t c = __shfl_sync(0xffffffffu, x, l), b0 = __shfl_sync(0xffffffffu, incl - x, l);
+				const uint32_t c = s_cnt[l];
 				const uint64_t *src = P.scratch + ((size_t)blk * IX_K + l) * (size_t)(BS + 1);
-				for (uint32_t i = lane; i < c; i += 32) ro[b0 + i] = src[i];
+				for (uint32_t i = tid; i < c; i += 32 * IX_K) ro[b0 + i] = src[i];
+				b0 += c;
 			}
-			if (lane == 0) ro[rows] = blkend;
+			if (tid == 0) ro[rows] = blkend;
 			done = true;
 		}
 	}
-	if (!done && lane == 0) { // ---- the whole block, alone
+	if (!done && tid == 0) { // ---- the whole block, alone
 		if (team) atomicAdd(P.fallbacks, 1);
 		uint32_t o = first_rel;
 		int r = 0;
@@ -258,11 +267,11 @@ __global__ void __launch_bounds__(32) pbf_index_kernel(const IndexParams P)
 		}
 		if (!bad) ro[rows] = base + o;
 	}
-	if (lane < IX_K) {
+	if (chaser) {
 		#pragma unroll 1
 		for (int s = 0; s < IX_SLOTS; ++s) if (C.R.inflight[s]) C.R.wait(s);   // no copy may be in flight when the CTA exits
 	}
-	if (bad && lane == 0) {
+	if (bad && tid == 0) {
 		// the records of this block do not parse: it decodes as an empty block and the load reports the corruption
 		atomicOr(P.err, 2);
 		P.rows_in_blk[blk] = 0;
@@ -276,7 +285,7 @@ cudaError_t launch_index(const IndexParams &P, int n_blk, cudaStream_t st)
 	const size_t smem = (size_t)IX_K * (IX_RING + 64);
 	cudaError_t e = cudaFuncSetAttribute(pbf_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
-	pbf_index_kernel<<<n_blk, 32, smem, st>>>(P);
+	pbf_index_kernel<<<n_blk, 32 * IX_K, smem, st>>>(P);
 	return cudaGetLastError();
 }
 

@@ -83,10 +83,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 // ------------------------------------------------------------------------------------------------ row meta
 
-// One warp per row: n1 (number of 1 bits) of both planes, and a check that the run lengths sum to m.
+// One warp per row: n1 (number of 1 bits) of both planes, a check that the run lengths sum to m, and the number of runs
+// of plane 0 (bytes of the same symbol merged, empty bytes skipped) -- what compose.cu needs to place the rows' maps.
 __global__ void __launch_bounds__(256) rowmeta_kernel(const uint8_t *__restrict__ img, const uint64_t *__restrict__ rowoff,
                                                       int n_blk, int shift, const int *__restrict__ rows_in_blk, uint32_t m,
-                                                      uint32_t *__restrict__ n1, unsigned long long *__restrict__ bad)
+                                                      uint32_t *__restrict__ n1, uint32_t *__restrict__ nrun0, unsigned long long *__restrict__ bad)
 {
 	const int lane = threadIdx.x & 31;
 	const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -98,10 +99,19 @@ __global__ void __launch_bounds__(256) rowmeta_kernel(const uint8_t *__restrict_
 		const uint32_t l = ld_u32_unaligned(p);
 		p += 4;
 		unsigned long long tot = 0, ones = 0;
-		for (uint32_t i = lane; i < l; i += 32) {
-			const uint32_t c = p[i], len = rle_len(c);
+		uint32_t nrun = 0, prev_bit = 2;
+		for (uint32_t base = 0; base < l; base += 32) {
+			const uint32_t i = base + lane;
+			const uint32_t c = i < l ? p[i] : 0u, len = rle_len(c), b = c & 1u;
 			tot += len;
-			if (c & 1) ones += len;
+			if (b) ones += len;
+			if (plane == 0 && nrun0) {
+				const uint32_t valid = __ballot_sync(FULL_MASK, len > 0), bitm = __ballot_sync(FULL_MASK, b != 0);
+				const uint32_t below = valid & ((1u << lane) - 1u);
+				const uint32_t pb = below ? (bitm >> (31 - __clz(below))) & 1u : prev_bit;
+				nrun += __popc(__ballot_sync(FULL_MASK, len > 0 && pb != b));
+				if (valid) prev_bit = (bitm >> (31 - __clz(valid))) & 1u;
+			}
 		}
 		#pragma unroll
 		for (int d = 16; d; d >>= 1) {
@@ -112,18 +122,19 @@ __global__ void __launch_bounds__(256) rowmeta_kernel(const uint8_t *__restrict_
 			const bool ok = (tot == m);
 			n1[((size_t)blk * BS + r) * 2 + plane] = ok ? (uint32_t)ones : 0u; // a corrupt row decodes as all-REF
 			if (!ok) atomicAdd(bad, 1ull);
+			if (plane == 0 && nrun0) nrun0[(size_t)blk * BS + r] = nrun;
 		}
 		p += l;
 	}
 }
 
 cudaError_t launch_rowmeta(const uint8_t *img, const uint64_t *rowoff, int n_blk, int shift, long long, const int *rows_in_blk,
-                           uint32_t m, uint32_t *n1, unsigned long long *bad, cudaStream_t st)
+                           uint32_t m, uint32_t *n1, uint32_t *nrun0, unsigned long long *bad, cudaStream_t st)
 {
 	const long long warps = (long long)n_blk << shift;
 	if (warps == 0) return cudaSuccess;
 	const long long blocks = (warps * 32 + 255) / 256;
-	rowmeta_kernel<<<(unsigned)blocks, 256, 0, st>>>(img, rowoff, n_blk, shift, rows_in_blk, m, n1, bad);
+	rowmeta_kernel<<<(unsigned)blocks, 256, 0, st>>>(img, rowoff, n_blk, shift, rows_in_blk, m, n1, nrun0, bad);
 	return cudaGetLastError();
 }
 

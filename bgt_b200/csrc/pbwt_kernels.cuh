@@ -70,6 +70,7 @@ struct ComposeParams {
 	const uint8_t  *img;
 	const uint64_t *rowoff;
 	const uint32_t *n1;
+	const uint32_t *nrun;       // nullptr, or runs per row (rowmeta_kernel; forward maps only): level 0 skips its counting pass
 	const int      *rows_in_blk;
 	const int      *blk_list;   // blocks handled by this launch; nullptr: blk_first + index
 	const uint8_t  *blk_ok;     // nullptr, or per block 1 = build (the device-side "sparse" flag of index.cu)
@@ -133,7 +134,7 @@ struct IndexParams {
 	int      *err;
 	int      *fallbacks;          // diagnostics: blocks whose pieces did not join up (chased again by one lane)
 };
-constexpr int IX_SCRATCH_LANES = 6;
+constexpr int IX_SCRATCH_LANES = 12;
 cudaError_t launch_index(const IndexParams &P, int n_blk, cudaStream_t st);
 cudaError_t launch_plan_tiles(const IndexParams &P, int n_blk, cudaStream_t st);
 
@@ -181,7 +182,7 @@ cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st)
 struct FinalizeSplit { const uint8_t *blk_split; const uint32_t *n1; const int32_t *n0g; int n_vec; long long row_lo, blk_row0; int shift; };
 
 cudaError_t launch_rowmeta(const uint8_t *img, const uint64_t *rowoff, int n_blk, int shift, long long n_rows_total_in_blocks,
-                           const int *rows_in_blk, uint32_t m, uint32_t *n1, unsigned long long *bad, cudaStream_t st);
+                           const int *rows_in_blk, uint32_t m, uint32_t *n1, uint32_t *nrun0, unsigned long long *bad, cudaStream_t st);
 cudaError_t launch_invert_snapshots(const uint8_t *img, const uint64_t *blkoff, int n_blk, int m, int32_t *rank0, int *err, cudaStream_t st);
 cudaError_t launch_finalize(const int32_t *cnt_raw, long long n_rows, int G, const int32_t *gsize, const flt_prog_t *prog, int use_flt,
                             int32_t *counts, uint8_t *pass, unsigned long long *totals, const FinalizeSplit &sp, cudaStream_t st);
