@@ -375,7 +375,7 @@ def run_b200(args, rank, world, local_rank):
                        "totals_allreduce": {"sum_AN": totals[0], "sum_AC": totals[1], "sites_passed": totals[3], "sites": totals[4]}},
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": int(e2e_bytes["h2d"]), "d2h_bytes_per_step": int(e2e_bytes["d2h"]),
                     "steps": e2e_steps, "matches_resident": same,
-                    "how": "host .pbf image (pinned) -> b200_pbf_load_ex (%d region shard(s); H2D in 16 chunks; row index, row meta, start ranks, plane-1 view and composite maps built on the device behind each chunk, no host walk) -> b200_scan -> host AC/AN + verdicts" % len(ranges)},
+                    "how": "host .pbf image (pinned) -> b200_pbf_load_ex (%d region shard(s); H2D in 16 chunks (short ones first); row index, row meta, start ranks, plane-1 view and composite maps built on the device behind each chunk, no host walk) -> b200_scan -> host AC/AN + verdicts" % len(ranges)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "pbwt_walk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": k_ms,

@@ -705,15 +705,17 @@ extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t 
 	size_t done = 0;
 	cudaEvent_t tev[LOAD_CHUNKS][4];
 	if (n_chunks == 0) ok = ok && CU_OK(cudaMemsetAsync(pb->d_img, 0, 64, c->st_copy));
-	// chunk bounds: even, except that a long image starts with two short chunks (1/64 and 1/32 of the blocks) so that the
-	// first index chain -- and with it the composite maps, which everything else queues behind -- starts early
+	// chunk bounds: even, except that a long image starts with a ramp of short chunks (1, 2, 3, 4, 6, 8 parts of 128) so that
+	// the first index chain -- and with it the composite maps, which everything else queues behind -- starts early and
+	// every later chain is hidden behind the composite maps of the chunk before
 	int cb[LOAD_CHUNKS + 1];
 	{
-		const int head = (n_chunks == LOAD_CHUNKS && nb >= 64) ? 2 : 0;
-		const int h0 = head ? nb / 64 : 0, h1 = head ? h0 + nb / 32 : 0;
+		static const int ramp[6] = {1, 2, 3, 4, 6, 8};
+		const int head = (n_chunks == LOAD_CHUNKS && nb >= 64) ? 6 : 0;
+		int h = 0;
 		cb[0] = 0;
-		if (head) { cb[1] = h0; cb[2] = h1; }
-		for (int k = head; k <= n_chunks; ++k) cb[k] = h1 + (int)((long long)(nb - h1) * (k - head) / (n_chunks - head > 0 ? n_chunks - head : 1));
+		for (int k = 0; k < head; ++k) { const int sz = nb * ramp[k] / 128; h += sz > 0 ? sz : 1; cb[k + 1] = h; }
+		for (int k = head; k <= n_chunks; ++k) cb[k] = h + (int)((long long)(nb - h) * (k - head) / (n_chunks - head > 0 ? n_chunks - head : 1));
 	}
 	for (int k = 0; ok && k < n_chunks; ++k) {
 		const int b0 = cb[k], b1 = cb[k + 1];
