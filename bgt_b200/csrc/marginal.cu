@@ -8,9 +8,12 @@
 // behind them, both in order.  The popcount of the part that moved behind is the group's number of ones.
 // m/32 words per row instead of m rank updates.
 //
-// grid = (blocks, groups-1); one CTA of 1024 threads owns one bit vector (two buffers in shared memory); the next vector
-// is GATHERED through the row's inverse run table (sorted by landing position).  Rows are
-// staged in tiles like in the walk kernel (plain cooperative loads here: this kernel is a few percent of the scan).
+// A CTA owns one bit vector (two buffers in shared memory); the next vector is GATHERED through the row's inverse run
+// table (sorted by landing position).  Rows are a dependent chain, so a block is cut into segments of 8 row groups: the
+// seed kernel pushes the block's start vector through the composite maps of the row groups (compose.cu; one scatter
+// per 32 rows) and stores it in front of every segment, then grid = (blocks x segments, groups-1) CTAs of 256 threads walk
+// their 256 rows side by side.  Without resident composite maps: grid = (blocks, groups-1), one CTA of 1024 threads per
+// block.  Rows are staged in tiles like in the walk kernel (plain cooperative loads).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "pbwt_kernels.cuh"
@@ -119,13 +122,15 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 		const bool big = roff[r0 + 1] - t_beg > (uint64_t)MG_RAW;
 		if (!big) {
 			const uint32_t nbytes = (uint32_t)(roff[r0 + nr] - t_beg);
+			uint32_t my_n1 = 0, my_o = 0;                   // (issued with the staging loads: one round trip, not two)
+			if (tid < nr) { my_n1 = P.n1[((size_t)blk * BS + r0 + tid) * 2]; my_o = (uint32_t)(roff[r0 + tid] - t_beg); }
 			for (uint32_t i = tid; i < nbytes; i += MG_NT) raw[i] = P.img[t_beg + i];
 			__syncthreads();
 			if (tid < nr) {
-				const uint32_t o = (uint32_t)(roff[r0 + tid] - t_beg);
+				const uint32_t o = my_o;
 				r_len[tid] = (uint32_t)raw[o + 1] | (uint32_t)raw[o + 2] << 8 | (uint32_t)raw[o + 3] << 16 | (uint32_t)raw[o + 4] << 24;
 				r_off[tid] = o + 5;
-				r_n1[tid] = P.n1[((size_t)blk * BS + r0 + tid) * 2];
+				r_n1[tid] = my_n1;
 			}
 			__syncthreads();
 			// per row the INVERSE run table of plane 0, one entry per run (RLE bytes of the same symbol merged): where the run's
@@ -259,8 +264,8 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 						}
 					}
 				}
-				__syncthreads();
-				// second pass: exactly one thread per word that holds an entry boundary -- the one whose boundary is the first in it
+				// second pass (no barrier: it reads the old vector and writes only words the first pass never touches): exactly one
+				// thread per word that holds an entry boundary -- the one whose boundary is the first in it
 				for (uint32_t i = tid; i + 1 < n; i += MG_NT) {
 					const uint32_t p = rts[i + 1];
 					if (p >= m || (p & 31u) == 0) continue;           // (a boundary at a word start leaves both words whole)
