@@ -40,6 +40,19 @@ def test_abi_exports_every_declared_symbol():
     assert L.b200_abi_version() == 1
 
 
+def test_python_binding_flags_match_the_header():
+    """The scan flags of the ctypes binding are the header's (include/bgt_b200.h), bit for bit, and do not overlap."""
+    from bgt_b200 import capi
+    txt = open(os.path.join(ROOT, "include", "bgt_b200.h")).read()
+    defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+B200_(SCAN_[A-Z_]+)\s+(0x[0-9a-fA-F]+|\d+)\b", txt)}
+    assert {"SCAN_COUNTS", "SCAN_HAP_BITS", "SCAN_HAP_BYTES", "SCAN_DEVICE_OUT", "SCAN_NO_SPLIT", "SCAN_NO_COMPOSE", "SCAN_NO_SEGMENTS"} <= set(defs)
+    for name, val in defs.items():
+        assert getattr(capi, name) == val, name
+    vals = list(defs.values())
+    assert all(v and v & (v - 1) == 0 for v in vals) and len(set(vals)) == len(vals)   # single, distinct bits
+    assert all(v < 0x100 for v in vals)                                                # bits 8-11 carry B200_SCAN_COLS_PER_THREAD
+
+
 def test_seam_a_library_exports_pbwt_api():
     path = os.path.join(ROOT, "bgt_b200", "lib", "libpbwt_b200.so")
     if not os.path.exists(path):
