@@ -85,3 +85,128 @@ def test_model_zero_length_and_split_runs(oracle):
     pbf = oracle.encode_pbf_rle(m, rows, shift=2)
     want = oracle.decode_all(pbf)
     assert (walk_file(pbf, oracle) == want).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Split scan: a row's effect on a rank is a piecewise translation -- one piece per run -- and so is the
+# composition of 32 rows (compose.cu); the per-group marginals push ONE BIT per rank through the same partition
+# (marginal.cu), and cross whole row groups by scattering the bit vector through the group's composite map.
+
+def run_map(rle, m):
+    """Forward map of one row, one piece per run (bytes of one symbol merged, empty bytes skipped): (starts, deltas, n1)."""
+    start, delta, n1 = tables(rle, m)
+    c = np.frombuffer(rle, dtype=np.uint8).astype(np.int64)
+    L, b = rle_len(c), c & 1
+    if n1 == 0 or n1 == m:
+        return np.zeros(1, np.int64), np.zeros(1, np.int64), n1          # a constant row moves nothing
+    keep, prev = [], 2
+    for i in range(len(c)):
+        if L[i] > 0 and b[i] != prev:
+            keep.append(i)
+        if L[i] > 0:
+            prev = b[i]
+    return start[keep], delta[keep], n1
+
+
+def apply_map(S, D, r):
+    return r + D[np.searchsorted(S, r, side="right") - 1]
+
+
+def compose(SA, DA, SB, DB, m):
+    """(B after A) as pieces in A's input coordinates: every piece of A is cut at the starts of B inside its image."""
+    S, D = [], []
+    for p in range(len(SA)):
+        s0, e0 = SA[p], (SA[p + 1] if p + 1 < len(SA) else m)
+        cur, end = s0 + DA[p], e0 + DA[p]                                 # image of the piece
+        k = np.searchsorted(SB, cur, side="right") - 1
+        S.append(s0); D.append(DA[p] + DB[k])
+        for j in range(k + 1, len(SB)):
+            if SB[j] >= end:
+                break
+            S.append(s0 + (SB[j] - cur)); D.append(DA[p] + DB[j])
+    return np.array(S, np.int64), np.array(D, np.int64)
+
+
+def composite(maps, m):
+    """Pairwise tree composition, like the levels of pbwt_compose_kernel."""
+    level = list(maps)
+    while len(level) > 1:
+        level = [compose(*level[i][:2], *level[i + 1][:2], m) if i + 1 < len(level) else level[i] for i in range(0, len(level), 2)]
+    return level[0]
+
+
+def plane0_rows(pbf_bytes, orc):
+    """(m, [plane-0 RLE of every row], [S0 of every block]) of a .pbf image."""
+    p = orc.Pbf(pbf_bytes)
+    m, n = p.m, p.n
+    p.close()
+    buf = np.frombuffer(pbf_bytes, dtype=np.uint8)
+    pos, rows, snaps = 16, [], []
+    for _ in range(n):
+        if buf[pos] == ord('S'):
+            snaps.append(np.frombuffer(pbf_bytes, dtype=np.int32, count=m, offset=pos + 1).astype(np.int64))
+            pos += 1 + 8 * m
+        pos += 1
+        l0 = int(np.frombuffer(pbf_bytes, dtype=np.int32, count=1, offset=pos)[0])
+        rows.append(pbf_bytes[pos + 4:pos + 4 + l0])
+        pos += 4 + l0
+        l1 = int(np.frombuffer(pbf_bytes, dtype=np.int32, count=1, offset=pos)[0])
+        pos += 4 + l1
+    return m, rows, snaps
+
+
+def test_composite_of_a_row_group_is_the_rows_applied_in_turn(oracle):
+    for mat, K in ((haplo_matrix(64, 301, 21), 32), (random_matrix(48, 97, 22), 16), (edge_rows(257)[:32], 32)):
+        pbf = oracle.encode_pbf(mat, shift=13)
+        m, rows, _ = plane0_rows(pbf, oracle)
+        r_all = np.arange(m, dtype=np.int64)
+        for g0 in range(0, len(rows) - K + 1, K):
+            maps = [run_map(rows[r], m) for r in range(g0, g0 + K)]
+            S, D = composite([(a, b) for a, b, _ in maps], m)
+            want = r_all.copy()
+            for a, b, _ in maps:
+                want = apply_map(a, b, want)
+            assert (apply_map(S, D, r_all) == want).all()
+            assert S[0] == 0 and (np.diff(S) > 0).all()
+            assert len(S) <= 1 + sum(len(a) for a, _, _ in maps)          # every run boundary has exactly one pre-image
+            assert sorted(want.tolist()) == list(range(m))                # still a permutation of the ranks
+
+
+def gather_partition(V, rle, m):
+    """Next group vector through the row's INVERSE run table (entries sorted by where they land), and the ones that land
+    behind the zeros -- marginal.cu's gather, bit by bit."""
+    S, D, n1 = run_map(rle, m)
+    if n1 == 0:
+        return V, 0
+    if n1 == m:
+        return V, int(V.sum())
+    dst = S + D
+    order = np.argsort(dst, kind="stable")
+    ts, back = dst[order], -D[order]                                      # landing start, distance back to the source
+    pos = np.arange(m, dtype=np.int64)
+    k = np.searchsorted(ts, pos, side="right") - 1
+    Vn = V[pos + back[k]]
+    return Vn, int(Vn[m - n1:].sum())
+
+
+def test_group_marginals_by_bit_vector_partition(oracle):
+    rng = np.random.default_rng(5)
+    for mat, shift, K in ((haplo_matrix(150, 203, 23), 6, 32), (random_matrix(70, 64, 24), 5, 32)):
+        pbf = oracle.encode_pbf(mat, shift=shift)
+        m, rows, snaps = plane0_rows(pbf, oracle)
+        in_group = rng.random(m) < 0.4
+        BS = 1 << shift
+        for r, rle in enumerate(rows):
+            if r % BS == 0:
+                V = in_group[snaps[r // BS]]                              # bit i = the column at rank i is in the group
+                V_seg = V.copy()                                          # the vector in front of the current row group
+            # crossing a whole row group through its composite map (the seed kernel's scatter) lands on the same vector
+            if r % BS and (r % BS) % K == 0:
+                g0 = r - K
+                S, D = composite([run_map(rows[q], m)[:2] for q in range(g0, r)], m)
+                Vs = np.zeros(m, bool)
+                Vs[apply_map(S, D, np.arange(m, dtype=np.int64))] = V_seg
+                assert (Vs == V).all()
+                V_seg = V.copy()
+            V, cnt = gather_partition(V, rle, m)
+            assert cnt == int(((mat[r] & 1) == 1)[in_group].sum())        # ones of the plane-0 row inside the group
