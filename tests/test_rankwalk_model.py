@@ -210,3 +210,61 @@ def test_group_marginals_by_bit_vector_partition(oracle):
                 V_seg = V.copy()
             V, cnt = gather_partition(V, rle, m)
             assert cnt == int(((mat[r] & 1) == 1)[in_group].sum())        # ones of the plane-0 row inside the group
+
+
+def both_planes(pbf_bytes, orc):
+    """(m, shift, [(plane-0 RLE, plane-1 RLE) per row], [(S0, S1) per block])."""
+    p = orc.Pbf(pbf_bytes)
+    m, n, shift = p.m, p.n, p.shift
+    p.close()
+    buf = np.frombuffer(pbf_bytes, dtype=np.uint8)
+    pos, rows, snaps = 16, [], []
+    for _ in range(n):
+        if buf[pos] == ord('S'):
+            snaps.append(tuple(np.frombuffer(pbf_bytes, dtype=np.int32, count=m, offset=pos + 1 + 4 * m * g).astype(np.int64) for g in range(2)))
+            pos += 1 + 8 * m
+        pos += 1
+        rec = []
+        for _g in range(2):
+            l = int(np.frombuffer(pbf_bytes, dtype=np.int32, count=1, offset=pos)[0])
+            rec.append(pbf_bytes[pos + 4:pos + 4 + l])
+            pos += 4 + l
+        rows.append(tuple(rec))
+    return m, shift, rows, snaps
+
+
+def test_plane1_pairs_backwards_then_plane0_forwards(oracle):
+    """The split scan's joint codes: every 1 bit of a plane-1 row is traced BACK through the non-empty plane-1 rows in front
+    of it to the block's snapshot (which names the column: plane1.cu), and that column is walked FORWARD through plane 0 to
+    the same row (WALK_QUERY), where it counts as other-ALT (plane-0 bit set, code 3) or missing (code 2)."""
+    for mat, shift in ((haplo_matrix(200, 151, 25, p_missing_row=0.3, p_multi_row=0.3), 6), (random_matrix(40, 33, 26), 4)):
+        pbf = oracle.encode_pbf(mat, shift=shift)
+        m, shift, rows, snaps = both_planes(pbf, oracle)
+        BS = 1 << shift
+        for v, (rle0, rle1) in enumerate(rows):
+            b0 = v - v % BS
+            start, _, n1 = tables(rle1, m)
+            c = np.frombuffer(rle1, dtype=np.uint8).astype(np.int64)
+            ones = np.concatenate([np.arange(s, s + l) for s, l, b in zip(start, rle_len(c), c & 1) if b and l] or [np.zeros(0, np.int64)])
+            assert len(ones) == n1
+            # backwards: undo the partitions of the plane-1 rows in front (constant rows move nothing)
+            x = ones.copy()
+            for u in range(v - 1, b0 - 1, -1):
+                S, D, k1 = run_map(rows[u][1], m)
+                if k1 == 0 or k1 == m:
+                    continue
+                dst = S + D
+                order = np.argsort(dst, kind="stable")
+                x = x - D[order][np.searchsorted(dst[order], x, side="right") - 1]
+            cols = snaps[v // BS][1][x]
+            # forwards through plane 0 up to (and including) row v
+            inv0 = np.empty(m, np.int64)
+            inv0[snaps[v // BS][0]] = np.arange(m)
+            r = inv0[cols]
+            for u in range(b0, v):
+                S, D, _ = run_map(rows[u][0], m)
+                r = apply_map(S, D, r)
+            S, D, k0 = run_map(rle0, m)
+            bit0 = np.full(len(r), k0 == m) if k0 in (0, m) else apply_map(S, D, r) >= m - k0
+            assert sorted(cols.tolist()) == np.flatnonzero(mat[v] & 2).tolist()
+            assert int(bit0.sum()) == int((mat[v] == 3).sum()) and int((~bit0).sum()) == int((mat[v] == 2).sum())
