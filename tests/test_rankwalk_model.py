@@ -268,3 +268,96 @@ def test_plane1_pairs_backwards_then_plane0_forwards(oracle):
             bit0 = np.full(len(r), k0 == m) if k0 in (0, m) else apply_map(S, D, r) >= m - k0
             assert sorted(cols.tolist()) == np.flatnonzero(mat[v] & 2).tolist()
             assert int(bit0.sum()) == int((mat[v] == 3).sum()) and int((~bit0).sum()) == int((mat[v] == 2).sum())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Row-offset chase (index.cu): the records of a block are a chain of dependent length reads; K chasers share it, chaser l
+# starting at the first position of its stretch of the byte range that VERIFIES as a record start.  The pieces count only
+# if every chaser lands exactly on its successor's start and the rows add up -- otherwise the block is walked alone.
+
+def verify_start(img, p, end, m, need=4):
+    def rec(q):
+        if q + 9 > end or img[q] != ord('B'):
+            return None
+        l0 = int.from_bytes(img[q + 1:q + 5], "little", signed=True)
+        if l0 < 0 or q + 9 + l0 > end:
+            return None
+        l1 = int.from_bytes(img[q + 5 + l0:q + 9 + l0], "little", signed=True)
+        if l1 < 0 or q + 9 + l0 + l1 > end:
+            return None
+        return l0, l1
+    first = rec(p)
+    if first is None:
+        return False
+    l0, l1 = first
+    for off, l in ((p + 5, l0), (p + 9 + l0, l1)):           # run lengths of both planes of the first record sum to m
+        c = np.frombuffer(img[off:off + l], dtype=np.uint8).astype(np.int64)
+        if int(rle_len(c).sum()) != m:
+            return False
+    for v in range(need):                                      # ... and `need` well-formed records chain from here
+        if p == end:
+            return v > 0
+        r = rec(p)
+        if r is None:
+            return False
+        p += 9 + r[0] + r[1]
+    return True
+
+
+def team_chase(img, first, end, m, rows, K):
+    span = end - first
+    starts = [first]
+    for l in range(1, K):
+        s = None
+        for p in range(first + span * l // K, first + span * (l + 1) // K):
+            if img[p] == ord('B') and verify_start(img, p, end, m):
+                s = p
+                break
+        starts.append(s)
+    pieces = []
+    for l in range(K):
+        if starts[l] is None:
+            pieces.append([])
+            continue
+        stop = next((s for s in starts[l + 1:] if s is not None), end)
+        o, mine = starts[l], []
+        while o < stop:
+            l0 = int.from_bytes(img[o + 1:o + 5], "little")
+            l1 = int.from_bytes(img[o + 5 + l0:o + 9 + l0], "little")
+            mine.append(o)
+            o += 9 + l0 + l1
+        if o != stop:
+            return None                                        # ran past the successor: fall back to one chaser
+        pieces.append(mine)
+    chain = [o for mine in pieces for o in mine]
+    return chain if len(chain) == rows else None
+
+
+def test_team_chase_stitches_the_true_chain(oracle):
+    rng = np.random.default_rng(9)
+    m = 2048
+    # runs of 256..511 zeros are coded with the byte 0x42 = 'B': the record bytes are full of fake tags
+    mat = np.zeros((300, m), np.uint8)
+    for r in range(300):
+        pos = 0
+        while pos < m:
+            gap = int(rng.integers(256, 512))
+            pos += gap
+            if pos < m:
+                mat[r, pos:pos + int(rng.integers(1, 4))] = 1 + 2 * int(rng.integers(0, 2))
+                pos += 3
+    pbf = oracle.encode_pbf(mat, shift=13)
+    assert pbf.count(b"B") > 4 * 300                            # far more 'B' bytes than records
+    first = 16 + 1 + 8 * m                                      # behind the 'S' record
+    true_chain, o = [], first
+    for _ in range(300):
+        l0 = int.from_bytes(pbf[o + 1:o + 5], "little")
+        l1 = int.from_bytes(pbf[o + 5 + l0:o + 9 + l0], "little")
+        true_chain.append(o)
+        o += 9 + l0 + l1
+    end = o
+    assert pbf[end:end + 1] == b"I"                             # the index record follows the last row
+    fakes = sum(1 for q in range(first, end) if pbf[q] == ord("B") and q not in set(true_chain))
+    assert fakes > 300 and not any(verify_start(pbf, q, end, m) for q in range(first, end) if pbf[q] == ord("B") and q not in set(true_chain))
+    for K in (2, 6, 12):
+        assert team_chase(pbf, first, end, m, 300, K) == true_chain
