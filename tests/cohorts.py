@@ -51,3 +51,18 @@ def edge_rows(m):
     rows.append(np.full(m, 2, np.uint8))
     rows.append(np.full(m, 3, np.uint8))
     return np.array(rows, dtype=np.uint8)
+
+
+def fake_tag_matrix(n_rows, m, seed):
+    """Rows whose plane-0 runs of 256..511 zeros are coded with the byte 0x42 = 'B', the record tag: the record bytes are
+    full of fake tags (the device-side row index starts its chasers in the middle of a block, index.cu)."""
+    rng = np.random.default_rng(seed)
+    mat = np.zeros((n_rows, m), np.uint8)
+    for r in range(n_rows):
+        pos = 0
+        while pos < m:
+            pos += int(rng.integers(256, 512))
+            if pos < m:
+                mat[r, pos:pos + int(rng.integers(1, 4))] = 1 + 2 * int(rng.integers(0, 2))
+                pos += 3
+    return mat

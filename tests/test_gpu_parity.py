@@ -268,6 +268,20 @@ def test_error_behaviour(b200, ctx, oracle):
         b200.Pbf.from_bytes(ctx, pbf[:-9])
 
 
+def test_row_index_chase_among_fake_tags(b200, ctx, oracle):
+    """Blocks of >= 768 rows are indexed by twelve chasers that start in the middle of the block (index.cu); here the record
+    bytes are full of 'B' bytes that are not record tags (tests/test_rankwalk_model.py has the CPU model of the scheme)."""
+    from cohorts import fake_tag_matrix
+    mat = fake_tag_matrix(1900, 2048, 9)
+    pbf = oracle.encode_pbf(mat, shift=10)                      # 1024 + 876 rows: both blocks take the team chase
+    assert pbf.count(b"B") > 4 * 1900
+    ref_pb = oracle.Pbf(pbf)
+    pb = b200.Pbf.from_bytes(ctx, pbf)
+    assert pb.bad_rows == 0 and pb.row_bytes(0, 1900) == ref_pb.row_bytes(0, 1900)
+    pb.close()
+    check_scan(b200, ctx, oracle, pbf, flt="AC>0")
+
+
 def test_device_index_reports_corruption(b200, ctx, oracle):
     """The row index is built on the device (index.cu); damaged tags / lengths / snapshots inside a block must fail the load
     (pbf_read would run off the rails: pbwt.c:318-328 has no checks), a row whose run lengths do not sum to m is counted."""

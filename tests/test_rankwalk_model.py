@@ -5,7 +5,7 @@ oracle's restated pbc_dec.  It guards the arithmetic the kernels rely on (pbwt_k
 """
 import numpy as np
 
-from cohorts import edge_rows, haplo_matrix, random_matrix
+from cohorts import edge_rows, fake_tag_matrix, haplo_matrix, random_matrix
 
 
 def rle_len(c):
@@ -334,18 +334,8 @@ def team_chase(img, first, end, m, rows, K):
 
 
 def test_team_chase_stitches_the_true_chain(oracle):
-    rng = np.random.default_rng(9)
     m = 2048
-    # runs of 256..511 zeros are coded with the byte 0x42 = 'B': the record bytes are full of fake tags
-    mat = np.zeros((300, m), np.uint8)
-    for r in range(300):
-        pos = 0
-        while pos < m:
-            gap = int(rng.integers(256, 512))
-            pos += gap
-            if pos < m:
-                mat[r, pos:pos + int(rng.integers(1, 4))] = 1 + 2 * int(rng.integers(0, 2))
-                pos += 3
+    mat = fake_tag_matrix(300, m, 9)            # runs of 256..511 zeros are coded with the byte 0x42 = 'B'
     pbf = oracle.encode_pbf(mat, shift=13)
     assert pbf.count(b"B") > 4 * 300                            # far more 'B' bytes than records
     first = 16 + 1 + 8 * m                                      # behind the 'S' record
