@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200_abi_version": (_int, []),
     "b200_device_count": (_int, []),
     "b200_strerror": (C.c_char_p, []),
+    "b200_errcode": (_int, []),
     "b200_ctx_create": (_vp, [_int]),
     "b200_ctx_destroy": (None, [_vp]),
     "b200_ctx_sync": (_int, [_vp]),
@@ -57,10 +58,13 @@ SIGNATURES = {
     "b200_query_create_cols": (_vp, [_vp, _vp, _int, _vp]),
     "b200_query_destroy": (None, [_vp]),
     "b200_query_n_track": (_int, [_vp]),
+    "b200_query_filter_needs_host": (_int, [_vp]),
     "b200_query_hap_words": (_int, [_vp]),
     "b200_query_counts_stride": (_int, [_vp]),
     "b200_scan": (_i64, [_vp, _vp, _vp, _i64, _i64, C.c_uint, C.POINTER(ScanOut)]),
     "b200_scan_collect": (_int, [_vp, C.POINTER(_i64)]),
+    "b200_last_totals": (_int, [_vp, C.POINTER(_i64)]),
+    "b200_allreduce_i64": (_int, [C.POINTER(_vp), _int, C.POINTER(_i64), _int]),
     "b200_last_ms": (C.c_double, [_vp, _int]),
     "b200_kernel_launches": (_i64, [_vp]),
     "b200_mark": (_int, [_vp, _int]),
@@ -74,11 +78,14 @@ SIGNATURES = {
     "b200_enc_write_bytes": (_int, [_vp, _vp, _vp, _i64]),
     "b200_enc_write_bits": (_int, [_vp, _vp, _i64]),
     "b200_enc_rows": (_i64, [_vp]),
+    "b200_enc_drain": (_i64, [_vp, C.POINTER(_vp)]),
     "b200_enc_finish": (_i64, [_vp, C.POINTER(_vp)]),
     "b200_enc_destroy": (None, [_vp]),
     "b200_bgzf_inflate": (_i64, [_vp, _vp, C.c_size_t, _vp, C.c_size_t]),
     "b200_sites_load": (_vp, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _int]),
     "b200_sites_n": (_i64, [_vp]),
+    "b200_sites_rows_sorted": (_int, [_vp]),
+    "b200_sites_rec_range": (_int, [_vp, _i64, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "b200_sites_header": (C.c_void_p, [_vp, C.POINTER(_i64)]),
     "b200_sites_rows": (_int, [_vp, _vp, _vp]),
     "b200_sites_destroy": (None, [_vp]),
@@ -221,8 +228,16 @@ class Encoder:
         if lib().b200_enc_write_bits(self.h, _ptr(bits), bits.shape[0]) != 0:
             raise B200Error(_err())
 
+    def drain(self):
+        """The file bytes assembled since the last drain (streaming writers, b200_enc_drain)."""
+        p = C.c_void_p()
+        n = lib().b200_enc_drain(self.h, C.byref(p))
+        if n < 0:
+            raise B200Error(_err())
+        return C.string_at(p, n) if n else b""
+
     def finish(self):
-        """The complete .pbf image as bytes."""
+        """The complete .pbf image as bytes (after drain() calls: the rest of it)."""
         p = C.c_void_p()
         n = lib().b200_enc_finish(self.h, C.byref(p))
         if n < 0:

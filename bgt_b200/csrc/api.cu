@@ -2,6 +2,8 @@
 // Host logic only; every per-site computation is in pbwt_kernels.cu / synth.cu.  No CPU fallback exists:
 // without a CUDA device b200_ctx_create() fails and nothing else can be called.
 #include <cuda_runtime.h>
+#include <nccl.h>      // types and prototypes only: libnccl.so.2 is loaded on the first b200_allreduce_i64 call, not linked
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -13,6 +15,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <mutex>
 #include <vector>
 #include <algorithm>
 #include <string>
@@ -25,6 +28,7 @@ using namespace b200;
 // ------------------------------------------------------------------------------------------------ errors
 
 static thread_local char g_err[512] = "";
+static thread_local int g_errcode = B200_OK;
 
 static void set_err(const char *fmt, ...)
 {
@@ -32,6 +36,17 @@ static void set_err(const char *fmt, ...)
 	va_start(ap, fmt);
 	vsnprintf(g_err, sizeof(g_err), fmt, ap);
 	va_end(ap);
+	g_errcode = B200_E_GENERIC;
+}
+
+// same, with one of the B200_E_* codes a caller can branch on (b200_errcode) instead of reading the text
+static void set_err_code(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	g_errcode = code;
 }
 
 static double now_ms()
@@ -45,7 +60,7 @@ static double now_ms()
 static bool cu_ok(cudaError_t e, const char *what, int line)
 {
 	if (e == cudaSuccess) return true;
-	set_err("CUDA error at api.cu:%d: %s: %s", line, what, cudaGetErrorString(e));
+	set_err_code(B200_E_CUDA, "CUDA error at api.cu:%d: %s: %s", line, what, cudaGetErrorString(e));
 	return false;
 }
 
@@ -83,8 +98,12 @@ struct b200_ctx_s {
 	cudaEvent_t mark[4] = {};
 	cudaEvent_t ev_zero = nullptr;
 	double last_ms[6] = {0, 0, 0, 0, 0, 0};
+	int64_t last_totals[4] = {0, 0, 0, 0};   // totals of the last scan whose results reached the host (b200_last_totals)
 	int64_t launches = 0;
-	int *d_err = nullptr;
+	// device error flags, one word per kind of operation so that they cannot wipe or taint each other:
+	// d_err = loads (row index, snapshots, composites built while loading), d_err_scan = b200_scan (zeroed when a scan
+	// starts, reported when it ends or is collected), d_err_sites = inflate / BCF parse / text assembly
+	int *d_err = nullptr, *d_err_scan = nullptr, *d_err_sites = nullptr;
 	unsigned long long *d_acc = nullptr; // [0..3] totals, [4] bad rows
 	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], qcol, qrow, qcount, blk_lists, blk_split, n0g, vseg, seg_ok;
 	int sm_count = 148;
@@ -212,11 +231,12 @@ extern "C" int b200_device_count(void)
 }
 
 extern "C" const char *b200_strerror(void) { return g_err; }
+extern "C" int b200_errcode(void) { return g_errcode; }
 
 extern "C" b200_ctx_t *b200_ctx_create(int device)
 {
 	int n = b200_device_count();
-	if (n <= 0) { set_err("no CUDA device: libbgt_b200 has no CPU fallback"); return nullptr; }
+	if (n <= 0) { set_err_code(B200_E_NO_DEVICE, "no CUDA device: libbgt_b200 has no CPU fallback"); return nullptr; }
 	if (device < 0 || device >= n) { set_err("device %d out of range (0..%d)", device, n - 1); return nullptr; }
 	if (!CU_OK(cudaSetDevice(device))) return nullptr;
 	cudaDeviceProp prop;
@@ -235,9 +255,10 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	for (int i = 0; ok && i < 12; ++i) ok = CU_OK(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; ok && i < 4; ++i) ok = CU_OK(cudaEventCreate(&c->mark[i]));
 	ok = ok && CU_OK(cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming));
-	ok = ok && CU_OK(cudaMalloc(&c->d_err, sizeof(int))) && CU_OK(cudaMalloc(&c->d_acc, 8 * sizeof(unsigned long long)));
-	ok = ok && CU_OK(cudaMemset(c->d_err, 0, sizeof(int))) && CU_OK(cudaMemset(c->d_acc, 0, 8 * sizeof(unsigned long long)));
+	ok = ok && CU_OK(cudaMalloc(&c->d_err, 4 * sizeof(int))) && CU_OK(cudaMalloc(&c->d_acc, 8 * sizeof(unsigned long long)));
+	ok = ok && CU_OK(cudaMemset(c->d_err, 0, 4 * sizeof(int))) && CU_OK(cudaMemset(c->d_acc, 0, 8 * sizeof(unsigned long long)));
 	if (!ok) { b200_ctx_destroy(c); return nullptr; }
+	c->d_err_scan = c->d_err + 1; c->d_err_sites = c->d_err + 2;
 	return c;
 }
 
@@ -415,7 +436,7 @@ static bool compose_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
 }
 
 // inverse composites of the plane-1 view rows of blocks [b0,b1), then the plane-1 select over them (needs the view)
-static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
+static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st, int *d_err)
 {
 	if (b1 <= b0) return true;
 	b200_ctx_t *c = pb->ctx;
@@ -430,15 +451,15 @@ static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
 	A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = nullptr; A.blk_first = b0; A.blk_ok = pb->d_blk_sparse;
 	A.m = pb->m; A.shift = pb->shift; A.cap = pb->p1_cap;
 	A.vcomp_start = pb->d_vcomp_start; A.vcomp_delta = pb->d_vcomp_delta; A.vcomp_n = pb->d_vcomp_n;
-	A.qcol = pb->d_qcol; A.qrow = pb->d_qrow; A.qcount = pb->d_qcount; A.err = c->d_err;
+	A.qcol = pb->d_qcol; A.qrow = pb->d_qrow; A.qcount = pb->d_qcount; A.err = d_err;
 	const bool ok = CU_OK(launch_compose(V, b1 - b0, st)) && CU_OK(launch_plane1_select(A, b1 - b0, st));
 	c->launches += 3;
 	return ok;
 }
 
-static bool build_composites(const b200_pbf_t *pb)
+static bool build_composites(const b200_pbf_t *pb, int *d_err)
 {
-	if (!compose_alloc(pb) || !compose_queue(pb, 0, pb->n_blk, pb->ctx->st) || !select_queue(pb, 0, pb->n_blk, pb->ctx->st)) return false;
+	if (!compose_alloc(pb) || !compose_queue(pb, 0, pb->n_blk, pb->ctx->st) || !select_queue(pb, 0, pb->n_blk, pb->ctx->st, d_err)) return false;
 	pb->comp_ready = true; pb->sel_ready = true;
 	return true;
 }
@@ -591,13 +612,13 @@ static b200_pbf_t *pbf_index_prepare(const uint8_t *f, size_t flen, int64_t row_
 	memcpy(hdr, f + 4, 12);
 	uint64_t ioff;
 	memcpy(&ioff, f + flen - 8, 8);
-	if (ioff + 13 > flen || f[ioff] != 'I') { set_err("PBF has no index record; it cannot be made resident"); return nullptr; } // pbwt.c:247-258
+	if (ioff > flen - 13 - 8 || f[ioff] != 'I') { set_err_code(B200_E_CORRUPT, "PBF has no index record; it cannot be made resident"); return nullptr; } // pbwt.c:247-258 (no wrap-around: ioff is untrusted)
 	int64_t n; int32_t n_idx;
 	memcpy(&n, f + ioff + 1, 8);
 	memcpy(&n_idx, f + ioff + 9, 4);
 	const int m = hdr[0], g = hdr[1], shift = hdr[2];
 	if (g != 2) { set_err("PBF has %d bit planes; the BGT genotype path uses exactly 2 (import.c:68)", g); return nullptr; }
-	if (m <= 0 || m >= (1 << 30) || shift < 0 || shift > 24 || n < 0 || n_idx < 0 || ioff + 13 + 8ull * n_idx > flen) { set_err("PBF header out of range (m=%d shift=%d n=%lld)", m, shift, (long long)n); return nullptr; }
+	if (m <= 0 || m >= (1 << 30) || shift < 0 || shift > 24 || n < 0 || n_idx < 0 || (uint64_t)n_idx > (flen - ioff - 13) / 8 || n > ((int64_t)n_idx << shift)) { set_err("PBF header out of range (m=%d shift=%d n=%lld)", m, shift, (long long)n); return nullptr; }
 	const int BS = 1 << shift;
 	if ((int64_t)n_idx != (n + BS - 1) / BS) { set_err("PBF index has %d entries for %lld rows", n_idx, (long long)n); return nullptr; }
 	if (row_end < 0 || row_end > n) row_end = n;
@@ -734,7 +755,7 @@ extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t 
 		ok = ok && queue_tiles_rowmeta(pb, b0, b1, sx) && queue_ranks_view(pb, b0, b1, sx);
 		ok = ok && CU_OK(cudaEventRecord(c->ev_idx[k], sx)) && CU_OK(cudaStreamWaitEvent(c->st, c->ev_idx[k], 0));
 		if (eager) { // forward composites on the main stream; the plane-1 side (inverse composites + select: small grids) stays on the index stream
-			ok = ok && compose_queue(pb, b0, b1, c->st) && select_queue(pb, b0, b1, sx) &&
+			ok = ok && compose_queue(pb, b0, b1, c->st) && select_queue(pb, b0, b1, sx, c->d_err) &&
 			     CU_OK(cudaEventRecord(c->ev_sel[k], sx));
 		}
 		if (trace) {
@@ -903,7 +924,7 @@ extern "C" b200_query_t *b200_query_create(b200_ctx_t *c, const b200_pbf_t *pb, 
 		gsize[gr - 1] += 2;
 	}
 	const int perr = flt_compile(flt, n_groups, &q->prog);
-	if (perr) { if (flt_err) *flt_err = perr; set_err("filter expression does not parse (kexpr error mask 0x%x)", perr); delete q; return nullptr; }
+	if (perr) { if (flt_err) *flt_err = perr; set_err_code(B200_E_FILTER_SYNTAX, "filter expression does not parse (kexpr error mask 0x%x)", perr); delete q; return nullptr; }
 	q->has_flt = q->prog.n > 0;
 	bool ok = CU_OK(cudaMalloc(&q->d_tgrp, tgrp.size() + 16)) && CU_OK(cudaMalloc(&q->d_gsize, sizeof(int32_t) * B200_MAX_GROUPS)) &&
 	          CU_OK(cudaMalloc(&q->d_prog, sizeof(flt_prog_t)));
@@ -943,6 +964,7 @@ extern "C" b200_query_t *b200_query_create_cols(b200_ctx_t *c, const b200_pbf_t 
 }
 
 extern "C" int b200_query_n_track(const b200_query_t *q) { return q ? q->n_track : -1; }
+extern "C" int b200_query_filter_needs_host(const b200_query_t *q) { return q && q->has_flt && q->prog.needs_host ? 1 : 0; }
 extern "C" int b200_query_hap_words(const b200_query_t *q) { return q ? q->words : -1; }
 extern "C" int b200_query_counts_stride(const b200_query_t *q) { return q ? 3 + 3 * q->G : -1; }
 
@@ -988,7 +1010,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	const bool emit = want_bits || want_bytes;
 	const bool want_counts = (flags & B200_SCAN_COUNTS) && out->counts;
 	const bool host_flt = q->has_flt && q->prog.needs_host;
-	if (host_flt && dev_out) { set_err("filters using ** are evaluated with the host libm; not available with B200_SCAN_DEVICE_OUT"); return -1; }
+	if (host_flt && dev_out) { set_err_code(B200_E_FILTER_NEEDS_HOST, "filters using ** are evaluated with the host libm; not available with B200_SCAN_DEVICE_OUT"); return -1; }
 	const int G = q->G, stride = 3 + 3 * G, words = q->words, n_track = q->n_track;
 	const size_t nr = (size_t)n_rows;
 
@@ -1019,7 +1041,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	P.rank0 = pb->d_rank0; P.track = q->full ? nullptr : q->d_track; P.tgrp = q->d_tgrp;
 	P.cnt_raw = (int32_t*)c->cnt_raw.p; P.hap[0] = d_bits[0]; P.hap[1] = d_bits[1];
 	P.m = pb->m; P.n_track = n_track; P.G = G; P.words = words; P.shift = pb->shift;
-	P.blk_first = b_first; P.blk_row0 = (long long)pb->blk0 << pb->shift; P.row_lo = row_beg; P.row_hi = row_beg + n_rows; P.err = c->d_err;
+	P.blk_first = b_first; P.blk_row0 = (long long)pb->blk0 << pb->shift; P.row_lo = row_beg; P.row_hi = row_beg + n_rows; P.err = c->d_err_scan;
 	const int forced = (int)((flags >> 8) & 15u);
 
 	// Split scan (all columns, one group, counts only): #ALT of a site is the number of ones of its plane-0 row, known
@@ -1042,6 +1064,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	bool ok = CU_OK(cudaEventRecord(c->ev[2], c->st)) &&
 	          CU_OK(cudaMemsetAsync(c->cnt_raw.p, 0, nr * G * 3 * sizeof(int32_t), c->st)) &&
 	          CU_OK(cudaMemsetAsync(c->d_acc, 0, 4 * sizeof(unsigned long long), c->st)) &&
+	          CU_OK(cudaMemsetAsync(c->d_err_scan, 0, sizeof(int), c->st)) &&
 	          CU_OK(cudaMemcpyAsync(c->blk_lists.p, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
 	          CU_OK(cudaMemcpyAsync(c->blk_split.p, split_flag.data(), (size_t)pb->n_blk, cudaMemcpyHostToDevice, c->st)) &&
 	          CU_OK(cudaEventRecord(c->ev[0], c->st));
@@ -1057,7 +1080,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		if (!c->qcol.reserve((size_t)pb->n_blk * cap * sizeof(int32_t)) || !c->qrow.reserve((size_t)pb->n_blk * cap * sizeof(uint16_t)) ||
 		    !c->qcount.reserve((size_t)pb->n_blk * sizeof(int))) return -1;
 		if (!pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) { // composite maps of the row groups: once per resident PBF
-			if (!build_composites(pb)) return -1;
+			if (!build_composites(pb, c->d_err_scan)) return -1;
 		}
 		// phase 1 (plane1.cu): the (column, row) pairs that carry a plane-1 bit, per block, in row order.  They do not depend
 		// on the query: found once per resident PBF next to the composite maps (select_queue); only the testing path without
@@ -1070,7 +1093,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
 			A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
 			A.m = pb->m; A.shift = pb->shift; A.cap = cap;
-			A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err;
+			A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err_scan;
 			ok = CU_OK(cudaEventRecord(c->ev[8], c->st)) && CU_OK(launch_plane1_select(A, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[9], c->st));
 			++c->launches;
 			qcol = (const int32_t*)c->qcol.p; qrow = (const uint16_t*)c->qrow.p; qcount = (const int*)c->qcount.p;
@@ -1146,12 +1169,13 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	}
 	unsigned long long dtot[4];
 	ok = ok && CU_OK(cudaMemcpyAsync(dtot, c->d_acc, sizeof(dtot), cudaMemcpyDeviceToHost, c->st)) &&
-	     CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(err), cudaMemcpyDeviceToHost, c->st)) &&
+	     CU_OK(cudaMemcpyAsync(&err, c->d_err_scan, sizeof(err), cudaMemcpyDeviceToHost, c->st)) &&
 	     CU_OK(cudaEventRecord(c->ev[7], c->st)) && CU_OK(cudaStreamSynchronize(c->st));
 	if (!ok) return -1;
 	if (err) { set_err("device error flags 0x%x during scan", err); return -1; }
 	out->totals[0] = (int64_t)dtot[0]; out->totals[1] = (int64_t)dtot[1]; out->totals[2] = (int64_t)dtot[2];
 	out->totals[3] = host_flt ? (int64_t)tot[3] : (int64_t)dtot[3];
+	for (int i = 0; i < 4; ++i) c->last_totals[i] = out->totals[i];
 	read_scan_timings(c);
 	float ms;
 	if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->last_ms[3] = ms;
@@ -1166,12 +1190,87 @@ extern "C" int b200_scan_collect(b200_ctx_t *c, int64_t totals[4])
 	unsigned long long dtot[4];
 	int err = 0;
 	bool ok = CU_OK(cudaMemcpyAsync(dtot, c->d_acc, sizeof(dtot), cudaMemcpyDeviceToHost, c->st)) &&
-	          CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(err), cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+	          CU_OK(cudaMemcpyAsync(&err, c->d_err_scan, sizeof(err), cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
 	if (!ok) return -1;
 	if (err) { set_err("device error flags 0x%x during scan", err); return -1; }
 	if (totals) for (int i = 0; i < 4; ++i) totals[i] = (int64_t)dtot[i];
+	for (int i = 0; i < 4; ++i) c->last_totals[i] = (int64_t)dtot[i];
 	read_scan_timings(c);
 	return 0;
+}
+
+extern "C" int b200_last_totals(b200_ctx_t *c, int64_t totals[4])
+{
+	if (!c || !totals) return -1;
+	for (int i = 0; i < 4; ++i) totals[i] = c->last_totals[i];
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU totals
+
+// The path's one collective: region shards are independent (pbwt.c:292-301), only the whole-cohort totals are summed.
+// NCCL is loaded lazily so that single-GPU users (and the CLI's start-up) do not pay for it.
+namespace {
+struct NcclApi {
+	void *h = nullptr;
+	ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	bool load() {
+		if (h) return true;
+		const char *names[] = {"libnccl.so.2", "libnccl.so"};
+		for (const char *nm : names) if ((h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+		if (!h) { set_err("cannot load NCCL (libnccl.so.2): %s", dlerror()); return false; }
+		CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll");
+		CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+		AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+		GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+		GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
+		GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+		if (!CommInitAll || !CommDestroy || !AllReduce || !GroupStart || !GroupEnd || !GetErrorString) { set_err("libnccl.so.2 lacks an entry point"); dlclose(h); h = nullptr; return false; }
+		return true;
+	}
+};
+NcclApi g_nccl;
+}
+
+extern "C" int b200_allreduce_i64(b200_ctx_t *const *ctxs, int n, int64_t *vals, int count)
+{
+	if (!ctxs || !vals || n < 1 || count < 1 || n > 64) { set_err("b200_allreduce_i64: bad argument"); return -1; }
+	for (int i = 0; i < n; ++i) if (!ctxs[i]) { set_err("b200_allreduce_i64: null context"); return -1; }
+	if (n == 1) return 0;
+	static std::mutex mu;
+	std::lock_guard<std::mutex> lk(mu);
+	if (!g_nccl.load()) return -1;
+	std::vector<int> devs(n);
+	std::vector<ncclComm_t> comms(n, nullptr);
+	std::vector<int64_t*> d(n, nullptr);
+	for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->dev;
+	ncclResult_t r = g_nccl.CommInitAll(comms.data(), n, devs.data());
+	if (r != ncclSuccess) { set_err("ncclCommInitAll over %d GPUs: %s", n, g_nccl.GetErrorString(r)); return -1; }
+	bool ok = true;
+	for (int i = 0; ok && i < n; ++i) {
+		ok = CU_OK(cudaSetDevice(devs[i])) && CU_OK(cudaMalloc(&d[i], sizeof(int64_t) * (size_t)count)) &&
+		     CU_OK(cudaMemcpyAsync(d[i], vals + (size_t)i * count, sizeof(int64_t) * (size_t)count, cudaMemcpyHostToDevice, ctxs[i]->st));
+	}
+	if (ok) {
+		g_nccl.GroupStart();
+		for (int i = 0; i < n; ++i) {
+			r = g_nccl.AllReduce(d[i], d[i], (size_t)count, ncclInt64, ncclSum, comms[i], ctxs[i]->st);
+			if (r != ncclSuccess) ok = false;
+		}
+		const ncclResult_t r2 = g_nccl.GroupEnd();
+		if (r2 != ncclSuccess) { r = r2; ok = false; }
+		if (!ok) set_err("ncclAllReduce: %s", g_nccl.GetErrorString(r));
+	}
+	for (int i = 0; ok && i < n; ++i)
+		ok = CU_OK(cudaSetDevice(devs[i])) && CU_OK(cudaMemcpyAsync(vals + (size_t)i * count, d[i], sizeof(int64_t) * (size_t)count, cudaMemcpyDeviceToHost, ctxs[i]->st)) &&
+		     CU_OK(cudaStreamSynchronize(ctxs[i]->st));
+	for (int i = 0; i < n; ++i) { cudaSetDevice(devs[i]); if (d[i]) cudaFree(d[i]); if (comms[i]) g_nccl.CommDestroy(comms[i]); ++ctxs[i]->launches; }
+	return ok ? 0 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------ synthetic cohort
@@ -1282,7 +1381,9 @@ struct b200_enc_s {
 	uint32_t *d_bitvec = nullptr;
 	unsigned long long *d_pos = nullptr; // [4]: stream offsets in / out
 	DevBuf in_bits, bytes[2], snap, out[2], row_len;
-	std::vector<uint8_t> image;          // the file so far
+	std::vector<uint8_t> image;          // the file so far, minus what b200_enc_drain has handed out
+	std::vector<uint8_t> drained;        // the bytes of the last b200_enc_drain (valid until the next call on this encoder)
+	uint64_t file_off = 0;               // file offset of image[0] = bytes drained so far
 	std::vector<uint64_t> idx;           // offsets of the 'S' records (pbwt.c:297)
 	std::vector<uint8_t> h_out[2];
 	std::vector<uint32_t> h_len;
@@ -1363,7 +1464,7 @@ static bool enc_batch(b200_enc_t *e, int R)
 	for (int r = 0; r < R; ++r) {
 		const int64_t arow = row0 + r;
 		if ((arow & (BS - 1)) == 0) {
-			e->idx.push_back((uint64_t)e->image.size());
+			e->idx.push_back(e->file_off + (uint64_t)e->image.size());
 			e->image.push_back('S');
 			const uint8_t *s = (const uint8_t*)(e->h_snap.data() + 2 * (size_t)m * (size_t)((arow >> e->shift) - k0));
 			e->image.insert(e->image.end(), s, s + 8 * (size_t)m);
@@ -1422,7 +1523,7 @@ extern "C" int64_t b200_enc_finish(b200_enc_t *e, const uint8_t **image)
 {
 	if (!e) { set_err("b200_enc_finish: null encoder"); return -1; }
 	if (!e->finished) { // the index record (pbwt.c:268-276)
-		const uint64_t off = (uint64_t)e->image.size();
+		const uint64_t off = e->file_off + (uint64_t)e->image.size();
 		const int64_t n = e->n;
 		const int32_t n_idx = (int32_t)e->idx.size();
 		e->image.push_back('I');
@@ -1434,6 +1535,18 @@ extern "C" int64_t b200_enc_finish(b200_enc_t *e, const uint8_t **image)
 	}
 	if (image) *image = e->image.data();
 	return (int64_t)e->image.size();
+}
+
+// Streaming writers (pbf_write writes every row as it goes, pbwt.c:288-311): hand out the bytes assembled since the last
+// drain and forget them; only the block index and the running file offset are kept for the 'I' record.
+extern "C" int64_t b200_enc_drain(b200_enc_t *e, const uint8_t **bytes)
+{
+	if (!e || !bytes) { set_err("b200_enc_drain: null argument"); return -1; }
+	e->drained.clear();
+	e->drained.swap(e->image);
+	e->file_off += (uint64_t)e->drained.size();
+	*bytes = e->drained.data();
+	return (int64_t)e->drained.size();
 }
 
 // ------------------------------------------------------------------------------------------------ BGZF (bgzf.c)
@@ -1487,15 +1600,15 @@ static bool bgzf_inflate_device(b200_ctx_t *c, const uint8_t *f, size_t n, uint8
 	     CU_OK(cudaMemcpyAsync(d_csize, ix.csize.data(), nb * 4, cudaMemcpyHostToDevice, c->st)) && CU_OK(cudaMemcpyAsync(d_usize, ix.usize.data(), nb * 4, cudaMemcpyHostToDevice, c->st));
 	InflateParams P;
 	memset(&P, 0, sizeof(P));
-	P.in = d_in; P.blk_coff = d_coff; P.blk_csize = d_csize; P.blk_usize = d_usize; P.blk_uoff = d_uoff; P.out = d_o; P.max_csize = ix.max_csize; P.err = c->d_err;
-	ok = ok && CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st)) && CU_OK(launch_bgzf_inflate(P, (int)nb, c->st));
+	P.in = d_in; P.blk_coff = d_coff; P.blk_csize = d_csize; P.blk_usize = d_usize; P.blk_uoff = d_uoff; P.out = d_o; P.max_csize = ix.max_csize; P.err = c->d_err_sites;
+	ok = ok && CU_OK(cudaMemsetAsync(c->d_err_sites, 0, sizeof(int), c->st)) && CU_OK(launch_bgzf_inflate(P, (int)nb, c->st));
 	++c->launches;
 	// the tables and the compressed image are read by the queued kernel: released after the stream has passed it
 	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
 	pool_free(c, d_in); pool_free(c, d_tab);
 	if (!ok) { pool_free(c, d_o); return false; }
 	int err = 0;
-	if (!CU_OK(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost))) { pool_free(c, d_o); return false; }
+	if (!CU_OK(cudaMemcpy(&err, c->d_err_sites, sizeof(int), cudaMemcpyDeviceToHost))) { pool_free(c, d_o); return false; }
 	if (err & 256) { set_err("corrupt BGZF file: a block does not inflate to its ISIZE"); pool_free(c, d_o); return false; }
 	*d_out = d_o; *out_len = ix.total;
 	return true;
@@ -1664,11 +1777,11 @@ extern "C" b200_sites_t *b200_sites_load(b200_ctx_t *c, const uint8_t *bcf, size
 		}
 	}
 	unsigned long long *d_seg = nullptr, *d_off = nullptr, *d_cnt = nullptr;
-	ok = CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
+	ok = CU_OK(cudaMemsetAsync(c->d_err_sites, 0, sizeof(int), c->st));
 	if (n_rec < 0) { // no usable RNI: count, then chase, from the first record with one thread
 		seg.assign(1, first);
 		ok = ok && CU_OK(cudaMalloc(&d_seg, 8)) && CU_OK(cudaMalloc(&d_cnt, 8)) && CU_OK(cudaMemcpyAsync(d_seg, seg.data(), 8, cudaMemcpyHostToDevice, c->st)) &&
-		     CU_OK(launch_bcf_chase(s->d_bcf, s->bcf_len, d_seg, 1, 0, 0, nullptr, d_cnt, c->d_err, c->st));
+		     CU_OK(launch_bcf_chase(s->d_bcf, s->bcf_len, d_seg, 1, 0, 0, nullptr, d_cnt, c->d_err_sites, c->st));
 		unsigned long long cnt = 0;
 		ok = ok && CU_OK(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
 		++c->launches;
@@ -1678,8 +1791,8 @@ extern "C" b200_sites_t *b200_sites_load(b200_ctx_t *c, const uint8_t *bcf, size
 	}
 	s->n = n_rec;
 	ok = ok && CU_OK(cudaMalloc(&d_off, 8 * (size_t)(n_rec + 1))) && CU_OK(cudaMalloc(&s->d_sites, sizeof(SiteRec) * (size_t)(n_rec + 1)));
-	ok = ok && CU_OK(launch_bcf_chase(s->d_bcf, s->bcf_len, d_seg, (int)seg.size(), seg_len, n_rec, d_off, nullptr, c->d_err, c->st)) &&
-	     CU_OK(launch_bcf_parse(s->d_bcf, s->bcf_len, d_off, n_rec, s->row_key, s->d_sites, c->d_err, c->st));
+	ok = ok && CU_OK(launch_bcf_chase(s->d_bcf, s->bcf_len, d_seg, (int)seg.size(), seg_len, n_rec, d_off, nullptr, c->d_err_sites, c->st)) &&
+	     CU_OK(launch_bcf_parse(s->d_bcf, s->bcf_len, d_off, n_rec, s->row_key, s->d_sites, c->d_err_sites, c->st));
 	c->launches += 2;
 	// contig names for the text kernels
 	std::string names; std::vector<int> coff(1, 0);
@@ -1689,7 +1802,7 @@ extern "C" b200_sites_t *b200_sites_load(b200_ctx_t *c, const uint8_t *bcf, size
 	     CU_OK(cudaMemcpyAsync(s->d_ctg, names.data(), names.size(), cudaMemcpyHostToDevice, c->st)) &&
 	     CU_OK(cudaMemcpyAsync(s->d_ctg_off, coff.data(), coff.size() * sizeof(int), cudaMemcpyHostToDevice, c->st));
 	int err = 0;
-	ok = ok && CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
+	ok = ok && CU_OK(cudaMemcpyAsync(&err, c->d_err_sites, sizeof(int), cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
 	if (d_seg) cudaFree(d_seg);
 	if (d_off) cudaFree(d_off);
 	if (d_cnt) cudaFree(d_cnt);
@@ -1706,6 +1819,17 @@ extern "C" b200_sites_t *b200_sites_load(b200_ctx_t *c, const uint8_t *bcf, size
 }
 
 extern "C" int64_t b200_sites_n(const b200_sites_t *s) { return s ? s->n : -1; }
+extern "C" int b200_sites_rows_sorted(const b200_sites_t *s) { return s && s->rows_sorted ? 1 : 0; }
+
+// the records whose row lies in [row_beg, row_end): how a region shard (rows) maps to its records
+extern "C" int b200_sites_rec_range(const b200_sites_t *s, int64_t row_beg, int64_t row_end, int64_t *rec_beg, int64_t *rec_end)
+{
+	if (!s || !rec_beg || !rec_end) { set_err("b200_sites_rec_range: null argument"); return -1; }
+	if (!s->rows_sorted) { set_err_code(B200_E_UNORDERED_RECORDS, "b200_sites_rec_range: the records are not in row order"); return -1; }
+	*rec_beg = std::lower_bound(s->h_rows.begin(), s->h_rows.end(), row_beg) - s->h_rows.begin();
+	*rec_end = std::lower_bound(s->h_rows.begin(), s->h_rows.end(), row_end) - s->h_rows.begin();
+	return 0;
+}
 extern "C" const char *b200_sites_header(const b200_sites_t *s, int64_t *len) { if (!s) return nullptr; if (len) *len = (int64_t)s->header.size(); return s->header.c_str(); }
 
 // (site, row) table to the host: for callers that keep assembling records themselves
@@ -1729,14 +1853,14 @@ extern "C" int64_t b200_view_text_ex(b200_ctx_t *c, b200_sites_t *s, const b200_
 	if (rec_beg < 0) rec_beg = 0;
 	if (rec_beg > rec_end) rec_beg = rec_end;
 	const int64_t n_rec = rec_end - rec_beg;
-	if (q->has_flt && q->prog.needs_host) { set_err("b200_view_text: filters using ** are evaluated with the host libm; use b200_scan"); return -1; }
+	if (q->has_flt && q->prog.needs_host) { set_err_code(B200_E_FILTER_NEEDS_HOST, "b200_view_text: filters using ** are evaluated with the host libm; use b200_scan"); return -1; }
 	bool with_counts = (flags & B200_VIEW_COUNTS) != 0;
 	const bool with_gt = (flags & B200_VIEW_GENOTYPES) != 0;
 	if (q->has_flt || q->G > 1) with_counts = true;                  // bgt.c:850: a filter or several groups imply AC/AN in the output
 	// rows behind the records of this window
 	int64_t row_lo = b200_pbf_row_beg(pb), row_hi = b200_pbf_row_end(pb);
 	if (s->rows_sorted && n_rec > 0) { row_lo = s->h_rows[(size_t)rec_beg]; row_hi = s->h_rows[(size_t)rec_end - 1] + 1; }
-	else if (!s->rows_sorted && (rec_beg != 0 || rec_end != s->n)) { set_err("b200_view_text: the records are not in row order; only the whole file can be formatted at once"); return -1; }
+	else if (!s->rows_sorted && (rec_beg != 0 || rec_end != s->n)) { set_err_code(B200_E_UNORDERED_RECORDS, "b200_view_text: the records are not in row order; only the whole file can be formatted at once"); return -1; }
 	if (row_lo < b200_pbf_row_beg(pb) || row_hi > b200_pbf_row_end(pb)) { set_err("b200_view_text: rows [%lld,%lld) of the records are not resident", (long long)row_lo, (long long)row_hi); return -1; }
 	const int64_t n_rows = row_hi - row_lo;
 	if (contig_names && n_contigs > 0) { // the output header's contig dictionary (bgt.c:626-662) instead of the file's own
@@ -1768,7 +1892,8 @@ extern "C" int64_t b200_view_text_ex(b200_ctx_t *c, b200_sites_t *s, const b200_
 		for (int p = 0; p < 2; ++p) { if (!c->hapbits[p].reserve((size_t)n_rows * q->words * sizeof(uint32_t) + 16)) return -1; so.hap_bits[p] = (uint32_t*)c->hapbits[p].p; }
 		sflags |= B200_SCAN_HAP_BITS;
 	}
-	if ((sflags & (B200_SCAN_COUNTS | B200_SCAN_HAP_BITS)) && b200_scan(c, pb, q, row_lo, n_rows, sflags, &so) != n_rows) return -1;
+	const bool scanned = (sflags & (B200_SCAN_COUNTS | B200_SCAN_HAP_BITS)) != 0;
+	if (scanned && b200_scan(c, pb, q, row_lo, n_rows, sflags, &so) != n_rows) return -1;
 	// ---- lines
 	const size_t tb = view_scan_temp_bytes(n_rec);
 	if (!s->len.reserve(8 * (size_t)(n_rec + 2)) || !s->off.reserve(8 * (size_t)(n_rec + 2)) || !s->temp.reserve(tb + 16)) return -1;
@@ -1777,8 +1902,9 @@ extern "C" int64_t b200_view_text_ex(b200_ctx_t *c, b200_sites_t *s, const b200_
 	P.sites = s->d_sites + rec_beg; P.n_rec = n_rec; P.bcf = s->d_bcf; P.ctg_names = s->d_ctg; P.ctg_off = s->d_ctg_off; P.n_ctg = (int)(s->contigs.empty() ? 1 : s->contigs.size());
 	P.counts = with_counts ? (const int32_t*)c->counts.p : nullptr; P.pass = q->has_flt ? (const uint8_t*)c->pass.p : nullptr; P.stride = stride; P.G = q->G; P.with_counts = with_counts ? 1 : 0;
 	P.with_gt = with_gt ? 1 : 0; P.n_out = q->n_out; P.words = q->words; P.hap[0] = (const uint32_t*)c->hapbits[0].p; P.hap[1] = (const uint32_t*)c->hapbits[1].p;
-	P.row_lo = row_lo; P.n_rows = n_rows; P.err = c->d_err;
+	P.row_lo = row_lo; P.n_rows = n_rows; P.err = c->d_err_sites;
 	unsigned long long total = 0, lines = 0;
+	if (!CU_OK(cudaMemsetAsync(c->d_err_sites, 0, sizeof(int), c->st))) return -1;
 	if (n_rec > 0) {
 		bool ok = CU_OK(cudaMemsetAsync(s->len.p, 0, 8 * (size_t)(n_rec + 2), c->st)) && CU_OK(cudaMemsetAsync(s->d_nlines, 0, 8, c->st)) &&
 		          CU_OK(launch_view_text(P, (unsigned long long*)s->len.p, (unsigned long long*)s->off.p, s->temp.p, tb, nullptr, nullptr, 0, c->st)) &&
@@ -1793,13 +1919,17 @@ extern "C" int64_t b200_view_text_ex(b200_ctx_t *c, b200_sites_t *s, const b200_
 		if (!CU_OK(cudaMallocHost((void**)&s->h_text, (size_t)total + 64))) return -1;
 		s->h_text_cap = (size_t)total + 64;
 	}
-	int err = 0;
+	int err = 0, serr = 0;
+	unsigned long long vtot[4] = {0, 0, 0, 0};
 	bool ok = (n_rec == 0 || CU_OK(launch_view_text(P, (unsigned long long*)s->len.p, (unsigned long long*)s->off.p, nullptr, 0, (char*)s->text.p, s->d_nlines, 1, c->st))) &&
 	          (total == 0 || CU_OK(cudaMemcpyAsync(s->h_text, s->text.p, (size_t)total, cudaMemcpyDeviceToHost, c->st))) &&
-	          CU_OK(cudaMemcpyAsync(&lines, s->d_nlines, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->st)) &&
-	          CU_OK(cudaStreamSynchronize(c->st));
+	          CU_OK(cudaMemcpyAsync(&lines, s->d_nlines, 8, cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaMemcpyAsync(&err, c->d_err_sites, sizeof(int), cudaMemcpyDeviceToHost, c->st)) &&
+	          CU_OK(cudaMemcpyAsync(&serr, c->d_err_scan, sizeof(int), cudaMemcpyDeviceToHost, c->st)) &&
+	          CU_OK(cudaMemcpyAsync(vtot, c->d_acc, sizeof(vtot), cudaMemcpyDeviceToHost, c->st)) && CU_OK(cudaStreamSynchronize(c->st));
 	++c->launches;
 	if (!ok) return -1;
+	if (scanned && serr) { set_err("device error flags 0x%x during scan", serr); return -1; }
+	for (int i = 0; i < 4; ++i) c->last_totals[i] = scanned ? (int64_t)vtot[i] : 0;
 	if (err & 2048) { set_err("a site record points at a row outside the scanned rows"); return -1; }
 	if (err) { set_err("device error flags 0x%x while formatting", err); return -1; }
 	s->h_text[total] = 0;

@@ -31,6 +31,11 @@ typedef struct b200_query_s b200_query_t;  /* tracked haplotypes + sample groups
 int         b200_abi_version(void);
 int         b200_device_count(void);                 /* <=0: no usable CUDA device */
 const char *b200_strerror(void);                     /* last error of the calling thread */
+/* ... and its class, for callers that branch on it (the text is for people) */
+enum { B200_OK = 0, B200_E_GENERIC = 1, B200_E_NO_DEVICE = 2, B200_E_CUDA = 3, B200_E_CORRUPT = 4, B200_E_FILTER_SYNTAX = 5,
+       B200_E_FILTER_NEEDS_HOST = 16,   /* the filter uses `**`: evaluated with the host libm from device counts (b200_scan does it itself) */
+       B200_E_UNORDERED_RECORDS = 17 }; /* b200_view_text_ex: site records are not in row order, windows cannot be mapped to row ranges */
+int         b200_errcode(void);
 b200_ctx_t *b200_ctx_create(int device);
 void        b200_ctx_destroy(b200_ctx_t *ctx);
 int         b200_ctx_sync(b200_ctx_t *ctx);
@@ -73,6 +78,8 @@ b200_query_t *b200_query_create(b200_ctx_t *ctx, const b200_pbf_t *pb, int n_out
 b200_query_t *b200_query_create_cols(b200_ctx_t *ctx, const b200_pbf_t *pb, int n_cols, const int32_t *cols);
 void          b200_query_destroy(b200_query_t *q);
 int           b200_query_n_track(const b200_query_t *q);     /* 2*n_out (or the number of columns) */
+int           b200_query_filter_needs_host(const b200_query_t *q); /* 1: the filter uses `**` (host libm, kexpr.c:150): b200_scan evaluates it on the host from the
+                                                                * device counts; DEVICE_OUT scans and b200_view_text refuse it (B200_E_FILTER_NEEDS_HOST) */
 int           b200_query_hap_words(const b200_query_t *q);   /* 32-bit words per plane per row of hap_bits */
 int           b200_query_counts_stride(const b200_query_t *q); /* 3 + 3*n_groups */
 
@@ -101,6 +108,18 @@ int64_t b200_scan(b200_ctx_t *ctx, const b200_pbf_t *pb, const b200_query_t *q, 
 
 /* After a B200_SCAN_DEVICE_OUT scan: wait for it, fetch its totals and kernel timings. */
 int     b200_scan_collect(b200_ctx_t *ctx, int64_t totals[4]);
+/* totals (as b200_scan_out_t.totals) of the last scan of this context whose results reached the host: b200_scan,
+ * b200_scan_collect, or the scan inside b200_view_text[_ex] */
+int     b200_last_totals(b200_ctx_t *ctx, int64_t totals[4]);
+
+/* ---------------------------------------------------------------- multi-GPU (view.c:150-155 is the loop that gets sharded) */
+/* Region shards = row ranges of whole checkpoint blocks (pbwt.c:292-301 snapshots, :268-276 block index): every GPU of a
+ * process gets its own context and b200_pbf_load[_ex](row_beg,row_end); no per-site exchange exists.  The one collective
+ * sums the per-shard totals: vals[n][count] int64, in = each context's values, out = the sums in every row
+ * (ncclAllReduce(sum) over the contexts' GPUs, one communicator per call; n == 1 is a no-op).  NCCL (libnccl.so.2) is
+ * loaded when this is first called, not linked.  Processes that own one GPU each (bench.py under torchrun) use their
+ * launcher's communicator instead. */
+int     b200_allreduce_i64(b200_ctx_t *const *ctxs, int n, int64_t *vals, int count);
 
 /* device time (ms) of the kernels of the last b200_scan on this context, measured with CUDA events on the
  * context's stream: which = 0 all decode phases (plane-1 select + rank walk + group marginals), 1 whole scan (all
@@ -147,8 +166,11 @@ int         b200_enc_write_bytes(b200_enc_t *e, const uint8_t *a0, const uint8_t
 /* the same rows as bit planes in column order: bits[row][plane][(m+31)/32], bit c of word w = haplotype 32w+c */
 int         b200_enc_write_bits(b200_enc_t *e, const uint32_t *bits, int64_t n_rows);
 int64_t     b200_enc_rows(const b200_enc_t *e);
-/* writes the index record (pbf_close, pbwt.c:268-276); *image = the complete file image (owned by the encoder, valid until
- * b200_enc_destroy); returns its size */
+/* streaming (pbf_write writes each row as it goes, pbwt.c:288-311): *bytes = the file bytes assembled since the last drain
+ * (owned by the encoder, valid until the next call on it); they are forgotten by the encoder.  Returns their number. */
+int64_t     b200_enc_drain(b200_enc_t *e, const uint8_t **bytes);
+/* writes the index record (pbf_close, pbwt.c:268-276); *image = the complete file image -- or, after b200_enc_drain calls, the
+ * rest of it behind the drained bytes -- (owned by the encoder, valid until b200_enc_destroy); returns its size */
 int64_t     b200_enc_finish(b200_enc_t *e, const uint8_t **image);
 void        b200_enc_destroy(b200_enc_t *e);
 
@@ -167,6 +189,9 @@ int64_t     b200_bgzf_inflate(b200_ctx_t *ctx, const uint8_t *bytes, size_t n_by
 typedef struct b200_sites_s b200_sites_t;
 b200_sites_t *b200_sites_load(b200_ctx_t *ctx, const uint8_t *bcf, size_t n_bcf, const uint8_t *csi, size_t n_csi, int row_key);
 int64_t     b200_sites_n(const b200_sites_t *s);                        /* records */
+int         b200_sites_rows_sorted(const b200_sites_t *s);              /* 1: INFO/_row ascends with the records (what `bgt import` writes) */
+/* the records whose row lies in [row_beg,row_end) (records in row order): maps a region shard to its record window */
+int         b200_sites_rec_range(const b200_sites_t *s, int64_t row_beg, int64_t row_end, int64_t *rec_beg, int64_t *rec_end);
 const char *b200_sites_header(const b200_sites_t *s, int64_t *len);      /* BCF header text (vcf.c:263-288) */
 int         b200_sites_rows(const b200_sites_t *s, int64_t *rows, int32_t *pos);  /* per record: INFO/_row and 0-based POS */
 void        b200_sites_destroy(b200_sites_t *s);

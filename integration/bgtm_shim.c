@@ -14,6 +14,9 @@
  *
  * Queries outside the accelerated path (several BGT files, -a/-S/-H allele queries) are passed to the
  * reference's own bgtm_read, whose row decode then goes through seam A (pbwt_shim.c), i.e. still the GPU.
+ *
+ * Library code: nothing here terminates the process.  A device failure makes bgtm_read return -2 (the reference's
+ * only negative value is -1 = end of data, bgt.c:880-888) with the message on stderr and in pbf_b200_strerror().
  */
 #include <pthread.h>
 #include <stdio.h>
@@ -32,12 +35,13 @@ int bgtm_pass_site_flt(const bgt_info_t *ss, kexpr_t *flt);      /* bgt.c:712-71
 void bgt_gen_gt(const bcf_hdr_t *h, bcf1_t *b, int m, const uint8_t **a, int32_t *mgs); /* bgt.c:290-313 */
 b200_ctx_t *pbf_b200_ctx(void);                                  /* pbwt_shim.c */
 const uint8_t *pbf_b200_image(const pbf_t *pb, size_t *len);
+void pbf_b200_route_add(int slot, int64_t n);
 
 typedef struct accel_s {
 	struct accel_s *next;
 	bgtm_t *bm;
 	char *flt;
-	int decided, eligible, host_flt;
+	int decided, eligible, host_flt, failed;
 	b200_pbf_t *win; int64_t win_beg, win_end;
 	b200_query_t *q;
 	int n_rec, cur, cap, eof, has_pending;
@@ -49,16 +53,25 @@ typedef struct accel_s {
 
 static accel_t *g_accel;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+/* bgtm_t is ABI (the Go server allocates it itself, bgt-server.go:22-30), so the per-reader state lives in a side table.
+ * The table is consulted once per reader and thread, not once per record: every thread remembers the reader it served
+ * last (a server thread works on one bgtm_t at a time); g_gen invalidates the memo when any reader is destroyed. */
+static volatile unsigned g_gen = 1;
+static __thread bgtm_t *t_bm;
+static __thread accel_t *t_accel;
+static __thread unsigned t_gen;
 
 static accel_t *accel_get(bgtm_t *bm, int create)
 {
 	accel_t *a;
+	if (t_bm == bm && t_gen == g_gen && t_accel) return t_accel;
 	pthread_mutex_lock(&g_lock);
 	for (a = g_accel; a; a = a->next) if (a->bm == bm) break;
 	if (a == 0 && create) {
 		a = (accel_t*)calloc(1, sizeof(accel_t));
 		a->bm = bm; a->next = g_accel; g_accel = a;
 	}
+	t_bm = bm; t_accel = a; t_gen = g_gen;
 	pthread_mutex_unlock(&g_lock);
 	return a;
 }
@@ -69,6 +82,7 @@ static void accel_drop(bgtm_t *bm)
 	int i;
 	pthread_mutex_lock(&g_lock);
 	for (pp = &g_accel; *pp; pp = &(*pp)->next) if ((*pp)->bm == bm) { a = *pp; *pp = a->next; break; }
+	++g_gen;
 	pthread_mutex_unlock(&g_lock);
 	if (a == 0) return;
 	if (a->q) b200_query_destroy(a->q);
@@ -84,6 +98,9 @@ int bgtm_set_flt_site(bgtm_t *bm, const char *expr)              /* bgt.c:444-45
 	accel_t *a = accel_get(bm, 1);
 	free(a->flt);
 	a->flt = expr ? strdup(expr) : 0;
+	/* a filter set or changed after the first read: the device query (compiled filter) and the routing decision are stale */
+	if (a->q) { b200_query_destroy(a->q); a->q = 0; }
+	a->decided = 0; a->host_flt = 0;
 	return ref_bgtm_set_flt_site(bm, expr);
 }
 
@@ -93,10 +110,13 @@ void bgtm_reader_destroy(bgtm_t *bm)                             /* bgt.c:376-40
 	ref_bgtm_reader_destroy(bm);
 }
 
-static void die(const char *what)
+/* a device failure: reported, remembered (the reader stays failed), never fatal to the host process and never papered over
+ * by the CPU path */
+static int fail(accel_t *a, const char *what)
 {
 	fprintf(stderr, "[E::bgt_b200] %s: %s\n", what, b200_strerror());
-	exit(1); /* the accelerated path has no CPU fallback */
+	a->failed = 1; a->n_rec = a->cur = 0;
+	return -1;
 }
 
 static int need_ac(const bgtm_t *bm) /* bgt.c:850 */
@@ -113,8 +133,8 @@ static void decide(accel_t *a)
 	              bm->bgt[0]->n_out > 0 && !(off && *off == '1');
 }
 
-/* pull the next batch of site records and run the GPU scan over their row range */
-static void fill_batch(accel_t *a)
+/* pull the next batch of site records and run the GPU scan over their row range; 0 or -1 (device failure) */
+static int fill_batch(accel_t *a)
 {
 	bgtm_t *bm = a->bm;
 	bgt_t *bgt = bm->bgt[0];
@@ -127,7 +147,8 @@ static void fill_batch(accel_t *a)
 	b200_scan_out_t so;
 	unsigned flags = 0;
 	int64_t n_rows;
-	if (map == 0) { fprintf(stderr, "[E::bgt_b200] the PBF handle was not opened by the B200 seam\n"); exit(1); }
+	if (ctx == 0) { a->failed = 1; return -1; }
+	if (map == 0) { fprintf(stderr, "[E::bgt_b200] the PBF handle was not opened by the B200 seam\n"); a->failed = 1; return -1; }
 	/* batch geometry: bounded by the decoded-plane bytes when genotypes are printed */
 	rows_cap = want_gt ? (64LL << 20) / (n_track > 0 ? n_track : 1) : 65536;
 	if (rows_cap < 1) rows_cap = 1;
@@ -159,7 +180,7 @@ static void fill_batch(accel_t *a)
 		}
 		++a->n_rec;
 	}
-	if (a->n_rec == 0) return;
+	if (a->n_rec == 0) return 0;
 	/* residency: the checkpoint blocks around the batch */
 	if (a->win == 0 || a->rows[0] < a->win_beg || a->rows[a->n_rec - 1] >= a->win_end) {
 		const int shift = pbf_get_shift(bgt->pb);
@@ -172,18 +193,18 @@ static void fill_batch(accel_t *a)
 		if (a->q) { b200_query_destroy(a->q); a->q = 0; }
 		if (a->win) b200_pbf_close(a->win);
 		a->win = b200_pbf_load(ctx, map, map_len, beg, end);
-		if (a->win == 0) die("loading the PBF window");
+		if (a->win == 0) return fail(a, "loading the PBF window");
 		a->win_beg = b200_pbf_row_beg(a->win); a->win_end = b200_pbf_row_end(a->win);
 	}
 	if (a->q == 0) {
 		int err = 0;
 		a->host_flt = 0;
 		a->q = b200_query_create(ctx, a->win, bgt->n_out, bgt->out, bm->group, bm->n_groups, a->flt, &err);
-		if (a->q == 0 && err) { /* kexpr accepted it but the device compiler did not: verdict on the host from device counts */
+		if (a->q == 0 && err && b200_errcode() == B200_E_FILTER_SYNTAX) { /* kexpr accepted it but the device compiler did not: verdict on the host from device counts */
 			a->host_flt = 1;
 			a->q = b200_query_create(ctx, a->win, bgt->n_out, bgt->out, bm->group, bm->n_groups, 0, &err);
 		}
-		if (a->q == 0) die("preparing the query");
+		if (a->q == 0) return fail(a, "preparing the query");
 		a->stride = b200_query_counts_stride(a->q);
 		a->n_track = b200_query_n_track(a->q);
 	}
@@ -206,7 +227,9 @@ static void fill_batch(accel_t *a)
 	memset(&so, 0, sizeof(so));
 	so.counts = a->counts; so.pass = a->pass; flags |= B200_SCAN_COUNTS;
 	if (want_gt) { so.hap_bytes[0] = a->hap[0]; so.hap_bytes[1] = a->hap[1]; flags |= B200_SCAN_HAP_BYTES; }
-	if (b200_scan(ctx, a->win, a->q, a->r0, n_rows, flags, &so) != n_rows) die("scan");
+	if (b200_scan(ctx, a->win, a->q, a->r0, n_rows, flags, &so) != n_rows) return fail(a, "scan");
+	pbf_b200_route_add(2, 1);
+	return 0;
 }
 
 int bgtm_read(bgtm_t *bm, bcf1_t *b)                             /* bgt.c:880-888 */
@@ -216,7 +239,8 @@ int bgtm_read(bgtm_t *bm, bcf1_t *b)                             /* bgt.c:880-88
 	if (bm->h_out == 0) bgtm_prepare(bm);
 	a = accel_get(bm, 1);
 	if (!a->decided) decide(a);
-	if (!a->eligible) return ref_bgtm_read(bm, b);
+	if (!a->eligible) { pbf_b200_route_add(3, 1); return ref_bgtm_read(bm, b); }
+	if (a->failed) return -2;
 	bgt = bm->bgt[0];
 	for (;;) {
 		const bcf1_t *b0;
@@ -225,7 +249,7 @@ int bgtm_read(bgtm_t *bm, bcf1_t *b)                             /* bgt.c:880-88
 		int l_ref;
 		if (a->cur >= a->n_rec) {
 			if (a->eof && !a->has_pending) return -1;
-			fill_batch(a);
+			if (fill_batch(a) != 0) return -2;
 			if (a->n_rec == 0) return -1;
 		}
 		b0 = a->rec[a->cur];

@@ -4,6 +4,7 @@ pbfview) must print byte-identical output to the unmodified reference (oracle/_r
 This is the differential matrix of SURVEY section 4 (seam A: pbfview; seam B: bgt view).
 """
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -23,6 +24,29 @@ def run(exe, args, env=None):
     r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
     assert r.returncode == 0, (exe, args, r.stderr.decode()[-500:])
     return r.stdout
+
+
+def run_routed(exe, args, env=None):
+    """stdout plus the route counters the seams print at exit with BGT_B200_ROUTE=1 (include/pbwt_b200.h): which path served
+    the output -- the device `view` pipeline (view_fast.c), seam B batches (bgtm_shim.c), seam A batches (pbwt_shim.c), or
+    the reference's own CPU loop (ref_bgtm_read)."""
+    e = dict(os.environ)
+    e.update(env or {})
+    e["BGT_B200_ROUTE"] = "1"
+    r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+    err = r.stderr.decode()
+    assert r.returncode == 0, (exe, args, err[-500:])
+    m = re.search(r"\[b200 route\] (.*)", err)
+    assert m, "no route line on stderr: %r" % err[-300:]
+    route = {k: int(v) for k, v in (kv.split("=") for kv in m.group(1).split())}
+    return r.stdout, route, err
+
+
+def on_device_pipeline(args):
+    """view_fast.c takes `view [-G] [-C] [-f ..] [-s ..] prefix`; everything else is seam B.  Filters with `**` are handed over
+    (host libm) before the first output byte."""
+    takes = all(a in ("-C", "-G", "-f", "-s") or not a.startswith("-") for a in args)
+    return takes, takes and any("**" in a for a in args)
 
 
 @pytest.fixture(scope="module")
@@ -76,9 +100,18 @@ VIEW_ARGS = [
 def test_view_matches_reference(tools, cohort_small, args):
     prefix, _ = cohort_small
     want = run(tools.REF_BGT, ["view"] + args + [prefix])
-    got = run(NEW_BGT, ["view"] + args + [prefix])
+    got, route, _ = run_routed(NEW_BGT, ["view"] + args + [prefix])
     assert got == want
     assert len(want) > 0
+    # ... and it was the device that produced it, not the reference's CPU loop behind a silent fall-back
+    fast, handed_over = on_device_pipeline(args)
+    assert route["ref_bgtm_read"] == 0, route
+    if fast and not handed_over:
+        assert route["view_fast"] == 1 and route["view_fast_to_ref"] == 0 and route["seamB_batches"] == 0 and route["seamA_batches"] == 0, route
+    elif handed_over:
+        assert route["view_fast"] == 1 and route["view_fast_to_ref"] == 1 and route["seamB_batches"] > 0, route
+    else:
+        assert route["view_fast"] == 0 and route["seamB_batches"] > 0, route
 
 
 def test_view_subset_file_and_wide_cohort(tools, cohort_wide, tmp_path):
@@ -146,3 +179,87 @@ def test_pbfview_pim_to_pbf_on_the_gpu_encoder(tools, tmp_path):
             subprocess.run([NEW_PBFVIEW, "-Sb", "-s", shift, str(pim)], stdout=f, check=True)
         assert a.read_bytes() == b.read_bytes(), shift
         assert run(NEW_PBFVIEW, [str(b)]) == run(tools.REF_PBFVIEW, [str(a)])
+
+
+def test_disabled_seam_is_visible_in_the_route(tools, cohort_small):
+    """the route counters do tell the paths apart: with the seams switched off the reference's own bgtm_read serves the records
+    (its row decode still goes through seam A)."""
+    prefix, _ = cohort_small
+    got, route, _ = run_routed(NEW_BGT, ["view", "-f", "AC>0", "-G", "-n", "50", prefix], {"BGT_B200_DISABLE": "1"})
+    assert got == run(tools.REF_BGT, ["view", "-f", "AC>0", "-G", "-n", "50", prefix])
+    assert route["ref_bgtm_read"] > 0 and route["view_fast"] == 0 and route["seamB_batches"] == 0 and route["seamA_batches"] > 0
+
+
+@pytest.fixture(scope="module")
+def cohort_100k(tools, tmp_path_factory):
+    """BASELINE width: 100 000 samples x 16 384 sites (two checkpoint blocks) of the bench's synthetic cohort, on disk."""
+    import bgt_b200
+    tmp = tmp_path_factory.mktemp("c100k")
+    prefix = os.path.join(str(tmp), "c.bgt")
+    with bgt_b200.Context(0) as ctx:
+        pb = bgt_b200.synth_cohort(ctx, 100000, 16384, seed=20261017)
+        with open(prefix + ".pbf", "wb") as f:
+            f.write(memoryview(pb.image()))
+        pb.close()
+    subprocess.run([tools.MKSITES, prefix], check=True, stderr=subprocess.DEVNULL)
+    return prefix
+
+
+def test_baseline_configs_2_3_4_at_full_width_against_the_reference(tools, cohort_100k, tmp_path):
+    """BASELINE configs 2, 3 and 4 through the drop-in CLI at 100 000 samples: byte-identical VCF to the unmodified reference,
+    produced by the device pipeline (route counters)."""
+    prefix = cohort_100k
+    rng = np.random.default_rng(1)
+    sel = sorted(rng.choice(100000, size=200, replace=False).tolist())
+    lst = tmp_path / "sub200.txt"
+    lst.write_text("".join("S%07d\n" % s for s in sel))
+    cases = {
+        "config2": ["-f", "AC>0", "-G"],
+        "config3": ["-s", 'grp=="A"', "-s", 'grp=="B"', "-f", "AC1/AN1>0.1&&AC2==0", "-G"],
+        "config4": ["-s", str(lst)],
+        "config4 -f": ["-s", str(lst), "-f", "AC>0"],
+        "config3 counts": ["-s", 'grp=="A"', "-s", 'grp=="B"', "-G"],
+    }
+    for name, args in cases.items():
+        want = run(tools.REF_BGT, ["view"] + args + [prefix])
+        got, route, _ = run_routed(NEW_BGT, ["view"] + args + [prefix])
+        assert got == want, name
+        assert want.count(b"\n") > 100, name
+        assert route["view_fast"] == 1 and route["view_fast_to_ref"] == 0 and route["ref_bgtm_read"] == 0 and route["seamB_batches"] == 0, (name, route)
+
+
+def vcf_totals(vcf):
+    n = an = ac = 0
+    for ln in vcf.split(b"\n"):
+        if ln and ln[:1] != b"#":
+            info = dict(kv.split(b"=") for kv in ln.split(b"\t")[7].split(b";") if b"=" in kv)
+            n += 1; an += int(info[b"AN"]); ac += int(info[b"AC"].split(b",")[0])
+    return n, an, ac
+
+
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0,0,0", "all"])
+def test_sharded_view_is_identical_and_totals_add_up(tools, tmp_path_factory, devices):
+    """Multi-GPU in the C product (the loop of view.c:150-155 cut into region shards): one host thread + context per
+    listed device over block-aligned row ranges, shard texts in order behind the single header, totals summed (ncclAllReduce
+    over distinct GPUs).  A device listed several times runs the same shard logic on one GPU."""
+    import bgt_b200
+    if devices == "all" and bgt_b200.lib().b200_device_count() < 2:
+        pytest.skip("one GPU visible")
+    tmp = tmp_path_factory.mktemp("shard")
+    mat = haplo_matrix(2600, 300, 9, switch=0.01)
+    prefix = make_bgt(tools, tmp, "five", mat, shift=9)          # 6 checkpoint blocks of 512 rows
+    for args in (["-f", "AC>0", "-G"], ["-C"], ["-s", 'grp=="A"', "-s", 'grp=="B"', "-f", "AC1>AC2", "-G"], ["-s", ",S0000004,S0000001,S0000100"]):
+        want = run(tools.REF_BGT, ["view"] + args + [prefix])
+        got, route, err = run_routed(NEW_BGT, ["view"] + args + [prefix], {"BGT_B200_DEVICES": devices, "BGT_B200_TOTALS": "1"})
+        assert got == want, (devices, args)
+        n_dev = bgt_b200.lib().b200_device_count() if devices == "all" else devices.count(",") + 1
+        assert route["view_fast"] == 1 and route["gpus"] == min(n_dev, 6) and route["ref_bgtm_read"] == 0, route
+        m = re.search(r"\[b200 totals\] gpus=(\d+) sites=(\d+) passed=(\d+) sum_AN=(\d+) sum_AC=(\d+)", err)
+        assert m, err[-300:]
+        assert int(m.group(2)) == 2600 and int(m.group(3)) == want.count(b"\n") - want.count(b"\n#") - (1 if want.startswith(b"#") else 0)
+        if "-C" in args or "-f" in args:
+            n, an, ac = vcf_totals(want)
+            if n == 2600:                                         # every site printed: the VCF carries all the counts
+                assert (int(m.group(4)), int(m.group(5))) == (an, ac)
+        if devices == "all":
+            assert "ncclAllReduce" in err

@@ -80,6 +80,40 @@ def test_config3_two_groups_add_up(b200, ctx, cohort, full_scan):
     assert res["totals"][3] == int(want.sum())
 
 
+def test_config3_two_groups_against_the_oracle_at_full_width(b200, ctx, cohort, oracle):
+    """BASELINE config 3 at 100 000 samples x 1 000 000 sites: all nine count columns (AN, AC, AC<M>, then AN#/AC#/AC#<M> of both
+    groups) and the -f verdict of the grouped split scan -- the segmented marginal path (seed vectors pushed through the composite
+    maps, one CTA per 256-row segment), the one-CTA-per-block variant and the general walk -- against the oracle's restatement of
+    bgtm_cal_info + bgtm_pass_site_flt (bgt.c:735-757, 712-719) on row windows at the start of the file, around a checkpoint deep
+    inside it (rows 8192*77 +- 150: both sides of the snapshot) and at its end."""
+    grp = (np.arange(SAMPLES) % 2 + 1).astype(np.uint32)
+    flt = "AC1/AN1>0.1&&AC2==0"
+    q = b200.Query(ctx, cohort, group=grp, n_groups=2, flt=flt)
+    full = b200.scan(ctx, cohort, q, 0, ROWS)
+    noseg = b200.scan(ctx, cohort, q, 0, ROWS, no_segments=True)
+    assert (noseg["counts"] == full["counts"]).all() and (noseg["passed"] == full["passed"]).all()
+    img = cohort.image()
+    p = oracle.Pbf(img.tobytes())
+    for beg, n in ((0, 600), (8192 * 77 - 150, 300), (ROWS - 64, 64)):
+        want = p.scan(beg, n, group=grp, n_groups=2, flt=flt)
+        assert want["counts"].shape[1] == 9
+        assert (full["counts"][beg:beg + n] == want["counts"]).all(), beg
+        assert (full["passed"][beg:beg + n] == want["passed"]).all(), beg
+        part = b200.scan(ctx, cohort, q, beg, n)                              # the same window as its own scan (mid-block start)
+        assert (part["counts"] == want["counts"]).all() and (part["passed"] == want["passed"]).all(), beg
+        gen = b200.scan(ctx, cohort, q, beg, n, no_split=True)                # general walk over all columns
+        assert (gen["counts"] == want["counts"]).all() and (gen["passed"] == want["passed"]).all(), beg
+    # a group assignment that is NOT symmetric (30 % / 70 %, interleaved irregularly): a per-group mix-up cannot cancel out
+    rng = np.random.default_rng(3)
+    grp2 = (rng.random(SAMPLES) < 0.7).astype(np.uint32) + 1
+    q2 = b200.Query(ctx, cohort, group=grp2, n_groups=2, flt="AC1>AC2")
+    beg, n = 8192 * 30 - 100, 260
+    got = b200.scan(ctx, cohort, q2, beg, n)
+    want = p.scan(beg, n, group=grp2, n_groups=2, flt="AC1>AC2")
+    assert (got["counts"] == want["counts"]).all() and (got["passed"] == want["passed"]).all()
+    q2.close(); q.close(); p.close()
+
+
 def test_config4_subset_is_columns_of_full_decode(b200, ctx, cohort):
     rng = np.random.default_rng(1)
     sel = np.sort(rng.choice(SAMPLES, size=200, replace=False)).astype(np.int32)

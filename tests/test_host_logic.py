@@ -241,3 +241,95 @@ def test_bgzf_block_walk_without_a_device():
         b2 = (C.c_uint8 * len(bad)).from_buffer_copy(bad)
         assert L.b200_bgzf_inflate(None, b2, len(bad), None, 0) < 0
         assert L.b200_strerror()
+
+
+# ------------------------------------------------------------------------------------------------ seam A: in-memory codec + library hygiene
+
+class _Pbc(C.Structure):   # pbwt.h:6-9
+    _fields_ = [("m", C.c_int32), ("l", C.c_int32), ("S0", C.POINTER(C.c_int32)), ("S", C.POINTER(C.c_int32)), ("u", C.POINTER(C.c_uint8))]
+
+
+def _codec(L):
+    L.pbc_init.restype = C.POINTER(_Pbc)
+    L.pbc_init.argtypes = [C.c_int]
+    L.pbc_enc.argtypes = [C.POINTER(_Pbc), C.c_void_p]
+    L.pbc_dec.argtypes = [C.POINTER(_Pbc), C.c_void_p]
+    L.pbs_dec.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+def test_seam_a_exports_the_whole_of_pbwt_h():
+    """pbwt.h:35-130 completely: the file API and the in-memory codec, so that pbwt.o can be dropped from a host application."""
+    L = C.CDLL(os.path.join(ROOT, "bgt_b200", "lib", "libpbwt_b200.so"))
+    for n in ("pbf_open_w", "pbf_open_r", "pbf_close", "pbf_write", "pbf_read", "pbf_seek", "pbf_subset", "pbf_get_g", "pbf_get_m", "pbf_get_n",
+              "pbf_get_shift", "pbc_init", "pbc_enc", "pbc_dec", "pbs_dec", "pbc_enc_core", "pbc_dec_core"):
+        assert hasattr(L, n), n
+    for n in header_functions(os.path.join(ROOT, "include", "pbwt_b200.h"), "pb[cfs]_"):
+        assert hasattr(L, n), n
+
+
+def test_host_codec_matches_the_reference(ref):
+    """pbc_enc / pbc_dec / pbs_dec of libpbwt_b200.so against the UNMODIFIED reference's (oracle/_ref/libbgtref.so) on the same rows:
+    same RLE bytes, same permutations, same decoded bits, same (rank, slot) lists after every row."""
+    mine = _codec(C.CDLL(os.path.join(ROOT, "bgt_b200", "lib", "libpbwt_b200.so")))
+    theirs = _codec(C.CDLL(ref.REF_LIB))
+    rng = np.random.default_rng(5)
+    for m, n_rows in ((1, 5), (2, 8), (37, 60), (300, 120), (70001, 12)):
+        mat = (haplo_matrix(n_rows, m, 100 + m) & 1).astype(np.uint8)
+        mat[n_rows // 2] = 0
+        mat[n_rows // 2 + 1] = 1                                   # constant rows (pbwt.c:75-77)
+        if m > 20:
+            mat[1, :] = (np.arange(m) // 17) & 1                   # runs of 17: two code bytes each
+        ea, eb = mine.pbc_init(m), theirs.pbc_init(m)
+        da, db = mine.pbc_init(m), theirs.pbc_init(m)
+        n_sub = min(m, 9)
+        cols = rng.choice(m, size=n_sub, replace=False)
+        sub_a = np.zeros((n_sub, 2), np.uint32)
+        sub_a[:, 0] = np.sort(cols); sub_a[:, 1] = np.argsort(cols)   # S = identity before row 0: rank = column (pbwt.c:343)
+        sub_b = sub_a.copy()
+        for k in range(n_rows):
+            row = np.ascontiguousarray(mat[k])
+            mine.pbc_enc(ea, row.ctypes.data); theirs.pbc_enc(eb, row.ctypes.data)
+            la, lb = ea.contents.l, eb.contents.l
+            ua, ub = bytes(ea.contents.u[:la + 1]), bytes(eb.contents.u[:lb + 1])
+            assert ua == ub and ua[-1] == 0, (m, k)
+            assert ea.contents.S[:m] == eb.contents.S[:m], (m, k)
+            buf = C.create_string_buffer(ua, la + 1)
+            mine.pbc_dec(da, buf); theirs.pbc_dec(db, buf)
+            assert bytes(da.contents.u[:m]) == bytes(db.contents.u[:m]) == row.tobytes(), (m, k)
+            assert da.contents.S[:m] == db.contents.S[:m]
+            if n_sub < m:                                           # pbf_subset falls back to full decoding otherwise (pbwt.c:377)
+                oa, ob = np.zeros(n_sub, np.uint8), np.zeros(n_sub, np.uint8)
+                mine.pbs_dec(m, n_sub, sub_a.ctypes.data, buf, oa.ctypes.data)
+                theirs.pbs_dec(m, n_sub, sub_b.ctypes.data, buf, ob.ctypes.data)
+                assert (oa == ob).all() and (sub_a == sub_b).all(), (m, k)
+                assert (oa == row[cols]).all()
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        for p in (ea, eb, da, db):
+            libc.free(C.cast(p, C.c_void_p))                        # "It should be freed with free()", pbwt.h:103
+
+
+def test_library_code_never_terminates_the_process():
+    """The seams are library code (bgt-server links them): no exit()/abort() -- failures return NULL / negative like the
+    reference's (pbwt.c:228-235, bgt.c:880-888)."""
+    for rel in ("bgt_b200/host/pbwt_shim.c", "bgt_b200/host/pbc_host.c", "integration/bgtm_shim.c", "bgt_b200/csrc/api.cu"):
+        txt = re.sub(r"/\*.*?\*/|//[^\n]*", "", open(os.path.join(ROOT, rel)).read(), flags=re.S)
+        assert not re.search(r"\b(exit|abort|_exit)\s*\(", txt), rel
+
+
+def test_seam_a_rejects_files_without_an_index(tmp_path, oracle):
+    """pbf_open_r: a PBF whose trailing index offset is missing or hostile is refused with a message (no silent empty result,
+    no read outside the image: the offset is untrusted)."""
+    L = C.CDLL(os.path.join(ROOT, "bgt_b200", "lib", "libpbwt_b200.so"))
+    L.pbf_open_r.restype = C.c_void_p
+    L.pbf_b200_strerror.restype = C.c_char_p
+    good = oracle.encode_pbf(haplo_matrix(20, 30, 3), shift=3)
+    for name, data in (("trunc", good[:-8]), ("wrap", good[:-8] + (0xFFFFFFFFFFFFFFF8).to_bytes(8, "little")), ("zero", good[:-8] + bytes(8))):
+        fn = tmp_path / (name + ".pbf")
+        fn.write_bytes(data)
+        assert not L.pbf_open_r(str(fn).encode()), name
+    import bgt_b200
+    for data in (good[:-8] + (0xFFFFFFFFFFFFFFF8).to_bytes(8, "little"), good[:-8] + (len(good) - 5).to_bytes(8, "little")):
+        with pytest.raises(bgt_b200.B200Error):
+            bgt_b200.pbf_plan(data)
