@@ -27,7 +27,7 @@ class ScanOut(C.Structure):
 
 class SynthCfg(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_rows", C.c_int64), ("shift", C.c_int32), ("seed", C.c_uint64),
-                ("r_max", C.c_int32), ("p1_one_in", C.c_int32)]
+                ("r_max", C.c_int32), ("p1_one_in", C.c_int32), ("p1_max_iv", C.c_int32), ("p1_max_len", C.c_int32)]
 
 
 # every symbol include/bgt_b200.h declares: name -> (restype, argtypes)
@@ -300,9 +300,9 @@ def bgzf_inflate(ctx, data):
     return out[:got].tobytes()
 
 
-def synth_cohort(ctx, n_samples, n_rows, seed=1, shift=13, r_max=64, p1_one_in=16):
+def synth_cohort(ctx, n_samples, n_rows, seed=1, shift=13, r_max=64, p1_one_in=16, p1_max_iv=3, p1_max_len=64):
     """Generate a truthful synthetic cohort on the device and return it resident."""
-    cfg = SynthCfg(n_samples, n_rows, shift, seed, r_max, p1_one_in)
+    cfg = SynthCfg(n_samples, n_rows, shift, seed, r_max, p1_one_in, p1_max_iv, p1_max_len)
     return Pbf(ctx, lib().b200_synth_generate(ctx.h, C.byref(cfg)))
 
 

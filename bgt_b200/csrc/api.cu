@@ -1283,6 +1283,7 @@ extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cf
 	SynthCfg sc;
 	sc.m = 2u * (uint32_t)cfg->n_samples; sc.n_rows = cfg->n_rows; sc.shift = cfg->shift; sc.seed = cfg->seed;
 	sc.r_max = cfg->r_max > 0 ? cfg->r_max : 64; sc.p1_one_in = cfg->p1_one_in > 0 ? cfg->p1_one_in : 16;
+	sc.p1_max_iv = cfg->p1_max_iv > 0 ? cfg->p1_max_iv : 3; sc.p1_max_len = cfg->p1_max_len > 0 ? cfg->p1_max_len : 64;
 	const int BS = 1 << sc.shift;
 	const int64_t n = sc.n_rows;
 	const int nb = (int)((n + BS - 1) / BS);

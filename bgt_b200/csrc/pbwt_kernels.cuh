@@ -245,7 +245,7 @@ cudaError_t launch_view_text(const ViewParams &P, unsigned long long *len, unsig
                              unsigned long long *n_lines, int phase, cudaStream_t st);
 
 // synthetic cohort generator (synth.cu)
-struct SynthCfg { uint32_t m; long long n_rows; int shift; uint64_t seed; int r_max; int p1_one_in; };
+struct SynthCfg { uint32_t m; long long n_rows; int shift; uint64_t seed; int r_max; int p1_one_in; int p1_max_iv; int p1_max_len; };
 cudaError_t launch_synth_lengths(const SynthCfg &c, uint32_t *len2 /*[n_rows][2]*/, cudaStream_t st);
 cudaError_t launch_synth_write(const SynthCfg &c, const uint64_t *rowoff_flat /*[n_rows] absolute*/, uint8_t *img, cudaStream_t st);
 

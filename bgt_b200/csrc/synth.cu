@@ -53,9 +53,11 @@ __device__ int draw_intervals(const SynthCfg &c, long long row, int plane, uint3
 	} else {
 		const int one_in = c.p1_one_in < 1 ? 1 : c.p1_one_in;
 		if (g.next() % (uint64_t)one_in) return 0;
-		n = 1 + (int)(g.next() % 3);
+		const int max_iv = c.p1_max_iv < 1 ? 3 : (c.p1_max_iv > SYNTH_MAX_IV ? SYNTH_MAX_IV : c.p1_max_iv);
+		const uint32_t max_len = c.p1_max_len < 1 ? 64u : (uint32_t)c.p1_max_len;
+		n = 1 + (int)(g.next() % (uint64_t)max_iv);
 		for (int i = 0; i < n; ++i) {
-			uint32_t len = 1 + (uint32_t)(g.next() % 64);
+			uint32_t len = 1 + (uint32_t)(g.next() % (uint64_t)max_len);
 			if (len > m) len = m;
 			ln[i] = len;
 			st[i] = (uint32_t)(g.next() % (uint64_t)(m - len + 1));

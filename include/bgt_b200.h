@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 #define B200_MAX_GROUPS 32      /* BGT_MAX_GROUPS, bgt.h:13 */
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 typedef struct b200_ctx_s   b200_ctx_t;    /* one GPU: device, stream, scratch */
 typedef struct b200_pbf_s   b200_pbf_t;    /* a .pbf (or a row shard of it) resident in HBM; stands in for pbf_t, pbwt.c:176-197 */
@@ -148,7 +148,9 @@ typedef struct {
 	int32_t  shift;          /* 13 */
 	uint64_t seed;
 	int32_t  r_max;          /* plane 0: the row's allele count is log-uniform in [1,m/2], spread over 1+U[0,r_max) intervals of 1s in rank order */
-	int32_t  p1_one_in;      /* plane 1 non-empty in one of p1_one_in rows (16), 1-3 short intervals */
+	int32_t  p1_one_in;      /* plane 1 (missing / other-ALT codes) non-empty in one of p1_one_in rows (16) ... */
+	int32_t  p1_max_iv;      /* ... with 1 + U[0,p1_max_iv) intervals (0 = default 3) ... */
+	int32_t  p1_max_len;     /* ... of 1 + U[0,p1_max_len) ones each (0 = default 64) */
 } b200_synth_t;
 /* Generates the .pbf image on the device and returns it resident for rows [0,n_rows). */
 b200_pbf_t *b200_synth_generate(b200_ctx_t *ctx, const b200_synth_t *cfg);

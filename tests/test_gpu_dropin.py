@@ -215,7 +215,8 @@ def test_baseline_configs_2_3_4_at_full_width_against_the_reference(tools, cohor
     lst.write_text("".join("S%07d\n" % s for s in sel))
     cases = {
         "config2": ["-f", "AC>0", "-G"],
-        "config3": ["-s", 'grp=="A"', "-s", 'grp=="B"', "-f", "AC1/AN1>0.1&&AC2==0", "-G"],
+        "config3": ["-s", 'grp=="A"', "-s", 'grp=="B"', "-f", "AC1/AN1>0.1&&AC2==0", "-G"],     # (passes no site of this cohort: header only)
+        "config3 passing": ["-s", 'grp=="A"', "-s", 'grp=="B"', "-f", "AC1/AN1>0.01&&AC2>0&&AC1!=AC2", "-G"],
         "config4": ["-s", str(lst)],
         "config4 -f": ["-s", str(lst), "-f", "AC>0"],
         "config3 counts": ["-s", 'grp=="A"', "-s", 'grp=="B"', "-G"],
@@ -224,7 +225,7 @@ def test_baseline_configs_2_3_4_at_full_width_against_the_reference(tools, cohor
         want = run(tools.REF_BGT, ["view"] + args + [prefix])
         got, route, _ = run_routed(NEW_BGT, ["view"] + args + [prefix])
         assert got == want, name
-        assert want.count(b"\n") > 100, name
+        assert want.count(b"\n") > (100 if name != "config3" else 10), name
         assert route["view_fast"] == 1 and route["view_fast_to_ref"] == 0 and route["ref_bgtm_read"] == 0 and route["seamB_batches"] == 0, (name, route)
 
 

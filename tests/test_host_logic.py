@@ -37,7 +37,7 @@ def test_abi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libbgt_b200.so does not export %s" % n
         assert n in capi.SIGNATURES, "python binding does not type %s" % n
-    assert L.b200_abi_version() == 1
+    assert L.b200_abi_version() == 2
 
 
 def test_python_binding_flags_match_the_header():
