@@ -42,6 +42,8 @@ SIGNATURES = {
     "b200_ctx_sync": (_int, [_vp]),
     "b200_host_alloc": (_vp, [C.c_size_t]),
     "b200_host_free": (None, [_vp]),
+    "b200_host_register": (_int, [_vp, C.c_size_t]),
+    "b200_host_unregister": (_int, [_vp]),
     "b200_pbf_load": (_vp, [_vp, _vp, C.c_size_t, _i64, _i64]),
     "b200_pbf_load_ex": (_vp, [_vp, _vp, C.c_size_t, _i64, _i64, C.c_uint]),
     "b200_pbf_open": (_vp, [_vp, C.c_char_p, _i64, _i64]),
@@ -54,6 +56,7 @@ SIGNATURES = {
     "b200_pbf_row_end": (_i64, [_vp]),
     "b200_pbf_row_bytes": (_i64, [_vp, _i64, _i64, _int]),
     "b200_pbf_bad_rows": (_i64, [_vp]),
+    "b200_pbf_split_blocks": (_int, [_vp]),
     "b200_query_create": (_vp, [_vp, _vp, _int, _vp, _vp, _int, C.c_char_p, C.POINTER(_int)]),
     "b200_query_create_cols": (_vp, [_vp, _vp, _int, _vp]),
     "b200_query_destroy": (None, [_vp]),
@@ -74,6 +77,8 @@ SIGNATURES = {
     "b200_synth_generate": (_vp, [_vp, C.POINTER(SynthCfg)]),
     "b200_pbf_image_size": (C.c_size_t, [_vp]),
     "b200_pbf_image_download": (_int, [_vp, _vp, C.c_size_t]),
+    "b200_pbf_image_download_range": (_int, [_vp, _vp, C.c_uint64, C.c_size_t]),
+    "b200_pbf_block_bytes": (_int, [_vp, _i64, _i64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "b200_enc_create": (_vp, [_vp, _int, _int]),
     "b200_enc_write_bytes": (_int, [_vp, _vp, _vp, _i64]),
     "b200_enc_write_bits": (_int, [_vp, _vp, _i64]),

@@ -302,6 +302,14 @@ extern "C" void *b200_host_alloc(size_t bytes)
 
 extern "C" void b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+// pin an existing host range (e.g. the part of a mapped .pbf a region shard will upload) so that its H2D copy runs at DMA speed
+extern "C" int b200_host_register(void *p, size_t bytes)
+{
+	if (!p || !bytes) { set_err("b200_host_register: null range"); return -1; }
+	return CU_OK(cudaHostRegister(p, bytes, cudaHostRegisterDefault)) ? 0 : -1;
+}
+extern "C" int b200_host_unregister(void *p) { return p && CU_OK(cudaHostUnregister(p)) ? 0 : -1; }
+
 extern "C" double b200_last_ms(b200_ctx_t *c, int which) { return (c && which >= 0 && which < 6) ? c->last_ms[which] : -1.0; }
 extern "C" int64_t b200_kernel_launches(b200_ctx_t *c) { return c ? c->launches : 0; }
 
@@ -851,6 +859,13 @@ extern "C" int64_t b200_pbf_row_end(const b200_pbf_t *pb)
 	return e < pb->n ? e : pb->n;
 }
 extern "C" int64_t b200_pbf_bad_rows(const b200_pbf_t *pb) { return pb ? pb->bad_rows : -1; }
+extern "C" int b200_pbf_split_blocks(const b200_pbf_t *pb)
+{
+	if (!pb) return -1;
+	int k = 0;
+	for (int b = 0; b < pb->n_blk && b < (int)pb->blk_sparse.size(); ++b) k += pb->blk_sparse[b] != 0;
+	return k;
+}
 extern "C" size_t b200_pbf_image_size(const b200_pbf_t *pb) { return pb ? pb->file_size : 0; }
 
 extern "C" int64_t b200_pbf_row_bytes(const b200_pbf_t *pb, int64_t row_beg, int64_t row_end, int with_snapshots)
@@ -871,6 +886,31 @@ extern "C" int64_t b200_pbf_row_bytes(const b200_pbf_t *pb, int64_t row_beg, int
 		k += take;
 	}
 	return bytes;
+}
+
+// file byte range [*byte_beg, *byte_end) of the checkpoint blocks that hold rows [row_beg,row_end): what a region shard uploads
+// (b200_pbf_load_ex reads the header, this range and the index record at the tail of the image, nothing else)
+extern "C" int b200_pbf_block_bytes(const b200_pbf_t *pb, int64_t row_beg, int64_t row_end, uint64_t *byte_beg, uint64_t *byte_end, uint64_t *index_beg)
+{
+	if (!pb || !byte_beg || !byte_end) { set_err("b200_pbf_block_bytes: null argument"); return -1; }
+	if (row_end < 0 || row_end > pb->n) row_end = pb->n;
+	if (row_beg < 0 || row_beg > row_end) { set_err("b200_pbf_block_bytes: bad row range"); return -1; }
+	const int64_t b0 = row_beg >> pb->shift, b1 = row_end > row_beg ? ((row_end + pb->BS - 1) >> pb->shift) : b0;
+	if (b1 > (int64_t)pb->h_idx.size()) { set_err("b200_pbf_block_bytes: rows beyond the block index"); return -1; }
+	*byte_beg = b0 < (int64_t)pb->h_idx.size() ? pb->h_idx[(size_t)b0] : pb->ioff;
+	*byte_end = b1 < (int64_t)pb->h_idx.size() ? pb->h_idx[(size_t)b1] : pb->ioff;
+	if (index_beg) *index_beg = pb->ioff;
+	return 0;
+}
+
+// part of the file image of a fully resident PBF (generated cohorts): bytes [off, off + n_bytes) -> dst
+extern "C" int b200_pbf_image_download_range(const b200_pbf_t *pb, uint8_t *dst, uint64_t off, size_t n_bytes)
+{
+	if (!pb || !dst) return -1;
+	if (!pb->file_size || off > pb->file_size || n_bytes > pb->file_size - off) { set_err("no complete file image resident, or range outside it"); return -1; }
+	cudaSetDevice(pb->ctx->dev);
+	if (!CU_OK(cudaMemcpyAsync(dst, pb->d_img + off, n_bytes, cudaMemcpyDeviceToHost, pb->ctx->st))) return -1;
+	return CU_OK(cudaStreamSynchronize(pb->ctx->st)) ? 0 : -1;
 }
 
 extern "C" int b200_pbf_image_download(const b200_pbf_t *pb, uint8_t *dst, size_t n_bytes)
@@ -1107,7 +1147,18 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		B.track = qcol; B.qrow = qrow; B.track_stride = cap;
 		B.n_track_blk = qcount; B.n_track = cap; B.blk_list = d_split_list;
 		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : (use_comp ? 2 : 8);
-		ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_QUERY, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
+		static const bool legacy_query = getenv("BGT_B200_LEGACY_QUERY") != nullptr;   // A/B testing: the round-1 QUERY mode of the walk kernel
+		if (use_comp && !legacy_query) {
+			PairParams K;
+			memset(&K, 0, sizeof(K));
+			K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rank0 = pb->d_rank0;
+			K.qcol = qcol; K.qrow = qrow; K.qcount = qcount; K.q_stride = cap; K.tgrp = q->d_tgrp;
+			K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n; K.comp_dir = pb->d_comp_dir;
+			K.dir_shift = pb->dir_shift; K.dir_n = pb->dir_n; K.blk_list = d_split_list; K.cnt_raw = P.cnt_raw;
+			K.m = pb->m; K.G = G; K.shift = pb->shift; K.blk_row0 = P.blk_row0; K.row_lo = row_beg; K.row_hi = row_beg + n_rows; K.err = c->d_err_scan;
+			ok = ok && CU_OK(launch_pairwalk(K, Cb > 4 ? 4 : Cb, cap, n_split, c->st));
+		} else
+			ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_QUERY, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
 		++c->launches;
 		if (G > 1) { // per-group plane-0 marginals for the first G-1 groups (the last one is the remainder)
 			if (!c->n0g.reserve(nr * (size_t)(G - 1) * sizeof(int32_t))) return -1;
@@ -1332,6 +1383,7 @@ extern "C" b200_pbf_t *b200_synth_generate(b200_ctx_t *c, const b200_synth_t *cf
 	}
 	pb->file_size = pb->img_bytes = (size_t)(ioff + tail.size());
 	pb->file_off0 = 0;
+	pb->h_idx = pb->h_blkoff; pb->ioff = ioff;
 	uint8_t hdr[16];
 	{ const int32_t v[3] = {(int32_t)sc.m, 2, sc.shift}; memcpy(hdr, "PBF\1", 4); memcpy(hdr + 4, v, 12); } // pbwt.c:214-216
 	ok = pool_malloc(c, (void**)&pb->d_img, pb->img_bytes + 64) && CU_OK(cudaMalloc(&d_flat, sizeof(uint64_t) * (size_t)n));

@@ -65,6 +65,32 @@ size_t walk_smem_bytes(int C, int G, bool query = false);
 enum { WALK_MODE_COUNT = 0, WALK_MODE_EMIT = 1, WALK_MODE_CHAIN = 2, WALK_MODE_QUERY = 3 };
 cudaError_t launch_walk(const WalkParams &P, int C, int mode, int slices, int n_blk, cudaStream_t st);
 
+// second phase of the split scan (pairwalk.cu): plane-0 bit of the (column,row) pairs that carry a plane-1 bit
+struct PairParams {
+	const uint8_t  *img;
+	const uint64_t *rowoff;
+	const uint32_t *n1;
+	const int32_t  *rank0;       // [blocks][2][m] start ranks under every resident block's snapshot
+	const int32_t  *qcol;        // pairs of every block, sorted by target row: column ...
+	const uint16_t *qrow;        // ... and target row within the block
+	const int      *qcount;      // [blocks] pairs per block
+	long long       q_stride;    // entries between the lists of consecutive blocks
+	const uint8_t  *tgrp;        // 0-based sample group of every column
+	const uint32_t *comp_start;  // composite maps of the 32-row groups (compose.cu) [blocks][groups][COMP_CAP]
+	const int32_t  *comp_delta;
+	const int      *comp_n;      // [blocks][groups] pieces (padded to 4), 0 = not available; nullptr = no maps at all
+	const uint16_t *comp_dir;    // [blocks][groups][COMP_DIR_STRIDE] bucket directories
+	int dir_shift, dir_n;
+	const int      *blk_list;    // resident-block indices handled by this launch (nullptr: blk_first + blockIdx.y)
+	int blk_first;
+	int32_t        *cnt_raw;     // [rows out][G][3] = #ALT, #missing, #other-ALT per group (accumulated)
+	int m, G, shift;
+	long long blk_row0, row_lo, row_hi;
+	int *err;
+};
+size_t pair_smem_bytes();
+cudaError_t launch_pairwalk(const PairParams &P, int C, int max_pairs, int n_blk, cudaStream_t st);
+
 // composite maps of row groups (compose.cu)
 struct ComposeParams {
 	const uint8_t  *img;

@@ -41,6 +41,8 @@ void        b200_ctx_destroy(b200_ctx_t *ctx);
 int         b200_ctx_sync(b200_ctx_t *ctx);
 void       *b200_host_alloc(size_t bytes);           /* pinned host memory for images/results */
 void        b200_host_free(void *p);
+int         b200_host_register(void *p, size_t bytes);   /* pin an existing host range (a shard's byte range of a mapped .pbf) */
+int         b200_host_unregister(void *p);
 
 /* ---------------------------------------------------------------- PBF image (pbwt.c:221-262 pbf_open_r, :264-286 pbf_close) */
 /* bytes = the complete .pbf file image in host memory.  Rows [row_beg,row_end) (row_end<0: to the end)
@@ -64,6 +66,9 @@ int64_t     b200_pbf_row_end(const b200_pbf_t *pb);
 int64_t     b200_pbf_row_bytes(const b200_pbf_t *pb, int64_t row_beg, int64_t row_end, int with_snapshots);
 /* number of rows whose RLE did not sum to m (corrupt stream); the reference has undefined behaviour there */
 int64_t     b200_pbf_bad_rows(const b200_pbf_t *pb);
+/* resident checkpoint blocks whose count-only full-cohort scans take the split path (plane-1 carriers only) rather than the
+ * general walk over every column -- decided per block on the device while loading (sparse plane 1) */
+int         b200_pbf_split_blocks(const b200_pbf_t *pb);
 
 /* ---------------------------------------------------------------- query (bgt.c:207-246 bgt_prepare, :408-416 bgtm_add_group, :444-455 bgtm_set_flt_site) */
 /* out_samples: ascending sample indices (bgt_t.out, bgt.c:214-220); tracked haplotype columns are 2s and
@@ -156,6 +161,10 @@ typedef struct {
 b200_pbf_t *b200_synth_generate(b200_ctx_t *ctx, const b200_synth_t *cfg);
 size_t      b200_pbf_image_size(const b200_pbf_t *pb);             /* bytes of the complete file image, 0 if only a shard is held */
 int         b200_pbf_image_download(const b200_pbf_t *pb, uint8_t *dst, size_t n_bytes); /* device image -> host */
+int         b200_pbf_image_download_range(const b200_pbf_t *pb, uint8_t *dst, uint64_t off, size_t n_bytes);
+/* file byte range of the checkpoint blocks holding rows [row_beg,row_end) and the offset of the index record: a region
+ * shard's b200_pbf_load_ex touches the 16-byte header, [byte_beg,byte_end) and [index_beg, end of file) of the image only */
+int         b200_pbf_block_bytes(const b200_pbf_t *pb, int64_t row_beg, int64_t row_end, uint64_t *byte_beg, uint64_t *byte_end, uint64_t *index_beg);
 
 /* ---------------------------------------------------------------- encoder (pbwt.c:199-219 pbf_open_w, :288-311 pbf_write, :264-286 pbf_close) */
 /* The PBWT encoder on the device: the column-owned rank walk run forward (pbc_enc_core, pbwt.c:57-66) + the run-length
