@@ -235,10 +235,14 @@ extern "C" int b200_errcode(void) { return g_errcode; }
 
 extern "C" b200_ctx_t *b200_ctx_create(int device)
 {
+	const bool trace = getenv("BGT_B200_TRACE") != nullptr;
+	const double t0 = now_ms();
 	int n = b200_device_count();
+	const double t1 = now_ms();
 	if (n <= 0) { set_err_code(B200_E_NO_DEVICE, "no CUDA device: libbgt_b200 has no CPU fallback"); return nullptr; }
 	if (device < 0 || device >= n) { set_err("device %d out of range (0..%d)", device, n - 1); return nullptr; }
-	if (!CU_OK(cudaSetDevice(device))) return nullptr;
+	if (!CU_OK(cudaSetDevice(device)) || !CU_OK(cudaFree(nullptr))) return nullptr;
+	const double t2 = now_ms();
 	cudaDeviceProp prop;
 	if (!CU_OK(cudaGetDeviceProperties(&prop, device))) return nullptr;
 	if (prop.major < 10) { set_err("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return nullptr; }
@@ -259,6 +263,7 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	ok = ok && CU_OK(cudaMemset(c->d_err, 0, 4 * sizeof(int))) && CU_OK(cudaMemset(c->d_acc, 0, 8 * sizeof(unsigned long long)));
 	if (!ok) { b200_ctx_destroy(c); return nullptr; }
 	c->d_err_scan = c->d_err + 1; c->d_err_sites = c->d_err + 2;
+	if (trace) fprintf(stderr, "[b200 trace] context: driver init + device count %.1f ms, primary context %.1f ms, streams/events/scratch %.1f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
 	return c;
 }
 
@@ -431,6 +436,7 @@ static ComposeParams compose_params(const b200_pbf_t *pb, int b0)
 	K.m = pb->m; K.shift = pb->shift; K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n;
 	K.n_grp = (pb->BS + COMP_K - 1) / COMP_K; K.cap = COMP_CAP; K.rle_off = 5; K.n1_plane = 0; K.inverse = 0; K.row_base = nullptr; K.n1_step = 2;
 	K.comp_dir = pb->d_comp_dir; K.dir_shift = pb->dir_shift; K.dir_n = pb->dir_n;
+	K.two_sided = 1; K.n_blk_res = pb->n_blk;   // inverse maps for the second half of every block that has a resident successor (pairwalk.cu)
 	return K;
 }
 
@@ -449,7 +455,7 @@ static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st, 
 	if (b1 <= b0) return true;
 	b200_ctx_t *c = pb->ctx;
 	ComposeParams V = compose_params(pb, b0);
-	V.comp_dir = nullptr; V.nrun = nullptr;
+	V.comp_dir = nullptr; V.nrun = nullptr; V.two_sided = 0;
 	V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
 	V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
 	V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
@@ -1147,8 +1153,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		B.track = qcol; B.qrow = qrow; B.track_stride = cap;
 		B.n_track_blk = qcount; B.n_track = cap; B.blk_list = d_split_list;
 		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : (use_comp ? 2 : 8);
-		static const bool legacy_query = getenv("BGT_B200_LEGACY_QUERY") != nullptr;   // A/B testing: the round-1 QUERY mode of the walk kernel
-		if (use_comp && !legacy_query) {
+		if (use_comp) {   // (without composite maps -- testing -- the QUERY mode of the walk kernel goes row by row)
 			PairParams K;
 			memset(&K, 0, sizeof(K));
 			K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rank0 = pb->d_rank0;
@@ -1156,7 +1161,24 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n; K.comp_dir = pb->d_comp_dir;
 			K.dir_shift = pb->dir_shift; K.dir_n = pb->dir_n; K.blk_list = d_split_list; K.cnt_raw = P.cnt_raw;
 			K.m = pb->m; K.G = G; K.shift = pb->shift; K.blk_row0 = P.blk_row0; K.row_lo = row_beg; K.row_hi = row_beg + n_rows; K.err = c->d_err_scan;
-			ok = ok && CU_OK(launch_pairwalk(K, Cb > 4 ? 4 : Cb, cap, n_split, c->st));
+			K.rows_in_blk = pb->d_rows_in_blk; K.two_sided = 1; K.n_blk_res = pb->n_blk;
+			static const bool prof = getenv("BGT_B200_PROF") != nullptr;
+			static unsigned long long *d_prof = nullptr;
+			if (prof) {
+				if (!d_prof) cudaMalloc(&d_prof, 8 * sizeof(unsigned long long));
+				cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), c->st);
+				K.prof = d_prof;
+			}
+			static const int env_c = getenv("BGT_B200_PAIR_C") ? atoi(getenv("BGT_B200_PAIR_C")) : 0;   // tuning
+			const int Cp = (forced == 1 || forced == 2 || forced == 4) ? forced : (env_c == 1 || env_c == 2 || env_c == 4 ? env_c : 4);
+			ok = ok && CU_OK(launch_pairwalk(K, Cp, cap, n_split, c->st));
+			if (prof) {
+				unsigned long long h[8];
+				cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, c->st);
+				cudaStreamSynchronize(c->st);
+				fprintf(stderr, "[b200 prof] pair walk: %llu CTAs, mean cycles phase A %.0f (%.1f groups), phase B %.0f (%.1f rows per warp)\n", h[2], (double)h[0] / (h[2] ? h[2] : 1),
+				        (double)h[3] / (h[2] ? h[2] : 1), (double)h[1] / (h[2] ? h[2] : 1), (double)h[4] / (h[2] ? h[2] * 16.0 : 1));
+			}
 		} else
 			ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_QUERY, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
 		++c->launches;
@@ -1173,7 +1195,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 				const int n_seg = (n_grp + seg_groups - 1) / seg_groups;
 				if (n_seg > 1) {
 					if (!c->vseg.reserve(per_seg * (size_t)n_seg) || !c->seg_ok.reserve((size_t)n_split * (size_t)(G - 1) + 16)) return -1;
-					M.comp_start = pb->d_comp_start; M.comp_delta = pb->d_comp_delta; M.comp_n = pb->d_comp_n;
+					M.comp_start = pb->d_comp_start; M.comp_delta = pb->d_comp_delta; M.comp_n = pb->d_comp_n; M.two_sided = 1; M.n_blk_res = pb->n_blk;
 					M.n_grp = n_grp; M.seg_groups = seg_groups; M.n_seg = n_seg; M.vseg = (uint32_t*)c->vseg.p; M.seg_ok = (uint8_t*)c->seg_ok.p;
 					++c->launches;
 				}

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	const int nrow = P.rows_in_blk[blk] - r_lo;
 	const size_t slot = ((size_t)blk * n_grp + g);
 	const int cap = P.cap;
+	const bool inverse = P.inverse || g >= comp_first_inverse(blk, P.n_blk_res, P.rows_in_blk[blk], BS, n_grp, P.two_sided);
 	if (CP_RUNS == CP_RUNS_BIG && P.retry && P.comp_n[slot] != 0) return;   // second launch: only the groups the small variant gave up on
 	if (nrow < COMP_K || (P.blk_ok && !P.blk_ok[blk])) { if (tid == 0) P.comp_n[slot] = 0; return; }   // partial last group: never crossed as a whole
 	if (tid == 0) { s_fail = 0; s_n = 0; }
@@ -88,12 +89,14 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 		}
 		__syncthreads();
 	};
-	const bool have_counts = P.nrun != nullptr && !P.inverse;   // counted while loading (rowmeta_kernel): no counting pass
+	const bool have_counts = P.nrun != nullptr;   // counted while loading (rowmeta_kernel): no counting pass
 	if (have_counts) {
 		if (tid < COMP_K) {
 			const size_t ri = (size_t)(rbase + r_lo + tid);
-			const uint32_t n1 = P.n1[ri * P.n1_step + P.n1_plane], nr = P.nrun[ri];
-			offA[tid + 1] = (n1 == 0 || n1 == m) ? 1 : (int)(nr < (1u << 20) ? nr : (1u << 20));
+			const uint32_t n1 = P.n1[ri * P.n1_step + P.n1_plane], nr = P.nrun[ri] & 0x7fffffffu, first = P.nrun[ri] >> 31;
+			const int k_map = inverse ? COMP_K - 1 - tid : tid;
+			offA[k_map + 1] = (n1 == 0 || n1 == m) ? 1 : (int)nr;
+			row_nz[k_map] = (int)(first ? nr >> 1 : (nr + 1) >> 1);         // runs alternate: the 0-runs among them
 		}
 		__syncthreads();
 		place_maps();
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 	}
 	for (int pass = have_counts ? 1 : 0; pass < 2; ++pass) {
 		for (int j = warp; j < COMP_K; j += CP_NW) {
-			const int k_map = P.inverse ? COMP_K - 1 - j : j;
+			const int k_map = inverse ? COMP_K - 1 - j : j;
 			const uint8_t *rec = staged ? (const uint8_t*)S1 + (roff[r_lo + j] - g_beg) : P.img + roff[r_lo + j];
 			const uint32_t l = cp_ld_u32_unaligned(rec + P.rle_off - 4);
 			const uint8_t *rle = rec + P.rle_off;
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 					const uint32_t zm_ = sm_ & ~bitm;                      // run starts of 0-runs
 					if (pass && is_start) {
 						const int32_t delta = b ? (int32_t)((m - n1) - (start - ones_before)) : -(int32_t)ones_before;
-						if (!P.inverse) {
+						if (!inverse) {
 							const int k = base_out + (int)nrun + __popc(sm_ & lt);
 							S0[k] = start; D0[k] = delta;
 						} else { // inverse map: runs ordered by where they land (0-runs, then 1-runs), translated back

@@ -421,7 +421,34 @@ __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const Margina
 		for (int w = tid; w < wpad; w += MS_NT) Vnew[w] = 0;
 		if (gg + 1 < g_end) fetch(gg + 1);
 		__syncthreads();
-		if (w_lo < w_hi) {
+		// two-sided maps (compose.cu): the groups of the second half carry the INVERSE map, whose pieces are cut in the coordinates
+		// behind the group -- the vector is gathered through it (every thread owns its output words) instead of scattered
+		const bool inv_map = gg >= comp_first_inverse(blk, P.n_blk_res, P.rows_in_blk[blk], 1 << P.shift, P.n_grp, P.two_sided);
+		if (w_lo < w_hi && inv_map) {
+			uint32_t k = 0;
+			{
+				const uint32_t pos0 = (uint32_t)w_lo * 32;
+				for (uint32_t len = np; len > 1;) { const uint32_t half = len >> 1; k += cs[k + half] <= pos0 ? half : 0u; len -= half; }
+			}
+			for (int w = w_lo; w < w_hi; ++w) {
+				const uint32_t pos = (uint32_t)w * 32, lim = pos + 32 < m ? pos + 32 : m;
+				uint32_t cur = pos, acc = 0;
+				while (cur < lim) {
+					const uint32_t next = k + 1 < np ? cs[k + 1] : m;
+					const uint32_t stop = next < lim ? next : lim;
+					if (stop > cur) {
+						const uint32_t take = stop - cur, src = cur + (uint32_t)cd[k], sw = src >> 5, sb = src & 31u;
+						if (src < m) {                                      // (a well-formed map never leaves [0, m))
+							const uint32_t word = __funnelshift_r(Vold[sw], Vold[sw + 1], sb);   // bits src .. src+31 (the vectors carry spare zero words)
+							acc |= (word & (take == 32 ? 0xffffffffu : ((1u << take) - 1u))) << (cur - pos);
+						}
+						cur = stop;
+					}
+					if (cur >= next) ++k;
+				}
+				Vnew[w] = acc;
+			}
+		} else if (w_lo < w_hi) {
 			uint32_t k = 0;
 			{
 				const uint32_t pos0 = (uint32_t)w_lo * 32;

@@ -33,7 +33,10 @@ namespace b200 {
 constexpr int PW_NT = 512, PW_NW = PW_NT / 32;
 constexpr int PW_STAGES = 3;
 constexpr uint32_t PW_STG_TD = COMP_CAP * 4u, PW_STG_DIR = COMP_CAP * 8u, PW_STG_BYTES = COMP_CAP * 8u + COMP_DIR_STRIDE * 2u;
-constexpr int PW_TAB = (int)((PW_STAGES * PW_STG_BYTES) / PW_NW / 8) & ~31;   // run-table entries per warp in phase B (overlays the stages)
+// phase B: every warp owns a slice of the (then idle) stages: a run table of PW_TAB2 entries (ts + td) and PW_RAW staged record bytes
+constexpr int PW_SLICE = (int)((PW_STAGES * PW_STG_BYTES) / PW_NW) & ~15;
+constexpr int PW_TAB2 = 256;
+constexpr int PW_RAW = PW_SLICE - PW_TAB2 * 8;
 
 __device__ __forceinline__ uint32_t pw_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t pw_lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -105,47 +108,128 @@ __device__ __forceinline__ void pw_lookup_comp(uint32_t (&r)[C], uint32_t tab, u
 	}
 }
 
-// One warp, one row, forward: the lanes in `act` move their rank through the row (rank' = rank + delta of the run that
-// holds it, pbwt.c:150) and learn the run's bit.  The row's RLE bytes come straight from global memory; its run table is
-// built piecewise in the warp's shared-memory slice (ts = run starts, td = deltas, PW_TAB entries a piece).
-__device__ __forceinline__ void pw_row_forward(const uint8_t *rle, uint32_t l, uint32_t m, uint32_t n1, uint32_t *ts, int32_t *td, int lane,
-                                               uint32_t &r, bool act, uint32_t &bit)
+// One warp, one row.  The row's RLE bytes (generic pointer: the warp's staged copy in shared memory, or global memory for a
+// record larger than the slice) are turned into a run table in the warp's slice, PW_TAB2 entries a piece: four bytes per lane
+// and pass -- a local prefix over the lane's bytes, one warp scan over the lane totals -- so a typical row (100-200 bytes)
+// takes two passes.  Then every slot c whose bit is set in the lane's `act` moves its rank through the row.
+//   BACK = false: rank in front of the row -> rank behind it (rank' = rank + delta of the run that holds it, pbwt.c:150);
+//                 `bits` bit c = the run's bit.  Table: one entry per byte in file order (ts = run start, td = delta).
+//   BACK = true : rank behind the row -> rank in front of it (the partition of pbwt.c:79-88 undone).  A rank below the zeros
+//                 total was the k-th 0 of the row, one above it the k-th 1.  Table, again per byte in file order: zb = zeros
+//                 in front of the byte, ob = ones in front of it -- both ascending, so the k-th 0 lies in the last byte with
+//                 zb <= k (bytes of the other class and empty bytes share the zb of the 0-byte behind them and are never last),
+//                 at rank k + ob; the k-th 1 in the last byte with ob <= k, at rank k + zb.
+template<int C, bool BACK>
+__device__ __forceinline__ void pw_row(const uint8_t *rle, uint32_t l, uint32_t m, uint32_t n1, uint32_t *ts, int lane,
+                                       uint32_t (&r)[C], uint32_t act, uint32_t &bits)
 {
 	const uint32_t zeros_total = m - n1;
-	uint32_t tot = 0, ones = 0;
-	bool done = !act;
-	for (uint32_t cb = 0; cb < l; cb += PW_TAB) {
-		const uint32_t n = l - cb < (uint32_t)PW_TAB ? l - cb : (uint32_t)PW_TAB;
-		const uint32_t cs = tot;
-		for (uint32_t base = 0; base < n; base += 32) {
-			const uint32_t i = base + lane;
-			const uint32_t c = i < n ? rle[cb + i] : 0u;
-			const uint32_t L = pw_rle_len(c), b = c & 1u, L1 = b ? L : 0u;
-			uint32_t x = L, y = L1;
+	const uint32_t tsa = pw_smem_u32(ts);
+	uint32_t tot = 0, ones = 0, todo = act;
+	for (uint32_t cb = 0; cb < l; cb += PW_TAB2) {
+		const uint32_t n = l - cb < (uint32_t)PW_TAB2 ? l - cb : (uint32_t)PW_TAB2;
+		const uint32_t cs = tot, os = ones;
+		for (uint32_t base = 0; base < n; base += 128) {
+			const uint32_t i0 = base + 4u * lane;
+			uint32_t L[4], O[4];
+			#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const uint32_t c = i0 + k < n ? rle[cb + i0 + k] : 0u;
+				L[k] = pw_rle_len(c); O[k] = (c & 1u) ? L[k] : 0u;
+			}
+			const uint32_t xl = L[0] + L[1] + L[2] + L[3], yl = O[0] + O[1] + O[2] + O[3];
+			uint32_t x = xl, y = yl;
 			#pragma unroll
 			for (int d = 1; d < 32; d <<= 1) {
 				const uint32_t tx = __shfl_up_sync(PW_FULL, x, d), ty = __shfl_up_sync(PW_FULL, y, d);
 				if (lane >= d) { x += tx; y += ty; }
 			}
-			const uint32_t start = tot + x - L, ones_before = ones + y - L1;
-			if (i < n) { ts[i] = start; td[i] = b ? (int32_t)(zeros_total - (start - ones_before)) : -(int32_t)ones_before; }
+			uint32_t start = tot + x - xl, ones_before = ones + y - yl;
+			if (!BACK) {
+				uint4 vs; int4 vd;
+				uint32_t *ps = &vs.x; int32_t *pd = &vd.x;
+				#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					ps[k] = start;
+					pd[k] = O[k] ? (int32_t)(zeros_total - (start - ones_before)) : -(int32_t)ones_before;   // (an empty byte is never the entry that is hit)
+					start += L[k]; ones_before += O[k];
+				}
+				*(uint4*)(ts + i0) = vs;
+				*(int4*)(ts + PW_TAB2 + i0) = vd;
+			} else {
+				uint4 vz, vo;
+				uint32_t *pz = &vz.x, *po = &vo.x;
+				#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					pz[k] = start - ones_before; po[k] = ones_before;
+					start += L[k]; ones_before += O[k];
+				}
+				*(uint4*)(ts + i0) = vz;
+				*(uint4*)(ts + PW_TAB2 + i0) = vo;
+			}
 			tot += __shfl_sync(PW_FULL, x, 31);
 			ones += __shfl_sync(PW_FULL, y, 31);
 		}
 		__syncwarp();
-		if (!done && r >= cs && r < tot) { // last entry whose start <= r (zero-length bytes share the start of their successor and are never the last)
-			uint32_t a = 0;
-			for (uint32_t len = n; len > 1;) { const uint32_t half = len >> 1; a += ts[a + half] <= r ? half : 0; len -= half; }
-			r += (uint32_t)td[a];
-			bit = r >= zeros_total ? 1u : 0u;
-			done = true;
+		if (!BACK) {
+			// all C searches of the lane in lock step (independent shared-memory reads): last entry whose start <= rank -- empty
+			// bytes share the start of their successor and are never last.  Slots that are not live, or whose rank lies in
+			// another piece of a long row, search along and discard the result.
+			uint32_t a[C];
+			#pragma unroll
+			for (int c = 0; c < C; ++c) a[c] = tsa;
+			for (uint32_t len = n; len > 1;) {
+				const uint32_t half = len >> 1, h4 = half << 2;
+				#pragma unroll
+				for (int c = 0; c < C; ++c) {
+					const uint32_t t = a[c] + h4;
+					a[c] = pw_lds_u32(t) <= r[c] ? t : a[c];
+				}
+				len -= half;
+			}
+			#pragma unroll
+			for (int c = 0; c < C; ++c) {
+				const uint32_t nr = r[c] + pw_lds_u32(a[c] + PW_TAB2 * 4u);
+				if (((todo >> c) & 1u) && r[c] >= cs && r[c] < tot) {
+					r[c] = nr;
+					bits |= (nr >= zeros_total ? 1u : 0u) << c;
+					todo &= ~(1u << c);
+				}
+			}
+		} else {
+			// this piece holds the zeros numbered [cs - os, tot - ones) and the ones numbered [os, ones)
+			const uint32_t z_lo = cs - os, z_hi = tot - ones;
+			uint32_t a[C], kk[C], inp = 0;
+			#pragma unroll
+			for (int c = 0; c < C; ++c) {
+				const bool one = r[c] >= zeros_total;
+				kk[c] = one ? r[c] - zeros_total : r[c];
+				const bool here = one ? (kk[c] >= os && kk[c] < ones) : (kk[c] >= z_lo && kk[c] < z_hi);
+				inp |= (((todo >> c) & 1u) && here ? 1u : 0u) << c;
+				a[c] = one ? tsa + PW_TAB2 * 4u : tsa;               // search ob[] or zb[]
+			}
+			for (uint32_t len = n; len > 1;) {
+				const uint32_t half = len >> 1, h4 = half << 2;
+				#pragma unroll
+				for (int c = 0; c < C; ++c) {
+					const uint32_t t = a[c] + h4;
+					a[c] = pw_lds_u32(t) <= kk[c] ? t : a[c];
+				}
+				len -= half;
+			}
+			#pragma unroll
+			for (int c = 0; c < C; ++c) {
+				const bool one = r[c] >= zeros_total;
+				const uint32_t other = pw_lds_u32(one ? a[c] - PW_TAB2 * 4u : a[c] + PW_TAB2 * 4u);   // zb of the byte for a 1, ob for a 0
+				if ((inp >> c) & 1u) { r[c] = kk[c] + other; todo &= ~(1u << c); }
+			}
 		}
 		__syncwarp();
-		if (__all_sync(PW_FULL, done)) break;
+		if (!__any_sync(PW_FULL, todo != 0)) break;
 	}
 }
 
-struct PairSmem { uint64_t bar[PW_STAGES]; int avail; };
+struct PairSmem { uint64_t bar[PW_STAGES]; int f_max, b_min, f_avail, b_avail; };
 
 template<int C>
 __global__ void __launch_bounds__(PW_NT, 2) pbwt_pair_kernel(const PairParams P)
@@ -165,104 +249,242 @@ __global__ void __launch_bounds__(PW_NT, 2) pbwt_pair_kernel(const PairParams P)
 	const int n_grp = (BS + COMP_K - 1) / COMP_K;
 	const uint64_t *roff = P.rowoff + (size_t)blk * (BS + 1);
 	const uint32_t *n1p = P.n1 + (size_t)blk * BS * 2;
+	// first group with an INVERSE map: pairs whose target lies in it or behind it come from the next block's snapshot
+	const int H = P.comp_n ? comp_first_inverse(blk, P.n_blk_res, P.rows_in_blk[blk], BS, n_grp, P.two_sided) : n_grp;
 
 	// ---- this thread's pairs: target row, group of the column, start rank; pairs outside the scanned rows are dropped
-	uint32_t r[C], tgt[C], grp[C], valid = 0;
+	uint32_t r[C], tgt[C], grp[C], valid = 0, back = 0;
+	int f_max = 0, b_min = n_grp;
 	#pragma unroll
 	for (int c = 0; c < C; ++c) {
-		const int e = slice_base + c * PW_NT + tid;
+		const int e = slice_base + warp * (C * 32) + lane * C + c;   // a lane's C pairs are neighbours in the sorted list (same rows in phase B), a warp's 32*C too
 		tgt[c] = 0xffffffffu; r[c] = 0; grp[c] = 0;
 		if (e < n_pairs) {
 			const uint32_t t = qrow[e];
 			const long long arow = blk_row + t;
 			if (arow >= P.row_lo && arow < P.row_hi) {
 				const int32_t col = qcol[e];
-				tgt[c] = t; valid |= 1u << c;
+				const int tg = (int)(t / COMP_K);
+				const bool bk = tg >= H;
+				tgt[c] = t; valid |= 1u << c; back |= (bk ? 1u : 0u) << c;
 				grp[c] = P.tgrp[col];
-				r[c] = (uint32_t)P.rank0[((size_t)blk * 2 + 0) * m + col];
+				r[c] = (uint32_t)P.rank0[((size_t)(blk + (bk ? 1 : 0)) * 2 + 0) * m + col];   // pbwt.c:343 under this / the next snapshot
+				if (bk) b_min = min(b_min, tg); else f_max = max(f_max, tg);
 			}
 		}
 	}
-	// the groups this CTA crosses by composite: those in front of its last live target's group, as far as maps are available
-	int g_last = 0;
-	#pragma unroll
-	for (int c = 0; c < C; ++c) if ((valid >> c) & 1u) g_last = max(g_last, (int)(tgt[c] / COMP_K));
-	g_last = __reduce_max_sync(PW_FULL, g_last);
-	if (tid == 0) { S.avail = 0; for (int s = 0; s < PW_STAGES; ++s) pw_mbar_init(&S.bar[s], 1); }
+	// the groups this CTA crosses by composite map: the forward maps in front of its last forward target's group and the inverse
+	// maps behind its first backward target's group, as far as maps are available
+	f_max = __reduce_max_sync(PW_FULL, f_max);
+	b_min = __reduce_min_sync(PW_FULL, b_min);
+	if (tid == 0) { S.f_max = 0; S.b_min = n_grp; for (int s = 0; s < PW_STAGES; ++s) pw_mbar_init(&S.bar[s], 1); }
 	__syncthreads();
-	if (lane == 0) atomicMax(&S.avail, g_last);
+	if (lane == 0) { atomicMax(&S.f_max, f_max); atomicMin(&S.b_min, b_min); }
 	__syncthreads();
-	g_last = S.avail;
+	f_max = S.f_max; b_min = S.b_min;
+	if (tid == 0) { S.f_avail = f_max; S.b_avail = b_min; }
 	__syncthreads();
-	if (tid == 0) S.avail = g_last;
+	for (int i = tid; i < n_grp; i += PW_NT) {
+		const bool have = P.comp_n != nullptr && P.comp_n[(size_t)blk * n_grp + i] != 0;
+		if (!have && i < f_max) atomicMin(&S.f_avail, i);
+		if (!have && i > b_min) atomicMax(&S.b_avail, i);
+	}
 	__syncthreads();
-	for (int i = tid; i < g_last; i += PW_NT) if (P.comp_n == nullptr || P.comp_n[(size_t)blk * n_grp + i] == 0) atomicMin(&S.avail, i);
-	__syncthreads();
-	const int g_end = S.avail;
+	const int gF = S.f_avail;                                   // forward maps of groups [0, gF) are crossed
+	const int gB = S.b_avail;                                   // inverse maps of groups (gB, n_grp) are crossed, last one first
+	const int nB = b_min < n_grp ? n_grp - 1 - gB : 0, nA = gF + nB;
 
-	// ---- phase A: composite maps through three TMA stages
+	const long long t_a = P.prof ? clock64() : 0;
+	// ---- phase A: composite maps through three TMA stages; step s crosses group s (s < gF) or group n_grp-1-(s-gF)
 	{
 		const uint32_t stg0 = pw_smem_u32(pw_sm);
-		auto fetch = [&](int g) {
-			const size_t slot = (size_t)blk * n_grp + g;
+		auto group_of = [&](int s2) { return s2 < gF ? s2 : n_grp - 1 - (s2 - gF); };
+		auto fetch = [&](int s2) {
+			const size_t slot = (size_t)blk * n_grp + group_of(s2);
 			const uint32_t np = (uint32_t)P.comp_n[slot];
-			uint64_t *bar = &S.bar[g % PW_STAGES];
-			uint8_t *dst = pw_sm + (size_t)(g % PW_STAGES) * PW_STG_BYTES;
+			uint64_t *bar = &S.bar[s2 % PW_STAGES];
+			uint8_t *dst = pw_sm + (size_t)(s2 % PW_STAGES) * PW_STG_BYTES;
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 			pw_mbar_expect_tx(bar, np * 8u + (uint32_t)P.dir_n * 2u);
 			pw_tma_g2s(dst, P.comp_start + slot * COMP_CAP, np * 4u, bar);
 			pw_tma_g2s(dst + PW_STG_TD, P.comp_delta + slot * COMP_CAP, np * 4u, bar);
 			pw_tma_g2s(dst + PW_STG_DIR, P.comp_dir + slot * COMP_DIR_STRIDE, (uint32_t)P.dir_n * 2u, bar);
 		};
-		if (tid == 0) for (int k = 0; k < PW_STAGES - 1 && k < g_end; ++k) fetch(k);
-		for (int g = 0; g < g_end; ++g) {
-			if (tid == 0 && g + PW_STAGES - 1 < g_end) fetch(g + PW_STAGES - 1);   // that stage was released by the barrier that ended group g-1
+		uint32_t tgq[C];                                        // target group, or a value that keeps the pair out of every step
+		#pragma unroll
+		for (int c = 0; c < C; ++c) tgq[c] = tgt[c] / COMP_K;
+		if (tid == 0) for (int k = 0; k < PW_STAGES - 1 && k < nA; ++k) fetch(k);
+		for (int s2 = 0; s2 < nA; ++s2) {
+			if (tid == 0 && s2 + PW_STAGES - 1 < nA) fetch(s2 + PW_STAGES - 1);   // that stage was released by the barrier that ended step s2-1
 			{
 				uint32_t spins = 0;
-				const uint32_t par = (uint32_t)(g / PW_STAGES) & 1u;
-				while (!pw_mbar_try_wait(&S.bar[g % PW_STAGES], par))
+				const uint32_t par = (uint32_t)(s2 / PW_STAGES) & 1u;
+				while (!pw_mbar_try_wait(&S.bar[s2 % PW_STAGES], par))
 					if (++spins > (1u << 26)) { atomicOr(P.err, 8); __trap(); }
 			}
+			const bool fw = s2 < gF;
+			const uint32_t g = (uint32_t)group_of(s2);
 			uint32_t act = 0;
 			#pragma unroll
-			for (int c = 0; c < C; ++c) act |= (((valid >> c) & 1u) && (int)(tgt[c] / COMP_K) > g ? 1u : 0u) << c;
-			const uint32_t tab = stg0 + (uint32_t)(g % PW_STAGES) * PW_STG_BYTES;
+			for (int c = 0; c < C; ++c) act |= (fw ? tgq[c] > g && !((back >> c) & 1u) : tgq[c] < g && ((back >> c) & 1u)) ? 1u << c : 0u;
+			act &= valid;
+			const uint32_t tab = stg0 + (uint32_t)(s2 % PW_STAGES) * PW_STG_BYTES;
 			pw_lookup_comp<C>(r, tab, tab + PW_STG_DIR, P.dir_shift, act);
 			__syncthreads();
 		}
 	}
 
-	// ---- phase B: every warp on its own, slot by slot.  A pair walks from the start of its group (or of the first group
-	// without a composite map) to its target row; the 32 pairs of a slot are neighbours in the sorted list.
-	uint32_t *ts = (uint32_t*)pw_sm + (size_t)warp * PW_TAB * 2;
-	int32_t *td = (int32_t*)(ts + PW_TAB);
+	// ---- phase B: every warp on its own.  A forward pair walks from the start of its group (or of the first group without a map)
+	// to its target row, whose run gives the bit; a backward pair is undone from the end of its group (or of the last group
+	// without a map) down to the row behind its target, where its rank tells the bit.  The 32*C pairs of a warp are neighbours
+	// in the sorted list: a few rows apart.
+	const long long t_b = P.prof ? clock64() : 0;
+	unsigned rows_walked = 0;
+	uint8_t *slice = pw_sm + (size_t)warp * PW_SLICE;
+	uint32_t *ts = (uint32_t*)slice;
+	uint32_t *raw32 = (uint32_t*)(slice + PW_TAB2 * 8);
+	const uint8_t *raw = (const uint8_t*)raw32;
 	const int per_row = P.G * 3;
-	#pragma unroll
-	for (int c = 0; c < C; ++c) {
-		const bool v = (valid >> c) & 1u;
-		const uint32_t tg = tgt[c] / COMP_K;
-		const uint32_t from = v ? (tg < (uint32_t)g_end ? tg : (uint32_t)g_end) * COMP_K : 0xffffffffu;
-		const uint32_t rlo = __reduce_min_sync(PW_FULL, from);
-		const uint32_t rhi = __reduce_max_sync(PW_FULL, v ? tgt[c] : 0u);
-		if (rlo == 0xffffffffu) continue;                      // no live pair in this slot of the warp
-		for (uint32_t row = rlo; row <= rhi; ++row) {
-			const bool act = v && row >= from && row <= tgt[c];
-			if (!__any_sync(PW_FULL, act)) continue;
-			const uint32_t n1 = n1p[(size_t)row * 2];
-			uint32_t bit = n1 ? 1u : 0u;                       // constant row: the order does not change (pbwt.c:75-77)
-			if (n1 != 0 && n1 != m) {
-				const uint8_t *rec = P.img + roff[row];
-				const uint32_t l0 = pw_ld_u32_unaligned(rec + 1);
-				pw_row_forward(rec + 5, l0, m, n1, ts, td, lane, r[c], act, bit);
+	// pairs whose target is `row`: code 3 (other-ALT) if the plane-0 bit is set, else 2 (missing) -- bgt.c:743-756
+	auto count_hits = [&](uint32_t row, uint32_t hit, uint32_t bits) {
+		#pragma unroll
+		for (int c = 0; c < C; ++c)
+			if ((hit >> c) & 1u)
+				atomicAdd(P.cnt_raw + (size_t)(blk_row + row - P.row_lo) * per_row + grp[c] * 3 + (((bits >> c) & 1u) ? 2 : 1), 1);
+	};
+	const uint32_t fwd = valid & ~back;
+	if (__any_sync(PW_FULL, fwd != 0)) { // ---- forward pairs, rows ascending
+		uint32_t from[C], rlo = 0xffffffffu, rhi = 0;
+		#pragma unroll
+		for (int c = 0; c < C; ++c) {
+			const bool v = (fwd >> c) & 1u;
+			const uint32_t tg = tgt[c] / COMP_K;
+			from[c] = v ? (tg < (uint32_t)gF ? tg : (uint32_t)gF) * COMP_K : 0xffffffffu;
+			rlo = min(rlo, from[c]);
+			rhi = max(rhi, v ? tgt[c] : 0u);
+		}
+		rlo = __reduce_min_sync(PW_FULL, rlo);
+		rhi = __reduce_max_sync(PW_FULL, rhi);
+		auto live = [&](uint32_t row) {
+			uint32_t a = 0;
+			#pragma unroll
+			for (int c = 0; c < C; ++c) a |= (row >= from[c] && row <= tgt[c] ? 1u : 0u) << c;
+			return a & fwd;
+		};
+		auto hits = [&](uint32_t row, uint32_t act) {
+			uint32_t h = 0;
+			#pragma unroll
+			for (int c = 0; c < C; ++c) h |= (row == tgt[c] ? 1u : 0u) << c;
+			return h & act;
+		};
+		for (uint32_t row = rlo; row <= rhi;) {
+			// the records of up to 32 rows lie back to back in the image: stage as many whole rows as fit the slice with one
+			// round of independent coalesced loads, then work on them out of shared memory
+			const uint32_t nmax = rhi - row + 1 < 32u ? rhi - row + 1 : 32u;
+			const uint32_t j = (uint32_t)lane < nmax ? (uint32_t)lane : nmax - 1;
+			const uint64_t off_l = roff[row + j], end_l = roff[row + j + 1];
+			const uint32_t n1_l = n1p[(size_t)(row + j) * 2];
+			const uint64_t base = __shfl_sync(PW_FULL, off_l, 0) & ~(uint64_t)3;
+			const uint32_t nb = __popc(__ballot_sync(PW_FULL, (uint32_t)lane < nmax && end_l - base <= (uint64_t)PW_RAW));
+			if (nb == 0) { // a single record larger than the slice: its bytes come straight from global memory
+				const uint32_t act = live(row);
+				const uint32_t n1 = __shfl_sync(PW_FULL, n1_l, 0);
+				uint32_t bits = n1 ? 0xffffffffu : 0u;
+				if (n1 != 0 && n1 != m && __any_sync(PW_FULL, act != 0)) {
+					const uint8_t *rec = P.img + __shfl_sync(PW_FULL, off_l, 0);
+					bits = 0;
+					pw_row<C, false>(rec + 5, pw_ld_u32_unaligned(rec + 1), m, n1, ts, lane, r, act, bits);
+				}
+				count_hits(row, hits(row, act), bits);
+				++rows_walked; ++row;
+				continue;
 			}
-			// pairs whose target is this row: code 3 (other-ALT) if the plane-0 bit is set, else 2 (missing) -- bgt.c:743-756
-			const bool hit = act && row == tgt[c];
-			if (__any_sync(PW_FULL, hit)) {
-				const uint32_t key = hit ? (grp[c] << 1 | bit) : 0xffffffffu;
-				const uint32_t peers = __match_any_sync(PW_FULL, key);
-				if (hit && lane == __ffs(peers) - 1)
-					atomicAdd(P.cnt_raw + (size_t)(blk_row + row - P.row_lo) * per_row + grp[c] * 3 + (bit ? 2 : 1), __popc(peers));
+			const uint32_t words = (uint32_t)((__shfl_sync(PW_FULL, end_l, nb - 1) - base + 3) >> 2);
+			const uint32_t *src = (const uint32_t*)(P.img + base);
+			__syncwarp();
+			for (uint32_t w = lane; w < words; w += 32) raw32[w] = src[w];
+			__syncwarp();
+			for (uint32_t k = 0; k < nb; ++k, ++row) {
+				const uint32_t act = live(row);
+				if (!__any_sync(PW_FULL, act != 0)) continue;
+				++rows_walked;
+				const uint32_t n1 = __shfl_sync(PW_FULL, n1_l, k);
+				uint32_t bits = n1 ? 0xffffffffu : 0u;         // constant row: the order does not change (pbwt.c:75-77)
+				if (n1 != 0 && n1 != m) {
+					const uint8_t *rec = raw + (uint32_t)(__shfl_sync(PW_FULL, off_l, k) - base);
+					const uint32_t l0 = (uint32_t)rec[1] | (uint32_t)rec[2] << 8 | (uint32_t)rec[3] << 16 | (uint32_t)rec[4] << 24;
+					bits = 0;
+					pw_row<C, false>(rec + 5, l0, m, n1, ts, lane, r, act, bits);
+				}
+				count_hits(row, hits(row, act), bits);
 			}
+		}
+	}
+	if (__any_sync(PW_FULL, back != 0)) { // ---- backward pairs, rows descending
+		uint32_t top[C], rlo = 0xffffffffu, rhi = 0;            // top[c]: first row to undo (the last row of the group the maps stop at)
+		#pragma unroll
+		for (int c = 0; c < C; ++c) {
+			const bool v = (back >> c) & 1u;
+			const uint32_t tg = tgt[c] / COMP_K;
+			top[c] = v ? min(((tg > (uint32_t)gB ? tg : (uint32_t)gB) + 1u) * COMP_K, (uint32_t)BS) - 1u : 0u;   // (a block with inverse maps is full: BS rows)
+			rlo = min(rlo, v ? tgt[c] : 0xffffffffu);
+			rhi = max(rhi, top[c]);
+		}
+		rlo = __reduce_min_sync(PW_FULL, rlo);
+		rhi = __reduce_max_sync(PW_FULL, rhi);
+		for (uint32_t row = rhi; (int)row >= (int)rlo;) {
+			// rows [row - nmax + 1, row]: stage the longest tail of them that fits, work downwards
+			const uint32_t nmax = row - rlo + 1 < 32u ? row - rlo + 1 : 32u;
+			const uint32_t lo = row - nmax + 1;
+			const uint32_t j = (uint32_t)lane < nmax ? (uint32_t)lane : nmax - 1;
+			const uint64_t off_l = roff[lo + j];
+			const uint32_t n1_l = n1p[(size_t)(lo + j) * 2];
+			const uint64_t end_top = roff[row + 1];
+			const uint32_t nb = __popc(__ballot_sync(PW_FULL, (uint32_t)lane < nmax && end_top - (off_l & ~(uint64_t)3) <= (uint64_t)PW_RAW));
+			const bool staged = nb > 0;
+			const uint32_t first = staged ? nmax - nb : nmax - 1; // lane that holds the lowest row handled in this round
+			const uint64_t base = __shfl_sync(PW_FULL, off_l, first) & ~(uint64_t)3;
+			if (staged) {
+				const uint32_t words = (uint32_t)((end_top - base + 3) >> 2);
+				const uint32_t *src = (const uint32_t*)(P.img + base);
+				__syncwarp();
+				for (uint32_t w = lane; w < words; w += 32) raw32[w] = src[w];
+				__syncwarp();
+			}
+			for (uint32_t k = nmax; k-- > first; --row) {
+				uint32_t undo = 0, hit = 0;
+				#pragma unroll
+				for (int c = 0; c < C; ++c) {
+					undo |= (row > tgt[c] && row <= top[c] ? 1u : 0u) << c;
+					hit |= (row == tgt[c] ? 1u : 0u) << c;
+				}
+				undo &= back; hit &= back;
+				if (!__any_sync(PW_FULL, (undo | hit) != 0)) continue;
+				++rows_walked;
+				const uint32_t n1 = __shfl_sync(PW_FULL, n1_l, k);
+				if (n1 != 0 && n1 != m && __any_sync(PW_FULL, undo != 0)) {
+					const uint64_t off = __shfl_sync(PW_FULL, off_l, k);
+					const uint8_t *rec = staged ? raw + (uint32_t)(off - base) : P.img + off;
+					const uint32_t l0 = staged ? ((uint32_t)rec[1] | (uint32_t)rec[2] << 8 | (uint32_t)rec[3] << 16 | (uint32_t)rec[4] << 24) : pw_ld_u32_unaligned(rec + 1);
+					uint32_t unused = 0;
+					pw_row<C, true>(rec + 5, l0, m, n1, ts, lane, r, undo, unused);
+				}
+				if (__any_sync(PW_FULL, hit != 0)) { // rank behind the target row: the ones sit behind the m - n1 zeros (pbwt.c:79-88)
+					uint32_t bits = 0;
+					#pragma unroll
+					for (int c = 0; c < C; ++c) bits |= (r[c] >= m - n1 ? 1u : 0u) << c;
+					count_hits(row, hit, bits);
+				}
+			}
+		}
+	}
+	if (P.prof) {
+		if (lane == 0) atomicAdd(P.prof + 4, (unsigned long long)rows_walked);
+		__syncthreads();
+		if (tid == 0) {
+			const long long t_e = clock64();
+			atomicAdd(P.prof + 0, (unsigned long long)(t_b - t_a)); atomicAdd(P.prof + 1, (unsigned long long)(t_e - t_b));
+			atomicAdd(P.prof + 2, 1ull); atomicAdd(P.prof + 3, (unsigned long long)nA);
 		}
 	}
 }

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) rowmeta_kernel(const uint8_t *__restrict_
 		const uint32_t l = ld_u32_unaligned(p);
 		p += 4;
 		unsigned long long tot = 0, ones = 0;
-		uint32_t nrun = 0, prev_bit = 2;
+		uint32_t nrun = 0, prev_bit = 2, first_bit = 0;
 		for (uint32_t base = 0; base < l; base += 32) {
 			const uint32_t i = base + lane;
 			const uint32_t c = i < l ? p[i] : 0u, len = rle_len(c), b = c & 1u;
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(256) rowmeta_kernel(const uint8_t *__restrict_
 				const uint32_t valid = __ballot_sync(FULL_MASK, len > 0), bitm = __ballot_sync(FULL_MASK, b != 0);
 				const uint32_t below = valid & ((1u << lane) - 1u);
 				const uint32_t pb = below ? (bitm >> (31 - __clz(below))) & 1u : prev_bit;
+				if (prev_bit == 2 && valid) first_bit = (bitm >> (__ffs(valid) - 1)) & 1u;
 				nrun += __popc(__ballot_sync(FULL_MASK, len > 0 && pb != b));
 				if (valid) prev_bit = (bitm >> (31 - __clz(valid))) & 1u;
 			}
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256) rowmeta_kernel(const uint8_t *__restrict_
 			const bool ok = (tot == m);
 			n1[((size_t)blk * BS + r) * 2 + plane] = ok ? (uint32_t)ones : 0u; // a corrupt row decodes as all-REF
 			if (!ok) atomicAdd(bad, 1ull);
-			if (plane == 0 && nrun0) nrun0[(size_t)blk * BS + r] = nrun;
+			if (plane == 0 && nrun0) nrun0[(size_t)blk * BS + r] = (nrun < (1u << 20) ? nrun : (1u << 20)) | first_bit << 31;   // compose.cu places the rows' maps with this
 		}
 		p += l;
 	}

@@ -28,6 +28,14 @@ constexpr int B200_MAX_GROUPS_K = 32;   // BGT_MAX_GROUPS, bgt.h:13
 
 struct RowMeta { uint32_t off[2], len[2], n1[2]; };
 
+// Two-sided composite maps (compose.cu, pairwalk.cu): in a full checkpoint block whose successor is resident too, the row
+// groups of the second half get INVERSE maps (rank behind the group -> rank in front of it), so that a (column,row) pair is
+// reached from the nearer of the two snapshots around it.  Returns the first group with an inverse map (n_grp: none).
+__host__ __device__ inline int comp_first_inverse(int blk, int n_blk_res, int rows_in_blk, int BS, int n_grp, int two_sided)
+{
+	return (two_sided && blk + 1 < n_blk_res && rows_in_blk == BS) ? n_grp / 2 : n_grp;
+}
+
 struct WalkParams {
 	const uint8_t  *img;
 	const uint64_t *rowoff;
@@ -86,7 +94,10 @@ struct PairParams {
 	int32_t        *cnt_raw;     // [rows out][G][3] = #ALT, #missing, #other-ALT per group (accumulated)
 	int m, G, shift;
 	long long blk_row0, row_lo, row_hi;
+	const int *rows_in_blk;
+	int two_sided, n_blk_res;    // see comp_first_inverse
 	int *err;
+	unsigned long long *prof;    // diagnostics (BGT_B200_PROF): [0] CTA cycles in phase A, [1] in phase B, [2] CTAs, [3] composite groups crossed, [4] rows walked by warps
 };
 size_t pair_smem_bytes();
 cudaError_t launch_pairwalk(const PairParams &P, int C, int max_pairs, int n_blk, cudaStream_t st);
@@ -96,7 +107,8 @@ struct ComposeParams {
 	const uint8_t  *img;
 	const uint64_t *rowoff;
 	const uint32_t *n1;
-	const uint32_t *nrun;       // nullptr, or runs per row (rowmeta_kernel; forward maps only): level 0 skips its counting pass
+	const uint32_t *nrun;       // nullptr, or runs per row | bit of the first run << 31 (rowmeta_kernel): level 0 skips its counting pass
+	int two_sided, n_blk_res;   // see comp_first_inverse: inverse maps for the second half of the groups of blocks with a resident successor
 	const int      *rows_in_blk;
 	const int      *blk_list;   // blocks handled by this launch; nullptr: blk_first + index
 	const uint8_t  *blk_ok;     // nullptr, or per block 1 = build (the device-side "sparse" flag of index.cu)
@@ -196,6 +208,7 @@ struct MarginalParams {
 	// in front of every segment of seg_groups groups (vseg [launch block][vector][segment][marginal_seg_words(m)]); every
 	// segment is then walked by its own CTA.  seg_ok [launch block][vector] = 0: a composite was missing, one CTA takes the block
 	const uint32_t *comp_start; const int32_t *comp_delta; const int *comp_n;
+	int two_sided, n_blk_res;   // see comp_first_inverse: the maps of those groups are gathered through instead of scattered through
 	int n_grp, seg_groups, n_seg;
 	uint32_t *vseg; uint8_t *seg_ok;
 };
