@@ -321,13 +321,17 @@ def e2e_step_fn(rig, host_img, n, q_kwargs, h_counts, h_pass, row_beg=0, hap_bit
     start ranks, plane-1 view and composite maps built on the device behind each chunk) -> b200_scan -> host results."""
     b = rig.b
 
+    m = b.pbf_peek(host_img)[0]
+
     def step():
-        pb = b.Pbf.from_bytes(rig.ctx, host_img, row_beg, row_beg + n, prepare_count_scan=hap_bits is None)
-        qq = b.Query(rig.ctx, pb, **q_kwargs)
         out = {"counts": h_counts, "passed": h_pass}
-        if hap_bits is not None:
+        qq = b.Query(rig.ctx, m, **q_kwargs)
+        if hap_bits is None:   # count-only queries: load and scan as one pipeline (b200_pbf_load_scan)
+            pb, _ = b.load_scan(rig.ctx, host_img, qq, row_beg, row_beg + n, out=out)
+        else:
+            pb = b.Pbf.from_bytes(rig.ctx, host_img, row_beg, row_beg + n)
             out["hap_bits"] = hap_bits
-        b.scan(rig.ctx, pb, qq, row_beg, n, hap_bits=hap_bits is not None, out=out)
+            b.scan(rig.ctx, pb, qq, row_beg, n, hap_bits=True, out=out)
         qq.close()
         pb.close()
     return step
@@ -657,7 +661,7 @@ def run_b200(args, rank, world, local_rank):
                        "totals_allreduce": {"sum_AN": totals[0], "sum_AC": totals[1], "sites_passed": totals[3], "sites": totals[4]}},
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": int(e2e_bytes["h2d"]), "d2h_bytes_per_step": int(e2e_bytes["d2h"]),
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_resident": same,
-                    "how": "host .pbf image (pinned) -> b200_pbf_load_ex (H2D in 16 chunks (short ones first); row index, row meta, start ranks, plane-1 view and composite maps built on the device behind each chunk, no host walk) -> b200_scan -> host AC/AN + verdicts"},
+                    "how": "host .pbf image (pinned) -> b200_pbf_load_scan: H2D in 16 chunks (short ones first); behind each chunk on the device: row index, row meta, start ranks, plane-1 view + pair select, composite maps, pair walk, AC/AN + verdict, D2H of the chunk's results to pinned host memory -- one pipeline, one synchronisation at the end"},
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_per_step),
             "roofline": {"bound": "hbm", "kernel": "pbwt_walk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": k_ms,

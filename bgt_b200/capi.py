@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200_pbf_bad_rows": (_i64, [_vp]),
     "b200_pbf_split_blocks": (_int, [_vp]),
     "b200_query_create": (_vp, [_vp, _vp, _int, _vp, _vp, _int, C.c_char_p, C.POINTER(_int)]),
+    "b200_query_create_m": (_vp, [_vp, _int, _int, _vp, _vp, _int, C.c_char_p, C.POINTER(_int)]),
     "b200_query_create_cols": (_vp, [_vp, _vp, _int, _vp]),
     "b200_query_destroy": (None, [_vp]),
     "b200_query_n_track": (_int, [_vp]),
@@ -66,6 +67,8 @@ SIGNATURES = {
     "b200_query_counts_stride": (_int, [_vp]),
     "b200_scan": (_i64, [_vp, _vp, _vp, _i64, _i64, C.c_uint, C.POINTER(ScanOut)]),
     "b200_scan_collect": (_int, [_vp, C.POINTER(_i64)]),
+    "b200_pbf_peek": (_int, [_vp, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_i64)]),
+    "b200_pbf_load_scan": (_vp, [_vp, _vp, C.c_size_t, _i64, _i64, _vp, C.POINTER(ScanOut), C.POINTER(_i64)]),
     "b200_last_totals": (_int, [_vp, C.POINTER(_i64)]),
     "b200_allreduce_i64": (_int, [C.POINTER(_vp), _int, C.POINTER(_i64), _int]),
     "b200_last_ms": (C.c_double, [_vp, _int]),
@@ -317,12 +320,13 @@ class Query:
     def __init__(self, ctx, pbf, out_samples=None, group=None, n_groups=1, flt=None):
         self.out_samples = None if out_samples is None else np.ascontiguousarray(out_samples, dtype=np.int32)
         self.group = None if group is None else np.ascontiguousarray(group, dtype=np.uint32)
-        n_out = pbf.m // 2 if self.out_samples is None else self.out_samples.size
+        m = pbf if isinstance(pbf, int) else pbf.m             # an int: the columns of a PBF that is not resident yet (load_scan)
+        n_out = m // 2 if self.out_samples is None else self.out_samples.size
         if self.group is not None and self.group.size != n_out:
             raise ValueError("group must have one entry per selected sample")
         err = C.c_int(0)
-        self.h = lib().b200_query_create(ctx.h, pbf.h, n_out, _ptr(self.out_samples), _ptr(self.group), n_groups,
-                                         flt.encode() if flt is not None else None, C.byref(err))
+        self.h = lib().b200_query_create_m(ctx.h, m, n_out, _ptr(self.out_samples), _ptr(self.group), n_groups,
+                                           flt.encode() if flt is not None else None, C.byref(err))
         self.flt_err = err.value
         if not self.h:
             raise B200Error(_err())
@@ -384,6 +388,37 @@ def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, h
         if k in res and res[k] is not None:
             res[k] = res[k][:done]
     return res
+
+
+def pbf_peek(data):
+    """(m, shift, rows) of a .pbf image (b200_pbf_peek)."""
+    buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    m, sh, n = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+    if lib().b200_pbf_peek(_ptr(buf), buf.size, C.byref(m), C.byref(sh), C.byref(n)) != 0:
+        raise B200Error(_err())
+    return m.value, sh.value, n.value
+
+
+def load_scan(ctx, data, query, row_beg=0, row_end=-1, out=None):
+    """b200_pbf_load_scan: host .pbf image -> resident PBF + per-site AC/AN and verdicts in ONE pipeline.  Returns (Pbf, dict)."""
+    buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    m, sh, n = pbf_peek(buf)
+    end = n if row_end < 0 or row_end > n else row_end
+    rows = max(end - row_beg, 0)
+    res = out or {}
+    if "counts" not in res:
+        res["counts"] = np.empty((rows, query.stride), dtype=np.int32)
+    if "passed" not in res:
+        res["passed"] = np.empty(rows, dtype=np.uint8)
+    so = ScanOut()
+    so.counts, so.passed = _ptr(res["counts"]), _ptr(res["passed"])
+    done = C.c_int64(0)
+    h = lib().b200_pbf_load_scan(ctx.h, _ptr(buf), buf.size, row_beg, row_end, query.h, C.byref(so), C.byref(done))
+    if not h:
+        raise B200Error(_err())
+    res["n"] = done.value
+    res["totals"] = [so.totals[i] for i in range(4)]
+    return Pbf(ctx, h), res
 
 
 def scan_device(ctx, pbf, query, row_beg, n_rows, d_counts=0, d_pass=0, d_hap_bits=(0, 0), no_split=False):

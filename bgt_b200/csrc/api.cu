@@ -91,6 +91,9 @@ struct b200_ctx_s {
 	int dev = 0;
 	cudaStream_t st = nullptr;
 	cudaStream_t st_copy = nullptr;   // H2D of PBF images, so that per-chunk kernels on `st` overlap the rest of the copy
+	cudaStream_t st_d2h = nullptr;    // fused load + scan: results of a chunk go home while the next chunks are still being worked on
+	cudaEvent_t ev_fin[LOAD_CHUNKS + 1] = {};
+	bool fused_pairs_done = false;    // b200_scan called from the fused path: cnt_raw already holds the pair-walk counts
 	cudaStream_t st_idx[N_IDX_STREAMS] = {};      // the row-index chase of a chunk is one long dependent chain per block (latency bound, a few
 	                                  // lanes): the chases of consecutive chunks overlap each other and the kernels of earlier chunks
 	cudaEvent_t ev_chunk[LOAD_CHUNKS] = {}, ev_idx[LOAD_CHUNKS] = {}, ev_sel[LOAD_CHUNKS] = {};
@@ -248,7 +251,9 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	if (prop.major < 10) { set_err("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return nullptr; }
 	b200_ctx_t *c = new b200_ctx_t();
 	c->dev = device; c->sm_count = prop.multiProcessorCount;
-	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) && CU_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) && CU_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking)) &&
+	          CU_OK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+	for (int i = 0; ok && i <= LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_fin[i], cudaEventDisableTiming));
 	{ // the small latency-bound index kernels must not queue behind the wide kernels they overlap: highest priority
 		int prio_lo = 0, prio_hi = 0;
 		cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -286,6 +291,8 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	if (c->d_acc) cudaFree(c->d_acc);
 	for (int i = 0; i < LOAD_CHUNKS; ++i) { if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]); if (c->ev_idx[i]) cudaEventDestroy(c->ev_idx[i]); if (c->ev_sel[i]) cudaEventDestroy(c->ev_sel[i]); }
 	if (c->st_copy) cudaStreamDestroy(c->st_copy);
+	if (c->st_d2h) { cudaStreamSynchronize(c->st_d2h); cudaStreamDestroy(c->st_d2h); }
+	for (int i = 0; i <= LOAD_CHUNKS; ++i) if (c->ev_fin[i]) cudaEventDestroy(c->ev_fin[i]);
 	for (int i = 0; i < N_IDX_STREAMS; ++i) if (c->st_idx[i]) cudaStreamDestroy(c->st_idx[i]);
 	if (c->st) cudaStreamDestroy(c->st);
 	delete c;
@@ -710,7 +717,17 @@ static b200_pbf_t *pbf_index_host(const uint8_t *f, size_t flen, int64_t row_beg
 }
 
 
-extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end, unsigned flags)
+// Fused load + count scan (b200_pbf_load_scan): what the chunk pipeline of the load queues behind every chunk's composite maps
+struct FusedScan {
+	const b200_query_t *q;
+	b200_scan_out_t *out;       // host outputs (counts, pass)
+	int64_t row_lo, row_hi;     // rows to produce (clipped to the file by the caller)
+	int32_t *d_counts; uint8_t *d_pass;
+	bool queued = false;        // pair walk + finalize + D2H were queued for every resident block
+};
+static PairParams pair_params(b200_ctx_t *c, const b200_pbf_t *pb, const b200_query_t *q, int64_t row_lo, int64_t row_hi);
+
+static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end, unsigned flags, FusedScan *fs)
 {
 	if (!c || !f) { set_err("b200_pbf_load: null argument"); return nullptr; }
 	cudaSetDevice(c->dev);
@@ -732,6 +749,50 @@ extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t 
 	const bool eager = pb->prepare_split;
 	const bool copy_only = getenv("BGT_B200_COPYONLY") != nullptr;   // diagnostics: time the bare H2D copy
 	if (eager) ok = ok && compose_alloc(pb);
+	// fused scan: per-site raw counters of the rows to produce, zeroed before the first pair walk is queued
+	PairParams FK;
+	FinalizeSplit fsp;
+	memset(&FK, 0, sizeof(FK)); memset(&fsp, 0, sizeof(fsp));
+	int64_t f_lo = 0, f_hi = 0;
+	if (fs && ok) {
+		f_lo = fs->row_lo; f_hi = fs->row_hi < pb->n ? fs->row_hi : pb->n;
+		const size_t nr = (size_t)(f_hi > f_lo ? f_hi - f_lo : 0);
+		ok = eager && nb > 0 && nr > 0 && c->cnt_raw.reserve(nr * 3 * sizeof(int32_t)) && c->counts.reserve(nr * 6 * sizeof(int32_t)) && c->pass.reserve(nr);
+		if (ok) {
+			fs->d_counts = (int32_t*)c->counts.p; fs->d_pass = (uint8_t*)c->pass.p;
+			ok = CU_OK(cudaMemsetAsync(c->cnt_raw.p, 0, nr * 3 * sizeof(int32_t), c->st)) && CU_OK(cudaMemsetAsync(c->d_acc, 0, 4 * sizeof(unsigned long long), c->st)) &&
+			     CU_OK(cudaMemsetAsync(c->d_err_scan, 0, sizeof(int), c->st));
+			FK = pair_params(c, pb, fs->q, f_lo, f_hi);
+			FK.blk_ok = pb->d_blk_sparse;
+			fsp.blk_split = pb->d_blk_sparse; fsp.n1 = pb->d_n1; fsp.blk_row0 = (long long)pb->blk0 << pb->shift; fsp.shift = pb->shift;
+		} else if (pb) { set_err("b200_pbf_load_scan: nothing to scan"); }
+	}
+	int fused_done_blk = 0;     // resident blocks [0, fused_done_blk) have their pair walk queued
+	auto fused_queue = [&](int hi, int k) { // pair walk of resident blocks [fused_done_blk, hi), their finalize, their results home
+		if (!fs || hi <= fused_done_blk) return true;
+		const int lo = fused_done_blk;
+		fused_done_blk = hi;
+		PairParams K = FK;
+		K.blk_list = nullptr; K.blk_first = lo;
+		bool good = CU_OK(launch_pairwalk(K, 4, pb->p1_cap, hi - lo, c->st));
+		++c->launches;
+		const long long blk_row0 = (long long)pb->blk0 << pb->shift;
+		long long r0 = blk_row0 + ((long long)lo << pb->shift), r1 = blk_row0 + ((long long)hi << pb->shift);
+		if (r0 < f_lo) r0 = f_lo;
+		if (r1 > f_hi) r1 = f_hi;
+		if (good && r1 > r0) {
+			const size_t off = (size_t)(r0 - f_lo), cnt = (size_t)(r1 - r0);
+			FinalizeSplit sp = fsp;
+			sp.row_lo = r0;
+			good = CU_OK(launch_finalize((const int32_t*)c->cnt_raw.p + off * 3, (long long)cnt, 1, fs->q->d_gsize, fs->q->d_prog, fs->q->has_flt, fs->d_counts + off * 6, fs->d_pass + off,
+			                             c->d_acc, sp, c->st)) &&
+			       CU_OK(cudaEventRecord(c->ev_fin[k], c->st)) && CU_OK(cudaStreamWaitEvent(c->st_d2h, c->ev_fin[k], 0));
+			++c->launches;
+			if (good && fs->out->counts) good = CU_OK(cudaMemcpyAsync(fs->out->counts + off * 6, fs->d_counts + off * 6, cnt * 6 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st_d2h));
+			if (good && fs->out->pass) good = CU_OK(cudaMemcpyAsync(fs->out->pass + off, fs->d_pass + off, cnt, cudaMemcpyDeviceToHost, c->st_d2h));
+		}
+		return good;
+	};
 	// the zeroing memsets on st must be done before kernels on the index streams write n1 / rank0
 	ok = ok && CU_OK(cudaEventRecord(c->ev_zero, c->st));
 	for (int i = 0; ok && i < N_IDX_STREAMS; ++i) ok = CU_OK(cudaStreamWaitEvent(c->st_idx[i], c->ev_zero, 0));
@@ -771,6 +832,10 @@ extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t 
 		if (eager) { // forward composites on the main stream; the plane-1 side (inverse composites + select: small grids) stays on the index stream
 			ok = ok && compose_queue(pb, b0, b1, c->st) && select_queue(pb, b0, b1, sx, c->d_err) &&
 			     CU_OK(cudaEventRecord(c->ev_sel[k], sx));
+			if (fs && ok) { // the pair walk of a block reads the start ranks of the block behind it (two-sided maps): the chunk's last
+			                // block waits for the next chunk
+				ok = CU_OK(cudaStreamWaitEvent(c->st, c->ev_sel[k], 0)) && fused_queue(k == n_chunks - 1 ? b1 : b1 - 1, k);
+			}
 		}
 		if (trace) {
 			for (int j = 0; j < 3; ++j) cudaEventCreate(&tev[k][j]);
@@ -779,6 +844,7 @@ extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t 
 	}
 	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st_copy));
 	if (eager && !copy_only) for (int k = 0; ok && k < n_chunks; ++k) ok = CU_OK(cudaStreamWaitEvent(c->st, c->ev_sel[k], 0));
+	if (fs && ok && !copy_only) { ok = fused_queue(nb, LOAD_CHUNKS); fs->queued = ok && fused_done_blk == nb; }
 	const double t1 = now_ms();
 	ok = ok && pbf_finish_load(pb);
 	if (ok && eager) { pb->comp_ready = true; pb->sel_ready = true; }
@@ -791,10 +857,15 @@ extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t 
 			for (int j = 0; j < 4; ++j) cudaEventDestroy(tev[k][j]);
 		}
 	}
-	if (!ok) { cudaStreamSynchronize(c->st_copy); for (int i = 0; i < N_IDX_STREAMS; ++i) cudaStreamSynchronize(c->st_idx[i]); cudaStreamSynchronize(c->st); pbf_free_device(pb); delete pb; return nullptr; }
+	if (!ok) { cudaStreamSynchronize(c->st_copy); for (int i = 0; i < N_IDX_STREAMS; ++i) cudaStreamSynchronize(c->st_idx[i]); cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_d2h); pbf_free_device(pb); delete pb; return nullptr; }
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
 	return pb;
+}
+
+extern "C" b200_pbf_t *b200_pbf_load_ex(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end, unsigned flags)
+{
+	return pbf_load_impl(c, f, flen, row_beg, row_end, flags, nullptr);
 }
 
 extern "C" b200_pbf_t *b200_pbf_load(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end)
@@ -947,16 +1018,25 @@ extern "C" b200_query_t *b200_query_create(b200_ctx_t *c, const b200_pbf_t *pb, 
 {
 	if (flt_err) *flt_err = 0;
 	if (!c || !pb) { set_err("b200_query_create: null argument"); return nullptr; }
+	return b200_query_create_m(c, pb->m, n_out, out_samples, group, n_groups, flt, flt_err);
+}
+
+// the same for a PBF that is not resident yet (b200_pbf_load_scan): m = its number of columns (b200_pbf_peek)
+extern "C" b200_query_t *b200_query_create_m(b200_ctx_t *c, int m, int n_out, const int32_t *out_samples,
+                                             const uint32_t *group, int n_groups, const char *flt, int *flt_err)
+{
+	if (flt_err) *flt_err = 0;
+	if (!c || m <= 0) { set_err("b200_query_create: null argument"); return nullptr; }
 	cudaSetDevice(c->dev);
-	const int n_samples = pb->m / 2;
+	const int n_samples = m / 2;
 	if (n_groups < 1 || n_groups > B200_MAX_GROUPS) { set_err("n_groups=%d out of range 1..%d", n_groups, B200_MAX_GROUPS); return nullptr; }
 	if (out_samples == nullptr) n_out = n_samples;
 	if (n_out < 0 || n_out > n_samples) { set_err("n_out=%d out of range", n_out); return nullptr; }
 	b200_query_t *q = new b200_query_t();
-	q->ctx = c; q->m = pb->m; q->n_out = n_out; q->n_track = 2 * n_out; q->G = n_groups;
+	q->ctx = c; q->m = m; q->n_out = n_out; q->n_track = 2 * n_out; q->G = n_groups;
 	q->words = (q->n_track + 31) / 32;
 	// pbwt.c:377: asking for >= m columns means "decode everything"; out[] is ascending, so that is the identity
-	q->full = (q->n_track >= pb->m);
+	q->full = (q->n_track >= m);
 	std::vector<int32_t> track(q->n_track ? q->n_track : 1);
 	std::vector<uint8_t> tgrp(q->n_track ? q->n_track : 1);
 	std::vector<int32_t> gsize(B200_MAX_GROUPS, 0);
@@ -1015,6 +1095,20 @@ extern "C" int b200_query_hap_words(const b200_query_t *q) { return q ? q->words
 extern "C" int b200_query_counts_stride(const b200_query_t *q) { return q ? 3 + 3 * q->G : -1; }
 
 // ------------------------------------------------------------------------------------------------ scan
+
+// the pair walk (pairwalk.cu) over the resident PBF's own pair lists and composite maps
+static PairParams pair_params(b200_ctx_t *c, const b200_pbf_t *pb, const b200_query_t *q, int64_t row_lo, int64_t row_hi)
+{
+	PairParams K;
+	memset(&K, 0, sizeof(K));
+	K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rank0 = pb->d_rank0;
+	K.qcol = pb->d_qcol; K.qrow = pb->d_qrow; K.qcount = pb->d_qcount; K.q_stride = pb->p1_cap; K.tgrp = q->d_tgrp;
+	K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n; K.comp_dir = pb->d_comp_dir;
+	K.dir_shift = pb->dir_shift; K.dir_n = pb->dir_n; K.cnt_raw = (int32_t*)c->cnt_raw.p;
+	K.m = pb->m; K.G = q->G; K.shift = pb->shift; K.blk_row0 = (long long)pb->blk0 << pb->shift; K.row_lo = row_lo; K.row_hi = row_hi; K.err = c->d_err_scan;
+	K.rows_in_blk = pb->d_rows_in_blk; K.two_sided = 1; K.n_blk_res = pb->n_blk;
+	return K;
+}
 
 static int pick_cols_per_thread(const b200_ctx_t *c, int n_track, int n_blk)
 {
@@ -1108,9 +1202,9 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	memset(&sp, 0, sizeof(sp));
 
 	bool ok = CU_OK(cudaEventRecord(c->ev[2], c->st)) &&
-	          CU_OK(cudaMemsetAsync(c->cnt_raw.p, 0, nr * G * 3 * sizeof(int32_t), c->st)) &&
+	          (c->fused_pairs_done || CU_OK(cudaMemsetAsync(c->cnt_raw.p, 0, nr * G * 3 * sizeof(int32_t), c->st))) &&
 	          CU_OK(cudaMemsetAsync(c->d_acc, 0, 4 * sizeof(unsigned long long), c->st)) &&
-	          CU_OK(cudaMemsetAsync(c->d_err_scan, 0, sizeof(int), c->st)) &&
+	          (c->fused_pairs_done || CU_OK(cudaMemsetAsync(c->d_err_scan, 0, sizeof(int), c->st))) &&
 	          CU_OK(cudaMemcpyAsync(c->blk_lists.p, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
 	          CU_OK(cudaMemcpyAsync(c->blk_split.p, split_flag.data(), (size_t)pb->n_blk, cudaMemcpyHostToDevice, c->st)) &&
 	          CU_OK(cudaEventRecord(c->ev[0], c->st));
@@ -1153,15 +1247,11 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		B.track = qcol; B.qrow = qrow; B.track_stride = cap;
 		B.n_track_blk = qcount; B.n_track = cap; B.blk_list = d_split_list;
 		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : (use_comp ? 2 : 8);
-		if (use_comp) {   // (without composite maps -- testing -- the QUERY mode of the walk kernel goes row by row)
-			PairParams K;
-			memset(&K, 0, sizeof(K));
-			K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rank0 = pb->d_rank0;
-			K.qcol = qcol; K.qrow = qrow; K.qcount = qcount; K.q_stride = cap; K.tgrp = q->d_tgrp;
-			K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n; K.comp_dir = pb->d_comp_dir;
-			K.dir_shift = pb->dir_shift; K.dir_n = pb->dir_n; K.blk_list = d_split_list; K.cnt_raw = P.cnt_raw;
-			K.m = pb->m; K.G = G; K.shift = pb->shift; K.blk_row0 = P.blk_row0; K.row_lo = row_beg; K.row_hi = row_beg + n_rows; K.err = c->d_err_scan;
-			K.rows_in_blk = pb->d_rows_in_blk; K.two_sided = 1; K.n_blk_res = pb->n_blk;
+		if (use_comp && c->fused_pairs_done) {
+			// (b200_pbf_load_scan: the pair walk of every block was queued behind the block's composite maps while loading)
+		} else if (use_comp) {   // (without composite maps -- testing -- the QUERY mode of the walk kernel goes row by row)
+			PairParams K = pair_params(c, pb, q, row_beg, row_beg + n_rows);
+			K.blk_list = d_split_list;
 			static const bool prof = getenv("BGT_B200_PROF") != nullptr;
 			static unsigned long long *d_prof = nullptr;
 			if (prof) {
@@ -1270,6 +1360,65 @@ extern "C" int b200_scan_collect(b200_ctx_t *c, int64_t totals[4])
 	for (int i = 0; i < 4; ++i) c->last_totals[i] = (int64_t)dtot[i];
 	read_scan_timings(c);
 	return 0;
+}
+
+// header fields of a .pbf image without loading it (pbwt.c:231-258)
+extern "C" int b200_pbf_peek(const uint8_t *f, size_t flen, int32_t *m, int32_t *shift, int64_t *n_rows)
+{
+	b200_pbf_t *pb = pbf_index_prepare(f, flen, 0, 0);
+	if (!pb) return -1;
+	if (m) *m = pb->m;
+	if (shift) *shift = pb->shift;
+	if (n_rows) *n_rows = pb->n;
+	delete pb;
+	return 0;
+}
+
+// Load + count scan in one call: the rows' pair walk, finalize and the copy of their results to the host are queued behind the
+// composite maps of every chunk of the image while later chunks are still on their way, instead of after the whole load.
+extern "C" b200_pbf_t *b200_pbf_load_scan(b200_ctx_t *c, const uint8_t *f, size_t flen, int64_t row_beg, int64_t row_end, const b200_query_t *q,
+                                          b200_scan_out_t *out, int64_t *n_scanned)
+{
+	if (!c || !f || !q || !out) { set_err("b200_pbf_load_scan: null argument"); return nullptr; }
+	if (q->ctx != c) { set_err("b200_pbf_load_scan: the query belongs to another context"); return nullptr; }
+	cudaSetDevice(c->dev);
+	int32_t m = 0; int64_t n = 0;
+	if (b200_pbf_peek(f, flen, &m, nullptr, &n) != 0) return nullptr;
+	if (m != q->m) { set_err("b200_pbf_load_scan: query was built for m=%d, PBF has m=%d", q->m, m); return nullptr; }
+	if (row_end < 0 || row_end > n) row_end = n;
+	if (row_beg < 0) row_beg = 0;
+	if (row_beg > row_end) row_beg = row_end;
+	out->totals[0] = out->totals[1] = out->totals[2] = out->totals[3] = 0;
+	if (n_scanned) *n_scanned = row_end - row_beg;
+	// what the pipeline fuses: the count-only full-cohort scan with one group and a device-side filter (BASELINE configs 2, 5);
+	// any other query is the load followed by b200_scan
+	const bool fuse = q->full && q->G == 1 && !(q->has_flt && q->prog.needs_host) && row_end > row_beg && getenv("BGT_B200_NO_FUSE") == nullptr;
+	FusedScan fs;
+	fs.q = q; fs.out = out; fs.row_lo = row_beg; fs.row_hi = row_end; fs.d_counts = nullptr; fs.d_pass = nullptr;
+	b200_pbf_t *pb = pbf_load_impl(c, f, flen, row_beg, row_end, B200_LOAD_PREPARE_COUNT_SCAN, fuse ? &fs : nullptr);
+	if (!pb) return nullptr;
+	if (row_end == row_beg) return pb;
+	bool all_split = fuse && fs.queued;
+	for (int b = 0; all_split && b < pb->n_blk; ++b) all_split = pb->blk_sparse[b] != 0;
+	if (all_split) { // everything was queued while loading: wait for the results, fetch totals and error flags
+		unsigned long long dtot[4];
+		int err = 0;
+		bool ok = CU_OK(cudaMemcpyAsync(dtot, c->d_acc, sizeof(dtot), cudaMemcpyDeviceToHost, c->st)) &&
+		          CU_OK(cudaMemcpyAsync(&err, c->d_err_scan, sizeof(err), cudaMemcpyDeviceToHost, c->st)) &&
+		          CU_OK(cudaStreamSynchronize(c->st)) && CU_OK(cudaStreamSynchronize(c->st_d2h));
+		if (ok && err) { set_err("device error flags 0x%x during scan", err); ok = false; }
+		if (!ok) { b200_pbf_close(pb); return nullptr; }
+		for (int i = 0; i < 4; ++i) out->totals[i] = c->last_totals[i] = (int64_t)dtot[i];
+		return pb;
+	}
+	// some block is off the split path (dense plane 1), or the query is not of the fused kind: the ordinary scan -- it keeps the
+	// pair-walk counts the pipeline has already produced
+	cudaStreamSynchronize(c->st_d2h);
+	c->fused_pairs_done = fuse && fs.queued;
+	const int64_t done = b200_scan(c, pb, q, row_beg, row_end - row_beg, B200_SCAN_COUNTS, out);
+	c->fused_pairs_done = false;
+	if (done != row_end - row_beg) { b200_pbf_close(pb); return nullptr; }
+	return pb;
 }
 
 extern "C" int b200_last_totals(b200_ctx_t *c, int64_t totals[4])

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(PW_NT, 2) pbwt_pair_kernel(const PairParams P)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int BS = 1 << P.shift;
 	const int blk = P.blk_list ? P.blk_list[blockIdx.y] : P.blk_first + (int)blockIdx.y;
+	if (P.blk_ok && !P.blk_ok[blk]) return;
 	const int n_pairs = P.qcount[blk];
 	const int slice_base = blockIdx.x * (PW_NT * C);
 	if (slice_base >= n_pairs) return;

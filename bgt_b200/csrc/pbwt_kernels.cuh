@@ -90,6 +90,7 @@ struct PairParams {
 	const uint16_t *comp_dir;    // [blocks][groups][COMP_DIR_STRIDE] bucket directories
 	int dir_shift, dir_n;
 	const int      *blk_list;    // resident-block indices handled by this launch (nullptr: blk_first + blockIdx.y)
+	const uint8_t  *blk_ok;      // nullptr, or per resident block 1 = on the split path (device-side verdict of index.cu); others are skipped
 	int blk_first;
 	int32_t        *cnt_raw;     // [rows out][G][3] = #ALT, #missing, #other-ALT per group (accumulated)
 	int m, G, shift;

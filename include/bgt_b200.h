@@ -81,6 +81,9 @@ b200_query_t *b200_query_create(b200_ctx_t *ctx, const b200_pbf_t *pb, int n_out
  * order (duplicates allowed); outputs come in list order.  n_cols <= 0 or >= m or cols == NULL selects every column
  * (pbwt.c:377).  One group, no filter. */
 b200_query_t *b200_query_create_cols(b200_ctx_t *ctx, const b200_pbf_t *pb, int n_cols, const int32_t *cols);
+/* the same before the PBF is resident (b200_pbf_load_scan): m = columns of the file (b200_pbf_peek) */
+b200_query_t *b200_query_create_m(b200_ctx_t *ctx, int m, int n_out, const int32_t *out_samples,
+                                  const uint32_t *group, int n_groups, const char *flt, int *flt_err);
 void          b200_query_destroy(b200_query_t *q);
 int           b200_query_n_track(const b200_query_t *q);     /* 2*n_out (or the number of columns) */
 int           b200_query_filter_needs_host(const b200_query_t *q); /* 1: the filter uses `**` (host libm, kexpr.c:150): b200_scan evaluates it on the host from the
@@ -111,6 +114,15 @@ typedef struct {
 int64_t b200_scan(b200_ctx_t *ctx, const b200_pbf_t *pb, const b200_query_t *q, int64_t row_beg, int64_t n_rows,
                   unsigned flags, b200_scan_out_t *out);
 
+/* header fields of a .pbf image (pbwt.c:231-258): columns, snapshot interval, rows; host logic only */
+int     b200_pbf_peek(const uint8_t *bytes, size_t n_bytes, int32_t *m, int32_t *shift, int64_t *n_rows);
+/* b200_pbf_load_ex(B200_LOAD_PREPARE_COUNT_SCAN) + b200_scan(B200_SCAN_COUNTS) of rows [row_beg,row_end) as ONE pipeline: for the
+ * count-only full-cohort scan with one group (`view -f .. -G`) the pair walk, the per-site AC/AN + verdict and the copy of the
+ * results to out->counts / out->pass (host memory, pinned for speed) are queued behind the composite maps of every chunk of
+ * the image while later chunks are still being copied; other queries get the load followed by the scan.  Returns the
+ * resident handle (close it with b200_pbf_close) or NULL; *n_scanned = rows produced. */
+b200_pbf_t *b200_pbf_load_scan(b200_ctx_t *ctx, const uint8_t *bytes, size_t n_bytes, int64_t row_beg, int64_t row_end,
+                               const b200_query_t *q, b200_scan_out_t *out, int64_t *n_scanned);
 /* After a B200_SCAN_DEVICE_OUT scan: wait for it, fetch its totals and kernel timings. */
 int     b200_scan_collect(b200_ctx_t *ctx, int64_t totals[4]);
 /* totals (as b200_scan_out_t.totals) of the last scan of this context whose results reached the host: b200_scan,

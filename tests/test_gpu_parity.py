@@ -399,3 +399,37 @@ def test_split_scan_equals_general_and_oracle(b200, ctx, oracle, case):
             assert (got["counts"] == wantg["counts"][beg:beg + cnt]).all(), (case, G, beg)
         qg.close()
     pb.close()
+
+
+@pytest.mark.parametrize("shape", [(300, 4480, 6, "sparse"), (300, 2100, 5, "sparse"), (200, 1500, 7, "dense"), (1200, 20000, 13, "sparse")])
+def test_load_scan_pipeline_equals_load_then_scan(b200, ctx, oracle, shape):
+    """b200_pbf_load_scan queues the pair walk, the per-site AC/AN + verdict and the copy home behind every chunk of the load
+    (the last block of a chunk waits for the next chunk: its backward pairs start from the next snapshot).  Results must
+    equal the oracle and the two-call path for whole files, row ranges that start and end inside blocks, blocks that are
+    off the split path (dense plane 1), several groups and host-evaluated filters (both not fused)."""
+    n_samples, n_rows, shift, kind = shape
+    pb0 = b200.synth_cohort(ctx, n_samples, n_rows, seed=n_rows, shift=shift, r_max=12, p1_one_in=8 if kind == "sparse" else 1,
+                            p1_max_iv=3 if kind == "sparse" else 30, p1_max_len=8 if kind == "sparse" else 64)
+    img = pb0.image()
+    pb0.close()
+    op = oracle.Pbf(img.tobytes())
+    m = 2 * n_samples
+    grp = (np.arange(n_samples) % 3 == 0).astype(np.uint32) + 1
+    cases = [dict(flt="AC>0"), dict(flt=None), dict(flt="AN<%d" % m), dict(group=grp, n_groups=2, flt="AC1>AC2"), dict(flt="AC**2>AN")]
+    BS = 1 << shift
+    ranges = [(0, n_rows), (BS * 3 + 5, min(n_rows, BS * 9 + 1)), (n_rows - BS - 3, n_rows), (BS, BS + 1)]
+    for kw in cases:
+        q = b200.Query(ctx, m, **kw)
+        for beg, end in ranges:
+            pb, got = b200.load_scan(ctx, img, q, beg, end)
+            want = op.scan(beg, end - beg, **kw)
+            assert got["n"] == end - beg
+            assert (got["counts"] == want["counts"]).all(), (kw, beg, end)
+            assert (got["passed"] == want["passed"]).all(), (kw, beg, end)
+            c = want["counts"].astype(np.int64)
+            assert got["totals"][:3] == [int(c[:, 0].sum()), int(c[:, 1].sum()), int(c[:, 2].sum())] and got["totals"][3] == int(want["passed"].sum())
+            again = b200.scan(ctx, pb, q, beg, end - beg)                     # the handle it returns is an ordinary resident PBF
+            assert (again["counts"] == want["counts"]).all()
+            pb.close()
+        q.close()
+    op.close()
