@@ -91,8 +91,10 @@ struct b200_ctx_s {
 	int dev = 0;
 	cudaStream_t st = nullptr;
 	cudaStream_t st_copy = nullptr;   // H2D of PBF images, so that per-chunk kernels on `st` overlap the rest of the copy
-	cudaStream_t st_d2h = nullptr;    // fused load + scan: results of a chunk go home while the next chunks are still being worked on
-	cudaEvent_t ev_fin[LOAD_CHUNKS + 1] = {};
+	// fused load + scan: the pair walk + finalize of a chunk run on st_walk beside the composite maps of the next chunks (st), and
+	// the chunk's results go home on st_d2h
+	cudaStream_t st_d2h = nullptr, st_walk = nullptr;
+	cudaEvent_t ev_fin[LOAD_CHUNKS + 1] = {}, ev_comp[LOAD_CHUNKS + 1] = {};
 	bool fused_pairs_done = false;    // b200_scan called from the fused path: cnt_raw already holds the pair-walk counts
 	cudaStream_t st_idx[N_IDX_STREAMS] = {};      // the row-index chase of a chunk is one long dependent chain per block (latency bound, a few
 	                                  // lanes): the chases of consecutive chunks overlap each other and the kernels of earlier chunks
@@ -253,11 +255,13 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	c->dev = device; c->sm_count = prop.multiProcessorCount;
 	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) && CU_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking)) &&
 	          CU_OK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
-	for (int i = 0; ok && i <= LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_fin[i], cudaEventDisableTiming));
+	for (int i = 0; ok && i <= LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_fin[i], cudaEventDisableTiming)) && CU_OK(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
 	{ // the small latency-bound index kernels must not queue behind the wide kernels they overlap: highest priority
 		int prio_lo = 0, prio_hi = 0;
 		cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
 		for (int i = 0; ok && i < N_IDX_STREAMS; ++i) ok = CU_OK(cudaStreamCreateWithPriority(&c->st_idx[i], cudaStreamNonBlocking, prio_hi));
+		// the walks of the fused pipeline follow their chunk's maps closely instead of queueing up behind the maps of later chunks
+		ok = ok && CU_OK(cudaStreamCreateWithPriority(&c->st_walk, cudaStreamNonBlocking, prio_hi));
 	}
 	for (int i = 0; ok && i < LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming)) && CU_OK(cudaEventCreateWithFlags(&c->ev_idx[i], cudaEventDisableTiming)) &&
 	                                              CU_OK(cudaEventCreateWithFlags(&c->ev_sel[i], cudaEventDisableTiming));
@@ -291,8 +295,9 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	if (c->d_acc) cudaFree(c->d_acc);
 	for (int i = 0; i < LOAD_CHUNKS; ++i) { if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]); if (c->ev_idx[i]) cudaEventDestroy(c->ev_idx[i]); if (c->ev_sel[i]) cudaEventDestroy(c->ev_sel[i]); }
 	if (c->st_copy) cudaStreamDestroy(c->st_copy);
+	if (c->st_walk) { cudaStreamSynchronize(c->st_walk); cudaStreamDestroy(c->st_walk); }
 	if (c->st_d2h) { cudaStreamSynchronize(c->st_d2h); cudaStreamDestroy(c->st_d2h); }
-	for (int i = 0; i <= LOAD_CHUNKS; ++i) if (c->ev_fin[i]) cudaEventDestroy(c->ev_fin[i]);
+	for (int i = 0; i <= LOAD_CHUNKS; ++i) { if (c->ev_fin[i]) cudaEventDestroy(c->ev_fin[i]); if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]); }
 	for (int i = 0; i < N_IDX_STREAMS; ++i) if (c->st_idx[i]) cudaStreamDestroy(c->st_idx[i]);
 	if (c->st) cudaStreamDestroy(c->st);
 	delete c;
@@ -761,7 +766,8 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 		if (ok) {
 			fs->d_counts = (int32_t*)c->counts.p; fs->d_pass = (uint8_t*)c->pass.p;
 			ok = CU_OK(cudaMemsetAsync(c->cnt_raw.p, 0, nr * 3 * sizeof(int32_t), c->st)) && CU_OK(cudaMemsetAsync(c->d_acc, 0, 4 * sizeof(unsigned long long), c->st)) &&
-			     CU_OK(cudaMemsetAsync(c->d_err_scan, 0, sizeof(int), c->st));
+			     CU_OK(cudaMemsetAsync(c->d_err_scan, 0, sizeof(int), c->st)) &&
+			     CU_OK(cudaEventRecord(c->ev_comp[LOAD_CHUNKS], c->st)) && CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_comp[LOAD_CHUNKS], 0));
 			FK = pair_params(c, pb, fs->q, f_lo, f_hi);
 			FK.blk_ok = pb->d_blk_sparse;
 			fsp.blk_split = pb->d_blk_sparse; fsp.n1 = pb->d_n1; fsp.blk_row0 = (long long)pb->blk0 << pb->shift; fsp.shift = pb->shift;
@@ -774,7 +780,7 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 		fused_done_blk = hi;
 		PairParams K = FK;
 		K.blk_list = nullptr; K.blk_first = lo;
-		bool good = CU_OK(launch_pairwalk(K, 4, pb->p1_cap, hi - lo, c->st));
+		bool good = CU_OK(launch_pairwalk(K, 4, pb->p1_cap, hi - lo, c->st_walk));
 		++c->launches;
 		const long long blk_row0 = (long long)pb->blk0 << pb->shift;
 		long long r0 = blk_row0 + ((long long)lo << pb->shift), r1 = blk_row0 + ((long long)hi << pb->shift);
@@ -785,8 +791,8 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 			FinalizeSplit sp = fsp;
 			sp.row_lo = r0;
 			good = CU_OK(launch_finalize((const int32_t*)c->cnt_raw.p + off * 3, (long long)cnt, 1, fs->q->d_gsize, fs->q->d_prog, fs->q->has_flt, fs->d_counts + off * 6, fs->d_pass + off,
-			                             c->d_acc, sp, c->st)) &&
-			       CU_OK(cudaEventRecord(c->ev_fin[k], c->st)) && CU_OK(cudaStreamWaitEvent(c->st_d2h, c->ev_fin[k], 0));
+			                             c->d_acc, sp, c->st_walk)) &&
+			       CU_OK(cudaEventRecord(c->ev_fin[k], c->st_walk)) && CU_OK(cudaStreamWaitEvent(c->st_d2h, c->ev_fin[k], 0));
 			++c->launches;
 			if (good && fs->out->counts) good = CU_OK(cudaMemcpyAsync(fs->out->counts + off * 6, fs->d_counts + off * 6, cnt * 6 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st_d2h));
 			if (good && fs->out->pass) good = CU_OK(cudaMemcpyAsync(fs->out->pass + off, fs->d_pass + off, cnt, cudaMemcpyDeviceToHost, c->st_d2h));
@@ -803,15 +809,18 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 	if (n_chunks == 0) ok = ok && CU_OK(cudaMemsetAsync(pb->d_img, 0, 64, c->st_copy));
 	// chunk bounds: even, except that a long image starts with a ramp of short chunks (1, 2, 3, 4, 6, 8 parts of 128) so that
 	// the first index chain -- and with it the composite maps, which everything else queues behind -- starts early and
-	// every later chain is hidden behind the composite maps of the chunk before
+	// every later chain is hidden behind the composite maps of the chunk before; and ends with the mirrored ramp, so that
+	// what is left to do behind the last chunk's copy (its maps, its pair walk, its results) is short
 	int cb[LOAD_CHUNKS + 1];
 	{
 		static const int ramp[6] = {1, 2, 3, 4, 6, 8};
-		const int head = (n_chunks == LOAD_CHUNKS && nb >= 64) ? 6 : 0;
-		int h = 0;
-		cb[0] = 0;
+		const int head = (n_chunks == LOAD_CHUNKS && nb >= 64) ? 6 : 0, tail = 0;   // (a mirrored ramp at the end was measured: more, smaller launches cost more than the shorter tail saves)
+		int h = 0, t = nb;
+		cb[0] = 0; cb[n_chunks] = nb;
 		for (int k = 0; k < head; ++k) { const int sz = nb * ramp[k] / 128; h += sz > 0 ? sz : 1; cb[k + 1] = h; }
-		for (int k = head; k <= n_chunks; ++k) cb[k] = h + (int)((long long)(nb - h) * (k - head) / (n_chunks - head > 0 ? n_chunks - head : 1));
+		for (int k = 0; k < tail; ++k) { const int sz = nb * ramp[k] / 128; t -= sz > 0 ? sz : 1; cb[n_chunks - 1 - k] = t; }
+		const int mid = n_chunks - head - tail;
+		for (int k = 1; k < mid; ++k) cb[head + k] = h + (int)((long long)(t - h) * k / mid);
 	}
 	for (int k = 0; ok && k < n_chunks; ++k) {
 		const int b0 = cb[k], b1 = cb[k + 1];
@@ -834,7 +843,8 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 			     CU_OK(cudaEventRecord(c->ev_sel[k], sx));
 			if (fs && ok) { // the pair walk of a block reads the start ranks of the block behind it (two-sided maps): the chunk's last
 			                // block waits for the next chunk
-				ok = CU_OK(cudaStreamWaitEvent(c->st, c->ev_sel[k], 0)) && fused_queue(k == n_chunks - 1 ? b1 : b1 - 1, k);
+				ok = CU_OK(cudaEventRecord(c->ev_comp[k], c->st)) && CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_comp[k], 0)) &&
+				     CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_sel[k], 0)) && fused_queue(k == n_chunks - 1 ? b1 : b1 - 1, k);
 			}
 		}
 		if (trace) {
@@ -844,7 +854,11 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 	}
 	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st_copy));
 	if (eager && !copy_only) for (int k = 0; ok && k < n_chunks; ++k) ok = CU_OK(cudaStreamWaitEvent(c->st, c->ev_sel[k], 0));
-	if (fs && ok && !copy_only) { ok = fused_queue(nb, LOAD_CHUNKS); fs->queued = ok && fused_done_blk == nb; }
+	if (fs && ok && !copy_only) {
+		ok = fused_queue(nb, LOAD_CHUNKS); fs->queued = ok && fused_done_blk == nb;
+		// the final synchronisation of the load (st) covers the walks as well
+		ok = ok && CU_OK(cudaEventRecord(c->ev_fin[LOAD_CHUNKS], c->st_walk)) && CU_OK(cudaStreamWaitEvent(c->st, c->ev_fin[LOAD_CHUNKS], 0));
+	}
 	const double t1 = now_ms();
 	ok = ok && pbf_finish_load(pb);
 	if (ok && eager) { pb->comp_ready = true; pb->sel_ready = true; }
@@ -857,7 +871,7 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 			for (int j = 0; j < 4; ++j) cudaEventDestroy(tev[k][j]);
 		}
 	}
-	if (!ok) { cudaStreamSynchronize(c->st_copy); for (int i = 0; i < N_IDX_STREAMS; ++i) cudaStreamSynchronize(c->st_idx[i]); cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_d2h); pbf_free_device(pb); delete pb; return nullptr; }
+	if (!ok) { cudaStreamSynchronize(c->st_copy); for (int i = 0; i < N_IDX_STREAMS; ++i) cudaStreamSynchronize(c->st_idx[i]); cudaStreamSynchronize(c->st_walk); cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_d2h); pbf_free_device(pb); delete pb; return nullptr; }
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
 	return pb;

@@ -417,7 +417,7 @@ def test_load_scan_pipeline_equals_load_then_scan(b200, ctx, oracle, shape):
     grp = (np.arange(n_samples) % 3 == 0).astype(np.uint32) + 1
     cases = [dict(flt="AC>0"), dict(flt=None), dict(flt="AN<%d" % m), dict(group=grp, n_groups=2, flt="AC1>AC2"), dict(flt="AC**2>AN")]
     BS = 1 << shift
-    ranges = [(0, n_rows), (BS * 3 + 5, min(n_rows, BS * 9 + 1)), (n_rows - BS - 3, n_rows), (BS, BS + 1)]
+    ranges = [(0, n_rows), (BS + 5, min(n_rows, BS * 9 + 1)), (n_rows - BS - 3, n_rows), (BS, BS + 1)]
     for kw in cases:
         q = b200.Query(ctx, m, **kw)
         for beg, end in ranges:
