@@ -145,7 +145,7 @@ struct b200_pbf_s {
 	std::vector<uint8_t> blk_sparse;     // [n_blk] 1 = the block's plane-1 ones fit p1_cap (split scan applies)
 	uint8_t *d_p1img = nullptr;
 	uint64_t *d_p1_rowoff = nullptr;
-	uint32_t *d_p1_n1 = nullptr;
+	uint32_t *d_p1_n1 = nullptr, *d_p1_prefix = nullptr;
 	uint16_t *d_p1_realrow = nullptr;
 	int *d_grp_tile_beg = nullptr;       // [n_blk][groups+1] first tile of every COMP_K-row group
 	// composite plane-0 maps of the row groups (compose.cu), built lazily by the first split scan and cached
@@ -162,6 +162,7 @@ struct b200_pbf_s {
 	mutable uint32_t *d_vcomp_start = nullptr;   // inverse composites of the plane-1 view rows (plane1_select_kernel)
 	mutable int32_t *d_vcomp_delta = nullptr;
 	mutable int *d_vcomp_n = nullptr;
+	mutable uint16_t *d_vcomp_dir = nullptr;
 	int *d_p1_rows_in_blk = nullptr;
 	long long *d_p1_vbase = nullptr;     // [n_blk+1] first view row of every block
 	int64_t p1_rows = 0;
@@ -366,6 +367,7 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_p1img);
 	pool_free(pb->ctx, pb->d_p1_rowoff);
 	pool_free(pb->ctx, pb->d_p1_n1);
+	pool_free(pb->ctx, pb->d_p1_prefix);
 	pool_free(pb->ctx, pb->d_p1_realrow);
 	pool_free(pb->ctx, pb->d_grp_tile_beg);
 	pool_free(pb->ctx, pb->d_comp_start);
@@ -376,6 +378,7 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_vcomp_start);
 	pool_free(pb->ctx, pb->d_vcomp_delta);
 	pool_free(pb->ctx, pb->d_vcomp_n);
+	pool_free(pb->ctx, pb->d_vcomp_dir);
 	pool_free(pb->ctx, pb->d_p1_rows_in_blk);
 	pool_free(pb->ctx, pb->d_p1_vbase);
 }
@@ -433,6 +436,7 @@ static bool compose_alloc(const b200_pbf_t *pb)
 	          pool_malloc(c, (void**)&pb->d_vcomp_start, vslots * SELECT_COMP_CAP * sizeof(uint32_t)) &&
 	          pool_malloc(c, (void**)&pb->d_vcomp_delta, vslots * SELECT_COMP_CAP * sizeof(int32_t)) &&
 	          pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16) &&
+	          pool_malloc(c, (void**)&pb->d_vcomp_dir, vslots * COMP_DIR_STRIDE * sizeof(uint16_t) + 16) &&
 	          pool_malloc(c, (void**)&pb->d_qcol, (size_t)pb->n_blk * pb->p1_cap * sizeof(int32_t) + 16) &&
 	          pool_malloc(c, (void**)&pb->d_qrow, (size_t)pb->n_blk * pb->p1_cap * sizeof(uint16_t) + 16) &&
 	          pool_malloc(c, (void**)&pb->d_qcount, (size_t)pb->n_blk * sizeof(int) + 16);
@@ -467,7 +471,7 @@ static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st, 
 	if (b1 <= b0) return true;
 	b200_ctx_t *c = pb->ctx;
 	ComposeParams V = compose_params(pb, b0);
-	V.comp_dir = nullptr; V.nrun = nullptr; V.two_sided = 0;
+	V.comp_dir = pb->d_vcomp_dir; V.nrun = nullptr; V.two_sided = 0;
 	V.img = pb->d_p1img; V.rowoff = pb->d_p1_rowoff; V.n1 = pb->d_p1_n1; V.rows_in_blk = pb->d_p1_rows_in_blk;
 	V.comp_start = pb->d_vcomp_start; V.comp_delta = pb->d_vcomp_delta; V.comp_n = pb->d_vcomp_n;
 	V.n_grp = SELECT_GROUPS; V.cap = SELECT_COMP_CAP; V.rle_off = 9; V.n1_plane = 0; V.inverse = 1; V.row_base = pb->d_p1_vbase; V.n1_step = 1;
@@ -476,7 +480,8 @@ static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st, 
 	A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
 	A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = nullptr; A.blk_first = b0; A.blk_ok = pb->d_blk_sparse;
 	A.m = pb->m; A.shift = pb->shift; A.cap = pb->p1_cap;
-	A.vcomp_start = pb->d_vcomp_start; A.vcomp_delta = pb->d_vcomp_delta; A.vcomp_n = pb->d_vcomp_n;
+	A.vcomp_start = pb->d_vcomp_start; A.vcomp_delta = pb->d_vcomp_delta; A.vcomp_n = pb->d_vcomp_n; A.vcomp_dir = pb->d_vcomp_dir;
+	A.dir_shift = pb->dir_shift; A.dir_n = pb->dir_n; A.p1_prefix = pb->d_p1_prefix;
 	A.qcol = pb->d_qcol; A.qrow = pb->d_qrow; A.qcount = pb->d_qcount; A.err = d_err;
 	const bool ok = CU_OK(launch_compose(V, b1 - b0, st)) && CU_OK(launch_plane1_select(A, b1 - b0, st));
 	c->launches += 3;
@@ -497,7 +502,9 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	b200_ctx_t *c = pb->ctx;
 	const int BS = pb->BS, nb = pb->n_blk;
 	const int n_grp = (BS + COMP_K - 1) / COMP_K;
-	pb->p1_cap = (((pb->m / 4 > 4096 ? pb->m / 4 : 4096) + 2047) / 2048) * 2048;
+	// capacity of a block's (column,row) pair list: 2 pairs per column -- a block whose plane 1 holds more ones (more than
+	// one haplotype in 4096 missing / other-ALT at every site) takes the general walk
+	pb->p1_cap = (int)((((long long)pb->m * 2 > 4096 ? (long long)pb->m * 2 : 4096) + 2047) / 2048 * 2048);
 	// bucket directory of the composite maps: the smallest bucket width whose directory (+ sentinel) fits COMP_DIR entries
 	pb->dir_shift = 0;
 	while ((((uint32_t)pb->m - 1) >> pb->dir_shift) + 2 > (uint32_t)COMP_DIR) ++pb->dir_shift;
@@ -517,6 +524,7 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	          pool_malloc(c, (void**)&pb->d_p1img, (size_t)nb * P1_SLOT_BYTES + 64) &&
 	          pool_malloc(c, (void**)&pb->d_p1_rowoff, sizeof(uint64_t) * (size_t)nb * (SELECT_MAX_ROWS + 1) + 8) &&
 	          pool_malloc(c, (void**)&pb->d_p1_n1, sizeof(uint32_t) * (size_t)nb * SELECT_MAX_ROWS + 8) &&
+	          pool_malloc(c, (void**)&pb->d_p1_prefix, sizeof(uint32_t) * (size_t)nb * (SELECT_MAX_ROWS + 1) + 8) &&
 	          pool_malloc(c, (void**)&pb->d_p1_realrow, sizeof(uint16_t) * (size_t)nb * SELECT_MAX_ROWS + 8) &&
 	          pool_malloc(c, (void**)&pb->d_p1_rows_in_blk, sizeof(int) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_p1_vbase, sizeof(long long) * (nb + 1)) &&
@@ -560,7 +568,7 @@ static bool queue_ranks_view(b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
 	memset(&V, 0, sizeof(V));
 	V.img = pb->d_img; V.rowoff = pb->d_rowoff; V.n1 = pb->d_n1; V.rows_in_blk = pb->d_rows_in_blk;
 	V.m = pb->m; V.shift = pb->shift; V.blk_first = b0; V.p1_cap = pb->p1_cap;
-	V.p1img = pb->d_p1img; V.p1_rowoff = pb->d_p1_rowoff; V.p1_n1 = pb->d_p1_n1; V.p1_realrow = pb->d_p1_realrow;
+	V.p1img = pb->d_p1img; V.p1_rowoff = pb->d_p1_rowoff; V.p1_n1 = pb->d_p1_n1; V.p1_realrow = pb->d_p1_realrow; V.p1_prefix = pb->d_p1_prefix;
 	V.p1_rows_in_blk = pb->d_p1_rows_in_blk; V.p1_vbase = pb->d_p1_vbase; V.blk_sparse = pb->d_blk_sparse;
 	c->launches += 2;
 	return CU_OK(launch_invert_snapshots(pb->d_img, pb->d_blkoff + b0, b1 - b0, pb->m, pb->d_rank0 + (size_t)b0 * 2 * (size_t)pb->m, c->d_err, st)) &&
@@ -1231,8 +1239,6 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	c->split_used = n_split > 0; c->marginal_used = n_split > 0 && G > 1;
 	if (ok && n_split > 0) {
 		const int cap = pb->p1_cap;
-		if (!c->qcol.reserve((size_t)pb->n_blk * cap * sizeof(int32_t)) || !c->qrow.reserve((size_t)pb->n_blk * cap * sizeof(uint16_t)) ||
-		    !c->qcount.reserve((size_t)pb->n_blk * sizeof(int))) return -1;
 		if (!pb->comp_ready && !(flags & B200_SCAN_NO_COMPOSE)) { // composite maps of the row groups: once per resident PBF
 			if (!build_composites(pb, c->d_err_scan)) return -1;
 		}
@@ -1242,9 +1248,12 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 		const bool use_comp = pb->comp_ready && pb->sel_ready && !(flags & B200_SCAN_NO_COMPOSE);
 		const int32_t *qcol = pb->d_qcol; const uint16_t *qrow = pb->d_qrow; const int *qcount = pb->d_qcount;
 		if (!use_comp) {
+			if (!c->qcol.reserve((size_t)pb->n_blk * cap * sizeof(int32_t)) || !c->qrow.reserve((size_t)pb->n_blk * cap * sizeof(uint16_t)) ||
+			    !c->qcount.reserve((size_t)pb->n_blk * sizeof(int))) return -1;
 			SelectParams A;
 			memset(&A, 0, sizeof(A));
 			A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
+			A.p1_prefix = pb->d_p1_prefix; A.dir_shift = pb->dir_shift; A.dir_n = pb->dir_n;
 			A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
 			A.m = pb->m; A.shift = pb->shift; A.cap = cap;
 			A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err_scan;

@@ -381,7 +381,10 @@ __global__ void __launch_bounds__(P1V_NT) p1view_kernel(const P1ViewParams P)
 	const size_t vb = (size_t)blk * SELECT_MAX_ROWS;
 	const uint64_t slot = (uint64_t)blk * P1_SLOT_BYTES;
 	uint64_t *vro = P.p1_rowoff + vb + blk;
-	if (tid == 0) { s_rows = 0; s_bytes = 0; s_allones = 0; s_ones = 0; }
+	uint32_t *vpre = P.p1_prefix + vb + blk;
+	__shared__ uint32_t wones[P1V_NT / 32];
+	__shared__ uint32_t s_pre;
+	if (tid == 0) { s_rows = 0; s_bytes = 0; s_allones = 0; s_ones = 0; s_pre = 0; }
 	__syncthreads();
 	for (int r0 = 0; r0 < rows; r0 += P1V_NT) {
 		const int r = r0 + tid;
@@ -397,21 +400,23 @@ __global__ void __launch_bounds__(P1V_NT) p1view_kernel(const P1ViewParams P)
 			}
 		}
 		const uint32_t f = n1 ? 1u : 0u, sz = n1 ? 9u + l1 : 0u;
-		uint32_t x = f, y = sz;
+		const uint32_t n1c = n1 < (1u << 24) ? n1 : (1u << 24);   // (a block whose plane 1 holds that many ones is not sparse anyway; keeps the prefix from wrapping)
+		uint32_t x = f, y = sz, z = n1c;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t tx = __shfl_up_sync(0xffffffffu, x, d), ty = __shfl_up_sync(0xffffffffu, y, d);
-			if (lane >= d) { x += tx; y += ty; }
+			const uint32_t tx = __shfl_up_sync(0xffffffffu, x, d), ty = __shfl_up_sync(0xffffffffu, y, d), tz = __shfl_up_sync(0xffffffffu, z, d);
+			if (lane >= d) { x += tx; y += ty; z += tz; }
 		}
-		if (lane == 31) { wrow[warp] = x; wbyte[warp] = y; }
+		if (lane == 31) { wrow[warp] = x; wbyte[warp] = y; wones[warp] = z; }
 		__syncthreads();
-		uint32_t v = s_rows + x - f, off = s_bytes + y - sz;
-		for (int w = 0; w < warp; ++w) { v += wrow[w]; off += wbyte[w]; }
+		uint32_t v = s_rows + x - f, off = s_bytes + y - sz, pre = s_pre + z - n1c;
+		for (int w = 0; w < warp; ++w) { v += wrow[w]; off += wbyte[w]; pre += wones[w]; }
 		if (n1) {
 			if (n1 == m) s_allones = 1;
 			atomicAdd(&s_ones, (unsigned long long)n1);
 			if (v < (uint32_t)SELECT_MAX_ROWS && off + sz <= (uint32_t)SELECT_MAX_BYTES) {
 				vro[v] = slot + off;
+				vpre[v] = pre;
 				P.p1_n1[vb + v] = n1;
 				P.p1_realrow[vb + v] = (uint16_t)r;
 				uint8_t *dst = P.p1img + slot + off;
@@ -421,16 +426,17 @@ __global__ void __launch_bounds__(P1V_NT) p1view_kernel(const P1ViewParams P)
 			}
 		}
 		__syncthreads();
-		if (tid == P1V_NT - 1) { s_rows = v + f; s_bytes = off + sz; }
+		if (tid == P1V_NT - 1) { s_rows = v + f; s_bytes = off + sz; s_pre = pre + n1c; }
 		__syncthreads();
 	}
 	if (tid == 0) {
-		const bool fits = s_rows < (uint32_t)SELECT_MAX_ROWS && s_bytes <= (uint32_t)SELECT_MAX_BYTES;
+		const bool fits = s_rows <= (uint32_t)SELECT_MAX_ROWS && s_bytes <= (uint32_t)SELECT_MAX_BYTES;
 		const bool sparse = fits && !s_allones && s_ones <= (unsigned long long)P.p1_cap && BS <= 65536;
 		P.blk_sparse[blk] = sparse ? 1 : 0;
 		P.p1_rows_in_blk[blk] = fits ? (int)s_rows : 0;
 		P.p1_vbase[blk] = (long long)vb;
 		vro[fits ? s_rows : 0] = slot + (fits ? s_bytes : 0);
+		vpre[fits ? s_rows : 0] = fits ? s_pre : 0u;
 		if (fits) { // zero padding behind the records (the view is read in aligned words)
 			uint8_t *dst = P.p1img + slot + s_bytes;
 			for (int i = 0; i < 16; ++i) dst[i] = 0;

@@ -146,17 +146,22 @@ struct SelectParams {
 	const uint8_t  *blk_ok;       // nullptr, or per block 1 = sparse (select it)
 	int blk_first;
 	int m, shift, cap;
+	const uint32_t *p1_prefix;    // plane-1 ones in front of every view row (one extra end entry per block): index vbase[blk] + blk + v
 	const uint32_t *vcomp_start;  // inverse composites of the view rows (compose.cu, inverse = 1) [blocks][SELECT_GROUPS][SELECT_COMP_CAP], or nullptr
 	const int32_t  *vcomp_delta;
 	const int      *vcomp_n;      // [blocks][SELECT_GROUPS]
+	const uint16_t *vcomp_dir;    // [blocks][SELECT_GROUPS][COMP_DIR_STRIDE] bucket directories
+	int dir_shift, dir_n;
 	int32_t  *qcol;               // out [blocks][cap]
 	uint16_t *qrow;               // out [blocks][cap]
 	int      *qcount;             // out [blocks]
 	int      *err;
 };
-constexpr int SELECT_MAX_ROWS = 4096, SELECT_MAX_BYTES = 48 * 1024;
+// the plane-1 view of a block: up to SELECT_MAX_ROWS non-empty rows (every row of an ordinary block) in SELECT_MAX_BYTES of
+// re-framed records; inverse composite maps of its 32-row groups with up to SELECT_COMP_CAP pieces
+constexpr int SELECT_MAX_ROWS = 8192, SELECT_MAX_BYTES = 1 << 20;
 constexpr int P1_SLOT_BYTES = SELECT_MAX_BYTES + 64;   // one block's slot in the plane-1 view image (index.cu)
-constexpr int SELECT_GROUPS = SELECT_MAX_ROWS / COMP_K, SELECT_COMP_CAP = 1024, SELECT_COMP_SMEM = 8192; // pieces of all groups of a block held in smem
+constexpr int SELECT_GROUPS = SELECT_MAX_ROWS / COMP_K, SELECT_COMP_CAP = 2048;
 cudaError_t launch_plane1_select(const SelectParams &P, int n_blk, cudaStream_t st);
 
 // row index of a resident PBF, built on the device (index.cu)
@@ -186,6 +191,7 @@ struct P1ViewParams {
 	uint8_t   *p1img;             // out [blocks][P1_SLOT_BYTES]
 	uint64_t  *p1_rowoff;         // out [blocks][SELECT_MAX_ROWS+1]
 	uint32_t  *p1_n1;             // out [blocks][SELECT_MAX_ROWS]
+	uint32_t  *p1_prefix;         // out [blocks][SELECT_MAX_ROWS+1] ones of plane 1 in front of every view row
 	uint16_t  *p1_realrow;        // out [blocks][SELECT_MAX_ROWS]
 	int       *p1_rows_in_blk;    // out [blocks]
 	long long *p1_vbase;          // out [blocks] = blk * SELECT_MAX_ROWS
