@@ -502,9 +502,9 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	b200_ctx_t *c = pb->ctx;
 	const int BS = pb->BS, nb = pb->n_blk;
 	const int n_grp = (BS + COMP_K - 1) / COMP_K;
-	// capacity of a block's (column,row) pair list: 2 pairs per column -- a block whose plane 1 holds more ones (more than
-	// one haplotype in 4096 missing / other-ALT at every site) takes the general walk
-	pb->p1_cap = (int)((((long long)pb->m * 2 > 4096 ? (long long)pb->m * 2 : 4096) + 2047) / 2048 * 2048);
+	// capacity of a block's (column,row) pair list: 3 pairs per column -- a block whose plane 1 holds more ones (more than
+	// one haplotype in 2700 missing / other-ALT at every site) takes the general walk
+	pb->p1_cap = (int)((((long long)pb->m * 3 > 4096 ? (long long)pb->m * 3 : 4096) + 2047) / 2048 * 2048);
 	// bucket directory of the composite maps: the smallest bucket width whose directory (+ sentinel) fits COMP_DIR entries
 	pb->dir_shift = 0;
 	while ((((uint32_t)pb->m - 1) >> pb->dir_shift) + 2 > (uint32_t)COMP_DIR) ++pb->dir_shift;
