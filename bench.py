@@ -663,12 +663,12 @@ def run_b200(args, rank, world, local_rank):
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_resident": same,
                     "how": "host .pbf image (pinned) -> b200_pbf_load_scan: H2D in 16 chunks (short ones first); behind each chunk on the device: row index, row meta, start ranks, plane-1 view + pair select, composite maps, pair walk, AC/AN + verdict, D2H of the chunk's results to pinned host memory -- one pipeline, one synchronisation at the end"},
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_per_step),
-            "roofline": {"bound": "hbm", "kernel": "pbwt_walk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "pbwt_pair_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": k_ms,
                          "equivalent_rank_updates_per_s": 2.0 * 2 * samples * n / (dev_ms / args.steps * 1e-3),
                          "other_kernels_ms": {"plane1_select_kernel": sum(sel_ms) / len(sel_ms)},
                          "other_kernels_note": "plane1_select_kernel does not depend on the query: it runs once per resident PBF (inside the load) and is 0 in resident steps",
-                         "note": "dominant kernel = pbwt_walk_kernel (QUERY mode of the split scan); it is bound by shared-memory run look-ups / issue slots, not HBM (SURVEY 8d); the HBM fraction is reported as asked"},
+                         "note": "dominant kernel = pbwt_pair_kernel (pairwalk.cu: plane-0 rank of every (column,row) pair that carries a plane-1 code, through two-sided composite maps staged by TMA and warp-built run tables); it is bound by issue slots / shared-memory look-ups, not HBM (SURVEY 8d); the HBM fraction is reported as asked"},
             "clocks": clocks,
         }
     # ---- the other BASELINE configs, the CLI, the density sweep (one GPU), or config 5 + the copy ceiling (several GPUs)

@@ -87,7 +87,7 @@ struct b200_ctx_s {
 	// device-memory pool: PBF windows are loaded and dropped repeatedly (seam A/B, end-to-end scans); cudaMalloc /
 	// cudaFree of hundreds of MB cost milliseconds to hundreds of milliseconds, so freed blocks are kept for reuse
 	std::vector<PoolBlock> pool_free_list, pool_live;
-	size_t pool_cached = 0;
+	size_t pool_cached = 0, pool_limit = (size_t)16 << 30;   // cached bytes are capped at half of the device memory
 	int dev = 0;
 	cudaStream_t st = nullptr;
 	cudaStream_t st_copy = nullptr;   // H2D of PBF images, so that per-chunk kernels on `st` overlap the rest of the copy
@@ -217,7 +217,7 @@ static void pool_free(b200_ctx_t *c, void *p)
 		if (c->pool_live[i].p == p) {
 			PoolBlock b = c->pool_live[i];
 			c->pool_live.erase(c->pool_live.begin() + i);
-			if (c->pool_cached + b.size > ((size_t)16 << 30)) { cudaFree(b.p); return; }
+			if (c->pool_cached + b.size > c->pool_limit) { cudaFree(b.p); return; }
 			c->pool_free_list.push_back(b);
 			c->pool_cached += b.size;
 			return;
@@ -254,6 +254,7 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	if (prop.major < 10) { set_err("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor); return nullptr; }
 	b200_ctx_t *c = new b200_ctx_t();
 	c->dev = device; c->sm_count = prop.multiProcessorCount;
+	c->pool_limit = prop.totalGlobalMem / 2;
 	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) && CU_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking)) &&
 	          CU_OK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
 	for (int i = 0; ok && i <= LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_fin[i], cudaEventDisableTiming)) && CU_OK(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
