@@ -657,7 +657,7 @@ def run_b200(args, rank, world, local_rank):
             "dtype": "u8", "data": "synthetic (device generator, seed %d+rank; rows drawn in PBWT-rank space, truthful snapshots)" % args.seed,
             "config": {"workload": workload_name(samples, n),
                        "m_haplotypes": 2 * samples, "sites_per_gpu": n, "shards": world, "l2": "inputs (%.0f MB .pbf image per GPU) larger than L2" % (img_bytes / 1e6),
-                       "resident_state": "`value` times b200_scan on a loaded PBF handle: the .pbf image plus what b200_pbf_load_ex derives from it on the device once per handle (row index, run totals, start ranks, composite maps of 32-row groups, the plane-1 (column,row) pair list) -- the HBM analogue of the warm page cache the reference is timed with. `e2e` builds all of that from the host image inside the timed region.",
+                       "resident_state": "`value` times b200_scan on a loaded PBF handle: the .pbf image plus what b200_pbf_load_ex derives from it on the device once per handle (row index, run totals, start ranks, two-sided composite maps of 32-row groups, the plane-1 (column,row) pair list) -- the HBM analogue of the warm page cache the reference is timed with. `e2e` builds all of that from the host image inside the timed region.",
                        "totals_allreduce": {"sum_AN": totals[0], "sum_AC": totals[1], "sites_passed": totals[3], "sites": totals[4]}},
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": int(e2e_bytes["h2d"]), "d2h_bytes_per_step": int(e2e_bytes["d2h"]),
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_resident": same,
