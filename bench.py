@@ -497,6 +497,10 @@ def config5_record(rig, args):
         raise RuntimeError(L.b200_strerror().decode())
     # sparse host image: untouched pages of the anonymous mapping cost nothing
     mm = mmap.mmap(-1, fsize + 4096)
+    try:
+        mm.madvise(mmap.MADV_HUGEPAGE)     # 2 MB pages under the part that gets touched: the DMA engine walks far fewer translations
+    except (AttributeError, OSError, ValueError):
+        pass
     img = np.frombuffer(mm, dtype=np.uint8, count=fsize)
     base = img.ctypes.data
     for off, ln in ((0, 16), (bb.value, be.value - bb.value), (ib.value, fsize - ib.value)):

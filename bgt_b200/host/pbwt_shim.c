@@ -72,6 +72,13 @@ static void route_print(void)
 	        (long long)g_route[6], (long long)g_route[7]);
 }
 
+/* for a process that leaves through _exit (the CLI's fast path skips the teardown): what atexit would have printed */
+void pbf_b200_route_report(void)
+{
+	const char *e = getenv("BGT_B200_ROUTE");
+	if (e && *e == '1') route_print();
+}
+
 void pbf_b200_route_add(int slot, int64_t n)
 {
 	if (slot < 0 || slot >= PBF_B200_ROUTE_SLOTS) return;

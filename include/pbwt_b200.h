@@ -78,6 +78,7 @@ const char *pbf_b200_strerror(void);
 #define PBF_B200_ROUTE_SLOTS 8
 void    pbf_b200_route_add(int slot, int64_t n);
 int64_t pbf_b200_route_get(int slot);
+void    pbf_b200_route_report(void);   /* print them now if BGT_B200_ROUTE=1 (for processes that leave through _exit) */
 
 /* optional hook: a host application that keeps its own writer registers its pbf_close
  * so that handles not created by pbf_open_r above are passed through */
