@@ -6,7 +6,7 @@ reader flow (open .pbf -> select samples/groups/filter -> read rows).  There is 
 if the library or a CUDA device is missing, calls raise.
 """
 from .capi import (B200Error, Context, Pbf, Query, lib, lib_path, load_library, scan, SCAN_COUNTS, SCAN_HAP_BITS,
-                   SCAN_HAP_BYTES, SCAN_DEVICE_OUT, Encoder, Sites, bgzf_inflate, synth_cohort, scan_device, collect, host_alloc, host_free, flt_eval_host, pbf_plan, load_scan, pbf_peek)
+                   SCAN_HAP_BYTES, SCAN_DEVICE_OUT, Encoder, Sites, bgzf_inflate, synth_cohort, scan_device, collect, host_alloc, host_free, flt_eval_host, pbf_plan, load_scan, pbf_peek, scan_regions)
 
-__all__ = ["B200Error", "Context", "Pbf", "Query", "Encoder", "Sites", "bgzf_inflate", "lib", "lib_path", "load_library", "scan", "synth_cohort", "scan_device", "collect", "host_alloc", "host_free", "flt_eval_host", "pbf_plan", "load_scan", "pbf_peek",
+__all__ = ["B200Error", "Context", "Pbf", "Query", "Encoder", "Sites", "bgzf_inflate", "lib", "lib_path", "load_library", "scan", "synth_cohort", "scan_device", "collect", "host_alloc", "host_free", "flt_eval_host", "pbf_plan", "load_scan", "pbf_peek", "scan_regions",
            "SCAN_COUNTS", "SCAN_HAP_BITS", "SCAN_HAP_BYTES", "SCAN_DEVICE_OUT"]

@@ -66,6 +66,7 @@ SIGNATURES = {
     "b200_query_hap_words": (_int, [_vp]),
     "b200_query_counts_stride": (_int, [_vp]),
     "b200_scan": (_i64, [_vp, _vp, _vp, _i64, _i64, C.c_uint, C.POINTER(ScanOut)]),
+    "b200_scan_regions": (_i64, [_vp, _vp, _vp, _int, C.POINTER(_i64), C.POINTER(_i64), C.c_uint, C.POINTER(ScanOut)]),
     "b200_scan_collect": (_int, [_vp, C.POINTER(_i64)]),
     "b200_pbf_peek": (_int, [_vp, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_i64)]),
     "b200_pbf_load_scan": (_vp, [_vp, _vp, C.c_size_t, _i64, _i64, _vp, C.POINTER(ScanOut), C.POINTER(_i64)]),
@@ -419,6 +420,32 @@ def load_scan(ctx, data, query, row_beg=0, row_end=-1, out=None):
     res["n"] = done.value
     res["totals"] = [so.totals[i] for i in range(4)]
     return Pbf(ctx, h), res
+
+
+def scan_regions(ctx, pbf, query, regions, counts=True, hap_bits=False, hap_bytes=False):
+    """b200_scan_regions: regions = [(row_beg, n_rows), ...]; outputs are the regions' rows back to back."""
+    n = len(regions)
+    beg = (C.c_int64 * max(n, 1))(*[int(r[0]) for r in regions])
+    cnt = (C.c_int64 * max(n, 1))(*[int(r[1]) for r in regions])
+    total = sum(int(r[1]) for r in regions)
+    res = {"counts": np.empty((total, query.stride), dtype=np.int32) if counts else None, "passed": np.empty(total, dtype=np.uint8)}
+    so = ScanOut()
+    so.counts, so.passed = _ptr(res["counts"]), _ptr(res["passed"])
+    flags = SCAN_COUNTS if counts else 0
+    if hap_bits:
+        res["hap_bits"] = [np.empty((total, query.words), dtype=np.uint32) for _ in range(2)]
+        flags |= SCAN_HAP_BITS
+        so.hap_bits[0], so.hap_bits[1] = _ptr(res["hap_bits"][0]), _ptr(res["hap_bits"][1])
+    if hap_bytes:
+        res["hap_bytes"] = [np.empty((total, query.n_track), dtype=np.uint8) for _ in range(2)]
+        flags |= SCAN_HAP_BYTES
+        so.hap_bytes[0], so.hap_bytes[1] = _ptr(res["hap_bytes"][0]), _ptr(res["hap_bytes"][1])
+    done = lib().b200_scan_regions(ctx.h, pbf.h, query.h, n, beg, cnt, flags, C.byref(so))
+    if done < 0:
+        raise B200Error(_err())
+    res["n"] = done
+    res["totals"] = [so.totals[i] for i in range(4)]
+    return res
 
 
 def scan_device(ctx, pbf, query, row_beg, n_rows, d_counts=0, d_pass=0, d_hap_bits=(0, 0), no_split=False):

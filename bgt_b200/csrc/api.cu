@@ -96,6 +96,8 @@ struct b200_ctx_s {
 	cudaStream_t st_d2h = nullptr, st_walk = nullptr;
 	cudaEvent_t ev_fin[LOAD_CHUNKS + 1] = {}, ev_comp[LOAD_CHUNKS + 1] = {};
 	bool fused_pairs_done = false;    // b200_scan called from the fused path: cnt_raw already holds the pair-walk counts
+	bool keep_totals = false;         // b200_scan called for a later region of b200_scan_regions: totals and error flags accumulate
+	DevBuf rg_counts, rg_pass, rg_bits[2], rg_bytes[2];   // outputs of a batch of regions
 	cudaStream_t st_idx[N_IDX_STREAMS] = {};      // the row-index chase of a chunk is one long dependent chain per block (latency bound, a few
 	                                  // lanes): the chases of consecutive chunks overlap each other and the kernels of earlier chunks
 	cudaEvent_t ev_chunk[LOAD_CHUNKS] = {}, ev_idx[LOAD_CHUNKS] = {}, ev_sel[LOAD_CHUNKS] = {};
@@ -287,6 +289,7 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	for (int i = 0; i < N_IDX_STREAMS; ++i) if (c->st_idx[i]) cudaStreamSynchronize(c->st_idx[i]);
 	c->cnt_raw.release(); c->counts.release(); c->pass.release();
 	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
+	c->rg_counts.release(); c->rg_pass.release(); for (int p = 0; p < 2; ++p) { c->rg_bits[p].release(); c->rg_bytes[p].release(); }
 	c->n0g.release(); c->vseg.release(); c->seg_ok.release(); c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
 	for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
@@ -1226,8 +1229,8 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 
 	bool ok = CU_OK(cudaEventRecord(c->ev[2], c->st)) &&
 	          (c->fused_pairs_done || CU_OK(cudaMemsetAsync(c->cnt_raw.p, 0, nr * G * 3 * sizeof(int32_t), c->st))) &&
-	          CU_OK(cudaMemsetAsync(c->d_acc, 0, 4 * sizeof(unsigned long long), c->st)) &&
-	          (c->fused_pairs_done || CU_OK(cudaMemsetAsync(c->d_err_scan, 0, sizeof(int), c->st))) &&
+	          (c->keep_totals || CU_OK(cudaMemsetAsync(c->d_acc, 0, 4 * sizeof(unsigned long long), c->st))) &&
+	          (c->fused_pairs_done || c->keep_totals || CU_OK(cudaMemsetAsync(c->d_err_scan, 0, sizeof(int), c->st))) &&
 	          CU_OK(cudaMemcpyAsync(c->blk_lists.p, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
 	          CU_OK(cudaMemcpyAsync(c->blk_split.p, split_flag.data(), (size_t)pb->n_blk, cudaMemcpyHostToDevice, c->st)) &&
 	          CU_OK(cudaEventRecord(c->ev[0], c->st));
@@ -1367,6 +1370,74 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	float ms;
 	if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->last_ms[3] = ms;
 	return n_rows;
+}
+
+// Batched regions: what the reference does with one pbf_seek + pbf_read loop per region (pbwt.c:349-372; bgt.c:333-345 behind
+// `-r` / `-B`), as ONE call: every region's scan is queued on the context's stream with device-side outputs at the region's
+// offset of the batch's buffers, nothing is waited for in between, and the results of all regions come home with one copy
+// and one synchronisation.  Rows of region i land at index sum(n_rows[0..i)) of the outputs.
+extern "C" int64_t b200_scan_regions(b200_ctx_t *c, const b200_pbf_t *pb, const b200_query_t *q, int n_regions, const int64_t *row_beg, const int64_t *n_rows,
+                                     unsigned flags, b200_scan_out_t *out)
+{
+	if (!c || !pb || !q || !out || n_regions < 0 || (n_regions && (!row_beg || !n_rows))) { set_err("b200_scan_regions: bad argument"); return -1; }
+	if (flags & B200_SCAN_DEVICE_OUT) { set_err("b200_scan_regions: outputs are host buffers"); return -1; }
+	cudaSetDevice(c->dev);
+	out->totals[0] = out->totals[1] = out->totals[2] = out->totals[3] = 0;
+	int64_t total = 0, widest = 0;
+	for (int i = 0; i < n_regions; ++i) {
+		if (row_beg[i] < b200_pbf_row_beg(pb) || n_rows[i] < 0 || row_beg[i] + n_rows[i] > b200_pbf_row_end(pb)) { set_err("b200_scan_regions: region %d is not resident", i); return -1; }
+		total += n_rows[i];
+		if (n_rows[i] > widest) widest = n_rows[i];
+	}
+	if (total == 0) return 0;
+	const bool host_flt = q->has_flt && q->prog.needs_host;
+	const int stride = 3 + 3 * q->G, words = q->words, n_track = q->n_track;
+	const bool want_counts = (flags & B200_SCAN_COUNTS) && out->counts, want_bits = (flags & B200_SCAN_HAP_BITS) && out->hap_bits[0] && out->hap_bits[1];
+	const bool want_bytes = (flags & B200_SCAN_HAP_BYTES) && out->hap_bytes[0] && out->hap_bytes[1];
+	if (host_flt || n_regions == 1) { // `**` filters are evaluated on the host from the counts: region by region through the ordinary scan
+		int64_t done = 0;
+		for (int i = 0; i < n_regions; ++i) {
+			b200_scan_out_t so = *out;
+			if (so.counts) so.counts += (size_t)done * stride;
+			if (so.pass) so.pass += done;
+			for (int p = 0; p < 2; ++p) { if (so.hap_bits[p]) so.hap_bits[p] += (size_t)done * words; if (so.hap_bytes[p]) so.hap_bytes[p] += (size_t)done * n_track; }
+			if (n_rows[i] && b200_scan(c, pb, q, row_beg[i], n_rows[i], flags, &so) != n_rows[i]) return -1;
+			for (int k = 0; k < 4; ++k) out->totals[k] += so.totals[k];
+			done += n_rows[i];
+		}
+		return done;
+	}
+	const size_t nt = (size_t)total;
+	bool ok = c->rg_counts.reserve(nt * stride * sizeof(int32_t) + 16) && c->rg_pass.reserve(nt + 16) &&
+	          c->cnt_raw.reserve((size_t)widest * q->G * 3 * sizeof(int32_t));      // (grown before the first region is queued, not between two)
+	if ((want_bits || want_bytes) && ok) for (int p = 0; p < 2 && ok; ++p) ok = c->rg_bits[p].reserve(nt * words * sizeof(uint32_t) + 16);
+	if (want_bytes && ok) for (int p = 0; p < 2 && ok; ++p) ok = c->rg_bytes[p].reserve(nt * (size_t)n_track + 16);
+	if (!ok) return -1;
+	int64_t done = 0;
+	for (int i = 0; ok && i < n_regions; ++i) {
+		if (n_rows[i] == 0) continue;
+		b200_scan_out_t so;
+		memset(&so, 0, sizeof(so));
+		so.counts = (int32_t*)c->rg_counts.p + (size_t)done * stride;
+		so.pass = (uint8_t*)c->rg_pass.p + done;
+		unsigned f = (flags & ~(unsigned)(B200_SCAN_HAP_BITS | B200_SCAN_HAP_BYTES)) | B200_SCAN_COUNTS | B200_SCAN_DEVICE_OUT;
+		if (want_bits || want_bytes) { f |= B200_SCAN_HAP_BITS; for (int p = 0; p < 2; ++p) so.hap_bits[p] = (uint32_t*)c->rg_bits[p].p + (size_t)done * words; }
+		if (want_bytes) { f |= B200_SCAN_HAP_BYTES; for (int p = 0; p < 2; ++p) so.hap_bytes[p] = (uint8_t*)c->rg_bytes[p].p + (size_t)done * n_track; }
+		c->keep_totals = done > 0;
+		ok = b200_scan(c, pb, q, row_beg[i], n_rows[i], f, &so) == n_rows[i];
+		c->keep_totals = false;
+		done += n_rows[i];
+	}
+	if (!ok) { cudaStreamSynchronize(c->st); return -1; }
+	if (want_counts) ok = CU_OK(cudaMemcpyAsync(out->counts, c->rg_counts.p, nt * stride * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+	if (ok && out->pass) ok = CU_OK(cudaMemcpyAsync(out->pass, c->rg_pass.p, nt, cudaMemcpyDeviceToHost, c->st));
+	for (int p = 0; p < 2 && ok; ++p) {
+		if (want_bits) ok = CU_OK(cudaMemcpyAsync(out->hap_bits[p], c->rg_bits[p].p, nt * words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
+		if (ok && want_bytes) ok = CU_OK(cudaMemcpyAsync(out->hap_bytes[p], c->rg_bytes[p].p, nt * (size_t)n_track, cudaMemcpyDeviceToHost, c->st));
+	}
+	if (!ok) { cudaStreamSynchronize(c->st); return -1; }
+	if (b200_scan_collect(c, out->totals) != 0) return -1;
+	return total;
 }
 
 // after a DEVICE_OUT scan + b200_ctx_sync: fetch kernel timings and totals

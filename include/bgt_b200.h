@@ -123,6 +123,12 @@ int     b200_pbf_peek(const uint8_t *bytes, size_t n_bytes, int32_t *m, int32_t 
  * resident handle (close it with b200_pbf_close) or NULL; *n_scanned = rows produced. */
 b200_pbf_t *b200_pbf_load_scan(b200_ctx_t *ctx, const uint8_t *bytes, size_t n_bytes, int64_t row_beg, int64_t row_end,
                                const b200_query_t *q, b200_scan_out_t *out, int64_t *n_scanned);
+/* Batched regions (`-r` / `-B` / server-style short queries; in the reference one pbf_seek + pbf_read loop per region,
+ * pbwt.c:349-372): the scans of all regions are queued back to back, their results come home with one copy and one
+ * synchronisation.  Regions must be resident; rows of region i land at index sum(n_rows[0..i)) of every output; totals are
+ * summed over the regions.  Returns the rows produced or <0. */
+int64_t b200_scan_regions(b200_ctx_t *ctx, const b200_pbf_t *pb, const b200_query_t *q, int n_regions, const int64_t *row_beg,
+                          const int64_t *n_rows, unsigned flags, b200_scan_out_t *out);
 /* After a B200_SCAN_DEVICE_OUT scan: wait for it, fetch its totals and kernel timings. */
 int     b200_scan_collect(b200_ctx_t *ctx, int64_t totals[4]);
 /* totals (as b200_scan_out_t.totals) of the last scan of this context whose results reached the host: b200_scan,

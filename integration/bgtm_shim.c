@@ -46,7 +46,9 @@ typedef struct accel_s {
 	b200_query_t *q;
 	int n_rec, cur, cap, eof, has_pending;
 	bcf1_t **rec; int64_t *rows;
-	int64_t r0; size_t out_cap_rows;
+	int64_t *ridx;                    /* per record: index of its row in the batch's outputs (regions back to back) */
+	int64_t *rg_beg, *rg_cnt; int rg_cap;   /* the batch's regions: runs of records whose rows lie close together */
+	size_t out_cap_rows;
 	int32_t *counts; uint8_t *pass, *hap[2];
 	int stride, n_track;
 } accel_t;
@@ -88,7 +90,7 @@ static void accel_drop(bgtm_t *bm)
 	if (a->q) b200_query_destroy(a->q);
 	if (a->win) b200_pbf_close(a->win);
 	for (i = 0; i < a->cap; ++i) if (a->rec[i]) bcf_destroy1(a->rec[i]);
-	free(a->rec); free(a->rows); free(a->flt);
+	free(a->rec); free(a->rows); free(a->ridx); free(a->rg_beg); free(a->rg_cnt); free(a->flt);
 	b200_host_free(a->counts); b200_host_free(a->pass); b200_host_free(a->hap[0]); b200_host_free(a->hap[1]);
 	free(a);
 }
@@ -143,22 +145,23 @@ static int fill_batch(accel_t *a)
 	const int n_track = bgt->n_out << 1;
 	size_t map_len;
 	const uint8_t *map = pbf_b200_image(bgt->pb, &map_len);
-	int64_t span_cap, rows_cap;
+	int64_t rows_cap, covered = 0, n_rows;
 	b200_scan_out_t so;
 	unsigned flags = 0;
-	int64_t n_rows;
+	int n_rg = 0, i;
+	const int64_t gap_max = 64;       /* rows between two records that are still scanned through rather than split into two regions */
 	if (ctx == 0) { a->failed = 1; return -1; }
 	if (map == 0) { fprintf(stderr, "[E::bgt_b200] the PBF handle was not opened by the B200 seam\n"); a->failed = 1; return -1; }
 	/* batch geometry: bounded by the decoded-plane bytes when genotypes are printed */
 	rows_cap = want_gt ? (64LL << 20) / (n_track > 0 ? n_track : 1) : 65536;
 	if (rows_cap < 1) rows_cap = 1;
 	if (rows_cap > 65536) rows_cap = 65536;
-	span_cap = rows_cap;
 	if (a->cap < rows_cap + 1) {
-		int i, old = a->cap;
+		int old = a->cap;
 		a->cap = (int)rows_cap + 1;
 		a->rec = (bcf1_t**)realloc(a->rec, a->cap * sizeof(void*));
 		a->rows = (int64_t*)realloc(a->rows, a->cap * sizeof(int64_t));
+		a->ridx = (int64_t*)realloc(a->ridx, a->cap * sizeof(int64_t));
 		for (i = old; i < a->cap; ++i) a->rec[i] = bcf_init1();
 	}
 	/* the record that closed the previous batch opens this one */
@@ -174,10 +177,15 @@ static int fill_batch(accel_t *a)
 		bcfcpy(a->rec[a->n_rec], bgt->b0);
 		a->rows[a->n_rec] = row;
 		if (a->n_rec > 0) {
-			const int64_t first = a->rows[0];
-			int64_t wend = a->win && first >= a->win_beg && first < a->win_end ? a->win_end : -1;
-			if (row - first >= span_cap || (wend >= 0 && row >= wend) || row < a->rows[a->n_rec - 1]) { a->has_pending = 1; break; }
-		}
+			/* rows the batch covers: records that lie close together are scanned through, a far jump (`-B` regions, sparse
+			 * site lists) starts a new region of the batch instead of dragging every row in between along */
+			const int64_t first = a->rows[0], prev = a->rows[a->n_rec - 1];
+			const int64_t wend = a->win && first >= a->win_beg && first < a->win_end ? a->win_end : -1;
+			const int64_t step = row - prev > gap_max ? 1 : row - prev;
+			const int64_t far = row - first >= (1LL << 30) / (8LL * pbf_get_m(bgt->pb) + 1) * (1LL << pbf_get_shift(bgt->pb));   /* beyond one window */
+			if (covered + step >= rows_cap || (wend >= 0 && row >= wend) || (wend < 0 && far) || row < prev) { a->has_pending = 1; break; }
+			covered += step;
+		} else covered = 1;
 		++a->n_rec;
 	}
 	if (a->n_rec == 0) return 0;
@@ -208,8 +216,21 @@ static int fill_batch(accel_t *a)
 		a->stride = b200_query_counts_stride(a->q);
 		a->n_track = b200_query_n_track(a->q);
 	}
-	a->r0 = a->rows[0];
-	n_rows = a->rows[a->n_rec - 1] - a->r0 + 1;
+	/* the batch's regions and every record's place in the outputs */
+	for (i = 0, n_rows = 0; i < a->n_rec; ++i) {
+		if (i == 0 || a->rows[i] - a->rows[i - 1] > gap_max) {
+			if (n_rg == a->rg_cap) {
+				a->rg_cap = a->rg_cap ? a->rg_cap << 1 : 64;
+				a->rg_beg = (int64_t*)realloc(a->rg_beg, a->rg_cap * sizeof(int64_t));
+				a->rg_cnt = (int64_t*)realloc(a->rg_cnt, a->rg_cap * sizeof(int64_t));
+			}
+			if (n_rg) n_rows += a->rg_cnt[n_rg - 1];
+			a->rg_beg[n_rg] = a->rows[i]; a->rg_cnt[n_rg] = 0; ++n_rg;
+		}
+		a->rg_cnt[n_rg - 1] = a->rows[i] - a->rg_beg[n_rg - 1] + 1;
+		a->ridx[i] = n_rows + (a->rows[i] - a->rg_beg[n_rg - 1]);
+	}
+	n_rows += a->rg_cnt[n_rg - 1];
 	if ((size_t)n_rows > a->out_cap_rows) {
 		b200_host_free(a->counts); b200_host_free(a->pass); b200_host_free(a->hap[0]); b200_host_free(a->hap[1]);
 		a->out_cap_rows = (size_t)n_rows;
@@ -227,8 +248,9 @@ static int fill_batch(accel_t *a)
 	memset(&so, 0, sizeof(so));
 	so.counts = a->counts; so.pass = a->pass; flags |= B200_SCAN_COUNTS;
 	if (want_gt) { so.hap_bytes[0] = a->hap[0]; so.hap_bytes[1] = a->hap[1]; flags |= B200_SCAN_HAP_BYTES; }
-	if (b200_scan(ctx, a->win, a->q, a->r0, n_rows, flags, &so) != n_rows) return fail(a, "scan");
+	if (b200_scan_regions(ctx, a->win, a->q, n_rg, a->rg_beg, a->rg_cnt, flags, &so) != n_rows) return fail(a, "scan");
 	pbf_b200_route_add(2, 1);
+	if (n_rg > 1) pbf_b200_route_add(7, 1);
 	return 0;
 }
 
@@ -253,7 +275,7 @@ int bgtm_read(bgtm_t *bm, bcf1_t *b)                             /* bgt.c:880-88
 			if (a->n_rec == 0) return -1;
 		}
 		b0 = a->rec[a->cur];
-		rr = a->rows[a->cur] - a->r0;
+		rr = a->ridx[a->cur];
 		++a->cur;
 		bm->n_gt_read += bgt->n_out;                             /* bgt.c:807 */
 		l_ref = bcfcpy_min(b, b0, b0->n_allele > 2 ? "<M>" : 0);  /* bgt.c:823 */

@@ -114,6 +114,21 @@ def test_view_matches_reference(tools, cohort_small, args):
         assert route["view_fast"] == 0 and route["seamB_batches"] > 0, route
 
 
+def test_view_bed_regions_are_batched(tools, cohort_small, tmp_path):
+    """`-B` with scattered intervals: seam B pulls the records through the reference's BED iterator and hands the GPU one batch
+    of REGIONS (b200_scan_regions) instead of every row from the first to the last record."""
+    prefix, _ = cohort_small
+    bed = tmp_path / "r.bed"
+    ivs = [(1500, 1700), (30000, 30400), (30900, 31000), (60000, 60010), (82900, 83100), (90000, 90990)]   # POS = 1000 + 10*row; crosses row 8192
+    bed.write_text("".join("11\t%d\t%d\n" % iv for iv in ivs))
+    for args in (["-B", str(bed), "-C"], ["-B", str(bed), "-f", "AC>0", "-G"], ["-B", str(bed), "-s", ",S0000003,S0000010"]):
+        want = run(tools.REF_BGT, ["view"] + args + [prefix])
+        got, route, _ = run_routed(NEW_BGT, ["view"] + args + [prefix])
+        assert got == want, args
+        assert want.count(b"\n") > 60
+        assert route["seamB_batches"] > 0 and route["region_launches"] > 0 and route["ref_bgtm_read"] == 0, route
+
+
 def test_view_subset_file_and_wide_cohort(tools, cohort_wide, tmp_path):
     prefix, mat = cohort_wide
     rng = np.random.default_rng(1)
