@@ -112,7 +112,7 @@ struct b200_ctx_s {
 	// starts, reported when it ends or is collected), d_err_sites = inflate / BCF parse / text assembly
 	int *d_err = nullptr, *d_err_scan = nullptr, *d_err_sites = nullptr;
 	unsigned long long *d_acc = nullptr; // [0..3] totals, [4] bad rows
-	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], qcol, qrow, qcount, blk_lists, blk_split, n0g, vseg, seg_ok;
+	DevBuf cnt_raw, counts, pass, hapbits[2], hapbytes[2], qcol, qrow, qcount, n0g, vseg, seg_ok;
 	int sm_count = 148;
 	bool split_used = false, marginal_used = false;
 };
@@ -290,7 +290,7 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	c->cnt_raw.release(); c->counts.release(); c->pass.release();
 	for (int p = 0; p < 2; ++p) { c->hapbits[p].release(); c->hapbytes[p].release(); }
 	c->rg_counts.release(); c->rg_pass.release(); for (int p = 0; p < 2; ++p) { c->rg_bits[p].release(); c->rg_bytes[p].release(); }
-	c->n0g.release(); c->vseg.release(); c->seg_ok.release(); c->qcol.release(); c->qrow.release(); c->qcount.release(); c->blk_lists.release(); c->blk_split.release();
+	c->n0g.release(); c->vseg.release(); c->seg_ok.release(); c->qcol.release(); c->qrow.release(); c->qcount.release();
 	for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	for (int i = 0; i < 4; ++i) if (c->mark[i]) cudaEventDestroy(c->mark[i]);
 	if (c->ev_zero) cudaEventDestroy(c->ev_zero);
@@ -1217,13 +1217,13 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	// (several groups: the per-group marginals come from marginal.cu -- one bit vector per group in shared memory)
 	const bool split = q->full && !emit && pb->p1_ready && !(flags & B200_SCAN_NO_SPLIT) && n_track > 0 &&
 	                   (G == 1 || (G <= 8 && marginal_smem_bytes(pb->m) <= 200 * 1024));
-	std::vector<int> lists;          // [general blocks..., split blocks...]
-	std::vector<uint8_t> split_flag(pb->n_blk, 0);
+	// Which block takes which path was decided on the device while loading (d_blk_sparse; the host holds a copy): every kernel
+	// is launched over the whole block range of the scan and the CTAs of the other path's blocks exit -- no per-scan lists to
+	// upload (an asynchronous upload from a host vector must not outlive it, and B200_SCAN_DEVICE_OUT scans return at once).
 	int n_gen = 0, n_split = 0;
-	for (int b = b_first; b <= b_last; ++b) if (!(split && pb->blk_sparse[b])) { lists.push_back(b); ++n_gen; }
-	for (int b = b_first; b <= b_last; ++b) if (split && pb->blk_sparse[b]) { lists.push_back(b); split_flag[b] = 1; ++n_split; }
-	if (!c->blk_lists.reserve(lists.size() * sizeof(int) + 16) || !c->blk_split.reserve((size_t)pb->n_blk + 16)) return -1;
-	const int *d_gen_list = (const int*)c->blk_lists.p, *d_split_list = d_gen_list + n_gen;
+	for (int b = b_first; b <= b_last; ++b) { if (split && pb->blk_sparse[b]) ++n_split; else ++n_gen; }
+	const int n_range = b_last - b_first + 1;
+	const uint8_t *d_split_flags = split ? pb->d_blk_sparse : nullptr;
 	FinalizeSplit sp;
 	memset(&sp, 0, sizeof(sp));
 
@@ -1231,14 +1231,12 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 	          (c->fused_pairs_done || CU_OK(cudaMemsetAsync(c->cnt_raw.p, 0, nr * G * 3 * sizeof(int32_t), c->st))) &&
 	          (c->keep_totals || CU_OK(cudaMemsetAsync(c->d_acc, 0, 4 * sizeof(unsigned long long), c->st))) &&
 	          (c->fused_pairs_done || c->keep_totals || CU_OK(cudaMemsetAsync(c->d_err_scan, 0, sizeof(int), c->st))) &&
-	          CU_OK(cudaMemcpyAsync(c->blk_lists.p, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, c->st)) &&
-	          CU_OK(cudaMemcpyAsync(c->blk_split.p, split_flag.data(), (size_t)pb->n_blk, cudaMemcpyHostToDevice, c->st)) &&
 	          CU_OK(cudaEventRecord(c->ev[0], c->st));
 	if (ok && n_track > 0 && n_gen > 0) {
-		P.blk_list = d_gen_list;
+		P.blk_list = nullptr; P.blk_first = b_first; P.blk_skip = d_split_flags;
 		const int Cg = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : pick_cols_per_thread(c, n_track, n_gen);
-		ok = CU_OK(launch_walk(P, Cg, emit ? WALK_MODE_EMIT : WALK_MODE_COUNT, (n_track + WALK_NT * Cg - 1) / (WALK_NT * Cg), n_gen, c->st));
-		c->launches += (n_gen + 32767) / 32768;
+		ok = CU_OK(launch_walk(P, Cg, emit ? WALK_MODE_EMIT : WALK_MODE_COUNT, (n_track + WALK_NT * Cg - 1) / (WALK_NT * Cg), n_range, c->st));
+		c->launches += (n_range + 32767) / 32768;
 	}
 	c->split_used = n_split > 0; c->marginal_used = n_split > 0 && G > 1;
 	if (ok && n_split > 0) {
@@ -1258,10 +1256,10 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			memset(&A, 0, sizeof(A));
 			A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
 			A.p1_prefix = pb->d_p1_prefix; A.dir_shift = pb->dir_shift; A.dir_n = pb->dir_n;
-			A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = d_split_list;
+			A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = nullptr; A.blk_first = b_first; A.blk_ok = d_split_flags;
 			A.m = pb->m; A.shift = pb->shift; A.cap = cap;
 			A.qcol = (int32_t*)c->qcol.p; A.qrow = (uint16_t*)c->qrow.p; A.qcount = (int*)c->qcount.p; A.err = c->d_err_scan;
-			ok = CU_OK(cudaEventRecord(c->ev[8], c->st)) && CU_OK(launch_plane1_select(A, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[9], c->st));
+			ok = CU_OK(cudaEventRecord(c->ev[8], c->st)) && CU_OK(launch_plane1_select(A, n_range, c->st)) && CU_OK(cudaEventRecord(c->ev[9], c->st));
 			++c->launches;
 			qcol = (const int32_t*)c->qcol.p; qrow = (const uint16_t*)c->qrow.p; qcount = (const int*)c->qcount.p;
 		} else c->split_used = false;   // (no select time in this scan)
@@ -1272,13 +1270,13 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			B.comp_dir = pb->d_comp_dir; B.dir_shift = pb->dir_shift; B.dir_n = pb->dir_n;
 		}
 		B.track = qcol; B.qrow = qrow; B.track_stride = cap;
-		B.n_track_blk = qcount; B.n_track = cap; B.blk_list = d_split_list;
+		B.n_track_blk = qcount; B.n_track = cap; B.blk_list = nullptr; B.blk_first = b_first; B.blk_skip = nullptr; B.blk_ok = d_split_flags;
 		const int Cb = (forced == 1 || forced == 2 || forced == 4 || forced == 8) ? forced : (use_comp ? 2 : 8);
 		if (use_comp && c->fused_pairs_done) {
 			// (b200_pbf_load_scan: the pair walk of every block was queued behind the block's composite maps while loading)
 		} else if (use_comp) {   // (without composite maps -- testing -- the QUERY mode of the walk kernel goes row by row)
 			PairParams K = pair_params(c, pb, q, row_beg, row_beg + n_rows);
-			K.blk_list = d_split_list;
+			K.blk_list = nullptr; K.blk_first = b_first; K.blk_ok = d_split_flags;
 			static const bool prof = getenv("BGT_B200_PROF") != nullptr;
 			static unsigned long long *d_prof = nullptr;
 			if (prof) {
@@ -1288,7 +1286,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			}
 			static const int env_c = getenv("BGT_B200_PAIR_C") ? atoi(getenv("BGT_B200_PAIR_C")) : 0;   // tuning
 			const int Cp = (forced == 1 || forced == 2 || forced == 4) ? forced : (env_c == 1 || env_c == 2 || env_c == 4 ? env_c : 4);
-			ok = ok && CU_OK(launch_pairwalk(K, Cp, cap, n_split, c->st));
+			ok = ok && CU_OK(launch_pairwalk(K, Cp, cap, n_range, c->st));
 			if (prof) {
 				unsigned long long h[8];
 				cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, c->st);
@@ -1297,7 +1295,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 				        (double)h[3] / (h[2] ? h[2] : 1), (double)h[1] / (h[2] ? h[2] : 1), (double)h[4] / (h[2] ? h[2] * 16.0 : 1));
 			}
 		} else
-			ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_QUERY, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_split, c->st));
+			ok = ok && CU_OK(launch_walk(B, Cb, WALK_MODE_QUERY, (cap + WALK_NT * Cb - 1) / (WALK_NT * Cb), n_range, c->st));
 		++c->launches;
 		if (G > 1) { // per-group plane-0 marginals for the first G-1 groups (the last one is the remainder)
 			if (!c->n0g.reserve(nr * (size_t)(G - 1) * sizeof(int32_t))) return -1;
@@ -1307,24 +1305,24 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			if (use_comp && !(flags & B200_SCAN_NO_SEGMENTS)) { // segments of 8+ row groups, as many as 512 MB of segment vectors allow
 				const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
 				int seg_groups = 8;
-				const size_t per_seg = (size_t)n_split * (size_t)(G - 1) * marginal_seg_words(pb->m) * sizeof(uint32_t);
+				const size_t per_seg = (size_t)n_range * (size_t)(G - 1) * marginal_seg_words(pb->m) * sizeof(uint32_t);
 				while (seg_groups < n_grp && per_seg * (size_t)((n_grp + seg_groups - 1) / seg_groups) > ((size_t)512 << 20)) seg_groups *= 2;
 				const int n_seg = (n_grp + seg_groups - 1) / seg_groups;
 				if (n_seg > 1) {
-					if (!c->vseg.reserve(per_seg * (size_t)n_seg) || !c->seg_ok.reserve((size_t)n_split * (size_t)(G - 1) + 16)) return -1;
+					if (!c->vseg.reserve(per_seg * (size_t)n_seg) || !c->seg_ok.reserve((size_t)n_range * (size_t)(G - 1) + 16)) return -1;
 					M.comp_start = pb->d_comp_start; M.comp_delta = pb->d_comp_delta; M.comp_n = pb->d_comp_n; M.two_sided = 1; M.n_blk_res = pb->n_blk;
 					M.n_grp = n_grp; M.seg_groups = seg_groups; M.n_seg = n_seg; M.vseg = (uint32_t*)c->vseg.p; M.seg_ok = (uint8_t*)c->seg_ok.p;
 					++c->launches;
 				}
 			}
 			M.img = pb->d_img; M.rowoff = pb->d_rowoff; M.n1 = pb->d_n1; M.blkoff = pb->d_blkoff; M.rows_in_blk = pb->d_rows_in_blk;
-			M.blk_list = d_split_list; M.tgrp = q->d_tgrp; M.n0g = (int32_t*)c->n0g.p; M.m = pb->m; M.shift = pb->shift; M.n_vec = G - 1;
+			M.blk_list = nullptr; M.blk_first = b_first; M.blk_ok = d_split_flags; M.tgrp = q->d_tgrp; M.n0g = (int32_t*)c->n0g.p; M.m = pb->m; M.shift = pb->shift; M.n_vec = G - 1;
 			M.blk_row0 = P.blk_row0; M.row_lo = row_beg; M.row_hi = row_beg + n_rows;
-			ok = ok && CU_OK(cudaEventRecord(c->ev[10], c->st)) && CU_OK(launch_marginal(M, n_split, c->st)) && CU_OK(cudaEventRecord(c->ev[11], c->st));
+			ok = ok && CU_OK(cudaEventRecord(c->ev[10], c->st)) && CU_OK(launch_marginal(M, n_range, c->st)) && CU_OK(cudaEventRecord(c->ev[11], c->st));
 			++c->launches;
 			sp.n0g = (const int32_t*)c->n0g.p; sp.n_vec = G - 1;
 		}
-		sp.blk_split = (const uint8_t*)c->blk_split.p; sp.n1 = pb->d_n1; sp.row_lo = row_beg; sp.blk_row0 = P.blk_row0; sp.shift = pb->shift;
+		sp.blk_split = d_split_flags; sp.n1 = pb->d_n1; sp.row_lo = row_beg; sp.blk_row0 = P.blk_row0; sp.shift = pb->shift;
 	}
 	ok = ok && CU_OK(cudaEventRecord(c->ev[1], c->st));
 	ok = ok && CU_OK(launch_finalize(P.cnt_raw, n_rows, G, q->d_gsize, q->d_prog, q->has_flt && !host_flt, d_counts, d_pass, c->d_acc, sp, c->st));
@@ -1401,7 +1399,8 @@ extern "C" int64_t b200_scan_regions(b200_ctx_t *c, const b200_pbf_t *pb, const 
 			if (so.counts) so.counts += (size_t)done * stride;
 			if (so.pass) so.pass += done;
 			for (int p = 0; p < 2; ++p) { if (so.hap_bits[p]) so.hap_bits[p] += (size_t)done * words; if (so.hap_bytes[p]) so.hap_bytes[p] += (size_t)done * n_track; }
-			if (n_rows[i] && b200_scan(c, pb, q, row_beg[i], n_rows[i], flags, &so) != n_rows[i]) return -1;
+			if (n_rows[i] == 0) continue;
+			if (b200_scan(c, pb, q, row_beg[i], n_rows[i], flags, &so) != n_rows[i]) return -1;
 			for (int k = 0; k < 4; ++k) out->totals[k] += so.totals[k];
 			done += n_rows[i];
 		}

@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int bi = (int)blockIdx.x / P.n_seg, seg = (int)blockIdx.x % P.n_seg;
-	const int blk = P.blk_list[bi], g = blockIdx.y;
+	const int blk = P.blk_list ? P.blk_list[bi] : P.blk_first + bi, g = blockIdx.y;
+	if (P.blk_ok && !P.blk_ok[blk]) return;
 	const int BS = 1 << P.shift;
 	const uint32_t m = (uint32_t)P.m;
 	const uint64_t *roff = P.rowoff + (size_t)blk * (BS + 1);
@@ -386,7 +387,8 @@ __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const Margina
 	__shared__ int s_bad;
 	constexpr int PER = COMP_CAP / MS_NT;
 	const int tid = threadIdx.x;
-	const int bi = blockIdx.x, blk = P.blk_list[bi], g = blockIdx.y;
+	const int bi = blockIdx.x, blk = P.blk_list ? P.blk_list[bi] : P.blk_first + bi, g = blockIdx.y;
+	if (P.blk_ok && !P.blk_ok[blk]) return;
 	const uint32_t m = (uint32_t)P.m;
 	const long long blk_row = P.blk_row0 + ((long long)blk << P.shift);
 	int rows = P.rows_in_blk[blk];

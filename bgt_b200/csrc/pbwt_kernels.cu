@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(WALK_NT, 2) pbwt_walk_kernel(const WalkParams 
 	// the checkpoint block of this CTA (a list when only some blocks take this path) and its tracked columns
 	// (one list for the whole scan, or one list per block when the set was derived per block)
 	const int blk_own = CHAIN ? 0 : (P.blk_list ? P.blk_list[blockIdx.y] : P.blk_first + (int)blockIdx.y);
+	if (!CHAIN && ((P.blk_skip && P.blk_skip[blk_own]) || (P.blk_ok && !P.blk_ok[blk_own]))) return;   // another kernel's block (device-side verdict of index.cu)
 	const int n_track = P.n_track_blk ? P.n_track_blk[blk_own] : P.n_track;
 	const int32_t *track = P.track ? P.track + (size_t)blk_own * P.track_stride : nullptr;
 	if (slice_base >= n_track) return;

@@ -56,6 +56,8 @@ struct WalkParams {
 	int dir_shift, dir_n;       // bucket width 2^dir_shift; dir_n = directory entries incl. sentinel, padded to 8
 	const int      *grp_tile_beg; // [blocks][groups+1] first tile of every row group
 	const int      *blk_list;  // resident-block indices handled by this launch (nullptr: blk_first + blockIdx.y)
+	const uint8_t  *blk_skip;  // nullptr, or per resident block 1 = not this kernel's (the block is on the split path): its CTAs exit
+	const uint8_t  *blk_ok;    // nullptr, or per resident block 1 = this kernel's (QUERY: the block is on the split path)
 	const int      *n_track_blk; // per-block number of tracked columns (nullptr: n_track)
 	long long       track_stride; // > 0: track holds one list per resident block, this many entries apart
 	uint8_t        *snap_img;  // CHAIN only: image to write 'S' snapshots into
@@ -206,7 +208,9 @@ struct MarginalParams {
 	const uint32_t *n1;
 	const uint64_t *blkoff;
 	const int      *rows_in_blk;
-	const int      *blk_list;
+	const int      *blk_list;  // nullptr: blk_first + launch index
+	const uint8_t  *blk_ok;    // nullptr, or per resident block 1 = on the split path; the CTAs of other blocks exit
+	int blk_first;
 	const uint8_t  *tgrp;      // 0-based group per column (full-cohort queries: tracked entry == column)
 	int32_t        *n0g;       // out [rows out][n_vec]
 	int m, shift, n_vec;
