@@ -826,7 +826,10 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 	int cb[LOAD_CHUNKS + 1];
 	{
 		static const int ramp[6] = {1, 2, 3, 4, 6, 8};
-		const int head = (n_chunks == LOAD_CHUNKS && nb >= 64) ? 6 : 0, tail = 0;   // (a mirrored ramp at the end was measured: more, smaller launches cost more than the shorter tail saves)
+		// (short chunks at the END as well shorten what is left to do behind the last copy -- which pays when the COPY is the limit
+		// (several GPUs sharing the host link) and costs when the SMs are: measured on one GPU 11.3 ms with a full mirrored ramp of
+		// 24 chunks, 10.5 ms with three short chunks at the end, 9.9 ms without.  Opt-in: BGT_B200_TAIL_RAMP=1.)
+		const int head = (n_chunks == LOAD_CHUNKS && nb >= 64) ? 6 : 0, tail = (head && getenv("BGT_B200_TAIL_RAMP")) ? 3 : 0;
 		int h = 0, t = nb;
 		cb[0] = 0; cb[n_chunks] = nb;
 		for (int k = 0; k < head; ++k) { const int sz = nb * ramp[k] / 128; h += sz > 0 ? sz : 1; cb[k + 1] = h; }
