@@ -476,6 +476,28 @@ def h2d_probe(rig, mb=256):
     return {"concurrent_gbs_per_rank": allg, "rank0_alone_gbs": None if alone is None else round(alone, 1), "mb": mb}
 
 
+def topo_affinity():
+    """CPU / NUMA affinity of every GPU as `nvidia-smi topo -m` reports it: on this pool's boxes all GPUs share one NUMA node
+    (0-31 / 0), so there is no NUMA-local placement of the pinned staging buffers to choose."""
+    exe = shutil.which("nvidia-smi")
+    if not exe:
+        return None
+    try:
+        out = subprocess.run([exe, "topo", "-m"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    import re
+    res = {}
+    for ln in out.splitlines():
+        ln = re.sub(r"\x1b\[[0-9;]*m", "", ln)
+        f = ln.split("\t")
+        if f and re.match(r"GPU\d+$", f[0].strip()):
+            tail = [x.strip() for x in f[1:] if x.strip()]
+            aff = [x for x in tail if re.match(r"^[0-9,\-]+$", x)]
+            res[f[0].strip()] = {"cpu_affinity": aff[0] if aff else None, "numa_affinity": aff[1] if len(aff) > 1 else None}
+    return res or None
+
+
 def config5_record(rig, args):
     """BASELINE configs[4]: ONE synthetic cohort of 500 000 samples x 10 M sites (1221 checkpoint blocks), region-sharded: rank r
     takes blocks [r*ceil(1221/N), (r+1)*ceil(1221/N)) -- b200_pbf_load_ex(row_beg,row_end) on the file image -- and the totals
@@ -693,6 +715,8 @@ def run_b200(args, rank, world, local_rank):
         probe = h2d_probe(rig)
         rec5 = config5_record(rig, args) if not args.quick else None
         if rank == 0:
+            probe["gpu_affinity"] = topo_affinity()
+            probe["note"] = "the end-to-end step has to move its .pbf image over this link: e2e at N GPUs cannot exceed N x (concurrent GB/s of the slowest rank / rank0_alone_gbs) of the 1-GPU e2e"
             line["h2d_probe"] = probe
             line["config5"] = rec5
     if rank == 0:

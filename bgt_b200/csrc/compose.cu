@@ -190,10 +190,16 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 			const uint32_t e = cur + ((p + 1 < off[o + 1] ? Sa[p + 1] : m) - s0);
 			const uint32_t *rs = Sa + off[o + 1];
 			const int nr = off[o + 2] - off[o + 1];
-			int l = 0;
-			for (int len = nr; len > 1;) { const int half = len >> 1; l += rs[l + half] <= cur ? half : 0; len -= half; }
-			int h = l;
-			while (h + 1 < nr && rs[h + 1] < e) ++h;
+			// l = last start <= cur, h = last start < e: two searches over the same starts in lock step (the cuts of a piece are
+			// few but unevenly spread, so counting them one by one keeps a warp waiting for its unluckiest lane)
+			int l = 0, h = 0;
+			for (int len = nr; len > 1;) {
+				const int half = len >> 1;
+				const uint32_t vl = rs[l + half], vh = rs[h + half];
+				l += vl <= cur ? half : 0;
+				h += vh < e ? half : 0;
+				len -= half;
+			}
 			lo = l; cnt = h - l + 1;
 		};
 		int lo_c[CP_CACHE], cnt_c[CP_CACHE];
