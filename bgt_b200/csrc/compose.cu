@@ -227,11 +227,10 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 		for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += t; }
 		if (lane == 31) warp_tot[warp] = x;
 		__syncthreads();
-		int out = x - mine;
-		for (int w = 0; w < warp; ++w) out += warp_tot[w];
-		if (tid == CP_NT - 1) { s_n = out + mine; if (out + mine > CPX - 4 || (nmaps == 2 && out + mine > cap - 4)) s_fail = 1; }
-		__syncthreads();
-		if (s_fail) { if (tid == 0) P.comp_n[slot] = 0; return; }
+		int out = x - mine, n_level = 0;                            // every thread adds up the warp totals itself: no second barrier
+		#pragma unroll
+		for (int w = 0; w < CP_NW; ++w) { const int t = warp_tot[w]; n_level += t; out += w < warp ? t : 0; }
+		if (n_level > CPX - 4 || (nmaps == 2 && n_level > cap - 4)) { if (tid == 0) P.comp_n[slot] = 0; return; }   // (uniform)
 		{
 			int o = j0, p = p_first;
 			auto place = [&](int lo, int cnt) {
@@ -255,8 +254,8 @@ __global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams
 				place(l, c);
 			}
 		}
-		if (tid == 0) noff[nmaps >> 1] = s_n;
-		__syncthreads();
+		if (tid == 0) noff[nmaps >> 1] = n_level;
+		__syncthreads();                                             // (also: warp_tot is free for the next level)
 		{ uint32_t *t = Sa; Sa = Sb; Sb = t; }
 		{ int32_t *t = Da; Da = Db; Db = t; }
 		{ int *t = off; off = noff; noff = t; }
