@@ -22,7 +22,7 @@
 namespace b200 {
 
 constexpr int CP_NT = 256, CP_NW = CP_NT / 32;
-constexpr int CP_RUNS_BIG = 4096, CP_RUNS_SMALL = 3040;   // merged runs of all rows of a group held in shared memory: the small
+constexpr int CP_RUNS_BIG = 4096, CP_RUNS_SMALL = 2752;   // merged runs of all rows of a group held in shared memory: the small
 // variant (49 KB, 4 CTAs per SM) takes every group first, the big one (66 KB, 3 per SM) re-does the few that did not fit
 constexpr int CP_CACHE = 10;       // look-ups per thread kept in registers between the two passes of a level (total/2/CP_NT ~ 8)
 
@@ -40,7 +40,7 @@ __device__ __forceinline__ uint32_t cp_ld_u32_unaligned(const uint8_t *p)
 // Pieces of the maps of one level live back to back in (S, D): S = start of the piece in the map's input coordinates,
 // D = translation.  off[i] .. off[i+1] are the pieces of map i.
 template<int CP_RUNS>
-__global__ void __launch_bounds__(CP_NT) pbwt_compose_kernel(const ComposeParams P)
+__global__ void __launch_bounds__(CP_NT, CP_RUNS == CP_RUNS_SMALL ? 5 : 3) pbwt_compose_kernel(const ComposeParams P)
 {
 	extern __shared__ __align__(16) uint8_t sm[];
 	constexpr int CPX = CP_RUNS + COMP_K + 8;
