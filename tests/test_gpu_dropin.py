@@ -279,3 +279,33 @@ def test_sharded_view_is_identical_and_totals_add_up(tools, tmp_path_factory, de
                 assert (int(m.group(4)), int(m.group(5))) == (an, ac)
         if devices == "all":
             assert "ncclAllReduce" in err
+
+
+def test_view_merges_several_files(tools, tmp_path):
+    """Several BGT files in one query (bgtm_read_core, bgt.c:797-878): sites are merged by (contig, pos, rlen, alleles), a file
+    that lacks a site contributes missing calls, AC/AN are taken over all files' selected samples.  Seam B serves it with one
+    feeder per file (device counts per file, summed on the host); nothing may come from the reference's CPU loop."""
+    rng = np.random.default_rng(31)
+    specs = [("A", 300, 40, 1000, 10, (0.6, 0.3, 0.05, 0.05)), ("B", 200, 24, 1000, 20, (0.5, 0.3, 0.1, 0.1)), ("C", 90, 10, 1490, 30, (0.7, 0.3, 0.0, 0.0))]
+    prefixes = []
+    for tag, n, m, pos0, step, probs in specs:
+        mat = random_matrix(n, m, int(rng.integers(1 << 30)), probs=probs)
+        vcf = tmp_path / (tag + ".vcf")
+        vcf.write_bytes(tools.vcf_text(mat, sample_names=["%s%07d" % (tag, i) for i in range(m // 2)], pos0=pos0, step=step))
+        prefix = str(tmp_path / (tag + ".bgt"))
+        run(tools.REF_BGT, ["import", "-S", prefix, str(vcf)])
+        prefixes.append(prefix)
+    cases = [["-C"], [], ["-f", "AC>0", "-G"], ["-f", "AC>5&&AN>30"], ["-t", "POS,AC,AN,ALT", "-G"], ["-r", "11:1500-2500", "-C"], ["-n", "7"],
+             ["-s", ",A0000001,B0000002", "-s", ",B0000003,C0000001,A0000005", "-f", "AC1>0", "-C"],
+             ["-s", ",A0000001,A0000003", "-C"],                   # no sample of files B and C selected: they never read (bgt.c:338)
+             ["-s", ",B0000001", "-f", "AC>0"]]
+    for args in cases:
+        for files in (prefixes, prefixes[::-1], prefixes[:2]):
+            want = run(tools.REF_BGT, ["view"] + args + files)
+            got, route, _ = run_routed(NEW_BGT, ["view"] + args + files)
+            assert got == want, (args, files)
+            assert want.count(b"\n") > 12, args
+            assert route["seamB_batches"] >= 1 and route["ref_bgtm_read"] == 0 and route["view_fast"] == 0, (args, route)
+    # sanity of the fixture: some sites are shared, some are not (total < sum of the files' sites, > the largest file)
+    single = [run(tools.REF_BGT, ["view", "-G", p]).count(b"\n11\t") for p in prefixes]
+    assert max(single) < run(tools.REF_BGT, ["view", "-G"] + prefixes).count(b"\n11\t") < sum(single)
