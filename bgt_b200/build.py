@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libbgt_b200.so")
-SOURCES = ["api.cu", "pbwt_kernels.cu", "pairwalk.cu", "plane1.cu", "marginal.cu", "compose.cu", "index.cu", "encode.cu", "inflate.cu", "sites.cu", "synth.cu", "flt.cpp"]
+SOURCES = ["api.cu", "pbwt_kernels.cu", "pairwalk.cu", "plane1.cu", "marginal.cu", "margpiece.cu", "compose.cu", "index.cu", "encode.cu", "inflate.cu", "sites.cu", "synth.cu", "flt.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
 LINK_FLAGS = ["--shared", "-cudart", "static", "-Xcompiler", "-fPIC", "-ldl"]

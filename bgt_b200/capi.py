@@ -6,7 +6,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SCAN_COUNTS, SCAN_HAP_BITS, SCAN_HAP_BYTES, SCAN_DEVICE_OUT, SCAN_NO_SPLIT = 0x01, 0x02, 0x04, 0x10, 0x20
-SCAN_NO_COMPOSE, SCAN_NO_SEGMENTS = 0x40, 0x80
+SCAN_NO_COMPOSE, SCAN_NO_SEGMENTS, SCAN_NO_PIECES = 0x40, 0x80, 0x1000
 MAX_GROUPS = 32
 
 _lib = None
@@ -356,7 +356,7 @@ class Query:
             self.h = None
 
 
-def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, hap_bytes=False, out=None, cols_per_thread=0, no_split=False, no_compose=False, no_segments=False):
+def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, hap_bytes=False, out=None, cols_per_thread=0, no_split=False, no_compose=False, no_segments=False, no_pieces=False):
     """b200_scan with host outputs.  Returns dict(n, counts, passed, hap_bits, hap_bytes, totals)."""
     if n_rows is None:
         n_rows = pbf.row_end - row_beg
@@ -373,7 +373,7 @@ def scan(ctx, pbf, query, row_beg=0, n_rows=None, counts=True, hap_bits=False, h
     so = ScanOut()
     so.counts = _ptr(res["counts"]) if counts else None
     so.passed = _ptr(res["passed"])
-    flags = (SCAN_COUNTS if counts else 0) | (int(cols_per_thread) << 8) | (SCAN_NO_SPLIT if no_split else 0) | (SCAN_NO_COMPOSE if no_compose else 0) | (SCAN_NO_SEGMENTS if no_segments else 0)
+    flags = (SCAN_COUNTS if counts else 0) | (int(cols_per_thread) << 8) | (SCAN_NO_SPLIT if no_split else 0) | (SCAN_NO_COMPOSE if no_compose else 0) | (SCAN_NO_SEGMENTS if no_segments else 0) | (SCAN_NO_PIECES if no_pieces else 0)
     if hap_bits:
         flags |= SCAN_HAP_BITS
         so.hap_bits[0], so.hap_bits[1] = _ptr(res["hap_bits"][0]), _ptr(res["hap_bits"][1])

@@ -1304,25 +1304,59 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			if (!c->n0g.reserve(nr * (size_t)(G - 1) * sizeof(int32_t))) return -1;
 			MarginalParams M;
 			memset(&M, 0, sizeof(M));
-			M.n_seg = 1;
-			if (use_comp && !(flags & B200_SCAN_NO_SEGMENTS)) { // segments of 8+ row groups, as many as 512 MB of segment vectors allow
-				const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
-				int seg_groups = 8;
-				const size_t per_seg = (size_t)n_range * (size_t)(G - 1) * marginal_seg_words(pb->m) * sizeof(uint32_t);
-				while (seg_groups < n_grp && per_seg * (size_t)((n_grp + seg_groups - 1) / seg_groups) > ((size_t)512 << 20)) seg_groups *= 2;
-				const int n_seg = (n_grp + seg_groups - 1) / seg_groups;
-				if (n_seg > 1) {
-					if (!c->vseg.reserve(per_seg * (size_t)n_seg) || !c->seg_ok.reserve((size_t)n_range * (size_t)(G - 1) + 16)) return -1;
-					M.comp_start = pb->d_comp_start; M.comp_delta = pb->d_comp_delta; M.comp_n = pb->d_comp_n; M.two_sided = 1; M.n_blk_res = pb->n_blk;
-					M.n_grp = n_grp; M.seg_groups = seg_groups; M.n_seg = n_seg; M.vseg = (uint32_t*)c->vseg.p; M.seg_ok = (uint8_t*)c->seg_ok.p;
-					++c->launches;
-				}
-			}
-			M.img = pb->d_img; M.rowoff = pb->d_rowoff; M.n1 = pb->d_n1; M.blkoff = pb->d_blkoff; M.rows_in_blk = pb->d_rows_in_blk;
+			M.n_seg = 1; M.seg_slots = 1; M.seg_slot_step = 1;
+			M.img = pb->d_img; M.rowoff = pb->d_rowoff; M.n1 = pb->d_n1; M.blkoff = pb->d_blkoff; M.rows_in_blk = pb->d_rows_in_blk; M.nrun = pb->d_nrun0;
 			M.blk_list = nullptr; M.blk_first = b_first; M.blk_ok = d_split_flags; M.tgrp = q->d_tgrp; M.n0g = (int32_t*)c->n0g.p; M.m = pb->m; M.shift = pb->shift; M.n_vec = G - 1;
 			M.blk_row0 = P.blk_row0; M.row_lo = row_beg; M.row_hi = row_beg + n_rows;
-			ok = ok && CU_OK(cudaEventRecord(c->ev[10], c->st)) && CU_OK(launch_marginal(M, n_range, c->st)) && CU_OK(cudaEventRecord(c->ev[11], c->st));
-			++c->launches;
+			const int n_grp = (pb->BS + COMP_K - 1) / COMP_K;
+			const size_t seg_bytes = marginal_seg_words(pb->m) * sizeof(uint32_t);
+			const bool segments = use_comp && !(flags & B200_SCAN_NO_SEGMENTS);
+			const bool pieces = segments && !(flags & B200_SCAN_NO_PIECES) && pb->BS % (8 * COMP_K) == 0 && n_grp < 65536;
+			ok = ok && CU_OK(cudaEventRecord(c->ev[10], c->st));
+			if (pieces) {
+				// margpiece.cu: a vector in front of every 32-row group (and behind the last full one) with prefix counts, then two CTAs per
+				// group that carry the MAP of up to 16 rows instead of the vector; blocks it cannot hold are redone by the row loop from
+				// every 8th vector.  Batches of blocks keep the vectors within 4 GB.
+				const size_t rec_bytes = marginal_rec_words64(pb->m) * 16;
+				const size_t per_blk = (size_t)(G - 1) * (size_t)(n_grp + 1) * (seg_bytes + rec_bytes);
+				int batch = (int)std::max<size_t>(1, ((size_t)4 << 30) / per_blk);
+				if (batch > n_range) batch = n_range;
+				const size_t n_flag = ((size_t)batch * (size_t)(G - 1) + 63) & ~(size_t)63;
+				const int retry_cap = 1 << 16;
+				if (!c->vseg.reserve(per_blk * (size_t)batch + 256) || !c->seg_ok.reserve(2 * n_flag + 64 + (size_t)retry_cap * sizeof(uint2))) return -1;
+				M.comp_start = pb->d_comp_start; M.comp_delta = pb->d_comp_delta; M.comp_n = pb->d_comp_n; M.two_sided = 1; M.n_blk_res = pb->n_blk;
+				M.n_grp = n_grp; M.vseg = (uint32_t*)c->vseg.p;
+				M.vrec = (uint4*)((uint8_t*)c->vseg.p + (((size_t)batch * (size_t)(G - 1) * (size_t)(n_grp + 1) * seg_bytes + 255) & ~(size_t)255));
+				M.seg_ok = (uint8_t*)c->seg_ok.p; M.blk_fail = M.seg_ok + n_flag; M.retry_n = (int*)(M.blk_fail + n_flag); M.retry = (uint2*)(M.blk_fail + n_flag + 64); M.retry_cap = retry_cap;
+				M.seg_slots = n_grp + 1; M.dense = 1;
+				for (int b0 = 0; b0 < n_range && ok; b0 += batch) {
+					const int nb = std::min(batch, n_range - b0);
+					M.blk_first = b_first + b0;
+					M.seg_groups = 1; M.n_seg = n_grp; M.seg_slot_step = 1; M.blk_only = nullptr;
+					ok = CU_OK(cudaMemsetAsync(M.blk_fail, 0, n_flag + 64, c->st)) && CU_OK(launch_marginal_seed(M, nb, c->st)) &&
+					     CU_OK(launch_marginal_pieces(M, nb, c->st));
+					M.seg_groups = 8; M.n_seg = n_grp / 8; M.seg_slot_step = 8; M.blk_only = M.blk_fail;
+					ok = ok && CU_OK(launch_marginal_rows(M, nb, c->st));
+					c->launches += 5;
+				}
+			} else {
+				if (segments) { // segments of 8+ row groups, as many as 512 MB of segment vectors allow
+					int seg_groups = 8;
+					const size_t per_seg = (size_t)n_range * (size_t)(G - 1) * seg_bytes;
+					while (seg_groups < n_grp && per_seg * (size_t)((n_grp + seg_groups - 1) / seg_groups) > ((size_t)512 << 20)) seg_groups *= 2;
+					const int n_seg = (n_grp + seg_groups - 1) / seg_groups;
+					if (n_seg > 1) {
+						if (!c->vseg.reserve(per_seg * (size_t)n_seg) || !c->seg_ok.reserve((size_t)n_range * (size_t)(G - 1) + 16)) return -1;
+						M.comp_start = pb->d_comp_start; M.comp_delta = pb->d_comp_delta; M.comp_n = pb->d_comp_n; M.two_sided = 1; M.n_blk_res = pb->n_blk;
+						M.n_grp = n_grp; M.seg_groups = seg_groups; M.n_seg = n_seg; M.vseg = (uint32_t*)c->vseg.p; M.seg_ok = (uint8_t*)c->seg_ok.p;
+						M.seg_slots = n_seg; M.seg_slot_step = 1;
+						++c->launches;
+					}
+				}
+				ok = ok && CU_OK(launch_marginal(M, n_range, c->st));
+				++c->launches;
+			}
+			ok = ok && CU_OK(cudaEventRecord(c->ev[11], c->st));
 			sp.n0g = (const int32_t*)c->n0g.p; sp.n_vec = G - 1;
 		}
 		sp.blk_split = d_split_flags; sp.n1 = pb->d_n1; sp.row_lo = row_beg; sp.blk_row0 = P.blk_row0; sp.shift = pb->shift;

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 	const int bi = (int)blockIdx.x / P.n_seg, seg = (int)blockIdx.x % P.n_seg;
 	const int blk = P.blk_list ? P.blk_list[bi] : P.blk_first + bi, g = blockIdx.y;
 	if (P.blk_ok && !P.blk_ok[blk]) return;
+	if (P.blk_only && !P.blk_only[(size_t)bi * P.n_vec + g]) return;
 	const int BS = 1 << P.shift;
 	const uint32_t m = (uint32_t)P.m;
 	const uint64_t *roff = P.rowoff + (size_t)blk * (BS + 1);
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 	// ---- the start vector
 	if (row_a == 0) mg_snapshot_vector<NT>(P, blk, g, wpad, V0, V1);
 	else {
-		const uint32_t *src = P.vseg + (((size_t)bi * P.n_vec + g) * P.n_seg + seg) * (size_t)wpad;
+		const uint32_t *src = P.vseg + (((size_t)bi * P.n_vec + g) * P.seg_slots + (size_t)seg * P.seg_slot_step) * (size_t)wpad;
 		for (int w = tid; w < wpad; w += MG_NT) { V0[w] = src[w]; V1[w] = 0; }
 	}
 	__syncthreads();
@@ -395,13 +396,18 @@ __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const Margina
 	if (blk_row + rows > P.row_hi) rows = (int)(P.row_hi - blk_row);
 	const int seg_rows = P.seg_groups * COMP_K;
 	const int n_seg_used = rows > 0 ? (rows + seg_rows - 1) / seg_rows : 0;
-	const int g_end = n_seg_used > 1 ? (n_seg_used - 1) * P.seg_groups : 0;   // groups in front of the last segment start
+	int g_end = n_seg_used > 1 ? (n_seg_used - 1) * P.seg_groups : 0;   // groups in front of the last segment start
+	if (P.dense) {    // a vector in front of every group the scan reaches and behind every full one of them (margpiece.cu)
+		const int n_full = P.rows_in_blk[blk] / COMP_K, n_used = rows > 0 ? (rows + COMP_K - 1) / COMP_K : 0;
+		g_end = n_full < n_used ? n_full : n_used;
+	}
+	const int store_every = P.dense ? 1 : P.seg_groups;
 	const size_t slot0 = (size_t)blk * P.n_grp;
 	if (tid == 0) s_bad = 0;
 	__syncthreads();
 	for (int i = tid; i < g_end; i += MS_NT) if (P.comp_n[slot0 + i] <= 0 || P.comp_n[slot0 + i] > COMP_CAP) s_bad = 1;
 	__syncthreads();
-	if (s_bad || g_end == 0) { if (tid == 0) P.seg_ok[(size_t)bi * P.n_vec + g] = s_bad ? 0 : 1; return; }
+	if (s_bad || (g_end == 0 && !P.dense) || rows <= 0) { if (tid == 0) P.seg_ok[(size_t)bi * P.n_vec + g] = s_bad ? 0 : 1; return; }
 	if (tid == 0) P.seg_ok[(size_t)bi * P.n_vec + g] = 1;
 	mg_snapshot_vector<MS_NT>(P, blk, g, wpad, V0, V1);
 	uint32_t *Vold = V0, *Vnew = V1;
@@ -413,7 +419,12 @@ __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const Margina
 		for (int j = 0; j < PER; ++j) { const int i = tid + j * MS_NT; if (i < np_next) { ps[j] = s[i]; pd[j] = d[i]; } }
 	};
 	fetch(0);
-	uint32_t *out = P.vseg + ((size_t)bi * P.n_vec + g) * P.n_seg * (size_t)wpad;
+	uint32_t *out = P.vseg + ((size_t)bi * P.n_vec + g) * P.seg_slots * (size_t)wpad;
+	if (P.dense) {
+		__syncthreads();
+		for (int w = tid; w < wpad; w += MS_NT) out[w] = w < words ? V0[w] : 0u;
+		if (g_end == 0) return;
+	}
 	const int per = (words + MS_NT - 1) / MS_NT;
 	const int w_lo = tid * per, w_hi = w_lo + per < words ? w_lo + per : words;
 	for (int gg = 0; gg < g_end; ++gg) {
@@ -480,8 +491,8 @@ __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const Margina
 		}
 		__syncthreads();
 		uint32_t *t = Vold; Vold = Vnew; Vnew = t;
-		if ((gg + 1) % P.seg_groups == 0) {
-			uint32_t *dst = out + (size_t)((gg + 1) / P.seg_groups) * wpad;
+		if ((gg + 1) % store_every == 0) {
+			uint32_t *dst = out + (size_t)((gg + 1) / store_every) * wpad;
 			for (int w = tid; w < wpad; w += MS_NT) dst[w] = w < words ? Vold[w] : 0u;
 		}
 	}
@@ -500,17 +511,21 @@ size_t marginal_smem_bytes(int m)
 	return marginal_smem_raw(m, MG_RAW);
 }
 
-cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st)
+cudaError_t launch_marginal_seed(const MarginalParams &P, int n_blk, cudaStream_t st)
 {
-	if (n_blk <= 0 || P.n_vec <= 0) return cudaSuccess;
+	const int words = (P.m + 31) / 32, wpad = (words + 4 + 3) & ~3;
+	const size_t smem_a = (size_t)wpad * 8 + (size_t)COMP_CAP * 8;
+	cudaError_t e = cudaFuncSetAttribute(pbwt_marginal_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+	if (e != cudaSuccess) return e;
+	pbwt_marginal_seed_kernel<<<dim3(n_blk, P.n_vec, 1), MS_NT, smem_a, st>>>(P);
+	return cudaGetLastError();
+}
+
+// the row loop alone (the vectors in front of the segments are there, or n_seg == 1: every block from its snapshot)
+cudaError_t launch_marginal_rows(const MarginalParams &P, int n_blk, cudaStream_t st)
+{
 	cudaError_t e;
-	if (P.n_seg > 1) { // segment vectors first, then every segment on its own (smaller CTAs, three to an SM)
-		const int words = (P.m + 31) / 32, wpad = (words + 4 + 3) & ~3;
-		const size_t smem_a = (size_t)wpad * 8 + (size_t)COMP_CAP * 8;
-		e = cudaFuncSetAttribute(pbwt_marginal_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-		if (e != cudaSuccess) return e;
-		pbwt_marginal_seed_kernel<<<dim3(n_blk, P.n_vec, 1), MS_NT, smem_a, st>>>(P);
-		if ((e = cudaGetLastError()) != cudaSuccess) return e;
+	if (P.n_seg > 1) {
 		const size_t smem_b = marginal_smem_raw(P.m, MG_RAW_SEG);
 		e = cudaFuncSetAttribute(pbwt_marginal_kernel<MG_NT_SEG, MG_RAW_SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
 		if (e != cudaSuccess) return e;
@@ -523,6 +538,16 @@ cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st)
 	dim3 grid(n_blk, P.n_vec, 1);
 	pbwt_marginal_kernel<MG_NT, MG_RAW><<<grid, MG_NT, smem, st>>>(P);
 	return cudaGetLastError();
+}
+
+cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st)
+{
+	if (n_blk <= 0 || P.n_vec <= 0) return cudaSuccess;
+	if (P.n_seg > 1) { // segment vectors first, then every segment on its own (smaller CTAs, three to an SM)
+		const cudaError_t e = launch_marginal_seed(P, n_blk, st);
+		if (e != cudaSuccess) return e;
+	}
+	return launch_marginal_rows(P, n_blk, st);
 }
 
 } // namespace b200

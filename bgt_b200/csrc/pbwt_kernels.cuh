@@ -222,10 +222,25 @@ struct MarginalParams {
 	int two_sided, n_blk_res;   // see comp_first_inverse: the maps of those groups are gathered through instead of scattered through
 	int n_grp, seg_groups, n_seg;
 	uint32_t *vseg; uint8_t *seg_ok;
+	// slots of one (block, vector) in vseg and the distance between the slots of two consecutive segments.  n_seg, 1: the vectors in
+	// front of the segments only.  n_grp + 1, seg_groups: `dense` vectors, one in front of every 32-row group and one behind the
+	// last full group (what margpiece.cu works from; the row loop of marginal.cu reads every seg_groups-th of them)
+	int seg_slots, seg_slot_step, dense;
+	// margpiece.cu
+	const uint32_t *nrun;      // runs of plane 0 per row | first bit << 31 (rowmeta_kernel)
+	uint8_t *blk_fail;         // [launch block][vector] raised by margpiece.cu: redo this block with the row loop
+	uint4 *vrec;               // look-up records of the dense vectors: [launch block][vector][slot][marginal_rec_words64(m)] {64 bits, members in front}
+	uint2 *retry; int *retry_n; int retry_cap;   // chains the small configuration of margpiece.cu gave up on
+	const uint8_t *blk_only;   // the row loop: nullptr, or [launch block][vector] 1 = run (everything else exits)
 };
 size_t marginal_smem_bytes(int m);
 size_t marginal_seg_words(int m);
+__host__ __device__ inline size_t marginal_seg_words_dev(int m) { return (size_t)(((m + 31) / 32 + 4 + 3) & ~3); }
 cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st);
+size_t marginal_rec_words64(int m);
+cudaError_t launch_marginal_seed(const MarginalParams &P, int n_blk, cudaStream_t st);
+cudaError_t launch_marginal_rows(const MarginalParams &P, int n_blk, cudaStream_t st);
+cudaError_t launch_marginal_pieces(const MarginalParams &P, int n_blk, cudaStream_t st);
 
 // split scan: rows of blocks flagged in blk_split take #ALT of group g from the plane-0 marginal -- n0g[row][g] for the
 // first n_vec groups, the rest of n1[row][0] for the last group -- minus the group's other-ALT count

@@ -99,6 +99,7 @@ int           b200_query_counts_stride(const b200_query_t *q); /* 3 + 3*n_groups
 #define B200_SCAN_NO_SPLIT   0x20  /* testing: always walk every tracked column (disable the split scan of count-only full-cohort queries) */
 #define B200_SCAN_NO_COMPOSE 0x40  /* testing: split scan without the composite maps of row groups */
 #define B200_SCAN_NO_SEGMENTS 0x80 /* testing: per-group marginals of the split scan with one CTA per checkpoint block (no segment vectors) */
+#define B200_SCAN_NO_PIECES  0x1000 /* testing: per-group marginals of the split scan by the row loop over bit vectors (marginal.cu) instead of the piece lists (margpiece.cu) */
 #define B200_SCAN_COLS_PER_THREAD(c) ((unsigned)(c) << 8)  /* testing/tuning: force 1, 2, 4 or 8 tracked columns per thread (0 = automatic) */
 
 typedef struct {

@@ -92,6 +92,8 @@ def test_config3_two_groups_against_the_oracle_at_full_width(b200, ctx, cohort, 
     full = b200.scan(ctx, cohort, q, 0, ROWS)
     noseg = b200.scan(ctx, cohort, q, 0, ROWS, no_segments=True)
     assert (noseg["counts"] == full["counts"]).all() and (noseg["passed"] == full["passed"]).all()
+    nopc = b200.scan(ctx, cohort, q, 0, ROWS, no_pieces=True)                 # the row loop over bit vectors instead of the piece lists
+    assert (nopc["counts"] == full["counts"]).all() and (nopc["passed"] == full["passed"]).all()
     img = cohort.image()
     p = oracle.Pbf(img.tobytes())
     for beg, n in ((0, 600), (8192 * 77 - 150, 300), (ROWS - 64, 64)):

@@ -382,14 +382,14 @@ def test_split_scan_equals_general_and_oracle(b200, ctx, oracle, case):
         got = b200.scan(ctx, pb, q, beg, cnt)
         assert (got["counts"] == want["counts"][beg:beg + cnt]).all(), (case, beg)
     q.close()
-    # grouped queries: per-group marginals by bit-vector partition (marginal.cu) + the plane-1 queries
+    # grouped queries: per-group marginals (margpiece.cu piece lists; marginal.cu bit-vector partition with no_pieces / no_segments) + the plane-1 queries
     ns = mat.shape[1] // 2
     for G in (2, 3, 8):
         grp = rng.integers(1, G + 1, size=ns).astype(np.uint32)
         flt = "AC1/AN1>0.1&&AC2==0"
         wantg = oracle.Pbf(pbf).scan(0, n, group=grp, n_groups=G, flt=flt)
         qg = b200.Query(ctx, pb, group=grp, n_groups=G, flt=flt)
-        for kw in (dict(), dict(no_split=True), dict(no_segments=True)):
+        for kw in (dict(), dict(no_split=True), dict(no_segments=True), dict(no_pieces=True)):
             got = b200.scan(ctx, pb, qg, 0, n, **kw)
             assert (got["counts"] == wantg["counts"]).all(), (case, G, kw)
             assert (got["passed"] == wantg["passed"]).all()
