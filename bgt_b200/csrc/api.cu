@@ -1318,26 +1318,40 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 				// group that carry the MAP of up to 16 rows instead of the vector; blocks it cannot hold are redone by the row loop from
 				// every 8th vector.  Batches of blocks keep the vectors within 4 GB.
 				const size_t rec_bytes = marginal_rec_words64(pb->m) * 16;
-				const size_t per_blk = (size_t)(G - 1) * (size_t)(n_grp + 1) * (seg_bytes + rec_bytes);
+				const size_t per_blk = (size_t)(G - 1) * (size_t)(n_grp + 1) * rec_bytes;
 				int batch = (int)std::max<size_t>(1, ((size_t)4 << 30) / per_blk);
 				if (batch > n_range) batch = n_range;
 				const size_t n_flag = ((size_t)batch * (size_t)(G - 1) + 63) & ~(size_t)63;
 				const int retry_cap = 1 << 16;
 				if (!c->vseg.reserve(per_blk * (size_t)batch + 256) || !c->seg_ok.reserve(2 * n_flag + 64 + (size_t)retry_cap * sizeof(uint2))) return -1;
 				M.comp_start = pb->d_comp_start; M.comp_delta = pb->d_comp_delta; M.comp_n = pb->d_comp_n; M.two_sided = 1; M.n_blk_res = pb->n_blk;
-				M.n_grp = n_grp; M.vseg = (uint32_t*)c->vseg.p;
-				M.vrec = (uint4*)((uint8_t*)c->vseg.p + (((size_t)batch * (size_t)(G - 1) * (size_t)(n_grp + 1) * seg_bytes + 255) & ~(size_t)255));
+				M.n_grp = n_grp; M.vseg = nullptr; M.vrec = (uint4*)c->vseg.p;
 				M.seg_ok = (uint8_t*)c->seg_ok.p; M.blk_fail = M.seg_ok + n_flag; M.retry_n = (int*)(M.blk_fail + n_flag); M.retry = (uint2*)(M.blk_fail + n_flag + 64); M.retry_cap = retry_cap;
-				M.seg_slots = n_grp + 1; M.dense = 1;
+				M.seg_slots = n_grp + 1;
+				const size_t vec_words = (size_t)(G - 1) * (size_t)(n_grp + 1) * marginal_rec_words64(pb->m);   // uint4 per block
 				for (int b0 = 0; b0 < n_range && ok; b0 += batch) {
 					const int nb = std::min(batch, n_range - b0);
 					M.blk_first = b_first + b0;
 					M.seg_groups = 1; M.n_seg = n_grp; M.seg_slot_step = 1; M.blk_only = nullptr;
-					ok = CU_OK(cudaMemsetAsync(M.blk_fail, 0, n_flag + 64, c->st)) && CU_OK(launch_marginal_seed(M, nb, c->st)) &&
-					     CU_OK(launch_marginal_pieces(M, nb, c->st));
-					M.seg_groups = 8; M.n_seg = n_grp / 8; M.seg_slot_step = 8; M.blk_only = M.blk_fail;
-					ok = ok && CU_OK(launch_marginal_rows(M, nb, c->st));
-					c->launches += 5;
+					ok = CU_OK(cudaMemsetAsync(M.seg_ok, 1, n_flag, c->st)) && CU_OK(cudaMemsetAsync(M.blk_fail, 0, n_flag + 64, c->st));
+					// The last block of the scan usually has nothing behind it to walk backward from (no resident successor, or the scan ends
+					// inside it): its vectors are one chain of up to 256 steps, twice as long as everybody else's two half chains.  It runs on a
+					// second stream beside the other blocks' vectors and chains.
+					const bool side = nb >= 2 && b0 + nb == n_range;
+					MarginalParams M2 = M;
+					const int nb1 = side ? nb - 1 : nb;
+					if (side) {
+						M2.blk_first = M.blk_first + nb1; M2.vrec = M.vrec + (size_t)nb1 * vec_words;
+						M2.seg_ok = M.seg_ok + (size_t)nb1 * (size_t)(G - 1); M2.blk_fail = M.blk_fail + (size_t)nb1 * (size_t)(G - 1);
+						M2.retry_n = M.retry_n + 1; M2.retry = M.retry + retry_cap / 2; M2.retry_cap = retry_cap / 2; M.retry_cap = retry_cap / 2;
+						ok = ok && CU_OK(cudaEventRecord(c->ev_fin[0], c->st)) && CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_fin[0], 0)) &&
+						     CU_OK(launch_marginal_dense_seed(M2, 1, c->st_walk)) && CU_OK(cudaEventRecord(c->ev_fin[1], c->st_walk));
+					}
+					ok = ok && CU_OK(launch_marginal_dense_seed(M, nb1, c->st)) && CU_OK(launch_marginal_pieces(M, nb1, c->st));
+					if (side) ok = ok && CU_OK(cudaStreamWaitEvent(c->st, c->ev_fin[1], 0)) && CU_OK(launch_marginal_pieces(M2, 1, c->st));
+					M.seg_groups = 8; M.n_seg = n_grp / 8; M.seg_slot_step = 8; M.blk_only = M.blk_fail; M.retry_cap = retry_cap;
+					ok = ok && CU_OK(launch_marginal_rows(M, nb, c->st));     // (flags and vectors of both parts lie back to back)
+					c->launches += side ? 7 : 4;
 				}
 			} else {
 				if (segments) { // segments of 8+ row groups, as many as 512 MB of segment vectors allow

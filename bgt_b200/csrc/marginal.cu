@@ -93,8 +93,18 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 	// ---- the start vector
 	if (row_a == 0) mg_snapshot_vector<NT>(P, blk, g, wpad, V0, V1);
 	else {
-		const uint32_t *src = P.vseg + (((size_t)bi * P.n_vec + g) * P.seg_slots + (size_t)seg * P.seg_slot_step) * (size_t)wpad;
-		for (int w = tid; w < wpad; w += MG_NT) { V0[w] = src[w]; V1[w] = 0; }
+		if (P.vrec) {   // (the vectors of margpiece.cu: look-up records {64 bits, members in front}, one in front of every 32-row group)
+			const int W64 = (int)marginal_rec_words64_dev(P.m);
+			const uint4 *rec = P.vrec + (((size_t)bi * P.n_vec + g) * P.seg_slots + (size_t)seg * P.seg_slot_step) * (size_t)W64;
+			for (int w = tid; w < wpad; w += MG_NT) {
+				uint32_t v = 0;
+				if ((w >> 1) < W64) { const uint4 r = rec[w >> 1]; v = (w & 1) ? r.y : r.x; }
+				V0[w] = v; V1[w] = 0;
+			}
+		} else {
+			const uint32_t *src = P.vseg + (((size_t)bi * P.n_vec + g) * P.seg_slots + (size_t)seg * P.seg_slot_step) * (size_t)wpad;
+			for (int w = tid; w < wpad; w += MG_NT) { V0[w] = src[w]; V1[w] = 0; }
+		}
 	}
 	__syncthreads();
 	int total = 0;                                   // columns of the group (for all-ones rows)
@@ -378,6 +388,57 @@ __global__ void __launch_bounds__(NT) pbwt_marginal_kernel(const MarginalParams 
 // A composite is a list of pieces (start, translation) ordered by start: every thread moves a contiguous stretch of
 // source words, piece by piece, with shared-memory atomicOr (the pieces of the next group are fetched meanwhile).
 constexpr int MS_NT = 1024;
+
+// One step of a vector through a composite map staged in shared memory (cs/cd: piece starts and translations, np pieces).  Every
+// thread owns the words [w_lo, w_hi).  gather: the pieces are cut in the coordinates of Vnew (the thread assembles its own output
+// words); otherwise in those of Vold (the thread scatters its source words with atomicOr; Vnew must be zero).
+__device__ __forceinline__ void mg_advance(const uint32_t *Vold, uint32_t *Vnew, const uint32_t *cs, const int32_t *cd, uint32_t np, uint32_t m,
+                                           int w_lo, int w_hi, bool gather)
+{
+	if (w_lo >= w_hi) return;
+	uint32_t cur = (uint32_t)w_lo * 32;
+	const uint32_t end = (uint32_t)w_hi * 32 < m ? (uint32_t)w_hi * 32 : m;
+	uint32_t k = 0;
+	for (uint32_t len = np; len > 1;) { const uint32_t half = len >> 1; k += cs[k + half] <= cur ? half : 0u; len -= half; }
+	uint32_t next = k + 1 < np ? cs[k + 1] : m;
+	uint32_t delta = (uint32_t)cd[k];
+	// ONE loop over the stretches between consecutive piece starts and word boundaries (a loop over words with a loop over pieces
+	// inside makes the lanes of a warp wait for each other at every word)
+	if (gather) {
+		uint32_t acc = 0;
+		while (cur < end) {
+			const uint32_t wend = (cur | 31u) + 1u;
+			uint32_t stop = next < wend ? next : wend;
+			if (stop > end) stop = end;
+			const uint32_t take = stop - cur, src = cur + delta, sw = src >> 5, sb = src & 31u;
+			if (src < m) {                                          // (a well-formed map never leaves [0, m))
+				const uint32_t word = __funnelshift_r(Vold[sw], Vold[sw + 1], sb);   // bits src .. src+31 (the vectors carry spare zero words)
+				acc |= (word & (take == 32 ? 0xffffffffu : ((1u << take) - 1u))) << (cur & 31u);
+			}
+			cur = stop;
+			if (cur == wend || cur == end) { Vnew[(cur - 1u) >> 5] = acc; acc = 0; }
+			if (cur >= next) { ++k; next = k + 1 < np ? cs[k + 1] : m; delta = (uint32_t)cd[k]; }
+		}
+	} else {
+		while (cur < end) {
+			const uint32_t wend = (cur | 31u) + 1u;
+			uint32_t stop = next < wend ? next : wend;
+			if (stop > end) stop = end;
+			const uint32_t take = stop - cur;
+			const uint32_t piece = (Vold[cur >> 5] >> (cur & 31u)) & (take == 32 ? 0xffffffffu : ((1u << take) - 1u));
+			if (piece) {
+				const uint32_t dst = cur + delta, dw = dst >> 5, db = dst & 31u;
+				if (dst < m) {                                      // (a well-formed map never leaves [0, m))
+					atomicOr(&Vnew[dw], piece << db);
+					if (db && (piece >> (32 - db))) atomicOr(&Vnew[dw + 1], piece >> (32 - db));
+				}
+			}
+			cur = stop;
+			if (cur >= next) { ++k; next = k + 1 < np ? cs[k + 1] : m; delta = (uint32_t)cd[k]; }
+		}
+	}
+}
+
 __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const MarginalParams P)
 {
 	extern __shared__ __align__(16) uint8_t sm[];
@@ -396,18 +457,13 @@ __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const Margina
 	if (blk_row + rows > P.row_hi) rows = (int)(P.row_hi - blk_row);
 	const int seg_rows = P.seg_groups * COMP_K;
 	const int n_seg_used = rows > 0 ? (rows + seg_rows - 1) / seg_rows : 0;
-	int g_end = n_seg_used > 1 ? (n_seg_used - 1) * P.seg_groups : 0;   // groups in front of the last segment start
-	if (P.dense) {    // a vector in front of every group the scan reaches and behind every full one of them (margpiece.cu)
-		const int n_full = P.rows_in_blk[blk] / COMP_K, n_used = rows > 0 ? (rows + COMP_K - 1) / COMP_K : 0;
-		g_end = n_full < n_used ? n_full : n_used;
-	}
-	const int store_every = P.dense ? 1 : P.seg_groups;
+	const int g_end = n_seg_used > 1 ? (n_seg_used - 1) * P.seg_groups : 0;   // groups in front of the last segment start
 	const size_t slot0 = (size_t)blk * P.n_grp;
 	if (tid == 0) s_bad = 0;
 	__syncthreads();
 	for (int i = tid; i < g_end; i += MS_NT) if (P.comp_n[slot0 + i] <= 0 || P.comp_n[slot0 + i] > COMP_CAP) s_bad = 1;
 	__syncthreads();
-	if (s_bad || (g_end == 0 && !P.dense) || rows <= 0) { if (tid == 0) P.seg_ok[(size_t)bi * P.n_vec + g] = s_bad ? 0 : 1; return; }
+	if (s_bad || g_end == 0) { if (tid == 0) P.seg_ok[(size_t)bi * P.n_vec + g] = s_bad ? 0 : 1; return; }
 	if (tid == 0) P.seg_ok[(size_t)bi * P.n_vec + g] = 1;
 	mg_snapshot_vector<MS_NT>(P, blk, g, wpad, V0, V1);
 	uint32_t *Vold = V0, *Vnew = V1;
@@ -420,11 +476,6 @@ __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const Margina
 	};
 	fetch(0);
 	uint32_t *out = P.vseg + ((size_t)bi * P.n_vec + g) * P.seg_slots * (size_t)wpad;
-	if (P.dense) {
-		__syncthreads();
-		for (int w = tid; w < wpad; w += MS_NT) out[w] = w < words ? V0[w] : 0u;
-		if (g_end == 0) return;
-	}
 	const int per = (words + MS_NT - 1) / MS_NT;
 	const int w_lo = tid * per, w_hi = w_lo + per < words ? w_lo + per : words;
 	for (int gg = 0; gg < g_end; ++gg) {
@@ -437,64 +488,112 @@ __global__ void __launch_bounds__(MS_NT) pbwt_marginal_seed_kernel(const Margina
 		// two-sided maps (compose.cu): the groups of the second half carry the INVERSE map, whose pieces are cut in the coordinates
 		// behind the group -- the vector is gathered through it (every thread owns its output words) instead of scattered
 		const bool inv_map = gg >= comp_first_inverse(blk, P.n_blk_res, P.rows_in_blk[blk], 1 << P.shift, P.n_grp, P.two_sided);
-		if (w_lo < w_hi && inv_map) {
-			uint32_t k = 0;
-			{
-				const uint32_t pos0 = (uint32_t)w_lo * 32;
-				for (uint32_t len = np; len > 1;) { const uint32_t half = len >> 1; k += cs[k + half] <= pos0 ? half : 0u; len -= half; }
-			}
-			for (int w = w_lo; w < w_hi; ++w) {
-				const uint32_t pos = (uint32_t)w * 32, lim = pos + 32 < m ? pos + 32 : m;
-				uint32_t cur = pos, acc = 0;
-				while (cur < lim) {
-					const uint32_t next = k + 1 < np ? cs[k + 1] : m;
-					const uint32_t stop = next < lim ? next : lim;
-					if (stop > cur) {
-						const uint32_t take = stop - cur, src = cur + (uint32_t)cd[k], sw = src >> 5, sb = src & 31u;
-						if (src < m) {                                      // (a well-formed map never leaves [0, m))
-							const uint32_t word = __funnelshift_r(Vold[sw], Vold[sw + 1], sb);   // bits src .. src+31 (the vectors carry spare zero words)
-							acc |= (word & (take == 32 ? 0xffffffffu : ((1u << take) - 1u))) << (cur - pos);
-						}
-						cur = stop;
-					}
-					if (cur >= next) ++k;
-				}
-				Vnew[w] = acc;
-			}
-		} else if (w_lo < w_hi) {
-			uint32_t k = 0;
-			{
-				const uint32_t pos0 = (uint32_t)w_lo * 32;
-				for (uint32_t len = np; len > 1;) { const uint32_t half = len >> 1; k += cs[k + half] <= pos0 ? half : 0u; len -= half; }
-			}
-			for (int w = w_lo; w < w_hi; ++w) {
-				const uint32_t bits = Vold[w], pos = (uint32_t)w * 32, lim = pos + 32 < m ? pos + 32 : m;
-				uint32_t cur = pos;
-				while (cur < lim) {
-					const uint32_t next = k + 1 < np ? cs[k + 1] : m;
-					const uint32_t stop = next < lim ? next : lim;
-					if (stop > cur) {
-						const uint32_t take = stop - cur;
-						const uint32_t piece = (bits >> (cur - pos)) & (take == 32 ? 0xffffffffu : ((1u << take) - 1u));
-						if (piece) {
-							const uint32_t dst = cur + (uint32_t)cd[k], dw = dst >> 5, db = dst & 31u;
-							if (dst < m) {                                  // (a well-formed map never leaves [0, m))
-								atomicOr(&Vnew[dw], piece << db);
-								if (db && (piece >> (32 - db))) atomicOr(&Vnew[dw + 1], piece >> (32 - db));
-							}
-						}
-						cur = stop;
-					}
-					if (cur >= next) ++k;
-				}
-			}
-		}
+		mg_advance(Vold, Vnew, cs, cd, np, m, w_lo, w_hi, inv_map);
 		__syncthreads();
 		uint32_t *t = Vold; Vold = Vnew; Vnew = t;
-		if ((gg + 1) % store_every == 0) {
-			uint32_t *dst = out + (size_t)((gg + 1) / store_every) * wpad;
+		if ((gg + 1) % P.seg_groups == 0) {
+			uint32_t *dst = out + (size_t)((gg + 1) / P.seg_groups) * wpad;
 			for (int w = tid; w < wpad; w += MS_NT) dst[w] = w < words ? Vold[w] : 0u;
 		}
+	}
+}
+
+// The vectors margpiece.cu works from: one in front of every 32-row group the scan reaches and one behind every full one of them,
+// as look-up records {64 bits of the vector, members of the group in front of them}.  Two CTAs per block where the block is full,
+// scanned to its end and followed by a resident block (the condition under which compose.cu builds inverse maps for the second half
+// of the groups): one walks forward from the block's snapshot to the middle, the other BACKWARD from the next block's snapshot --
+// an inverse map, cut in the coordinates behind its group, scatters a vector from behind the group to in front of it.
+// seg_ok must have been set to 1 on the stream; a missing composite map clears it.
+__global__ void __launch_bounds__(MS_NT, 2) pbwt_marginal_dense_seed_kernel(const MarginalParams P)
+{
+	extern __shared__ __align__(16) uint8_t sm[];
+	const int words = (P.m + 31) / 32, wpad = (words + 4 + 3) & ~3;
+	uint32_t *V0 = (uint32_t*)sm, *V1 = V0 + wpad;
+	uint32_t *cs = V1 + wpad;                        // [COMP_CAP] piece starts
+	int32_t *cd = (int32_t*)(cs + COMP_CAP);         // [COMP_CAP] translations
+	__shared__ int s_bad;
+	__shared__ uint32_t s_warp[MS_NT / 32];
+	constexpr int PER = COMP_CAP / MS_NT;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int bi = (int)(blockIdx.x >> 1), side = (int)(blockIdx.x & 1), blk = P.blk_first + bi, g = blockIdx.y;
+	if (P.blk_ok && !P.blk_ok[blk]) return;
+	const uint32_t m = (uint32_t)P.m;
+	const int BS = 1 << P.shift, n_grp = P.n_grp;
+	const long long blk_row = P.blk_row0 + ((long long)blk << P.shift);
+	const int rows_all = P.rows_in_blk[blk];
+	int rows = rows_all;
+	if (blk_row + rows > P.row_hi) rows = (int)(P.row_hi - blk_row);
+	if (rows <= 0) return;
+	const int n_full = rows_all / COMP_K, n_used = (rows + COMP_K - 1) / COMP_K;
+	const int n_adv = n_full < n_used ? n_full : n_used;             // vectors 0 .. n_adv are wanted
+	const int first_inv = comp_first_inverse(blk, P.n_blk_res, rows_all, BS, n_grp, P.two_sided);
+	const bool two = first_inv < n_grp && rows == BS && n_grp >= 4;
+	if (side == 1 && !two) return;
+	// the groups this CTA crosses, in order: forward g_a, g_a + 1, ... g_b - 1, or backward g_a - 1, g_a - 2, ... g_b
+	const int g_a = side ? n_grp : 0, g_b = side ? n_grp / 2 + 1 : (two ? n_grp / 2 : n_adv);
+	const int n_cross = side ? g_a - g_b : g_b - g_a;
+	const size_t slot0 = (size_t)blk * n_grp;
+	if (tid == 0) s_bad = 0;
+	__syncthreads();
+	for (int i = tid; i < n_cross; i += MS_NT) { const int gg = side ? g_a - 1 - i : g_a + i; if (P.comp_n[slot0 + gg] <= 0 || P.comp_n[slot0 + gg] > COMP_CAP) s_bad = 1; }
+	__syncthreads();
+	if (s_bad) { if (tid == 0) P.seg_ok[(size_t)bi * P.n_vec + g] = 0; return; }
+	mg_snapshot_vector<MS_NT>(P, side ? blk + 1 : blk, g, wpad, V0, V1);
+	uint32_t *Vold = V0, *Vnew = V1;
+	uint32_t ps[PER]; int32_t pd[PER]; int np_next = 0;
+	auto fetch = [&](int gg) {
+		np_next = P.comp_n[slot0 + gg];
+		const uint32_t *s = P.comp_start + (slot0 + gg) * COMP_CAP; const int32_t *d = P.comp_delta + (slot0 + gg) * COMP_CAP;
+		#pragma unroll
+		for (int j = 0; j < PER; ++j) { const int i = tid + j * MS_NT; if (i < np_next) { ps[j] = s[i]; pd[j] = d[i]; } }
+	};
+	if (n_cross > 0) fetch(side ? g_a - 1 : g_a);
+	const int W64 = (int)marginal_rec_words64_dev(P.m);
+	uint4 *out = P.vrec + ((size_t)bi * P.n_vec + g) * P.seg_slots * (size_t)W64;
+	const int per64 = (W64 + MS_NT - 1) / MS_NT;
+	const int r_lo = tid * per64, r_hi = r_lo + per64 < W64 ? r_lo + per64 : W64;
+	// the vector as look-up records (all threads; V complete and not written meanwhile)
+	auto store = [&](const uint32_t *V, int slot) {
+		uint32_t s = 0;
+		for (int w = r_lo; w < r_hi; ++w) s += (uint32_t)(__popc(V[2 * w]) + __popc(V[2 * w + 1]));
+		uint32_t x = s;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += t; }
+		if (lane == 31) s_warp[warp] = x;
+		__syncthreads();
+		uint32_t run = x - s;
+		{
+			const uint32_t v = lane < warp ? s_warp[lane] : 0u;       // (32 warps: one lane per warp total)
+			uint32_t y = v;
+			#pragma unroll
+			for (int d = 16; d; d >>= 1) y += __shfl_xor_sync(0xffffffffu, y, d);
+			run += y;
+		}
+		uint4 *dst = out + (size_t)slot * W64;
+		for (int w = r_lo; w < r_hi; ++w) {
+			const uint32_t a = V[2 * w], b = V[2 * w + 1];
+			dst[w] = make_uint4(a, b, run, 0u);
+			run += (uint32_t)(__popc(a) + __popc(b));
+		}
+	};
+	__syncthreads();
+	store(Vold, g_a);
+	const int per = (words + MS_NT - 1) / MS_NT;
+	const int w_lo = tid * per, w_hi = w_lo + per < words ? w_lo + per : words;
+	for (int i = 0; i < n_cross; ++i) {
+		const int gg = side ? g_a - 1 - i : g_a + i;
+		const uint32_t np = (uint32_t)np_next;
+		#pragma unroll
+		for (int j = 0; j < PER; ++j) { const uint32_t q = tid + j * MS_NT; if (q < np) { cs[q] = ps[j]; cd[q] = pd[j]; } }
+		for (int w = tid; w < wpad; w += MS_NT) Vnew[w] = 0;
+		if (i + 1 < n_cross) fetch(side ? gg - 1 : gg + 1);
+		__syncthreads();                                              // (also: everybody is done with s_warp and with reading Vnew's old content)
+		// forward through a forward map and backward through an inverse map: the pieces are cut where the vector comes from -> scatter;
+		// forward through an inverse map (a block that is not walked from both ends): gather
+		mg_advance(Vold, Vnew, cs, cd, np, m, w_lo, w_hi, !side && gg >= first_inv);
+		__syncthreads();
+		uint32_t *t = Vold; Vold = Vnew; Vnew = t;
+		store(Vold, side ? gg : gg + 1);
 	}
 }
 
@@ -518,6 +617,16 @@ cudaError_t launch_marginal_seed(const MarginalParams &P, int n_blk, cudaStream_
 	cudaError_t e = cudaFuncSetAttribute(pbwt_marginal_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
 	if (e != cudaSuccess) return e;
 	pbwt_marginal_seed_kernel<<<dim3(n_blk, P.n_vec, 1), MS_NT, smem_a, st>>>(P);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_marginal_dense_seed(const MarginalParams &P, int n_blk, cudaStream_t st)
+{
+	const int words = (P.m + 31) / 32, wpad = (words + 4 + 3) & ~3;
+	const size_t smem_a = (size_t)wpad * 8 + (size_t)COMP_CAP * 8;
+	cudaError_t e = cudaFuncSetAttribute(pbwt_marginal_dense_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+	if (e != cudaSuccess) return e;
+	pbwt_marginal_dense_seed_kernel<<<dim3(2 * n_blk, P.n_vec, 1), MS_NT, smem_a, st>>>(P);
 	return cudaGetLastError();
 }
 

@@ -19,8 +19,8 @@
 // list with one more row is a segmented copy: every run takes the pieces it overlaps, clipped, to its landing place.
 //
 // Reference rows come from the seed kernel of marginal.cu (the block's start vector pushed through the composite maps of
-// compose.cu), stored in front of EVERY 32-row group; marginal_rank_kernel turns each into look-up records {64 bits, members in
-// front of them}.  A group is worked on from both ends, by two CTAs ("chains"): rows 0..15 forward from the vector in front of
+// compose.cu), stored in front of EVERY 32-row group as look-up records {64 bits, members in front of them}
+// (pbwt_marginal_dense_seed_kernel).  A group is worked on from both ends, by two CTAs ("chains"): rows 0..15 forward from the vector in front of
 // the group (list_k: row k -> group start), rows 31..16 backward from the vector behind it (list_k: row k -> group end), so that
 // no list holds the cuts of more than 16 rows.  The look-ups of a row are issued when its list is ready and consumed one row
 // later: their latency hides behind the next row's composition.
@@ -67,55 +67,6 @@ __device__ __forceinline__ uint32_t mp_rank(const uint4 r, uint32_t x)   // memb
 {
 	const unsigned long long bits = (unsigned long long)r.x | (unsigned long long)r.y << 32;
 	return r.z + (uint32_t)__popcll(bits & ((1ull << (x & 63u)) - 1ull));
-}
-
-// groups of a block the scan reaches and that have a vector behind them (same rule in the seed kernel, marginal.cu)
-__device__ __forceinline__ int mp_n_adv(int rows_all, int rows)
-{
-	const int n_full = rows_all / COMP_K, n_used = rows > 0 ? (rows + COMP_K - 1) / COMP_K : 0;
-	return n_full < n_used ? n_full : n_used;
-}
-
-// ------------------------------------------------------------------------------------------------ look-up records
-
-// one CTA per stored vector: {64 bits of the vector, members in front of them} per 64 ranks
-__global__ void __launch_bounds__(256) marginal_rank_kernel(const MarginalParams P)
-{
-	__shared__ uint32_t s_warp[8];
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int slot = (int)(blockIdx.x % (unsigned)P.seg_slots), bi = (int)(blockIdx.x / (unsigned)P.seg_slots), g = blockIdx.y;
-	const int blk = P.blk_first + bi;
-	if (P.blk_ok && !P.blk_ok[blk]) return;
-	if (!P.seg_ok[(size_t)bi * P.n_vec + g]) return;
-	const long long blk_row = P.blk_row0 + ((long long)blk << P.shift);
-	const int rows_all = P.rows_in_blk[blk];
-	int rows = rows_all;
-	if (blk_row + rows > P.row_hi) rows = (int)(P.row_hi - blk_row);
-	if (rows <= 0 || slot > mp_n_adv(rows_all, rows)) return;
-	const int W64 = (P.m + 63) / 64 + 1, wpad = (int)marginal_seg_words_dev(P.m);
-	const size_t vec = ((size_t)bi * P.n_vec + g) * P.seg_slots + slot;
-	const uint32_t *src = P.vseg + vec * (size_t)wpad;
-	uint4 *dst = P.vrec + vec * (size_t)W64;
-	const int per = (W64 + 255) / 256;
-	const int w0 = tid * per, w1 = w0 + per < W64 ? w0 + per : W64;
-	uint32_t s = 0;
-	for (int w = w0; w < w1; ++w) {
-		const uint32_t a = 2 * w < wpad ? src[2 * w] : 0u, b = 2 * w + 1 < wpad ? src[2 * w + 1] : 0u;
-		s += (uint32_t)(__popc(a) + __popc(b));
-	}
-	uint32_t x = s;
-	#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += t; }
-	if (lane == 31) s_warp[warp] = x;
-	__syncthreads();
-	uint32_t run = x - s;
-	#pragma unroll
-	for (int w = 0; w < 8; ++w) if (w < warp) run += s_warp[w];
-	for (int w = w0; w < w1; ++w) {
-		const uint32_t a = 2 * w < wpad ? src[2 * w] : 0u, b = 2 * w + 1 < wpad ? src[2 * w + 1] : 0u;
-		dst[w] = make_uint4(a, b, run, 0u);
-		run += (uint32_t)(__popc(a) + __popc(b));
-	}
 }
 
 // ------------------------------------------------------------------------------------------------ one chain
@@ -437,7 +388,7 @@ __global__ void __launch_bounds__(MP_NT) pbwt_marginal_piece_long_kernel(const M
 
 size_t marginal_rec_words64(int m) { return (size_t)((m + 63) / 64) + 1; }
 
-// Queues the look-up records and the two chain launches.  blk_fail and retry_n must have been cleared on the stream.
+// Queues the two chain launches (the vectors are there: launch_marginal_dense_seed).  blk_fail and retry_n must have been cleared on the stream.
 cudaError_t launch_marginal_pieces(const MarginalParams &P, int n_blk, cudaStream_t st)
 {
 	if (n_blk <= 0 || P.n_vec <= 0) return cudaSuccess;
@@ -445,8 +396,6 @@ cudaError_t launch_marginal_pieces(const MarginalParams &P, int n_blk, cudaStrea
 	const size_t sa = mp_smem_bytes<MpSmall>(), sb = mp_smem_bytes<MpLong>();
 	if ((e = cudaFuncSetAttribute(pbwt_marginal_piece_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa)) != cudaSuccess) return e;
 	if ((e = cudaFuncSetAttribute(pbwt_marginal_piece_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)) != cudaSuccess) return e;
-	marginal_rank_kernel<<<dim3((unsigned)((long long)n_blk * P.seg_slots), P.n_vec, 1), 256, 0, st>>>(P);
-	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	pbwt_marginal_piece_kernel<<<dim3((unsigned)((long long)n_blk * P.n_grp * 2), P.n_vec, 1), MP_NT, sa, st>>>(P);
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	pbwt_marginal_piece_long_kernel<<<dim3(n_blk + MP_RETRY_CTAS, P.n_vec, 1), MP_NT, sb, st>>>(P, n_blk);

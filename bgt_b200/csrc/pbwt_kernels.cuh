@@ -225,7 +225,7 @@ struct MarginalParams {
 	// slots of one (block, vector) in vseg and the distance between the slots of two consecutive segments.  n_seg, 1: the vectors in
 	// front of the segments only.  n_grp + 1, seg_groups: `dense` vectors, one in front of every 32-row group and one behind the
 	// last full group (what margpiece.cu works from; the row loop of marginal.cu reads every seg_groups-th of them)
-	int seg_slots, seg_slot_step, dense;
+	int seg_slots, seg_slot_step;
 	// margpiece.cu
 	const uint32_t *nrun;      // runs of plane 0 per row | first bit << 31 (rowmeta_kernel)
 	uint8_t *blk_fail;         // [launch block][vector] raised by margpiece.cu: redo this block with the row loop
@@ -238,6 +238,8 @@ size_t marginal_seg_words(int m);
 __host__ __device__ inline size_t marginal_seg_words_dev(int m) { return (size_t)(((m + 31) / 32 + 4 + 3) & ~3); }
 cudaError_t launch_marginal(const MarginalParams &P, int n_blk, cudaStream_t st);
 size_t marginal_rec_words64(int m);
+__host__ __device__ inline size_t marginal_rec_words64_dev(int m) { return (size_t)((m + 63) / 64) + 1; }
+cudaError_t launch_marginal_dense_seed(const MarginalParams &P, int n_blk, cudaStream_t st);
 cudaError_t launch_marginal_seed(const MarginalParams &P, int n_blk, cudaStream_t st);
 cudaError_t launch_marginal_rows(const MarginalParams &P, int n_blk, cudaStream_t st);
 cudaError_t launch_marginal_pieces(const MarginalParams &P, int n_blk, cudaStream_t st);

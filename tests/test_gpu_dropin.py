@@ -35,6 +35,8 @@ def run_routed(exe, args, env=None):
     e["BGT_B200_ROUTE"] = "1"
     r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
     err = r.stderr.decode()
+    if r.returncode != 0:
+        print(err)                                                # (pytest shortens the assertion's repr)
     assert r.returncode == 0, (exe, args, err[-500:])
     m = re.search(r"\[b200 route\] (.*)", err)
     assert m, "no route line on stderr: %r" % err[-300:]
