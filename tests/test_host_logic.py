@@ -45,12 +45,12 @@ def test_python_binding_flags_match_the_header():
     from bgt_b200 import capi
     txt = open(os.path.join(ROOT, "include", "bgt_b200.h")).read()
     defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+B200_(SCAN_[A-Z_]+)\s+(0x[0-9a-fA-F]+|\d+)\b", txt)}
-    assert {"SCAN_COUNTS", "SCAN_HAP_BITS", "SCAN_HAP_BYTES", "SCAN_DEVICE_OUT", "SCAN_NO_SPLIT", "SCAN_NO_COMPOSE", "SCAN_NO_SEGMENTS"} <= set(defs)
+    assert {"SCAN_COUNTS", "SCAN_HAP_BITS", "SCAN_HAP_BYTES", "SCAN_DEVICE_OUT", "SCAN_NO_SPLIT", "SCAN_NO_COMPOSE", "SCAN_NO_SEGMENTS", "SCAN_NO_PIECES"} <= set(defs)
     for name, val in defs.items():
         assert getattr(capi, name) == val, name
     vals = list(defs.values())
     assert all(v and v & (v - 1) == 0 for v in vals) and len(set(vals)) == len(vals)   # single, distinct bits
-    assert all(v < 0x100 for v in vals)                                                # bits 8-11 carry B200_SCAN_COLS_PER_THREAD
+    assert all(v & 0xf00 == 0 for v in vals)                                           # bits 8-11 carry B200_SCAN_COLS_PER_THREAD
 
 
 def test_seam_a_library_exports_pbwt_api():
