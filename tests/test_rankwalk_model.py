@@ -212,6 +212,102 @@ def test_group_marginals_by_bit_vector_partition(oracle):
             assert cnt == int(((mat[r] & 1) == 1)[in_group].sum())        # ones of the plane-0 row inside the group
 
 
+def run_table(rle, m):
+    """margpiece.cu's run table of a plane-0 row: per run (RLE bytes of the same symbol merged, empty bytes skipped) its start,
+    its landing place (0-runs in front in order, 1-runs behind the m - n1 zeros in order, pbwt.c:79-88) and its index in landing
+    order; runs alternate, so with b0 = bit of the first run and nzr = number of 0-runs:  zi(j) = (bit_j ? nzr : 0) + (j >> 1)."""
+    c = np.frombuffer(rle, dtype=np.uint8).astype(np.int64)
+    L, b = rle_len(c), c & 1
+    keep = L > 0
+    L, b = L[keep], b[keep]
+    first = np.ones(len(L), bool)
+    first[1:] = b[1:] != b[:-1]
+    run_id = np.cumsum(first) - 1
+    R = int(run_id[-1]) + 1
+    length = np.bincount(run_id, weights=L, minlength=R).astype(np.int64)
+    bit = b[first]
+    start = np.cumsum(length) - length
+    ones_before = np.cumsum(length * bit) - length * bit
+    n1 = int((length * bit).sum())
+    zt = m - n1
+    land = np.where(bit == 1, zt + ones_before, start - ones_before)
+    nzr = int((bit == 0).sum())
+    j = np.arange(R)
+    zi = np.where(bit == 1, nzr, 0) + (j >> 1)
+    assert sorted(zi.tolist()) == list(range(R)) and (np.diff(land[np.argsort(zi)]) > 0).all()   # landing order is a permutation, ascending
+    return start, land, zi, zt, R
+
+
+def compose_list(d, dl, m, U, V, S):
+    """One more row on a piece list (d, dl): the runs tile the list's axis at U (ascending), run t goes to V[t] on the other side of
+    the row and is the S[t]-th run there; every run takes the pieces it overlaps, clipped -- margpiece.cu's segmented copy."""
+    R = len(U)
+    UU = np.append(U, m)
+    lo = np.searchsorted(d, U, side="right") - 1
+    hi = np.searchsorted(d, UU[1:] - 1, side="right") - 1
+    C = np.zeros(R, dtype=np.int64)
+    C[S] = hi - lo + 1
+    off = np.concatenate([[0], np.cumsum(C)])
+    t_of = np.zeros(R, dtype=np.int64)
+    t_of[S] = np.arange(R)
+    o = np.arange(off[-1])
+    s = np.searchsorted(off, o, side="right") - 1
+    t = t_of[s]
+    i = lo[t] + (o - off[s])
+    return V[t] + np.maximum(d[i], U[t]) - U[t], dl[i] + U[t] - V[t]
+
+
+def tail_count(d, dl, m, zt, P):
+    """members of the group on ranks [zt, m) of the list's axis: per piece two look-ups in the reference row's prefix counts"""
+    e = np.append(d[1:], m)
+    a = np.maximum(d, zt)
+    ok = e > a
+    return int((P[e[ok] + dl[ok]] - P[a[ok] + dl[ok]]).sum())
+
+
+def test_group_marginals_by_piece_lists(oracle):
+    """The chains of margpiece.cu on encoded files: rows 0..15 of every 32-row group forward from the group vector in front of
+    it, rows 31..16 backward from the one behind it; ones of the group in row k = members on ranks [m - n1_k, m) behind row k."""
+    rng = np.random.default_rng(7)
+    for mat, shift in ((haplo_matrix(200, 203, 29), 6), (random_matrix(96, 64, 30), 5), (edge_rows(300), 5)):
+        pbf = oracle.encode_pbf(mat, shift=shift)
+        m, rows, snaps = plane0_rows(pbf, oracle)
+        in_group = rng.random(m) < 0.4
+        BS, K, H = 1 << shift, 32, 16
+        want = [int(((mat[r] & 1) == 1)[in_group].sum()) for r in range(len(rows))]
+        # the group vector in front of every row (what the seed kernel stores every 32 rows), by the bit-vector partition
+        vec = []
+        for r, rle in enumerate(rows):
+            if r % BS == 0:
+                V = in_group[snaps[r // BS]]
+            vec.append(V)
+            V, _ = gather_partition(V, rle, m)
+        vec.append(V)
+        got = [None] * len(rows)
+        for g0 in range(0, len(rows), K):
+            full = g0 + K <= len(rows) and (g0 % BS) + K <= BS
+            # forward
+            P = np.concatenate([[0], np.cumsum(vec[g0])])
+            d, dl = np.array([0]), np.array([0])
+            for r in range(g0, min(g0 + (H if full else K), len(rows))):
+                start, land, zi, zt, R = run_table(rows[r], m)
+                d, dl = compose_list(d, dl, m, start, land, zi)
+                assert d[0] == 0 and (np.diff(d) > 0).all() and len(d) <= 1 + sum(run_table(rows[q], m)[4] - 1 for q in range(g0, r + 1))
+                got[r] = tail_count(d, dl, m, zt, P)
+            if not full:
+                continue
+            # backward from the vector behind the group: in landing order the runs are U = land, V = start, and go back to run order
+            P = np.concatenate([[0], np.cumsum(vec[g0 + K])])
+            d, dl = np.array([0]), np.array([0])
+            for r in range(g0 + K - 1, g0 + H - 1, -1):
+                start, land, zi, zt, R = run_table(rows[r], m)
+                got[r] = tail_count(d, dl, m, zt, P)               # (the list still belongs to row r + 1)
+                U, V, S = np.zeros(R, np.int64), np.zeros(R, np.int64), np.zeros(R, np.int64)
+                U[zi], V[zi], S[zi] = land, start, np.arange(R)
+                d, dl = compose_list(d, dl, m, U, V, S)
+        assert got == want
+
+
 def both_planes(pbf_bytes, orc):
     """(m, shift, [(plane-0 RLE, plane-1 RLE) per row], [(S0, S1) per block])."""
     p = orc.Pbf(pbf_bytes)
