@@ -94,6 +94,9 @@ struct b200_ctx_s {
 	// fused load + scan: the pair walk + finalize of a chunk run on st_walk beside the composite maps of the next chunks (st), and
 	// the chunk's results go home on st_d2h
 	cudaStream_t st_d2h = nullptr, st_walk = nullptr;
+	// the composite maps of consecutive chunks alternate between st and st_comp2: the last wave of one launch overlaps the first of the next
+	cudaStream_t st_comp2 = nullptr;
+	cudaEvent_t ev_comp2 = nullptr;
 	cudaEvent_t ev_fin[LOAD_CHUNKS + 1] = {}, ev_comp[LOAD_CHUNKS + 1] = {};
 	bool fused_pairs_done = false;    // b200_scan called from the fused path: cnt_raw already holds the pair-walk counts
 	bool keep_totals = false;         // b200_scan called for a later region of b200_scan_regions: totals and error flags accumulate
@@ -258,7 +261,8 @@ extern "C" b200_ctx_t *b200_ctx_create(int device)
 	c->dev = device; c->sm_count = prop.multiProcessorCount;
 	c->pool_limit = prop.totalGlobalMem / 2;
 	bool ok = CU_OK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) && CU_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking)) &&
-	          CU_OK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+	          CU_OK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking)) && CU_OK(cudaStreamCreateWithFlags(&c->st_comp2, cudaStreamNonBlocking)) &&
+	          CU_OK(cudaEventCreateWithFlags(&c->ev_comp2, cudaEventDisableTiming));
 	for (int i = 0; ok && i <= LOAD_CHUNKS; ++i) ok = CU_OK(cudaEventCreateWithFlags(&c->ev_fin[i], cudaEventDisableTiming)) && CU_OK(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
 	{ // the small latency-bound index kernels must not queue behind the wide kernels they overlap: highest priority
 		int prio_lo = 0, prio_hi = 0;
@@ -302,6 +306,8 @@ extern "C" void b200_ctx_destroy(b200_ctx_t *c)
 	if (c->st_copy) cudaStreamDestroy(c->st_copy);
 	if (c->st_walk) { cudaStreamSynchronize(c->st_walk); cudaStreamDestroy(c->st_walk); }
 	if (c->st_d2h) { cudaStreamSynchronize(c->st_d2h); cudaStreamDestroy(c->st_d2h); }
+	if (c->st_comp2) { cudaStreamSynchronize(c->st_comp2); cudaStreamDestroy(c->st_comp2); }
+	if (c->ev_comp2) cudaEventDestroy(c->ev_comp2);
 	for (int i = 0; i <= LOAD_CHUNKS; ++i) { if (c->ev_fin[i]) cudaEventDestroy(c->ev_fin[i]); if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]); }
 	for (int i = 0; i < N_IDX_STREAMS; ++i) if (c->st_idx[i]) cudaStreamDestroy(c->st_idx[i]);
 	if (c->st) cudaStreamDestroy(c->st);
@@ -818,6 +824,7 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 	const int n_chunks = nb >= 2 * LOAD_CHUNKS ? LOAD_CHUNKS : (nb >= 16 ? 8 : (nb > 0 ? 1 : 0));
 	size_t done = 0;
 	cudaEvent_t tev[LOAD_CHUNKS][4];
+	bool comp2_used = false;
 	if (n_chunks == 0) ok = ok && CU_OK(cudaMemsetAsync(pb->d_img, 0, 64, c->st_copy));
 	// chunk bounds: even, except that a long image starts with a ramp of short chunks (1, 2, 3, 4, 6, 8 parts of 128) so that
 	// the first index chain -- and with it the composite maps, which everything else queues behind -- starts early and
@@ -852,22 +859,26 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 		ok = ok && CU_OK(cudaStreamWaitEvent(sx, c->ev_chunk[k], 0)) && CU_OK(launch_index(index_params(pb, b0), b1 - b0, sx));
 		++c->launches;
 		ok = ok && queue_tiles_rowmeta(pb, b0, b1, sx) && queue_ranks_view(pb, b0, b1, sx);
-		ok = ok && CU_OK(cudaEventRecord(c->ev_idx[k], sx)) && CU_OK(cudaStreamWaitEvent(c->st, c->ev_idx[k], 0));
-		if (eager) { // forward composites on the main stream; the plane-1 side (inverse composites + select: small grids) stays on the index stream
-			ok = ok && compose_queue(pb, b0, b1, c->st) && select_queue(pb, b0, b1, sx, c->d_err) &&
+		static const bool one_comp_stream = getenv("BGT_B200_ONE_COMP_STREAM") != nullptr;   // (A/B measurements)
+		cudaStream_t sc = (eager && (k & 1) && !one_comp_stream) ? c->st_comp2 : c->st;
+		if (sc != c->st && !comp2_used) { comp2_used = true; ok = ok && CU_OK(cudaEventRecord(c->ev_comp2, c->st)) && CU_OK(cudaStreamWaitEvent(sc, c->ev_comp2, 0)); }   // (behind whatever was queued on st before this load)
+		ok = ok && CU_OK(cudaEventRecord(c->ev_idx[k], sx)) && CU_OK(cudaStreamWaitEvent(sc, c->ev_idx[k], 0));
+		if (eager) { // forward composites on the main stream and its twin, alternating; the plane-1 side (inverse composites + select: small grids) stays on the index stream
+			ok = ok && compose_queue(pb, b0, b1, sc) && select_queue(pb, b0, b1, sx, c->d_err) &&
 			     CU_OK(cudaEventRecord(c->ev_sel[k], sx));
 			if (fs && ok) { // the pair walk of a block reads the start ranks of the block behind it (two-sided maps): the chunk's last
 			                // block waits for the next chunk
-				ok = CU_OK(cudaEventRecord(c->ev_comp[k], c->st)) && CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_comp[k], 0)) &&
+				ok = CU_OK(cudaEventRecord(c->ev_comp[k], sc)) && CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_comp[k], 0)) &&
 				     CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_sel[k], 0)) && fused_queue(k == n_chunks - 1 ? b1 : b1 - 1, k);
 			}
 		}
 		if (trace) {
 			for (int j = 0; j < 3; ++j) cudaEventCreate(&tev[k][j]);
-			cudaEventRecord(tev[k][1], sx); cudaEventRecord(tev[k][2], c->st);
+			cudaEventRecord(tev[k][1], sx); cudaEventRecord(tev[k][2], sc);
 		}
 	}
 	ok = ok && CU_OK(cudaEventRecord(c->ev[5], c->st_copy));
+	if (comp2_used) ok = ok && CU_OK(cudaEventRecord(c->ev_comp2, c->st_comp2)) && CU_OK(cudaStreamWaitEvent(c->st, c->ev_comp2, 0));   // st covers its twin again
 	if (eager && !copy_only) for (int k = 0; ok && k < n_chunks; ++k) ok = CU_OK(cudaStreamWaitEvent(c->st, c->ev_sel[k], 0));
 	if (fs && ok && !copy_only) {
 		ok = fused_queue(nb, LOAD_CHUNKS); fs->queued = ok && fused_done_blk == nb;
@@ -886,7 +897,7 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 			for (int j = 0; j < 4; ++j) cudaEventDestroy(tev[k][j]);
 		}
 	}
-	if (!ok) { cudaStreamSynchronize(c->st_copy); for (int i = 0; i < N_IDX_STREAMS; ++i) cudaStreamSynchronize(c->st_idx[i]); cudaStreamSynchronize(c->st_walk); cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_d2h); pbf_free_device(pb); delete pb; return nullptr; }
+	if (!ok) { cudaStreamSynchronize(c->st_copy); for (int i = 0; i < N_IDX_STREAMS; ++i) cudaStreamSynchronize(c->st_idx[i]); cudaStreamSynchronize(c->st_walk); cudaStreamSynchronize(c->st_comp2); cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_d2h); pbf_free_device(pb); delete pb; return nullptr; }
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last_ms[2] = ms;
 	return pb;

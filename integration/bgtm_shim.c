@@ -17,8 +17,9 @@
  * the site contributes missing calls, i.e. nothing to AN/AC -- bgt.c:837-840, 746-756) and the -f verdict is taken on
  * the sums with the reference's own evaluator, bgtm_pass_site_flt.
  *
- * Queries outside the accelerated path (-a/-S/-H allele queries) are passed to the reference's own bgtm_read, whose
- * row decode then goes through seam A (pbwt_shim.c), i.e. still the GPU.
+ * Allele queries (-a, with -S / -H: bgt.c:844-848, 859-876): the reference's bgt_read_core already drops the sites that carry none
+ * of the listed alleles, so a feeder's batch is a handful of scattered rows (one region each); the per-sample bookkeeping of -S/-H
+ * runs on the device-decoded planes exactly where the reference runs it on pbf_read's.
  *
  * Library code: nothing here terminates the process.  A device failure makes bgtm_read return -2 (the reference's
  * only negative value is -1 = end of data, bgt.c:880-888) with the message on stderr and in pbf_b200_strerror().
@@ -28,7 +29,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include "bgt.h"
+#include "khash.h"
 #include "../include/bgt_b200.h"
+
+KHASH_SET_INIT_STR(str)                                          /* the same instantiation as bgt.c:12: bm->h_al points to one of these */
 
 int ref_bgtm_read(bgtm_t *bm, bcf1_t *b);
 int ref_bgtm_set_flt_site(bgtm_t *bm, const char *expr);
@@ -148,13 +152,38 @@ static int need_ac(const bgtm_t *bm) /* bgt.c:850 */
 	return (bm->flag & BGT_F_SET_AC) || bm->site_flt || bm->n_fields > 0 || bm->n_groups > 1;
 }
 
+/* which of the listed alleles a site carries (bgt.c:252-270): 1 its ALT, 2 its REF, 0 neither */
+static int allele_listed(void *h_al, const bcf_hdr_t *hdr, const bcf1_t *b)
+{
+	khash_t(str) *h = (khash_t(str)*)h_al;
+	bgt_allele_t alt, ref;
+	kstring_t key = {0,0,0};
+	int ret = 0;
+	memset(&alt, 0, sizeof(alt)); memset(&ref, 0, sizeof(ref));
+	bgt_al_from_bcf(hdr, b, &alt, &ref);
+	bgt_al_format(&alt, &key);
+	if (kh_get(str, h, key.s) != kh_end(h)) ret = 1;
+	else {
+		bgt_al_format(&ref, &key);
+		if (kh_get(str, h, key.s) != kh_end(h)) ret = 2;
+	}
+	free(key.s); free(alt.chr.s); free(ref.chr.s);
+	return ret;
+}
+
+/* the decoded planes are wanted for the genotype columns and for the per-sample bookkeeping of -S / -H */
+static int want_planes(const bgtm_t *bm)
+{
+	return !(bm->flag & BGT_F_NO_GT) || (bm->h_al && (bm->flag & (BGT_F_CNT_AL | BGT_F_CNT_HAP)));
+}
+
 static void decide(accel_t *a)
 {
 	bgtm_t *bm = a->bm;
 	const char *off = getenv("BGT_B200_DISABLE");
 	int i, o;
 	a->decided = 1;
-	a->eligible = bm->n_bgt >= 1 && bm->h_al == 0 && !(bm->flag & (BGT_F_CNT_AL | BGT_F_CNT_HAP)) && bm->n_out > 0 && !(off && *off == '1');
+	a->eligible = bm->n_bgt >= 1 && bm->n_out > 0 && !(off && *off == '1');
 	if (!a->eligible) return;
 	/* several files: the verdict is taken on the counts summed over the files, by the reference's evaluator on the host */
 	a->host_flt = bm->n_bgt > 1;
@@ -174,7 +203,7 @@ static int fill_batch(accel_t *a, feeder_t *f)
 	bgtm_t *bm = a->bm;
 	bgt_t *bgt = f->bgt;
 	b200_ctx_t *ctx = pbf_b200_ctx();
-	const int want_gt = !(bm->flag & BGT_F_NO_GT);
+	const int want_gt = want_planes(bm);
 	const int n_track = bgt->n_out << 1;
 	size_t map_len;
 	const uint8_t *map = pbf_b200_image(bgt->pb, &map_len);
@@ -290,15 +319,16 @@ static int fill_batch(accel_t *a, feeder_t *f)
 int bgtm_read(bgtm_t *bm, bcf1_t *b)                             /* bgt.c:880-888 and bgtm_read_core, bgt.c:797-878 */
 {
 	accel_t *a;
-	const int want_gt = !(bm->flag & BGT_F_NO_GT);
+	int want_gt;
 	if (bm->h_out == 0) bgtm_prepare(bm);
+	want_gt = want_planes(bm);
 	a = accel_get(bm, 1);
 	if (!a->decided) decide(a);
 	if (!a->eligible) { pbf_b200_route_add(3, 1); return ref_bgtm_read(bm, b); }
 	if (a->failed) return -2;
 	for (;;) {
 		const bcf1_t *b0 = 0;
-		int i, g, max_allele = 0, n_rest = 0, l_ref, pass_dev = 1;
+		int i, g, max_allele = 0, n_rest = 0, l_ref, pass_dev = 1, al_ret = 0;
 		bgt_info_t ss;
 		/* every file's next site (bgt.c:803-808); a feeder refills its batch when it has run dry */
 		for (i = 0; i < a->n_f; ++i) {
@@ -349,12 +379,25 @@ int bgtm_read(bgtm_t *bm, bcf1_t *b)                             /* bgt.c:880-88
 				memset(bm->a[1] + 2 * f->off, 1, n2);
 			}
 		}
+		if (bm->h_al && (al_ret = allele_listed(bm->h_al, bm->h_out, b)) == 0) continue;   /* bgt.c:844-848 */
 		if (need_ac(bm)) {                                       /* bgt.c:850-857 with device-computed counts */
 			bgtm_fill_info(bm->h_out, &ss, b);
 			if (bm->n_fields > 0) bgtm_gen_tbl_line(bm, &ss, b);
 			if (bm->site_flt && !(a->host_flt ? bgtm_pass_site_flt(&ss, bm->site_flt) : pass_dev)) continue;
 		}
-		if (want_gt) bgt_gen_gt(bm->h_out, b, bm->n_out, (const uint8_t**)bm->a, bm->mgs); /* bgt.c:885-886 */
+		if (bm->h_al) {                                          /* bgt.c:859-876 on the device-decoded planes */
+			const uint8_t *a0 = bm->a[0], *a1 = bm->a[1];
+			if ((bm->flag & BGT_F_CNT_AL) && bm->alcnt) {            /* -S: one more listed allele seen in these samples */
+				const int code = al_ret == 2 ? 0 : 1;                /* the listed allele is the site's REF (code 0) or its ALT (code 1) */
+				for (i = 0; i < bm->n_out; ++i)
+					bm->alcnt[i] += (a0[2 * i] | a1[2 * i] << 1) == code || (a0[2 * i + 1] | a1[2 * i + 1] << 1) == code;
+			}
+			if ((bm->flag & BGT_F_CNT_HAP) && bm->hap)                /* -H: bit n_aal of every haplotype that carries the ALT */
+				for (i = 0; i < bm->n_out << 1; ++i)
+					if (a0[i] == 1 && a1[i] == 0) bm->hap[i] |= 1ULL << bm->n_aal;
+			bgt_al_from_bcf(bm->h_out, b, &bm->aal[bm->n_aal++], 0);
+		}
+		if (!(bm->flag & BGT_F_NO_GT)) bgt_gen_gt(bm->h_out, b, bm->n_out, (const uint8_t**)bm->a, bm->mgs); /* bgt.c:885-886 */
 		return 0;
 	}
 }

@@ -311,3 +311,53 @@ def test_view_merges_several_files(tools, tmp_path):
     # sanity of the fixture: some sites are shared, some are not (total < sum of the files' sites, > the largest file)
     single = [run(tools.REF_BGT, ["view", "-G", p]).count(b"\n11\t") for p in prefixes]
     assert max(single) < run(tools.REF_BGT, ["view", "-G"] + prefixes).count(b"\n11\t") < sum(single)
+
+
+def allele_names(vcf, picks):
+    """`chr:1basedPos:refLen:seq` (view.c:69) of the ALT allele of the picks-th records of a VCF text"""
+    recs = [ln.split(b"\t") for ln in vcf.split(b"\n") if ln and ln[:1] != b"#"]
+    return [b"%s:%s:%d:%s" % (recs[i][0], recs[i][1], len(recs[i][3]), recs[i][4].split(b",")[0]) for i in picks]
+
+
+def test_view_allele_queries(tools, cohort_small, tmp_path):
+    """`-a` with and without `-S` / `-H` (bgt.c:844-848, 859-876: sites that carry a listed allele, samples that carry all of them,
+    haplotype patterns over them), one file and several: served by seam B from device-decoded planes, byte-identical."""
+    prefix, _ = cohort_small
+    sites = run(tools.REF_BGT, ["view", "-f", "AC>30", "-G", prefix])         # (alleles that many samples carry, so that -S has something to print)
+    n_site = sites.count(b"\n11\t")
+    assert n_site > 200
+    names = allele_names(sites, [3, 4, n_site // 3, n_site // 2, n_site // 2 + 1, n_site - 2, n_site - 1])   # rows on both sides of the checkpoint at 8192
+    al = "," + b",".join(names).decode()
+    lst = tmp_path / "alleles.txt"
+    lst.write_bytes(b"\n".join(names[:4]) + b"\n")
+    cases = [["-a", al, "-C"], ["-a", al], ["-a", al, "-S"], ["-a", al, "-H"], ["-a", str(lst), "-H"], ["-a", al, "-f", "AC>0", "-G"],
+             ["-a", al, "-s", 'grp=="A"', "-s", 'grp=="B"', "-H"], ["-a", al, "-s", ",S0000001,S0000007,S0000100", "-S"],
+             ["-a", "," + names[0].decode(), "-S"], ["-a", "," + (names[1] + b"," + names[5]).decode(), "-S"], ["-a", al, "-r", "11:1000-50000", "-H"]]
+    n_out = 0
+    for args in cases:
+        want = run(tools.REF_BGT, ["view"] + args + [prefix])
+        got, route, _ = run_routed(NEW_BGT, ["view"] + args + [prefix])
+        assert got == want, args
+        assert route["seamB_batches"] >= 1 and route["ref_bgtm_read"] == 0 and route["view_fast"] == 0, (args, route)
+        n_out += len(want)
+    assert n_out > 2000
+    # several files: alleles of sites that one, two or all files hold
+    rng = np.random.default_rng(32)
+    prefixes, vcfs = [], []
+    for tag, n, m, pos0, step in (("A", 120, 40, 1000, 10), ("B", 80, 24, 1000, 20), ("C", 40, 10, 1090, 30)):
+        mat = random_matrix(n, m, int(rng.integers(1 << 30)), probs=(0.55, 0.4, 0.05, 0.0))
+        vcf = tmp_path / (tag + ".vcf")
+        vcf.write_bytes(tools.vcf_text(mat, sample_names=["%s%07d" % (tag, i) for i in range(m // 2)], pos0=pos0, step=step))
+        p = str(tmp_path / (tag + ".bgt"))
+        run(tools.REF_BGT, ["import", "-S", p, str(vcf)])
+        prefixes.append(p)
+    merged = run(tools.REF_BGT, ["view", "-G"] + prefixes)
+    names = allele_names(merged, [0, 1, 2, 9, 10, 40, 77])
+    al = "," + b",".join(names).decode()
+    for args in (["-a", al, "-C"], ["-a", al, "-S"], ["-a", al, "-H"], ["-a", al, "-s", ",A0000001,B0000002,C0000003", "-s", ",A0000005,B0000001", "-H"],
+                 ["-a", "," + names[3].decode(), "-S"]):
+        want = run(tools.REF_BGT, ["view"] + args + prefixes)
+        got, route, _ = run_routed(NEW_BGT, ["view"] + args + prefixes)
+        assert got == want, args
+        assert len(want) > 20 or "-S" in args                    # (no sample need carry all the listed alleles)
+        assert route["seamB_batches"] >= 1 and route["ref_bgtm_read"] == 0, (args, route)
