@@ -443,7 +443,7 @@ def p1_sweep(rig, samples, rows):
     pts = []
     d_counts = torch.empty((rows, 6), dtype=torch.int32, device=dev)
     d_pass = torch.empty((rows,), dtype=torch.uint8, device=dev)
-    for one_in, max_iv in ((64, 3), (16, 3), (4, 3), (2, 3), (1, 3), (16, 30), (1, 30)):
+    for one_in, max_iv in ((64, 3), (16, 3), (4, 3), (2, 3), (1, 3), (16, 30), (4, 30), (1, 30)):
         pb = b.synth_cohort(ctx, samples, rows, seed=_SEED[0] + 1000 + one_in * 64 + max_iv, p1_one_in=one_in, p1_max_iv=max_iv)
         q = b.Query(ctx, pb, flt=FILTER)
         ms, tot = resident_ms(rig, pb, q, 0, rows, d_counts.data_ptr(), d_pass.data_ptr(), 3, 2)

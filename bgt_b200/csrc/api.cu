@@ -146,8 +146,12 @@ struct b200_pbf_s {
 	// "plane-1 view" of the resident blocks: only the rows whose second bit plane (missing / other-ALT codes) is not
 	// empty, as a miniature PBF image the walk kernel can run on (first phase of the split scan)
 	bool p1_ready = false;
-	int p1_cap = 0;                      // capacity of the per-block column set W
-	std::vector<uint8_t> blk_sparse;     // [n_blk] 1 = the block's plane-1 ones fit p1_cap (split scan applies)
+	int p1_cap = 0;                      // capacity of a block's (column,row) pair list
+	int p1_base = 0;                     // pairs the launches queued without knowing the data cover (the load pipeline's); blocks flagged 2 hold more
+	std::vector<uint8_t> blk_sparse;     // [n_blk] != 0: the block's plane-1 ones fit p1_cap (split scan applies); 2: more than p1_base of them
+	std::vector<uint32_t> blk_ones;      // [n_blk] plane-1 ones (= pairs) of every block
+	uint32_t *d_blk_ones = nullptr;
+	bool sel_ext_ready = false;          // the select has been extended to the slices behind p1_base of the blocks flagged 2
 	uint8_t *d_p1img = nullptr;
 	uint64_t *d_p1_rowoff = nullptr;
 	uint32_t *d_p1_n1 = nullptr, *d_p1_prefix = nullptr;
@@ -369,7 +373,7 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_blk_tile_end);
 	pool_free(pb->ctx, pb->d_blkend);
 	pool_free(pb->ctx, pb->d_ix_scratch);
-	pool_free(pb->ctx, pb->d_blk_sparse);
+	pool_free(pb->ctx, pb->d_blk_sparse); pool_free(pb->ctx, pb->d_blk_ones);
 	pool_free(pb->ctx, pb->d_tiles);
 	pool_free(pb->ctx, pb->d_n1);
 	pool_free(pb->ctx, pb->d_nrun0);
@@ -489,13 +493,34 @@ static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st, 
 	memset(&A, 0, sizeof(A));
 	A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
 	A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = nullptr; A.blk_first = b0; A.blk_ok = pb->d_blk_sparse;
-	A.m = pb->m; A.shift = pb->shift; A.cap = pb->p1_cap;
+	A.m = pb->m; A.shift = pb->shift; A.cap = pb->p1_cap; A.slice0 = 0; A.n_slices = (pb->p1_base + 2047) / 2048;   // (a slice = 512 threads x 4 pairs)
 	A.vcomp_start = pb->d_vcomp_start; A.vcomp_delta = pb->d_vcomp_delta; A.vcomp_n = pb->d_vcomp_n; A.vcomp_dir = pb->d_vcomp_dir;
 	A.dir_shift = pb->dir_shift; A.dir_n = pb->dir_n; A.p1_prefix = pb->d_p1_prefix;
 	A.qcol = pb->d_qcol; A.qrow = pb->d_qrow; A.qcount = pb->d_qcount; A.err = d_err;
 	const bool ok = CU_OK(launch_compose(V, b1 - b0, st)) && CU_OK(launch_plane1_select(A, b1 - b0, st));
 	c->launches += 3;
 	return ok;
+}
+
+// Blocks flagged 2 hold more pairs than the select launches of the load are sized for: the slices behind p1_base, once per resident
+// PBF, sized from the real pair counts (the host has them after the load)
+static bool select_extend(b200_pbf_t *pb, cudaStream_t st, int *d_err)
+{
+	if (pb->sel_ext_ready) return true;
+	uint32_t most = 0;
+	for (int b = 0; b < pb->n_blk; ++b) if (pb->blk_sparse[b] == 2 && pb->blk_ones[b] > most) most = pb->blk_ones[b];
+	pb->sel_ext_ready = true;
+	if (most <= (uint32_t)pb->p1_base) return true;
+	SelectParams A;
+	memset(&A, 0, sizeof(A));
+	A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
+	A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = nullptr; A.blk_first = 0; A.blk_ok = pb->d_blk_sparse;
+	A.m = pb->m; A.shift = pb->shift; A.cap = pb->p1_cap; A.slice0 = pb->p1_base / 2048; A.n_slices = (int)((most + 2047) / 2048) - A.slice0;
+	A.vcomp_start = pb->d_vcomp_start; A.vcomp_delta = pb->d_vcomp_delta; A.vcomp_n = pb->d_vcomp_n; A.vcomp_dir = pb->d_vcomp_dir;
+	A.dir_shift = pb->dir_shift; A.dir_n = pb->dir_n; A.p1_prefix = pb->d_p1_prefix;
+	A.qcol = pb->d_qcol; A.qrow = pb->d_qrow; A.qcount = pb->d_qcount; A.err = d_err;
+	++pb->ctx->launches;
+	return CU_OK(launch_plane1_select(A, pb->n_blk, st));
 }
 
 static bool build_composites(const b200_pbf_t *pb, int *d_err)
@@ -514,7 +539,24 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	const int n_grp = (BS + COMP_K - 1) / COMP_K;
 	// capacity of a block's (column,row) pair list: 3 pairs per column -- a block whose plane 1 holds more ones (more than
 	// one haplotype in 2700 missing / other-ALT at every site) takes the general walk
-	pb->p1_cap = (int)((((long long)pb->m * 3 > 4096 ? (long long)pb->m * 3 : 4096) + 2047) / 2048 * 2048);
+	// (r2: two tiers.  p1_base = 3 pairs per column is what the launches of the load pipeline are sized for -- nobody has seen the
+	// data then, and slices without pairs cost a CTA each; p1_cap = up to 24 per column (one haplotype in 340 missing / other-ALT at
+	// every site), memory permitting, is what the lists hold: blocks in between are flagged 2 and get extension launches sized from
+	// their real pair counts once the host has them)
+	{
+		static const int mult = getenv("BGT_B200_P1_CAP_MULT") ? atoi(getenv("BGT_B200_P1_CAP_MULT")) : 24;   // (tuning)
+		const long long base = (((long long)pb->m * 3 > 4096 ? (long long)pb->m * 3 : 4096) + 2047) / 2048 * 2048;
+		size_t free_b = 0, total_b = 0;
+		long long want = (long long)pb->m * (mult > 3 ? mult : 3);
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && nb > 0) {   // at most 1/16 of the device for the pair lists (6 bytes per slot)
+			const long long fit = (long long)(total_b / 16 / 6 / (size_t)nb);
+			if (want > fit) want = fit;
+		}
+		if (want > (1LL << 30)) want = 1LL << 30;
+		if (want < base) want = base;
+		pb->p1_base = (int)base;
+		pb->p1_cap = (int)((want + 2047) / 2048 * 2048);
+	}
 	// bucket directory of the composite maps: the smallest bucket width whose directory (+ sentinel) fits COMP_DIR entries
 	pb->dir_shift = 0;
 	while ((((uint32_t)pb->m - 1) >> pb->dir_shift) + 2 > (uint32_t)COMP_DIR) ++pb->dir_shift;
@@ -538,7 +580,7 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	          pool_malloc(c, (void**)&pb->d_p1_realrow, sizeof(uint16_t) * (size_t)nb * SELECT_MAX_ROWS + 8) &&
 	          pool_malloc(c, (void**)&pb->d_p1_rows_in_blk, sizeof(int) * (nb + 1)) &&
 	          pool_malloc(c, (void**)&pb->d_p1_vbase, sizeof(long long) * (nb + 1)) &&
-	          pool_malloc(c, (void**)&pb->d_blk_sparse, (size_t)nb + 16);
+	          pool_malloc(c, (void**)&pb->d_blk_sparse, (size_t)nb + 16) && pool_malloc(c, (void**)&pb->d_blk_ones, sizeof(uint32_t) * (size_t)nb + 16);
 	if (!ok) return false;
 	return CU_OK(cudaMemsetAsync(c->d_acc + 4, 0, 2 * sizeof(unsigned long long), up)) &&
 	       CU_OK(cudaMemsetAsync(c->d_err, 0, sizeof(int), up)) &&
@@ -577,7 +619,7 @@ static bool queue_ranks_view(b200_pbf_t *pb, int b0, int b1, cudaStream_t st)
 	P1ViewParams V;
 	memset(&V, 0, sizeof(V));
 	V.img = pb->d_img; V.rowoff = pb->d_rowoff; V.n1 = pb->d_n1; V.rows_in_blk = pb->d_rows_in_blk;
-	V.m = pb->m; V.shift = pb->shift; V.blk_first = b0; V.p1_cap = pb->p1_cap;
+	V.m = pb->m; V.shift = pb->shift; V.blk_first = b0; V.p1_cap = pb->p1_cap; V.p1_base = pb->p1_base; V.blk_ones = pb->d_blk_ones;
 	V.p1img = pb->d_p1img; V.p1_rowoff = pb->d_p1_rowoff; V.p1_n1 = pb->d_p1_n1; V.p1_realrow = pb->d_p1_realrow; V.p1_prefix = pb->d_p1_prefix;
 	V.p1_rows_in_blk = pb->d_p1_rows_in_blk; V.p1_vbase = pb->d_p1_vbase; V.blk_sparse = pb->d_blk_sparse;
 	c->launches += 2;
@@ -594,7 +636,9 @@ static bool pbf_finish_load(b200_pbf_t *pb)
 	pb->blk_sparse.assign(pb->n_blk ? pb->n_blk : 1, 0);
 	bool ok = CU_OK(cudaMemcpyAsync(&bad, c->d_acc + 4, sizeof(bad), cudaMemcpyDeviceToHost, c->st)) &&
 	          CU_OK(cudaMemcpyAsync(&err, c->d_err, sizeof(err), cudaMemcpyDeviceToHost, c->st));
-	if (ok && pb->n_blk) ok = CU_OK(cudaMemcpyAsync(pb->blk_sparse.data(), pb->d_blk_sparse, (size_t)pb->n_blk, cudaMemcpyDeviceToHost, c->st));
+	pb->blk_ones.assign(pb->n_blk ? pb->n_blk : 1, 0);
+	if (ok && pb->n_blk) ok = CU_OK(cudaMemcpyAsync(pb->blk_sparse.data(), pb->d_blk_sparse, (size_t)pb->n_blk, cudaMemcpyDeviceToHost, c->st)) &&
+	                          CU_OK(cudaMemcpyAsync(pb->blk_ones.data(), pb->d_blk_ones, sizeof(uint32_t) * (size_t)pb->n_blk, cudaMemcpyDeviceToHost, c->st));
 	ok = ok && CU_OK(cudaStreamSynchronize(c->st));
 	if (!ok) return false;
 	pb->bad_rows = (int64_t)bad;
@@ -798,7 +842,7 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 		fused_done_blk = hi;
 		PairParams K = FK;
 		K.blk_list = nullptr; K.blk_first = lo;
-		bool good = CU_OK(launch_pairwalk(K, 4, pb->p1_cap, hi - lo, c->st_walk));
+		bool good = CU_OK(launch_pairwalk(K, 4, pb->p1_base, hi - lo, c->st_walk));   // (blocks flagged 2 are redone by the ordinary scan)
 		++c->launches;
 		const long long blk_row0 = (long long)pb->blk0 << pb->shift;
 		long long r0 = blk_row0 + ((long long)lo << pb->shift), r1 = blk_row0 + ((long long)hi << pb->shift);
@@ -1300,7 +1344,18 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			}
 			static const int env_c = getenv("BGT_B200_PAIR_C") ? atoi(getenv("BGT_B200_PAIR_C")) : 0;   // tuning
 			const int Cp = (forced == 1 || forced == 2 || forced == 4) ? forced : (env_c == 1 || env_c == 2 || env_c == 4 ? env_c : 4);
-			ok = ok && CU_OK(launch_pairwalk(K, Cp, cap, n_range, c->st));
+			// grid from the real pair counts (the host has them since the load); the slices behind p1_base -- blocks flagged 2 -- in a
+			// second launch, after the select has been extended to them
+			uint32_t most = 0; bool ext = false;
+			for (int b = b_first; b <= b_last; ++b) if (pb->blk_sparse[b]) { if (pb->blk_ones[b] > most) most = pb->blk_ones[b]; ext = ext || pb->blk_sparse[b] == 2; }
+			const int base_pairs = most < (uint32_t)pb->p1_base ? (int)most : pb->p1_base;
+			if (base_pairs > 0) ok = ok && CU_OK(launch_pairwalk(K, Cp, base_pairs, n_range, c->st));
+			if (ext && most > (uint32_t)pb->p1_base) {
+				ok = ok && select_extend(const_cast<b200_pbf_t*>(pb), c->st, c->d_err_scan);
+				K.slice0 = pb->p1_base / (PAIR_SLICE_THREADS * Cp);
+				ok = ok && CU_OK(launch_pairwalk(K, Cp, (int)(most - (uint32_t)pb->p1_base), n_range, c->st));
+				++c->launches;
+			}
 			if (prof) {
 				unsigned long long h[8];
 				cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, c->st);
@@ -1554,8 +1609,8 @@ extern "C" b200_pbf_t *b200_pbf_load_scan(b200_ctx_t *c, const uint8_t *f, size_
 	b200_pbf_t *pb = pbf_load_impl(c, f, flen, row_beg, row_end, B200_LOAD_PREPARE_COUNT_SCAN, fuse ? &fs : nullptr);
 	if (!pb) return nullptr;
 	if (row_end == row_beg) return pb;
-	bool all_split = fuse && fs.queued;
-	for (int b = 0; all_split && b < pb->n_blk; ++b) all_split = pb->blk_sparse[b] != 0;
+	bool all_split = fuse && fs.queued, none_ext = true;
+	for (int b = 0; b < pb->n_blk; ++b) { all_split = all_split && pb->blk_sparse[b] == 1; none_ext = none_ext && pb->blk_sparse[b] != 2; }
 	if (all_split) { // everything was queued while loading: wait for the results, fetch totals and error flags
 		unsigned long long dtot[4];
 		int err = 0;
@@ -1570,7 +1625,7 @@ extern "C" b200_pbf_t *b200_pbf_load_scan(b200_ctx_t *c, const uint8_t *f, size_
 	// some block is off the split path (dense plane 1), or the query is not of the fused kind: the ordinary scan -- it keeps the
 	// pair-walk counts the pipeline has already produced
 	cudaStreamSynchronize(c->st_d2h);
-	c->fused_pairs_done = fuse && fs.queued;
+	c->fused_pairs_done = fuse && fs.queued && none_ext;      // (a block flagged 2 was only walked as far as the pipeline's launches reach: all over again)
 	const int64_t done = b200_scan(c, pb, q, row_beg, row_end - row_beg, B200_SCAN_COUNTS, out);
 	c->fused_pairs_done = false;
 	if (done != row_end - row_beg) { b200_pbf_close(pb); return nullptr; }

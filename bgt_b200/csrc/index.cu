@@ -432,7 +432,8 @@ __global__ void __launch_bounds__(P1V_NT) p1view_kernel(const P1ViewParams P)
 	if (tid == 0) {
 		const bool fits = s_rows <= (uint32_t)SELECT_MAX_ROWS && s_bytes <= (uint32_t)SELECT_MAX_BYTES;
 		const bool sparse = fits && !s_allones && s_ones <= (unsigned long long)P.p1_cap && BS <= 65536;
-		P.blk_sparse[blk] = sparse ? 1 : 0;
+		P.blk_sparse[blk] = sparse ? (s_ones <= (unsigned long long)P.p1_base ? 1 : 2) : 0;
+		if (P.blk_ones) P.blk_ones[blk] = s_ones < 0xffffffffull ? (uint32_t)s_ones : 0xffffffffu;
 		P.p1_rows_in_blk[blk] = fits ? (int)s_rows : 0;
 		P.p1_vbase[blk] = (long long)vb;
 		vro[fits ? s_rows : 0] = slot + (fits ? s_bytes : 0);

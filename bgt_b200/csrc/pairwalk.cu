@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(PW_NT, 2) pbwt_pair_kernel(const PairParams P)
 	const int blk = P.blk_list ? P.blk_list[blockIdx.y] : P.blk_first + (int)blockIdx.y;
 	if (P.blk_ok && !P.blk_ok[blk]) return;
 	const int n_pairs = P.qcount[blk];
-	const int slice_base = blockIdx.x * (PW_NT * C);
+	const int slice_base = ((int)blockIdx.x + P.slice0) * (PW_NT * C);
 	if (slice_base >= n_pairs) return;
 	const uint32_t m = (uint32_t)P.m;
 	const int32_t *qcol = P.qcol + (size_t)blk * P.q_stride;

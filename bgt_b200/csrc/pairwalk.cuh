@@ -11,7 +11,7 @@ namespace b200 {
 
 #define PW_FULL 0xffffffffu
 
-constexpr int PW_NT = 512, PW_NW = PW_NT / 32;
+constexpr int PW_NT = PAIR_SLICE_THREADS, PW_NW = PW_NT / 32;
 constexpr int PW_STAGES = 3;
 constexpr uint32_t PW_STG_TD = COMP_CAP * 4u, PW_STG_DIR = COMP_CAP * 8u, PW_STG_BYTES = COMP_CAP * 8u + COMP_DIR_STRIDE * 2u;
 // phase B: every warp owns a slice of the (then idle) stages: a run table of PW_TAB2 entries (ts + td) and PW_RAW staged record bytes

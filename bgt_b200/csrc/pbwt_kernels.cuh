@@ -101,7 +101,9 @@ struct PairParams {
 	int two_sided, n_blk_res;    // see comp_first_inverse
 	int *err;
 	unsigned long long *prof;    // diagnostics (BGT_B200_PROF): [0] CTA cycles in phase A, [1] in phase B, [2] CTAs, [3] composite groups crossed, [4] rows walked by warps
+	int slice0;                  // this launch covers the slices from slice0 on (the extension launch of blocks flagged 2)
 };
+constexpr int PAIR_SLICE_THREADS = 512;   // threads of a pair-walk / select CTA; a slice of a block's pair list = PAIR_SLICE_THREADS x C pairs
 size_t pair_smem_bytes();
 cudaError_t launch_pairwalk(const PairParams &P, int C, int max_pairs, int n_blk, cudaStream_t st);
 
@@ -158,6 +160,7 @@ struct SelectParams {
 	uint16_t *qrow;               // out [blocks][cap]
 	int      *qcount;             // out [blocks]
 	int      *err;
+	int slice0, n_slices;         // this launch covers the slices [slice0, slice0 + n_slices) of every block's pair list (n_slices 0: all that cap holds)
 };
 // the plane-1 view of a block: up to SELECT_MAX_ROWS non-empty rows (every row of an ordinary block) in SELECT_MAX_BYTES of
 // re-framed records; inverse composite maps of its 32-row groups with up to SELECT_COMP_CAP pieces
@@ -190,6 +193,8 @@ struct P1ViewParams {
 	const uint32_t *n1;
 	const int      *rows_in_blk;
 	int m, shift, blk_first, p1_cap;
+	int p1_base;                  // blocks with more plane-1 ones than this (and at most p1_cap) are flagged 2 instead of 1 (see blk_sparse)
+	uint32_t  *blk_ones;          // out [blocks] plane-1 ones (= (column,row) pairs) of the block
 	uint8_t   *p1img;             // out [blocks][P1_SLOT_BYTES]
 	uint64_t  *p1_rowoff;         // out [blocks][SELECT_MAX_ROWS+1]
 	uint32_t  *p1_n1;             // out [blocks][SELECT_MAX_ROWS]
@@ -197,7 +202,9 @@ struct P1ViewParams {
 	uint16_t  *p1_realrow;        // out [blocks][SELECT_MAX_ROWS]
 	int       *p1_rows_in_blk;    // out [blocks]
 	long long *p1_vbase;          // out [blocks] = blk * SELECT_MAX_ROWS
-	uint8_t   *blk_sparse;        // out [blocks] 1 = the split scan applies to the block
+	uint8_t   *blk_sparse;        // out [blocks] != 0: the split scan applies to the block.  1: its pairs fit the launches that are sized
+	                              // without knowing the data (p1_base: the load pipeline's); 2: they need the extension launches (slices behind
+	                              // p1_base, queued once the host has seen blk_ones)
 };
 cudaError_t launch_p1view(const P1ViewParams &P, int n_blk, cudaStream_t st);
 

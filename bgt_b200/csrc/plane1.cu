@@ -39,16 +39,16 @@ __global__ void __launch_bounds__(PW_NT, 2) plane1_select_kernel(const SelectPar
 	extern __shared__ __align__(128) uint8_t p1_sm[];
 	__shared__ SelSmem S;
 	const int blk = P.blk_list ? P.blk_list[blockIdx.y] : P.blk_first + (int)blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (P.blk_ok && !P.blk_ok[blk]) { if (tid == 0 && blockIdx.x == 0) P.qcount[blk] = 0; return; }   // not a sparse block: the general walk takes it
+	if (P.blk_ok && !P.blk_ok[blk]) { if (tid == 0 && blockIdx.x == 0 && P.slice0 == 0) P.qcount[blk] = 0; return; }   // not a sparse block: the general walk takes it
 	const int nv = P.p1_rows_in_blk[blk];
 	const long long vb = P.p1_vbase[blk];
 	const uint64_t *ro = P.p1_rowoff + vb + blk;
 	const uint32_t *prefix = P.p1_prefix + vb + blk;
 	const uint32_t *n1v = P.p1_n1 + vb;
 	const uint32_t Q = prefix[nv];
-	if (Q > (uint32_t)P.cap) { if (tid == 0 && blockIdx.x == 0) { atomicOr(P.err, 32); P.qcount[blk] = 0; } return; }
-	if (tid == 0 && blockIdx.x == 0) P.qcount[blk] = (int)Q;
-	const uint32_t slice_base = blockIdx.x * (uint32_t)(PW_NT * C);
+	if (Q > (uint32_t)P.cap) { if (tid == 0 && blockIdx.x == 0 && P.slice0 == 0) { atomicOr(P.err, 32); P.qcount[blk] = 0; } return; }
+	if (tid == 0 && blockIdx.x == 0 && P.slice0 == 0) P.qcount[blk] = (int)Q;
+	const uint32_t slice_base = (blockIdx.x + (uint32_t)P.slice0) * (uint32_t)(PW_NT * C);
 	if (slice_base >= Q) return;
 	const uint32_t m = (uint32_t)P.m;
 
@@ -202,7 +202,8 @@ cudaError_t launch_plane1_select(const SelectParams &P, int n_blk, cudaStream_t 
 	const size_t smem = (size_t)PW_STAGES * P1_STG_BYTES;
 	cudaError_t e = cudaFuncSetAttribute(plane1_select_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
-	const int slices = (P.cap + PW_NT * C - 1) / (PW_NT * C);
+	const int slices = P.n_slices > 0 ? P.n_slices : (P.cap + PW_NT * C - 1) / (PW_NT * C) - P.slice0;
+	if (slices <= 0) return cudaSuccess;
 	for (int b0 = 0; b0 < n_blk; b0 += 32768) {
 		SelectParams Q = P;
 		if (P.blk_list) Q.blk_list = P.blk_list + b0; else Q.blk_first = P.blk_first + b0;

@@ -468,3 +468,36 @@ def test_batched_regions_equal_one_scan_per_region(b200, ctx, oracle):
         assert got["totals"] == [int(x) for x in tot], kw
         q.close()
     pb.close()
+
+
+def test_blocks_between_the_two_pair_capacities_stay_on_the_split_path(b200, ctx, oracle):
+    """Plane 1 with more ones per block than the launches of the load pipeline are sized for (3 per column) but within what the pair
+    lists hold (up to 24 per column): such blocks are flagged 2, keep the split scan, and get extension launches of the select and
+    of the pair walk sized from their real counts; b200_pbf_load_scan must notice and redo them.  One group, groups, row ranges."""
+    n_samples, n_rows, shift = 1500, 1200, 8
+    pb0 = b200.synth_cohort(ctx, n_samples, n_rows, seed=77, shift=shift, r_max=12, p1_one_in=1, p1_max_iv=6, p1_max_len=40)
+    img = pb0.image()
+    n_blk = (n_rows + (1 << shift) - 1) >> shift
+    assert b200.lib().b200_pbf_split_blocks(pb0.h) == n_blk                    # every block on the split path ...
+    op = oracle.Pbf(img.tobytes())
+    m = 2 * n_samples
+    want = op.scan(0, n_rows, flt="AC>0")
+    plane1 = (m * n_rows - int(want["counts"][:, 0].astype(np.int64).sum())) + int(want["counts"][:, 2].astype(np.int64).sum())
+    assert plane1 / n_blk > 3.5 * m                                             # ... although they hold more pairs than 3 per column
+    q = b200.Query(ctx, m, flt="AC>0")
+    for kw in (dict(), dict(no_split=True)):
+        got = b200.scan(ctx, pb0, q, 0, n_rows, **kw)
+        assert (got["counts"] == want["counts"]).all() and (got["passed"] == want["passed"]).all(), kw
+    for beg, cnt in ((300, 500), (255, 2), (n_rows - 100, 100)):
+        got = b200.scan(ctx, pb0, q, beg, cnt)
+        assert (got["counts"] == want["counts"][beg:beg + cnt]).all(), beg
+    pb, got = b200.load_scan(ctx, img, q, 0, n_rows)                            # the pipeline's launches do not reach all pairs: redone
+    assert (got["counts"] == want["counts"]).all() and (got["passed"] == want["passed"]).all()
+    assert got["totals"][3] == int(want["passed"].sum())
+    pb.close(); q.close()
+    grp = (np.arange(n_samples) % 3 == 0).astype(np.uint32) + 1
+    wantg = op.scan(0, n_rows, group=grp, n_groups=2, flt="AC1>AC2")
+    qg = b200.Query(ctx, m, group=grp, n_groups=2, flt="AC1>AC2")
+    got = b200.scan(ctx, pb0, qg, 0, n_rows)
+    assert (got["counts"] == wantg["counts"]).all() and (got["passed"] == wantg["passed"]).all()
+    qg.close(); pb0.close(); op.close()
