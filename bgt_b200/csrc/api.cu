@@ -151,7 +151,9 @@ struct b200_pbf_s {
 	std::vector<uint8_t> blk_sparse;     // [n_blk] != 0: the block's plane-1 ones fit p1_cap (split scan applies); 2: more than p1_base of them
 	std::vector<uint32_t> blk_ones;      // [n_blk] plane-1 ones (= pairs) of every block
 	uint32_t *d_blk_ones = nullptr;
-	bool sel_ext_ready = false;          // the select has been extended to the slices behind p1_base of the blocks flagged 2
+	bool sel_ext_ready = false;          // the select has been extended to the slices behind p1_base of the blocks flagged 2: their pairs
+	int32_t *d_qcol_ext = nullptr; uint16_t *d_qrow_ext = nullptr; long long *d_ext_off = nullptr;   // from p1_base on live here, block after block
+	std::vector<long long> ext_off;
 	uint8_t *d_p1img = nullptr;
 	uint64_t *d_p1_rowoff = nullptr;
 	uint32_t *d_p1_n1 = nullptr, *d_p1_prefix = nullptr;
@@ -374,6 +376,7 @@ static void pbf_free_device(b200_pbf_t *pb)
 	pool_free(pb->ctx, pb->d_blkend);
 	pool_free(pb->ctx, pb->d_ix_scratch);
 	pool_free(pb->ctx, pb->d_blk_sparse); pool_free(pb->ctx, pb->d_blk_ones);
+	pool_free(pb->ctx, pb->d_qcol_ext); pool_free(pb->ctx, pb->d_qrow_ext); pool_free(pb->ctx, pb->d_ext_off);
 	pool_free(pb->ctx, pb->d_tiles);
 	pool_free(pb->ctx, pb->d_n1);
 	pool_free(pb->ctx, pb->d_nrun0);
@@ -451,8 +454,8 @@ static bool compose_alloc(const b200_pbf_t *pb)
 	          pool_malloc(c, (void**)&pb->d_vcomp_delta, vslots * SELECT_COMP_CAP * sizeof(int32_t)) &&
 	          pool_malloc(c, (void**)&pb->d_vcomp_n, vslots * sizeof(int) + 16) &&
 	          pool_malloc(c, (void**)&pb->d_vcomp_dir, vslots * COMP_DIR_STRIDE * sizeof(uint16_t) + 16) &&
-	          pool_malloc(c, (void**)&pb->d_qcol, (size_t)pb->n_blk * pb->p1_cap * sizeof(int32_t) + 16) &&
-	          pool_malloc(c, (void**)&pb->d_qrow, (size_t)pb->n_blk * pb->p1_cap * sizeof(uint16_t) + 16) &&
+	          pool_malloc(c, (void**)&pb->d_qcol, (size_t)pb->n_blk * pb->p1_base * sizeof(int32_t) + 16) &&   // (the first p1_base pairs of every block;
+	          pool_malloc(c, (void**)&pb->d_qrow, (size_t)pb->n_blk * pb->p1_base * sizeof(uint16_t) + 16) &&  //  the rest: select_extend)
 	          pool_malloc(c, (void**)&pb->d_qcount, (size_t)pb->n_blk * sizeof(int) + 16);
 	return ok && CU_OK(cudaMemsetAsync(pb->d_comp_n, 0, slots * sizeof(int), c->st)) && CU_OK(cudaMemsetAsync(pb->d_vcomp_n, 0, vslots * sizeof(int), c->st));
 }
@@ -494,6 +497,7 @@ static bool select_queue(const b200_pbf_t *pb, int b0, int b1, cudaStream_t st, 
 	A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
 	A.p1_rows_in_blk = pb->d_p1_rows_in_blk; A.img = pb->d_img; A.blkoff = pb->d_blkoff; A.blk_list = nullptr; A.blk_first = b0; A.blk_ok = pb->d_blk_sparse;
 	A.m = pb->m; A.shift = pb->shift; A.cap = pb->p1_cap; A.slice0 = 0; A.n_slices = (pb->p1_base + 2047) / 2048;   // (a slice = 512 threads x 4 pairs)
+	A.q_stride = pb->p1_base;
 	A.vcomp_start = pb->d_vcomp_start; A.vcomp_delta = pb->d_vcomp_delta; A.vcomp_n = pb->d_vcomp_n; A.vcomp_dir = pb->d_vcomp_dir;
 	A.dir_shift = pb->dir_shift; A.dir_n = pb->dir_n; A.p1_prefix = pb->d_p1_prefix;
 	A.qcol = pb->d_qcol; A.qrow = pb->d_qrow; A.qcount = pb->d_qcount; A.err = d_err;
@@ -511,6 +515,16 @@ static bool select_extend(b200_pbf_t *pb, cudaStream_t st, int *d_err)
 	for (int b = 0; b < pb->n_blk; ++b) if (pb->blk_sparse[b] == 2 && pb->blk_ones[b] > most) most = pb->blk_ones[b];
 	pb->sel_ext_ready = true;
 	if (most <= (uint32_t)pb->p1_base) return true;
+	b200_ctx_t *c = pb->ctx;
+	long long total = 0;
+	pb->ext_off.assign(pb->n_blk, 0);
+	for (int b = 0; b < pb->n_blk; ++b) {
+		pb->ext_off[b] = total;
+		if (pb->blk_sparse[b] == 2 && pb->blk_ones[b] > (uint32_t)pb->p1_base) total += ((long long)pb->blk_ones[b] - pb->p1_base + 15) & ~15LL;
+	}
+	if (!pool_malloc(c, (void**)&pb->d_qcol_ext, (size_t)total * sizeof(int32_t) + 16) || !pool_malloc(c, (void**)&pb->d_qrow_ext, (size_t)total * sizeof(uint16_t) + 16) ||
+	    !pool_malloc(c, (void**)&pb->d_ext_off, (size_t)pb->n_blk * sizeof(long long) + 16) ||
+	    !CU_OK(cudaMemcpyAsync(pb->d_ext_off, pb->ext_off.data(), (size_t)pb->n_blk * sizeof(long long), cudaMemcpyHostToDevice, st))) { pb->sel_ext_ready = false; return false; }
 	SelectParams A;
 	memset(&A, 0, sizeof(A));
 	A.p1img = pb->d_p1img; A.p1_rowoff = pb->d_p1_rowoff; A.p1_n1 = pb->d_p1_n1; A.p1_realrow = pb->d_p1_realrow; A.p1_vbase = pb->d_p1_vbase;
@@ -518,7 +532,7 @@ static bool select_extend(b200_pbf_t *pb, cudaStream_t st, int *d_err)
 	A.m = pb->m; A.shift = pb->shift; A.cap = pb->p1_cap; A.slice0 = pb->p1_base / 2048; A.n_slices = (int)((most + 2047) / 2048) - A.slice0;
 	A.vcomp_start = pb->d_vcomp_start; A.vcomp_delta = pb->d_vcomp_delta; A.vcomp_n = pb->d_vcomp_n; A.vcomp_dir = pb->d_vcomp_dir;
 	A.dir_shift = pb->dir_shift; A.dir_n = pb->dir_n; A.p1_prefix = pb->d_p1_prefix;
-	A.qcol = pb->d_qcol; A.qrow = pb->d_qrow; A.qcount = pb->d_qcount; A.err = d_err;
+	A.qcol = pb->d_qcol_ext; A.qrow = pb->d_qrow_ext; A.ext_off = pb->d_ext_off; A.ext_shift = pb->p1_base; A.qcount = pb->d_qcount; A.err = d_err;
 	++pb->ctx->launches;
 	return CU_OK(launch_plane1_select(A, pb->n_blk, st));
 }
@@ -540,18 +554,13 @@ static bool pbf_alloc_index(b200_pbf_t *pb, cudaStream_t up)
 	// capacity of a block's (column,row) pair list: 3 pairs per column -- a block whose plane 1 holds more ones (more than
 	// one haplotype in 2700 missing / other-ALT at every site) takes the general walk
 	// (r2: two tiers.  p1_base = 3 pairs per column is what the launches of the load pipeline are sized for -- nobody has seen the
-	// data then, and slices without pairs cost a CTA each; p1_cap = up to 24 per column (one haplotype in 340 missing / other-ALT at
-	// every site), memory permitting, is what the lists hold: blocks in between are flagged 2 and get extension launches sized from
-	// their real pair counts once the host has them)
+	// data then, and slices without pairs cost a CTA each -- and for which the lists are allocated up front; p1_cap = 24 per column
+	// (one haplotype in 340 missing / other-ALT at every site) is what a block may hold: blocks in between are flagged 2 and get
+	// extension launches and extension lists sized from their real pair counts once the host has them)
 	{
 		static const int mult = getenv("BGT_B200_P1_CAP_MULT") ? atoi(getenv("BGT_B200_P1_CAP_MULT")) : 24;   // (tuning)
 		const long long base = (((long long)pb->m * 3 > 4096 ? (long long)pb->m * 3 : 4096) + 2047) / 2048 * 2048;
-		size_t free_b = 0, total_b = 0;
 		long long want = (long long)pb->m * (mult > 3 ? mult : 3);
-		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && nb > 0) {   // at most 1/16 of the device for the pair lists (6 bytes per slot)
-			const long long fit = (long long)(total_b / 16 / 6 / (size_t)nb);
-			if (want > fit) want = fit;
-		}
 		if (want > (1LL << 30)) want = 1LL << 30;
 		if (want < base) want = base;
 		pb->p1_base = (int)base;
@@ -1186,7 +1195,7 @@ static PairParams pair_params(b200_ctx_t *c, const b200_pbf_t *pb, const b200_qu
 	PairParams K;
 	memset(&K, 0, sizeof(K));
 	K.img = pb->d_img; K.rowoff = pb->d_rowoff; K.n1 = pb->d_n1; K.rank0 = pb->d_rank0;
-	K.qcol = pb->d_qcol; K.qrow = pb->d_qrow; K.qcount = pb->d_qcount; K.q_stride = pb->p1_cap; K.tgrp = q->d_tgrp;
+	K.qcol = pb->d_qcol; K.qrow = pb->d_qrow; K.qcount = pb->d_qcount; K.q_stride = pb->p1_base; K.tgrp = q->d_tgrp;
 	K.comp_start = pb->d_comp_start; K.comp_delta = pb->d_comp_delta; K.comp_n = pb->d_comp_n; K.comp_dir = pb->d_comp_dir;
 	K.dir_shift = pb->dir_shift; K.dir_n = pb->dir_n; K.cnt_raw = (int32_t*)c->cnt_raw.p;
 	K.m = pb->m; K.G = q->G; K.shift = pb->shift; K.blk_row0 = (long long)pb->blk0 << pb->shift; K.row_lo = row_lo; K.row_hi = row_hi; K.err = c->d_err_scan;
@@ -1353,6 +1362,7 @@ extern "C" int64_t b200_scan(b200_ctx_t *c, const b200_pbf_t *pb, const b200_que
 			if (ext && most > (uint32_t)pb->p1_base) {
 				ok = ok && select_extend(const_cast<b200_pbf_t*>(pb), c->st, c->d_err_scan);
 				K.slice0 = pb->p1_base / (PAIR_SLICE_THREADS * Cp);
+				K.qcol = pb->d_qcol_ext; K.qrow = pb->d_qrow_ext; K.ext_off = pb->d_ext_off; K.ext_shift = pb->p1_base;
 				ok = ok && CU_OK(launch_pairwalk(K, Cp, (int)(most - (uint32_t)pb->p1_base), n_range, c->st));
 				++c->launches;
 			}

@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(PW_NT, 2) pbwt_pair_kernel(const PairParams P)
 	const int slice_base = ((int)blockIdx.x + P.slice0) * (PW_NT * C);
 	if (slice_base >= n_pairs) return;
 	const uint32_t m = (uint32_t)P.m;
-	const int32_t *qcol = P.qcol + (size_t)blk * P.q_stride;
-	const uint16_t *qrow = P.qrow + (size_t)blk * P.q_stride;
+	const long long list_at = P.ext_off ? P.ext_off[blk] - P.ext_shift : (long long)blk * P.q_stride;
+	const int32_t *qcol = P.qcol + list_at;
+	const uint16_t *qrow = P.qrow + list_at;
 	const long long blk_row = P.blk_row0 + ((long long)blk << P.shift);
 	const int n_grp = (BS + COMP_K - 1) / COMP_K;
 	const uint64_t *roff = P.rowoff + (size_t)blk * (BS + 1);

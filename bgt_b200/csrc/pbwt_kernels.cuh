@@ -102,6 +102,8 @@ struct PairParams {
 	int *err;
 	unsigned long long *prof;    // diagnostics (BGT_B200_PROF): [0] CTA cycles in phase A, [1] in phase B, [2] CTAs, [3] composite groups crossed, [4] rows walked by warps
 	int slice0;                  // this launch covers the slices from slice0 on (the extension launch of blocks flagged 2)
+	const long long *ext_off;    // extension launch: qcol/qrow are the extension arrays, pair q of block b lives at ext_off[b] + q - ext_shift
+	long long ext_shift;
 };
 constexpr int PAIR_SLICE_THREADS = 512;   // threads of a pair-walk / select CTA; a slice of a block's pair list = PAIR_SLICE_THREADS x C pairs
 size_t pair_smem_bytes();
@@ -161,6 +163,9 @@ struct SelectParams {
 	int      *qcount;             // out [blocks]
 	int      *err;
 	int slice0, n_slices;         // this launch covers the slices [slice0, slice0 + n_slices) of every block's pair list (n_slices 0: all that cap holds)
+	long long q_stride;           // entries between the lists of consecutive blocks in qcol/qrow (0: cap)
+	const long long *ext_off;     // extension launch: qcol/qrow are the extension arrays, pair q of block b goes to ext_off[b] + q - ext_shift
+	long long ext_shift;
 };
 // the plane-1 view of a block: up to SELECT_MAX_ROWS non-empty rows (every row of an ordinary block) in SELECT_MAX_BYTES of
 // re-framed records; inverse composite maps of its 32-row groups with up to SELECT_COMP_CAP pieces

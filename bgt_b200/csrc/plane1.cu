@@ -190,8 +190,9 @@ __global__ void __launch_bounds__(PW_NT, 2) plane1_select_kernel(const SelectPar
 		const uint32_t q = slice_base + warp * (C * 32) + lane * C + c;
 		const uint32_t col = r[c] < m ? pw_ld_u32_unaligned(S1 + 4 * (size_t)r[c]) : 0xffffffffu;
 		if (col >= m) { atomicOr(P.err, 64); continue; }
-		P.qcol[(size_t)blk * P.cap + q] = (int32_t)col;
-		P.qrow[(size_t)blk * P.cap + q] = P.p1_realrow[vb + vrow[c]];
+		const long long at = (P.ext_off ? P.ext_off[blk] - P.ext_shift : (long long)blk * (P.q_stride ? P.q_stride : (long long)P.cap)) + q;
+		P.qcol[at] = (int32_t)col;
+		P.qrow[at] = P.p1_realrow[vb + vrow[c]];
 	}
 }
 
