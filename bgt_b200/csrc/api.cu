@@ -922,7 +922,13 @@ static b200_pbf_t *pbf_load_impl(b200_ctx_t *c, const uint8_t *f, size_t flen, i
 			if (fs && ok) { // the pair walk of a block reads the start ranks of the block behind it (two-sided maps): the chunk's last
 			                // block waits for the next chunk
 				ok = CU_OK(cudaEventRecord(c->ev_comp[k], sc)) && CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_comp[k], 0)) &&
-				     CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_sel[k], 0)) && fused_queue(k == n_chunks - 1 ? b1 : b1 - 1, k);
+				     CU_OK(cudaStreamWaitEvent(c->st_walk, c->ev_sel[k], 0));
+				// (a chunk's pair walk is fewer CTAs than the device holds, each alive for hundreds of microseconds with 110 KB of shared
+				// memory beside the composite maps of the next chunks.  Queueing it behind every second chunk -- fewer, fuller launches --
+				// measured 8.45 against 8.64 ms per step (two boxes, interleaved runs); every 4th: no gain, every 8th: 9.1 ms, the
+				// last walk behind the last copy gets too long.  BGT_B200_PAIR_EVERY for A/B runs.)
+				static const int pair_every = getenv("BGT_B200_PAIR_EVERY") ? atoi(getenv("BGT_B200_PAIR_EVERY")) : 2;
+				if (ok && ((k + 1) % (pair_every > 0 ? pair_every : 1) == 0 || k == n_chunks - 1)) ok = fused_queue(k == n_chunks - 1 ? b1 : b1 - 1, k);
 			}
 		}
 		if (trace) {
